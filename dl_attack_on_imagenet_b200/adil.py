@@ -1,0 +1,579 @@
+"""B200-native ADiL ("Adversarial Dictionary Learning") attack: drop-in mirror of the reference class
+`attacks/attacks_classes/adil.py::ADIL` (constructor signature adil.py:63-66, `attack(images, labels)`,
+saved-dictionary format adil.py:210), with the attack-learning hot path running in hand-written sm_100a
+kernels behind the C ABI of include/adil_b200.h:
+
+    synthesis      x + D.v, Normalize, clamps             -> adil_synth          (adil.py:24-27)
+    backward       dD = g^T v, dv = g D, AdamW(D), clamp  -> adil_grad_dict_step (adil.py:185-186,188)
+    code update    scatter, AdamW(v) on all rows, l1 proj -> adil_code_step      (adil.py:186-187)
+
+The classifier forward/backward stays in PyTorch/cuDNN.  There is no CPU fallback: the model must live on a
+CUDA device and libadil_b200.so must be built.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import distributed as dsh
+from . import ops
+from .attack_base import Attack
+from .utils import QuickAttackDataset
+
+
+def split_normalize(model):
+    """Peel a leading Normalize-like module (3-element `mean`/`std` buffers, no parameters -- the module of
+    demo_dL_attack.py:16-25) off `model`.  Returns (net, mean, std) or (model, None, None)."""
+    if isinstance(model, nn.Sequential) and len(model) >= 2:
+        first = model[0]
+        mean, std = getattr(first, 'mean', None), getattr(first, 'std', None)
+        if torch.is_tensor(mean) and torch.is_tensor(std) and mean.numel() == std.numel() <= 8 \
+                and not list(first.parameters()):
+            rest = model[1] if len(model) == 2 else nn.Sequential(*list(model)[1:])
+            return rest, [float(a) for a in mean.reshape(-1).cpu()], [float(a) for a in std.reshape(-1).cpu()]
+    return model, None, None
+
+
+class _IndexOnly(torch.utils.data.Dataset):
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, item):
+        return item
+
+
+class AdilState(object):
+    """Learnables and AdamW state, all resident in HBM.  D: [C,H,W,K] (atoms innermost), v: [N,K]."""
+
+    def __init__(self, D, v):
+        self.D = D.contiguous()
+        self.K = D.shape[-1]
+        self.D2 = self.D.view(-1, self.K)
+        self.v = v.contiguous()
+        self.mD = torch.zeros_like(self.D2)
+        self.sD = torch.zeros_like(self.D2)
+        self.mv = torch.zeros_like(self.v)
+        self.sv = torch.zeros_like(self.v)
+        self.tD = 0
+        self.tv = 0
+
+
+class Attack_dict_model(nn.Module):
+    """Mirror of adil.py:16-35 (learnables d, v; forward = synthesis + classifier; projections)."""
+
+    def __init__(self, d, v, eps):
+        super().__init__()
+        self.d = nn.Parameter(d)
+        self.v = nn.Parameter(v)
+        self.eps = eps
+
+    def forward(self, x, index, model):
+        net, mean, std = split_normalize(model)
+        index = torch.as_tensor(index, dtype=torch.long, device=self.d.device)
+        flags = ops.SYNTH_NORMALIZE if mean is not None else 0
+        xin = ops.SynthFunction.apply(self.d, self.v, x.contiguous(), index, mean, std, flags)
+        return net(xin)
+
+    def update_v(self):
+        ops.project_rows(self.v.data, ops.ROWS_L1BALL, self.eps)
+
+    def update_d(self):
+        ops.project_atoms(self.d.data, ops.ATOMS_CLAMP1)
+
+
+class ADIL(Attack):
+    """ADiL attack (paper 'Adversarial Dictionary Learning').  Same arguments as the reference (adil.py:38-66):
+
+        model, eps, steps, norm ('linf' | 'l2'), targeted, n_atoms, batch_size, data_train, data_val, trials,
+        attack ('supervised' | 'unsupervised'), model_name, step_size, is_distributed, steps_in, loss
+        ('ce' | 'logits'), method ('gd' | 'alter'), warm_start, kappa, steps_inference.
+
+    Like the reference, constructing the object learns the dictionary when `trained_dicts/ImageNet_{model_name}.bin`
+    does not exist, and `attack(images, labels)` returns adversarial images in [0, 1].  `fit` / `perturb` are
+    explicit aliases.  Class attributes below switch off reference work that does not change results.
+    """
+
+    cache_clean_labels = True   # model(x).argmax is constant per image (adil.py:172 recomputes it every batch)
+    resident_data = True        # keep tensor-backed datasets in HBM and gather rows inside the synthesis kernel
+    run_validation = True       # per-epoch validation coder (adil.py:198-205)
+    fuse_normalize = True       # fold a leading Normalize module into the kernels
+    verbose = True
+    dict_dir = 'trained_dicts/'
+
+    def __init__(self, model, eps=None, steps=5e2, norm='linf', targeted=False, n_atoms=100, batch_size=100,
+                 data_train=None, data_val=None, trials=10, attack='supervised', model_name=None, step_size=0.01,
+                 is_distributed=False, steps_in=None, loss='ce', method='gd', warm_start=False, kappa=50,
+                 steps_inference=30):
+        super().__init__("ADIL", model.eval())
+        if self.device.type != 'cuda':
+            raise RuntimeError("ADIL (B200) needs the classifier on a CUDA device; there is no CPU fallback")
+        self.norm = norm.lower()
+        self.eps = eps
+        self.n_atoms = n_atoms
+        self.dictionary = None
+        self.targeted = targeted
+        self.attack = attack
+        self.trials = trials
+        self.step_size = step_size
+        self.steps_inference = steps_inference
+        self.steps = steps
+        self.steps_inner = steps_in
+        self.batch_size = batch_size
+        self.loss = loss
+        self.model_name = model_name
+        self.method = method
+        self.kappa = kappa
+        self.model_file = os.path.join(self.dict_dir, f"ImageNet_{model_name}.bin")
+        self.state = None
+        self._net, self._mean, self._std = split_normalize(self.model) if self.fuse_normalize else (self.model, None, None)
+        self._batch_schedule = None  # optional: callable(epoch) -> list of CPU index tensors (tests / sharding)
+        if not os.path.exists(self.model_file) and data_train is not None:
+            self.fit(data_train, data_val, warm_start=warm_start, is_distributed=is_distributed)
+
+    # ------------------------------------------------------------------------------------------------
+    # public aliases
+    # ------------------------------------------------------------------------------------------------
+    def fit(self, data_train, data_val=None, warm_start=False, is_distributed=False):
+        if is_distributed:
+            return self.learn_dictionary_distributed(data_train, data_val)
+        if self.method == 'gd':
+            return self.learn_dictionary_a(dataset=data_train, val=data_val, warm_start=warm_start)
+        if self.method == 'alter':
+            return self.learn_dictionary_b(dataset=data_train, val=data_val, warm_start=warm_start)
+        raise ValueError("method must be 'gd' or 'alter'")
+
+    def perturb(self, images, labels):
+        return self(images, labels)
+
+    # ------------------------------------------------------------------------------------------------
+    # losses
+    # ------------------------------------------------------------------------------------------------
+    def f_loss(self, outputs, labels):
+        """CW-style logit margin (adil.py:103-112): the label slot is zeroed, not masked to -inf."""
+        onehot = torch.nn.functional.one_hot(labels, outputs.shape[1]).to(outputs.dtype)
+        other = ((1 - onehot) * outputs).max(dim=1).values
+        true = (onehot * outputs).sum(dim=1)
+        margin = (other - true) if self._targeted else (true - other)
+        return torch.clamp(margin, min=-self.kappa)
+
+    def _attack_loss(self, outputs, labels, reduction):
+        if self.loss == 'ce':
+            coeff = 1. if self.targeted else -1.
+            return coeff * nn.functional.cross_entropy(outputs, labels, reduction=reduction)
+        if self.loss == 'logits':
+            return self.f_loss(outputs, labels).sum()
+        raise ValueError("loss must be 'ce' or 'logits'")
+
+    def _classifier_grad(self, xin, labels, reduction):
+        """Loss, d loss / d xin and logits through the frozen classifier (PyTorch / cuDNN).  Only the input
+        gradient is requested, so no weight gradients are computed (the reference accumulates them unused)."""
+        xin.requires_grad_(True)
+        out = self._net(xin)
+        loss = self._attack_loss(out, labels, reduction)
+        (g,) = torch.autograd.grad(loss, xin)
+        return loss.detach(), g.contiguous(), out.detach()
+
+    def _clean_labels(self, x):
+        with torch.no_grad():
+            return self.model(x).argmax(dim=-1)
+
+    # ------------------------------------------------------------------------------------------------
+    # projections / sampling (adil.py:625-655)
+    # ------------------------------------------------------------------------------------------------
+    def projection_v(self, var):
+        out = var.detach().clone().contiguous()
+        return ops.project_rows(out, ops.ROWS_L2BALL if self.norm == 'l2' else ops.ROWS_L1BALL, self.eps)
+
+    def projection_d(self, var):
+        out = var.detach().clone().contiguous()
+        return ops.project_atoms(out, ops.ATOMS_L2BALL if self.norm == 'l2' else ops.ATOMS_CLAMP1)
+
+    def sample_sphere(self, n_samples):
+        """Random codes: l2 sphere or sparse points of the l1 sphere (adil.py:644-655; CPU RNG like the
+        reference, projection on the device)."""
+        if self.norm == 'l2':
+            var = (2 * torch.rand(n_samples, self.n_atoms) - 1)
+            return self.eps * torch.div(var, torch.norm(var, p='fro', dim=1, keepdim=True))
+        m = torch.distributions.uniform.Uniform(torch.tensor([self.eps]), torch.tensor([2 * self.eps]))
+        raw = m.sample(sample_shape=[n_samples, self.n_atoms])[:, :, 0]
+        return self.projection_v(raw.to(self.device))
+
+    # ------------------------------------------------------------------------------------------------
+    # fitting
+    # ------------------------------------------------------------------------------------------------
+    def _probe(self, dataset):
+        dataset.indexed = False
+        n_img = len(dataset)
+        x, _ = next(iter(dataset))
+        nc, nx, ny = x.shape
+        dataset.indexed = True
+        return n_img, nc, nx, ny
+
+    def _init_state(self, n_img, nc, nx, ny, warm_start, v_zero=False):
+        """Initial D, v with the reference's RNG draws on the device generator (adil.py:138-150,235-246)."""
+        dev = self.device
+        if warm_start:
+            path = "dict_model_ImageNet_version_constrained/"
+            fname = f"ImageNet_{self.model_name}_num_atom_{self.n_atoms}_nepoch_{self.steps}_AdamW_{200}.bin"
+            d, _, _, _ = torch.load(os.path.join(path, fname), weights_only=False)
+            d = d.to(dev).float().contiguous()
+        elif self.norm == 'l2':
+            d = self.projection_d(torch.randn(nc, nx, ny, self.n_atoms, device=dev))
+        else:
+            d = (-1 + 2 * torch.rand(nc, nx, ny, self.n_atoms, device=dev))
+        v0 = torch.zeros(n_img, self.n_atoms, device=dev) if v_zero else torch.rand(n_img, self.n_atoms, device=dev)
+        return AdilState(d, self.projection_v(v0))
+
+    def _epoch_batches(self, dataset, n_img, batch_size, epoch):
+        """Yields (cpu_index, x_source, x_index, labels_or_None).  Tensor-backed datasets stay resident in HBM and
+        only the shuffled indices are produced (same CPU-RNG draws as the reference's shuffling DataLoader,
+        adil.py:130); other datasets go through a pinned-memory DataLoader like the reference."""
+        if self._batch_schedule is not None:
+            for index in self._batch_schedule(epoch):
+                yield index, self._resident_x, index.to(self.device), None
+        elif self._resident_x is not None:
+            loader = torch.utils.data.DataLoader(_IndexOnly(n_img), batch_size=batch_size, shuffle=True, num_workers=0)
+            for index in loader:
+                yield index, self._resident_x, index.to(self.device, non_blocking=True), None
+        else:
+            loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=True, pin_memory=True,
+                                                 num_workers=0)
+            for index, x, _ in loader:
+                x = x.to(self.device, non_blocking=True).contiguous()
+                yield index, x.view(x.shape[0], -1), None, None
+
+    def _make_resident(self, dataset, n_img, P):
+        images = getattr(dataset, 'images', None)
+        if self.resident_data and torch.is_tensor(images) and images.shape[0] == n_img:
+            self._resident_x = images.to(self.device, dtype=torch.float32).contiguous().view(n_img, P)
+        else:
+            self._resident_x = None
+        self._label_cache = None
+
+    def _labels_for(self, index_dev, index_cpu, x_src, x_index, shape):
+        """Clean-prediction labels of the batch (adil.py:172).  Cached per image when allowed."""
+        if self.cache_clean_labels and self._resident_x is not None:
+            if self._label_cache is None:
+                n = self._resident_x.shape[0]
+                cache = torch.empty(n, dtype=torch.long, device=self.device)
+                for lo in range(0, n, 256):
+                    cache[lo:lo + 256] = self._clean_labels(self._resident_x[lo:lo + 256].view(-1, *shape))
+                self._label_cache = cache
+            return self._label_cache[index_dev]
+        xb = x_src[x_index] if x_index is not None else x_src
+        return self._clean_labels(xb.view(-1, *shape))
+
+    def _fit_step(self, st, x_src, x_index, v_index, labels, shape, update, lr_d, lr_v):
+        """One minibatch of adil.py:168-188 (update='both'), :268-284 ('v') or :295-311 ('d')."""
+        flags = ops.SYNTH_NORMALIZE if self._mean is not None else 0
+        xin, _ = ops.synth(st.D2, st.v, v_index, x=x_src, x_index=x_index, mean=self._mean, std=self._std, flags=flags,
+                           n_channels=shape[0])
+        loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
+        g = g.view(g.shape[0], -1)
+        fooled = (out.argmax(dim=-1) != labels).sum()
+        dvb = None
+        if update == 'both':
+            st.tD += 1
+            dvb = ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, v_index, ops.adamw_params(st.tD, lr_d), self._std,
+                                     ops.ATOMS_CLAMP1)
+        elif update == 'd':
+            st.tD += 1
+            ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, v_index, ops.adamw_params(st.tD, lr_d), self._std,
+                               ops.ATOMS_CLAMP1, want_dv=False)
+        else:
+            _, dvb = ops.grad(g, st.D2, st.v, v_index, self._std, want_dD=False)
+        if update in ('both', 'v'):
+            st.tv += 1
+            ops.code_step(st.v, st.mv, st.sv, dvb, v_index, ops.adamw_params(st.tv, lr_v), ops.ROWS_L1BALL, self.eps)
+        return loss, fooled
+
+    def fit_batch(self, index, x, labels=None):
+        """One joint ('gd') learning step on one minibatch -- the body of the loop at adil.py:168-188 -- on the
+        state created by `begin_fit`.  `index`: int64 rows of v (host or device); `x`: [B,C,H,W] images (host,
+        e.g. pinned, or device).  Returns (loss, fooled_count) as device scalars."""
+        st = self.state
+        if st is None:
+            raise RuntimeError("fit_batch: call begin_fit(n_img, image_shape) or fit() first")
+        x = x.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        shape = tuple(x.shape[1:])
+        v_index = torch.as_tensor(index, dtype=torch.long).to(self.device, non_blocking=True)
+        if labels is None:
+            labels = self._clean_labels(x)                                 # adil.py:172
+        return self._fit_step(st, x.view(x.shape[0], -1), None, v_index, labels, shape, 'both', self.step_size,
+                              self.step_size)
+
+    def begin_fit(self, n_img, image_shape, warm_start=False):
+        """Allocate and initialise D, v and the AdamW state for `n_img` images (adil.py:138-154)."""
+        nc, nx, ny = image_shape
+        self.state = self._init_state(n_img, nc, nx, ny, warm_start)
+        return self.state
+
+    def _validate(self, val, batch_size, D):
+        if val is None or not self.run_validation or len(val) == 0:
+            return torch.zeros((), device=self.device)
+        loader = torch.utils.data.DataLoader(val, batch_size=batch_size, shuffle=True, pin_memory=True, num_workers=0)
+        fooled = 0
+        for x, label in loader:
+            fooled = fooled + self.forward_supervised_AdamW(x, label, D, 'train')
+        return fooled / len(val)
+
+    def _save(self, st, loss_all, fooling_rate_all, val_fool):
+        os.makedirs(os.path.dirname(self.model_file) or '.', exist_ok=True)
+        torch.save([st.D.data, st.v.data, loss_all, fooling_rate_all, val_fool], self.model_file)  # adil.py:210
+
+    def learn_dictionary_a(self, dataset, val, warm_start=False):
+        """Joint ('gd') learning of D and v: AdamW on both, l1-ball projection of every code row, clamp of D
+        (adil.py:114-210)."""
+        n_img, nc, nx, ny = self._probe(dataset)
+        shape, P = (nc, nx, ny), nc * nx * ny
+        batch_size = n_img if self.batch_size is None else self.batch_size
+        self._make_resident(dataset, n_img, P)
+        st = self._init_state(n_img, nc, nx, ny, warm_start)
+        self.state = st
+        loss_all, fooling_rate_all = [], []
+        val_fool = torch.zeros((), device=self.device)
+        for iteration in range(int(self.steps)):
+            loss_full = torch.zeros((), device=self.device)
+            fooling_sample = torch.zeros((), dtype=torch.long, device=self.device)
+            for index, x_src, x_index, _ in self._epoch_batches(dataset, n_img, batch_size, iteration):
+                v_index = x_index if x_index is not None else index.to(self.device, non_blocking=True)
+                labels = self._labels_for(v_index, index, x_src, x_index, shape)
+                loss, fooled = self._fit_step(st, x_src, x_index, v_index, labels, shape, 'both', self.step_size,
+                                              self.step_size)
+                loss_full += loss
+                fooling_sample += fooled
+            loss_all.append(loss_full.item() / n_img)
+            fooling_rate_all.append(fooling_sample.item() / n_img)
+            if self.verbose:
+                print(loss_all[-1], fooling_rate_all[-1])
+            val_fool = self._validate(val, batch_size, st.D)
+            if self.verbose and val is not None and self.run_validation:
+                print(float(val_fool))
+            if iteration > 1 and abs(loss_all[iteration] - loss_all[iteration - 1]) < 1e-6:
+                break
+        self._save(st, loss_all, fooling_rate_all, val_fool)
+        return st
+
+    def learn_dictionary_b(self, dataset, val, warm_start=False):
+        """Alternating ('alter') learning: `steps_inner` epochs of code updates with D frozen, then `steps_inner`
+        epochs of dictionary updates (lr doubled) with v frozen (adil.py:212-332)."""
+        n_img, nc, nx, ny = self._probe(dataset)
+        shape, P = (nc, nx, ny), nc * nx * ny
+        batch_size = n_img if self.batch_size is None else self.batch_size
+        self._make_resident(dataset, n_img, P)
+        st = self._init_state(n_img, nc, nx, ny, warm_start, v_zero=True)
+        self.state = st
+        loss_all, fooling_rate_all = [], []
+        val_fool = torch.zeros((), device=self.device)
+        epoch = 0
+        for iteration in range(int(self.steps // self.steps_inner)):
+            for phase in ('v', 'd'):
+                for _ in range(self.steps_inner):
+                    loss_full = torch.zeros((), device=self.device)
+                    fooling_sample = torch.zeros((), dtype=torch.long, device=self.device)
+                    for index, x_src, x_index, _ in self._epoch_batches(dataset, n_img, batch_size, epoch):
+                        v_index = x_index if x_index is not None else index.to(self.device, non_blocking=True)
+                        labels = self._labels_for(v_index, index, x_src, x_index, shape)
+                        loss, fooled = self._fit_step(st, x_src, x_index, v_index, labels, shape, phase,
+                                                      2 * self.step_size, self.step_size)
+                        loss_full = loss_full + loss if phase == 'v' else loss  # adil.py:313: last d-batch only
+                        fooling_sample += fooled
+                    epoch += 1
+                    if self.verbose:
+                        print(phase + '_step: ', loss_full.item() / n_img, fooling_sample.item() / n_img)
+            loss_all.append(loss_full.item() / n_img)
+            fooling_rate_all.append(fooling_sample.item() / n_img)
+            val_fool = self._validate(val, batch_size, st.D)
+            if iteration > 1 and abs(loss_all[iteration] - loss_all[iteration - 1]) < 1e-6:
+                break
+        self._save(st, loss_all, fooling_rate_all, val_fool)
+        return st
+
+    def learn_dictionary_distributed(self, dataset, val=None):
+        """Image-sharded joint learning over the ranks of torch.distributed (one process per GPU, NCCL).
+
+        The reference's DDP variant (adil.py:334-430) is non-functional; this implements its intent: each rank
+        owns a contiguous shard of the images and of their code rows (v never crosses the wire), D is
+        replicated, and the per-step dictionary gradient is SUM-all-reduced (the reference loss is
+        CrossEntropy(reduction='sum'), so R ranks x B images == one GPU with batch R*B)."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("learn_dictionary_distributed needs an initialised torch.distributed process group")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        n_img, nc, nx, ny = self._probe(dataset)
+        shape, P = (nc, nx, ny), nc * nx * ny
+        batch_size = n_img if self.batch_size is None else self.batch_size
+        lo, hi = dsh.shard_bounds(n_img, world, rank)
+        images = getattr(dataset, 'images', None)
+        if not torch.is_tensor(images):
+            raise ValueError("distributed fit needs a tensor-backed dataset (`.images`)")
+        x_local = images[lo:hi].to(self.device, dtype=torch.float32).contiguous().view(hi - lo, P)
+        # identical initial state on every rank: rank 0 draws, everyone receives
+        st_full = self._init_state(n_img, nc, nx, ny, False) if rank == 0 else None
+        D = st_full.D if rank == 0 else torch.empty(nc, nx, ny, self.n_atoms, device=self.device)
+        v_full = st_full.v if rank == 0 else torch.empty(n_img, self.n_atoms, device=self.device)
+        dist.broadcast(D, 0)
+        dist.broadcast(v_full, 0)
+        st = AdilState(D, v_full[lo:hi].clone())
+        self.state = st
+        del v_full, st_full
+        with torch.no_grad():
+            labels_local = torch.cat([self.model(x_local[i:i + 256].view(-1, *shape)).argmax(-1)
+                                      for i in range(0, hi - lo, 256)]) if hi > lo else torch.empty(0, dtype=torch.long)
+        dD2 = torch.empty_like(st.D2)
+        flags = ops.SYNTH_NORMALIZE if self._mean is not None else 0
+        loss_all, fooling_rate_all = [], []
+        for iteration in range(int(self.steps)):
+            stats = torch.zeros(2, device=self.device, dtype=torch.float64)
+            for per_rank in dsh.epoch_schedule(n_img, world, batch_size, iteration, seed=dsh.schedule_seed(self)):
+                idx_local = (per_rank[rank] - lo).to(self.device)
+                if idx_local.numel() > 0:
+                    xin, _ = ops.synth(st.D2, st.v, idx_local, x=x_local, x_index=idx_local, mean=self._mean,
+                                       std=self._std, flags=flags, n_channels=nc)
+                    labels = labels_local[idx_local]
+                    loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
+                    _, dvb = ops.grad(g.view(g.shape[0], -1), st.D2, st.v, idx_local, self._std, dD2=dD2)
+                    stats[0] += loss.double()
+                    stats[1] += (out.argmax(-1) != labels).sum().double()
+                else:
+                    dD2.zero_()
+                    dvb, idx_local = None, None
+                dist.all_reduce(dD2, op=dist.ReduceOp.SUM)
+                st.tD += 1
+                ops.dict_step(st.D2, st.mD, st.sD, dD2, ops.adamw_params(st.tD, self.step_size), ops.ATOMS_CLAMP1)
+                st.tv += 1
+                ops.code_step(st.v, st.mv, st.sv, dvb, idx_local, ops.adamw_params(st.tv, self.step_size),
+                              ops.ROWS_L1BALL, self.eps)
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+            loss_all.append(stats[0].item() / n_img)
+            fooling_rate_all.append(stats[1].item() / n_img)
+            if self.verbose and rank == 0:
+                print(loss_all[-1], fooling_rate_all[-1])
+            if iteration > 1 and abs(loss_all[iteration] - loss_all[iteration - 1]) < 1e-6:
+                break
+        v_all = dsh.gather_rows(st.v, n_img, world, rank)
+        if rank == 0:
+            full = AdilState(st.D, v_all)
+            self._save(full, loss_all, fooling_rate_all, torch.zeros(()))
+        dist.barrier()
+        return st
+
+    # ------------------------------------------------------------------------------------------------
+    # attacking unseen images
+    # ------------------------------------------------------------------------------------------------
+    def _load_dictionary(self):
+        if self.state is not None:
+            return self.state.D
+        if self.dictionary is None:
+            if not os.path.exists(self.model_file):
+                raise RuntimeError("no learned dictionary: %s does not exist and fit() was not called" % self.model_file)
+            rlts = torch.load(self.model_file, weights_only=False)      # adil.py:444-445
+            self.dictionary = rlts[0].to(self.device).float().contiguous()
+        return self.dictionary
+
+    def forward(self, images, labels):
+        images = images.to(self.device)
+        labels = labels.to(self.device)
+        if self.state is None and self.dictionary is None and not os.path.exists(self.model_file):
+            # the reference falls back to learning on the given images (adil.py:438-442, via a missing method)
+            self.fit(QuickAttackDataset(images=images.cpu(), labels=labels.cpu()), None)
+        D = self._load_dictionary()
+        if self.attack == 'supervised':
+            return self.forward_supervised_DDrague(images, labels, D)
+        return self.forward_unsupervised(images)
+
+    def forward_unsupervised(self, images):
+        """Sample codes, keep the best of `trials` per image (adil.py:460-506).  Returns (adv_best, dv_norm_inf)
+        like the reference."""
+        D = self._load_dictionary()
+        K = D.shape[-1]
+        D2 = D.reshape(-1, K)
+        images = images.to(self.device).float().contiguous()
+        n = images.shape[0]
+        x2 = images.view(n, -1)
+        flag = torch.zeros(n, dtype=torch.bool, device=self.device)
+        best = torch.full((n,), float('inf'), device=self.device)
+        adv_best = images.clone()
+        delta = torch.empty_like(x2)
+        with torch.no_grad():
+            pre_labels = self.model(images).argmax(dim=1)
+            for _ in range(int(self.trials)):
+                v = self.sample_sphere(n).to(self.device).contiguous()
+                adv, _ = ops.synth(D2, v, None, x=x2, eps=self.eps, flags=ops.SYNTH_CLAMP_DELTA | ops.SYNTH_CLAMP01,
+                                   delta_out=delta)
+                adv = adv.view_as(images)
+                fooling = self.model(adv).argmax(dim=1) != pre_labels
+                mse = ((images - adv) ** 2).sum(dim=[1, 2, 3])
+                first = ~flag & fooling                                    # adil.py:492-496
+                same = ~first & ((flag & fooling) | (~flag & ~fooling)) & (mse < best)   # adil.py:497-501
+                best = torch.where(same, mse, best)
+                take = first | same
+                adv_best = torch.where(take.view(-1, 1, 1, 1), adv, adv_best)
+                flag = flag | first
+            dv_norm_inf = delta.abs().amax(dim=1).tolist()
+        return adv_best, dv_norm_inf
+
+    def forward_supervised_DDrague(self, images, labels, d):
+        """Optimise an image-shaped variable z with delta = D D^+ z (adil.py:508-567): AdamW(lr=1e-2) on z, clamp
+        to +-eps, `steps_inference` iterations, CE with mean reduction."""
+        images = images.to(self.device).float().contiguous()
+        n = images.shape[0]
+        shape = tuple(images.shape[1:])
+        K = d.shape[-1]
+        D2 = d.reshape(-1, K).contiguous()
+        P = D2.shape[0]
+        gram = D2.t() @ D2                                                 # adil.py:523 (K x K, library GEMM, once)
+        pinv2 = (D2 @ gram.inverse().t()).contiguous()                     # [P,K] = (dtd^-1 D^T)^T, adil.py:524-525
+        x2 = images.view(n, P)
+        z = torch.zeros(n, P, device=self.device)
+        mz, sz = torch.zeros_like(z), torch.zeros_like(z)
+        flags = ops.SYNTH_NORMALIZE if self._mean is not None else 0
+        labels = self._clean_labels(images)                                # adil.py:539 (constant over iterations)
+        gz = torch.empty_like(z)
+        for it in range(1, int(self.steps_inference) + 1):
+            _, v = ops.grad(z, pinv2, z, None, None, want_dD=False)        # v = z . D^+^T   (adil.py:542)
+            xin, _ = ops.synth(D2, v, None, x=x2, mean=self._mean, std=self._std, flags=flags, n_channels=shape[0])
+            _, g, _ = self._classifier_grad(xin.view(n, *shape), labels, 'mean')
+            _, gv = ops.grad(g.view(n, P), D2, v, None, self._std, want_dD=False)
+            ops.synth(pinv2, gv, None, delta_out=gz, want_out=False)       # dz = gv . D^+
+            z_old = z.clone()
+            ops.adamw_clamp(z, mz, sz, gz, ops.adamw_params(it, 1e-2), self.eps)
+            if (z - z_old).abs().max() < 1e-6:
+                break
+        _, v = ops.grad(z, pinv2, z, None, None, want_dD=False)
+        adv, _ = ops.synth(D2, v, None, x=x2, flags=ops.SYNTH_CLAMP01)
+        return adv.view_as(images)
+
+    def forward_supervised_AdamW(self, images, labels, d, model='train'):
+        """Code-only learning with D frozen (adil.py:569-623): v starts at 0, AdamW(lr=1e-2), l1 projection,
+        at most 100 iterations.  'train' returns the number of fooled images, anything else the adversarial
+        images."""
+        images = images.to(self.device).float().contiguous()
+        n = images.shape[0]
+        shape = tuple(images.shape[1:])
+        K = d.shape[-1]
+        D2 = d.reshape(-1, K).contiguous()
+        x2 = images.view(n, -1)
+        v = torch.zeros(n, K, device=self.device)
+        mv, sv = torch.zeros_like(v), torch.zeros_like(v)
+        flags = ops.SYNTH_NORMALIZE if self._mean is not None else 0
+        labels = self._clean_labels(images)
+        idx = torch.arange(n, device=self.device)
+        for it in range(1, 101):
+            xin, _ = ops.synth(D2, v, None, x=x2, mean=self._mean, std=self._std, flags=flags, n_channels=shape[0])
+            _, g, _ = self._classifier_grad(xin.view(n, *shape), labels, 'mean')
+            _, dvb = ops.grad(g.view(n, -1), D2, v, None, self._std, want_dD=False)
+            v_old = v.clone()
+            ops.code_step(v, mv, sv, dvb, idx, ops.adamw_params(it, 1e-2), ops.ROWS_L1BALL, self.eps)
+            if (v - v_old).abs().max() < 1e-6:
+                break
+        vproj = self.projection_v(v)                                       # adil.py:617
+        if model == 'train':
+            adv, _ = ops.synth(D2, vproj, None, x=x2)
+            with torch.no_grad():
+                return torch.sum(self.model(adv.view_as(images)).argmax(-1) != labels)
+        adv, _ = ops.synth(D2, vproj, None, x=x2, flags=ops.SYNTH_CLAMP01)
+        return adv.view_as(images)

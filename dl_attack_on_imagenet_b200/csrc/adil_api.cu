@@ -1,0 +1,196 @@
+// C ABI entry points + host-side plumbing of libadil_b200.so (see include/adil_b200.h).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "adil_common.cuh"
+
+namespace adil {
+
+namespace {
+thread_local char g_err[512] = "";
+int g_impl = ADIL_IMPL_AUTO;
+}  // namespace
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return (int)e;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+AdamwDev make_adamw(const adil_adamw_t* hp) {
+  AdamwDev d;
+  const double t = (double)hp->step;
+  const double bc1 = 1.0 - std::pow(hp->beta1, t);
+  const double bc2 = 1.0 - std::pow(hp->beta2, t);
+  d.decay = (float)(1.0 - hp->lr * hp->weight_decay);
+  d.w1 = (float)(1.0 - hp->beta1);
+  d.beta2 = (float)hp->beta2;
+  d.w2 = (float)(1.0 - hp->beta2);
+  d.bc2_sqrt = (float)std::sqrt(bc2);
+  d.eps = (float)hp->eps;
+  d.neg_step = (float)(-(hp->lr / bc1));
+  d.lerp_hi = std::fabs(1.0 - hp->beta1) >= 0.5 ? 1 : 0;
+  return d;
+}
+
+ChannelConsts make_consts(int C, int hw, const float* mean_host, const float* std_host, bool use) {
+  ChannelConsts cc;
+  memset(&cc, 0, sizeof(cc));
+  cc.C = C;
+  cc.hw = hw > 0 ? hw : 1;
+  cc.use = use ? 1 : 0;
+  for (int c = 0; c < kMaxC; ++c) {
+    cc.mean[c] = (use && mean_host && c < C) ? mean_host[c] : 0.0f;
+    cc.stdv[c] = (use && std_host && c < C) ? std_host[c] : 1.0f;
+  }
+  return cc;
+}
+
+namespace {
+
+int check_shape(const char* fn, int B, int P, int K, int C, int hw, bool need_channels) {
+  if (B < 0 || P <= 0 || K < 1) return set_error(-1, "%s: bad shape B=%d P=%d K=%d", fn, B, P, K);
+  if (K > ADIL_MAX_ATOMS) return set_error(-1, "%s: K=%d exceeds ADIL_MAX_ATOMS=%d", fn, K, ADIL_MAX_ATOMS);
+  if (P % 4 != 0) return set_error(-1, "%s: P=%d must be a multiple of 4", fn, P);
+  if (need_channels) {
+    if (C < 1 || C > kMaxC) return set_error(-1, "%s: C=%d out of range [1,%d]", fn, C, kMaxC);
+    if (hw <= 0 || (long long)C * hw != P) return set_error(-1, "%s: C*hw = %d*%d != P = %d", fn, C, hw, P);
+  }
+  return 0;
+}
+
+bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+bool use_tc(int B, int P, int K, int* rc, const char* fn) {
+  *rc = 0;
+  if (g_impl == ADIL_IMPL_FMA) return false;
+  const bool ok = tc_shape_ok(B, P, K);
+  if (g_impl == ADIL_IMPL_TC && !ok) {
+    *rc = set_error(-4, "%s: ADIL_IMPL_TC requested but shape B=%d P=%d K=%d does not qualify", fn, B, P, K);
+    return false;
+  }
+  return ok;
+}
+
+}  // namespace
+}  // namespace adil
+
+using namespace adil;
+
+extern "C" int adil_version(void) { return ADIL_VERSION; }
+
+extern "C" const char* adil_last_error(void) { return g_err; }
+
+extern "C" int adil_device_info(int* sm, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  rc = check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+  if (rc) return rc;
+  if (sm) *sm = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+extern "C" int adil_set_impl(int impl) {
+  if (impl < ADIL_IMPL_AUTO || impl > ADIL_IMPL_TC) return set_error(-1, "adil_set_impl: bad impl %d", impl);
+  g_impl = impl;
+  return 0;
+}
+
+extern "C" int adil_get_impl(void) { return g_impl; }
+
+extern "C" int adil_tc_supported(int B, int P, int K) { return tc_shape_ok(B, P, K) ? 1 : 0; }
+
+extern "C" int adil_synth(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
+                          const float* v, const int64_t* v_index, int B, int P, int K, int C, int hw,
+                          const float* mean_host, const float* std_host, float eps, int flags, void* stream) {
+  const bool norm = (flags & ADIL_SYNTH_NORMALIZE) != 0;
+  int rc = check_shape("adil_synth", B, P, K, C, hw, norm);
+  if (rc) return rc;
+  if (!D2 || !v || (!out && !delta_out)) return set_error(-1, "adil_synth: null pointer");
+  if (norm && (!mean_host || !std_host)) return set_error(-1, "adil_synth: NORMALIZE needs mean/std");
+  if (!aligned16(out) || !aligned16(delta_out) || !aligned16(x) || !aligned16(D2))
+    return set_error(-1, "adil_synth: out/delta/x/D2 must be 16-byte aligned");
+  if (B == 0) return 0;
+  ChannelConsts cc = make_consts(C, hw, mean_host, std_host, norm);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(B, P, K, &rc, "adil_synth"))
+    return launch_synth_tc(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
+  if (rc) return rc;
+  return launch_synth_fma(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
+}
+
+extern "C" size_t adil_grad_scratch_bytes(int B, int K) {
+  if (B <= 0 || K <= 0) return 0;
+  return (size_t)kMaxGradCtas * (size_t)B * (size_t)K * sizeof(float);
+}
+
+namespace {
+int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g,
+                const float* D2, const float* v, const int64_t* v_index, int B, int P, int K, int C, int hw,
+                const float* std_host, const adil_adamw_t* hp, int atoms_mode, void* scratch, size_t scratch_bytes,
+                void* stream) {
+  const bool scale = std_host != nullptr;
+  int rc = check_shape(fn, B, P, K, C, hw, scale);
+  if (rc) return rc;
+  if (!g || !D2 || !v) return set_error(-1, "%s: null pointer", fn);
+  if (!aligned16(g) || !aligned16(D2) || !aligned16(dD2) || !aligned16(m) || !aligned16(s))
+    return set_error(-1, "%s: g/D2/dD2/m/s must be 16-byte aligned", fn);
+  if (B == 0) return set_error(-1, "%s: empty batch", fn);
+  ChannelConsts cc = make_consts(C, hw, nullptr, std_host, scale);
+  AdamwDev dev;
+  memset(&dev, 0, sizeof(dev));
+  if (hp) dev = make_adamw(hp);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(B, P, K, &rc, fn))
+    return launch_grad_tc(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
+                          scratch_bytes, st);
+  if (rc) return rc;
+  return launch_grad_fma(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
+                         scratch_bytes, st);
+}
+}  // namespace
+
+extern "C" int adil_grad(float* dD2, float* dvb, const float* g, const float* D2, const float* v,
+                         const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host,
+                         void* scratch, size_t scratch_bytes, void* stream) {
+  if (!dD2 && !dvb) return set_error(-1, "adil_grad: nothing to compute (dD2 and dvb both NULL)");
+  return grad_common("adil_grad", dD2, nullptr, nullptr, nullptr, dvb, g, D2, v, v_index, B, P, K, C, hw, std_host,
+                     nullptr, ADIL_ATOMS_NONE, scratch, scratch_bytes, stream);
+}
+
+extern "C" int adil_grad_dict_step(float* D2, float* m, float* s, float* dvb, const float* g, const float* v,
+                                   const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host,
+                                   const adil_adamw_t* hp, int atoms_mode, void* scratch, size_t scratch_bytes,
+                                   void* stream) {
+  if (!D2 || !m || !s || !hp) return set_error(-1, "adil_grad_dict_step: null pointer");
+  if (atoms_mode != ADIL_ATOMS_NONE && atoms_mode != ADIL_ATOMS_CLAMP1)
+    return set_error(-1, "adil_grad_dict_step: atoms_mode %d cannot be fused (use adil_project_atoms)", atoms_mode);
+  return grad_common("adil_grad_dict_step", nullptr, D2, m, s, dvb, g, D2, v, v_index, B, P, K, C, hw, std_host, hp,
+                     atoms_mode, scratch, scratch_bytes, stream);
+}

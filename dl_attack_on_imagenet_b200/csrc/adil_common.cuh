@@ -1,0 +1,103 @@
+// Shared device/host helpers for libadil_b200 (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "adil_b200.h"
+
+namespace adil {
+
+constexpr int kMaxC = ADIL_MAX_CHANNELS;
+
+// Per-channel constants passed by value in kernel parameters (mean/std of demo_dL_attack.py:55).
+struct ChannelConsts {
+  float mean[kMaxC];
+  float stdv[kMaxC];
+  int C;
+  int hw;
+  int use;  // 0: identity
+};
+
+// AdamW scalars of one update, evaluated on the host in double like torch/optim/adam.py:526-547 and rounded to
+// fp32 where torch hands a Python scalar to an fp32 elementwise op.
+struct AdamwDev {
+  float decay;      // 1 - lr*wd
+  float w1;         // 1 - beta1
+  float beta2;      // beta2
+  float w2;         // 1 - beta2
+  float bc2_sqrt;   // sqrt(1 - beta2^t)
+  float eps;        // eps
+  float neg_step;   // -(lr / (1 - beta1^t))
+  int lerp_hi;      // 1 when (1-beta1) >= 0.5: torch's lerp switches formula
+};
+
+// One AdamW element update; op order and roundings follow the torch sequence
+//   p.mul_(1-lr*wd); m.lerp_(g,1-b1); s.mul_(b2).addcmul_(g,g,1-b2); denom=(s.sqrt()/bc2_sqrt).add_(eps);
+//   p.addcdiv_(m, denom, -step_size)                                        (adil.py:154,186)
+__device__ __forceinline__ void adamw_update(float& p, float& m, float& s, float g, const AdamwDev& h) {
+  p = __fmul_rn(p, h.decay);
+  float diff = __fsub_rn(g, m);
+  m = h.lerp_hi ? __fsub_rn(g, __fmul_rn(diff, __fsub_rn(1.0f, h.w1))) : __fmaf_rn(h.w1, diff, m);
+  s = __fmul_rn(s, h.beta2);
+  s = __fmaf_rn(__fmul_rn(h.w2, g), g, s);
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(s), h.bc2_sqrt), h.eps);
+  p = __fmaf_rn(h.neg_step, __fdiv_rn(m, denom), p);
+}
+
+__device__ __forceinline__ float clamp1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int warp_max_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit accesses (read-once / write-once data: x, g, out)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// host-side error plumbing (adil_api.cu)
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int sm_count();
+AdamwDev make_adamw(const adil_adamw_t* hp);
+ChannelConsts make_consts(int C, int hw, const float* mean_host, const float* std_host, bool use);
+
+// FMA-path launchers (adil_fma.cu)
+int launch_synth_fma(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
+                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
+                     int flags, cudaStream_t st);
+int launch_grad_fma(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
+                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
+                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, cudaStream_t st);
+
+// tcgen05-path launchers (adil_tc.cu)
+bool tc_shape_ok(int B, int P, int K);
+int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
+                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
+                    int flags, cudaStream_t st);
+int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
+                   const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
+                   const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, cudaStream_t st);
+
+// number of partial [B,K] slabs the grad kernels may write into scratch
+constexpr int kMaxGradCtas = 592;  // 148 SMs x 4
+
+}  // namespace adil

@@ -1,0 +1,377 @@
+// Optimizer / projection kernels of the ADiL hot path (all HBM- or latency-bound elementwise / row work):
+//   dict_step   : AdamW + clamp on a slice of D          (adil.py:186,188 ; 310-311)
+//   code_step   : scatter + AdamW on all rows of v + row projection (adil.py:186-187 ; utils.py:21-41)
+//   project_rows / project_atoms : initial / final projections (adil.py:625-642 ; utils.py:44-57)
+//   adamw_clamp : z update of forward_supervised_DDrague (adil.py:554-555)
+#include "adil_common.cuh"
+
+namespace adil {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// elementwise AdamW (+ clamp) -- 128-bit vectorised, grid-stride, 7 arrays touched once each
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_elem_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                         float* __restrict__ s, const float* __restrict__ g,
+                                                         long long n, AdamwDev hp, float bound) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 sv = reinterpret_cast<float4*>(s)[i];
+    const float4 gv = ld_stream4(g + 4 * i);
+    adamw_update(pv.x, mv.x, sv.x, gv.x, hp);
+    adamw_update(pv.y, mv.y, sv.y, gv.y, hp);
+    adamw_update(pv.z, mv.z, sv.z, gv.z, hp);
+    adamw_update(pv.w, mv.w, sv.w, gv.w, hp);
+    if (bound > 0.0f) {
+      pv.x = fminf(fmaxf(pv.x, -bound), bound);
+      pv.y = fminf(fmaxf(pv.y, -bound), bound);
+      pv.z = fminf(fmaxf(pv.z, -bound), bound);
+      pv.w = fminf(fmaxf(pv.w, -bound), bound);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(s)[i] = sv;
+  }
+  // tail (n % 4 elements)
+  const long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    float pv = p[t], mv = m[t], sv = s[t];
+    adamw_update(pv, mv, sv, g[t], hp);
+    if (bound > 0.0f) pv = fminf(fmaxf(pv, -bound), bound);
+    p[t] = pv; m[t] = mv; s[t] = sv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row projections: one warp per row, EPL elements per lane (k = lane + 32*i), K <= 32*EPL
+// ---------------------------------------------------------------------------------------------
+template <int EPL>
+__device__ __forceinline__ void project_row(float (&x)[EPL], int K, int lane, int mode, float radius, float* sorted) {
+  if (mode == ADIL_ROWS_NONE) return;
+  if (mode == ADIL_ROWS_SOFTSHRINK) {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const float v = x[i];
+      x[i] = v > radius ? v - radius : (v < -radius ? v + radius : 0.0f);
+    }
+    return;
+  }
+  if (mode == ADIL_ROWS_L2BALL) {
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) ss = fmaf(x[i], x[i], ss);
+    ss = warp_sum(ss);
+    const float den = fmaxf(__fsqrt_rn(ss), radius);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) x[i] = __fmul_rn(radius, __fdiv_rn(x[i], den));  // adil.py:629
+    return;
+  }
+  // ---- l1 ball (utils.py:21-41) ----
+  float a[EPL];
+  float l1 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    a[i] = fabsf(x[i]);
+    l1 += a[i];
+  }
+  l1 = warp_sum(l1);
+  if (l1 < radius) return;  // strictly inside: untouched (utils.py:33)
+  // rank sort (descending, ties by index): rank = #elements that precede mine
+  int rank[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) rank[i] = 0;
+#pragma unroll
+  for (int i2 = 0; i2 < EPL; ++i2) {
+    for (int src = 0; src < 32; ++src) {
+      const float o = __shfl_sync(0xffffffffu, a[i2], src);
+      const int ok = src + 32 * i2;  // index of the other element
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int mk = lane + 32 * i;
+        rank[i] += (o > a[i] || (o == a[i] && ok < mk)) ? 1 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int mk = lane + 32 * i;
+    if (mk < K) sorted[rank[i]] = a[i];
+  }
+  __syncwarp();
+  // blocked layout for the prefix sum: lane owns sorted[lane*EPL .. lane*EPL+EPL-1]
+  float mu[EPL], cs[EPL];
+  float run = 0.0f;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int j = lane * EPL + i;
+    mu[i] = j < K ? sorted[j] : 0.0f;
+    run += mu[i];
+    cs[i] = run;
+  }
+  float incl = run;  // inclusive scan of lane totals
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const float offset = incl - run;
+  int rho = 0;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int j = lane * EPL + i;  // 0-based
+    cs[i] += offset;
+    if (j < K && __fmul_rn(mu[i], (float)(j + 1)) > __fsub_rn(cs[i], radius)) rho = j + 1;  // utils.py:37
+  }
+  rho = warp_max_int(rho);
+  float theta = 0.0f;
+  if (rho > 0) {
+    const int owner = (rho - 1) / EPL, slot = (rho - 1) - owner * EPL;
+    float c = 0.0f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i)
+      if (i == slot) c = cs[i];
+    c = __shfl_sync(0xffffffffu, c, owner);
+    theta = __fdiv_rn(__fsub_rn(c, radius), (float)rho);  // utils.py:38
+  }
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const float pr = fmaxf(__fsub_rn(a[i], theta), 0.0f);
+    x[i] = x[i] > 0.0f ? pr : (x[i] < 0.0f ? -pr : 0.0f);  // proj * sign(x)
+  }
+  __syncwarp();
+}
+
+struct CodeArgs {
+  float* v;
+  float* m;
+  float* s;
+  const float* dvb;
+  const int64_t* vidx;
+  int B, N, K;
+  int do_adamw, mode;
+  float radius;
+  AdamwDev hp;
+};
+
+template <int EPL>
+__global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
+  __shared__ float sorted_all[8][32 * EPL];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = a.K;
+  for (int row = blockIdx.x * 8 + warp; row < a.N; row += gridDim.x * 8) {
+    float x[EPL];
+    const size_t base = (size_t)row * K;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int k = lane + 32 * i;
+      x[i] = k < K ? a.v[base + k] : 0.0f;
+    }
+    if (a.do_adamw) {
+      float g[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) g[i] = 0.0f;
+      if (a.dvb != nullptr) {
+        // gather the batch slots that map to this row (ascending slot order; duplicates accumulate)
+        for (int b0 = 0; b0 < a.B; b0 += 32) {
+          const int b = b0 + lane;
+          const bool hit = b < a.B && (a.vidx ? a.vidx[b] : (int64_t)b) == (int64_t)row;
+          unsigned mask = __ballot_sync(0xffffffffu, hit);
+          while (mask) {
+            const int bb = b0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+              const int k = lane + 32 * i;
+              if (k < K) g[i] += a.dvb[(size_t)bb * K + k];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int k = lane + 32 * i;
+        if (k < K) {
+          float mv = a.m[base + k], sv = a.s[base + k];
+          adamw_update(x[i], mv, sv, g[i], a.hp);
+          a.m[base + k] = mv;
+          a.s[base + k] = sv;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < EPL; ++i)
+      if (lane + 32 * i >= K) x[i] = 0.0f;
+    // padding lanes hold 0 and indices >= K, so the index tie-break keeps them behind every real element
+    {
+      float xs[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) xs[i] = x[i];
+      project_row<EPL>(xs, K, lane, a.mode, a.radius, sorted_all[warp]);
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) x[i] = xs[i];
+    }
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) a.v[base + k] = x[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-atom l2 projection: column norms over P (two-stage, deterministic) then a scaling pass
+// ---------------------------------------------------------------------------------------------
+constexpr int kNormCtas = 296;
+
+__global__ void __launch_bounds__(256) atom_sumsq_kernel(const float* __restrict__ D2, int P, int K,
+                                                         float* __restrict__ partial /*[grid][K]*/) {
+  extern __shared__ float sh[];  // [256]
+  // thread t handles atom k = t % K for rows r = t / K + i*(256 / K)  (K <= 256)
+  const int per = 256 / K;  // rows handled per CTA pass
+  const int k = threadIdx.x % K, r0 = threadIdx.x / K;
+  float acc = 0.0f;
+  if (r0 < per) {
+    for (long long r = (long long)blockIdx.x * per + r0; r < P; r += (long long)gridDim.x * per) {
+      const float d = D2[r * K + k];
+      acc = fmaf(d, d, acc);
+    }
+  }
+  sh[threadIdx.x] = (r0 < per) ? acc : 0.0f;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float t = 0.0f;
+    for (int j = 0; j < per; ++j) t += sh[j * K + threadIdx.x];
+    partial[(size_t)blockIdx.x * K + threadIdx.x] = t;
+  }
+}
+
+__global__ void atom_scale_finalize_kernel(const float* __restrict__ partial, int nslabs, int K, int mode,
+                                           float* __restrict__ scale /*[K]: divisor*/) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float t = 0.0f;
+  for (int c = 0; c < nslabs; ++c) t += partial[(size_t)c * K + k];
+  const float nrm = __fsqrt_rn(t);
+  scale[k] = (mode == ADIL_ATOMS_L2SPHERE) ? nrm : fmaxf(nrm, 1.0f);
+}
+
+__global__ void __launch_bounds__(256) atom_scale_kernel(float* __restrict__ D2, long long n, int K,
+                                                         const float* __restrict__ scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    D2[i] = __fdiv_rn(D2[i], scale[i % K]);
+  }
+}
+
+__global__ void __launch_bounds__(256) clamp1_kernel(float* __restrict__ D2, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) D2[i] = clamp1(D2[i]);
+}
+
+int elem_grid(long long work_items) {
+  long long g = (work_items + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int launch_code(const CodeArgs& a, cudaStream_t st) {
+  if (a.K < 1 || a.K > ADIL_MAX_ATOMS) return set_error(-1, "adil_code_step: K=%d out of range [1,%d]", a.K, ADIL_MAX_ATOMS);
+  if (a.N <= 0) return 0;
+  int grid = (a.N + 7) / 8;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (a.K <= 32) code_step_kernel<1><<<grid, 256, 0, st>>>(a);
+  else if (a.K <= 64) code_step_kernel<2><<<grid, 256, 0, st>>>(a);
+  else if (a.K <= 128) code_step_kernel<4><<<grid, 256, 0, st>>>(a);
+  else code_step_kernel<8><<<grid, 256, 0, st>>>(a);
+  return check_cuda(cudaGetLastError(), "code_step_kernel launch");
+}
+
+}  // namespace
+
+}  // namespace adil
+
+using namespace adil;
+
+extern "C" int adil_dict_step(float* D2, float* m, float* s, const float* dD2, long long n, const adil_adamw_t* hp,
+                              int atoms_mode, void* stream) {
+  if (!D2 || !m || !s || !dD2 || !hp) return set_error(-1, "adil_dict_step: null pointer");
+  if (atoms_mode != ADIL_ATOMS_NONE && atoms_mode != ADIL_ATOMS_CLAMP1)
+    return set_error(-1, "adil_dict_step: atoms_mode %d cannot be fused (use adil_project_atoms)", atoms_mode);
+  if (n <= 0) return 0;
+  if ((((uintptr_t)D2 | (uintptr_t)m | (uintptr_t)s | (uintptr_t)dD2) & 15) != 0)
+    return set_error(-1, "adil_dict_step: pointers must be 16-byte aligned");
+  adamw_elem_kernel<<<elem_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(
+      D2, m, s, dD2, n, make_adamw(hp), atoms_mode == ADIL_ATOMS_CLAMP1 ? 1.0f : 0.0f);
+  return check_cuda(cudaGetLastError(), "adamw_elem_kernel launch");
+}
+
+extern "C" int adil_adamw_clamp(float* p, float* m, float* s, const float* grad, long long n, const adil_adamw_t* hp,
+                                float bound, void* stream) {
+  if (!p || !m || !s || !grad || !hp) return set_error(-1, "adil_adamw_clamp: null pointer");
+  if (n <= 0) return 0;
+  if ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)s | (uintptr_t)grad) & 15) != 0)
+    return set_error(-1, "adil_adamw_clamp: pointers must be 16-byte aligned");
+  adamw_elem_kernel<<<elem_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(p, m, s, grad, n, make_adamw(hp), bound);
+  return check_cuda(cudaGetLastError(), "adamw_elem_kernel launch");
+}
+
+extern "C" int adil_code_step(float* v, float* m, float* s, const float* dvb, const int64_t* v_index, int B, int N,
+                              int K, const adil_adamw_t* hp, int rows_mode, float radius, void* stream) {
+  if (!v || !m || !s || !hp) return set_error(-1, "adil_code_step: null pointer");
+  if (rows_mode < ADIL_ROWS_NONE || rows_mode > ADIL_ROWS_SOFTSHRINK)
+    return set_error(-1, "adil_code_step: bad rows_mode %d", rows_mode);
+  CodeArgs a;
+  a.v = v; a.m = m; a.s = s; a.dvb = dvb; a.vidx = v_index; a.B = dvb ? B : 0; a.N = N; a.K = K;
+  a.do_adamw = 1; a.mode = rows_mode; a.radius = radius; a.hp = make_adamw(hp);
+  return launch_code(a, (cudaStream_t)stream);
+}
+
+extern "C" int adil_project_rows(float* v, int N, int K, int rows_mode, float radius, void* stream) {
+  if (!v) return set_error(-1, "adil_project_rows: null pointer");
+  if (rows_mode < ADIL_ROWS_NONE || rows_mode > ADIL_ROWS_SOFTSHRINK)
+    return set_error(-1, "adil_project_rows: bad rows_mode %d", rows_mode);
+  CodeArgs a;
+  a.v = v; a.m = nullptr; a.s = nullptr; a.dvb = nullptr; a.vidx = nullptr; a.B = 0; a.N = N; a.K = K;
+  a.do_adamw = 0; a.mode = rows_mode; a.radius = radius; a.hp = AdamwDev();
+  return launch_code(a, (cudaStream_t)stream);
+}
+
+extern "C" size_t adil_project_atoms_scratch_bytes(int K) {
+  if (K < 1) return 0;
+  return ((size_t)kNormCtas * K + K) * sizeof(float);
+}
+
+extern "C" int adil_project_atoms(float* D2, int P, int K, int atoms_mode, void* scratch, void* stream) {
+  if (!D2) return set_error(-1, "adil_project_atoms: null pointer");
+  if (K < 1 || K > ADIL_MAX_ATOMS) return set_error(-1, "adil_project_atoms: K=%d out of range", K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)P * K;
+  if (atoms_mode == ADIL_ATOMS_NONE || n == 0) return 0;
+  if (atoms_mode == ADIL_ATOMS_CLAMP1) {
+    clamp1_kernel<<<elem_grid(n), 256, 0, st>>>(D2, n);
+    return check_cuda(cudaGetLastError(), "clamp1_kernel launch");
+  }
+  if (atoms_mode != ADIL_ATOMS_L2BALL && atoms_mode != ADIL_ATOMS_L2SPHERE)
+    return set_error(-1, "adil_project_atoms: unsupported atoms_mode %d", atoms_mode);
+  if (!scratch) return set_error(-1, "adil_project_atoms: scratch required for l2 modes");
+  float* partial = (float*)scratch;
+  float* scale = partial + (size_t)kNormCtas * K;
+  const int per = 256 / K;
+  int grid = (P + per - 1) / per;
+  if (grid > kNormCtas) grid = kNormCtas;
+  atom_sumsq_kernel<<<grid, 256, 256 * sizeof(float), st>>>(D2, P, K, partial);
+  int rc = check_cuda(cudaGetLastError(), "atom_sumsq_kernel launch");
+  if (rc) return rc;
+  atom_scale_finalize_kernel<<<(K + 127) / 128, 128, 0, st>>>(partial, grid, K, atoms_mode, scale);
+  rc = check_cuda(cudaGetLastError(), "atom_scale_finalize_kernel launch");
+  if (rc) return rc;
+  atom_scale_kernel<<<elem_grid(n), 256, 0, st>>>(D2, n, K, scale);
+  return check_cuda(cudaGetLastError(), "atom_scale_kernel launch");
+}

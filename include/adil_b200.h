@@ -1,0 +1,137 @@
+/*
+ * adil_b200.h -- C ABI of libadil_b200.so: the B200 (sm_100a) kernels of ADiL's attack-learning hot path.
+ *
+ * The reference (flavie-yuan-liu/DL_attack_on_ImageNet) has no FFI: its boundary is the Python class
+ * `ADIL` (attacks/attacks_classes/adil.py:38).  Each entry point below replaces the PyTorch op sequence of
+ * one piece of that class; the reference lines replaced are cited per function.  The Python mirror
+ * (dl_attack_on_imagenet_b200/adil.py) binds these through ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous fp32 unless stated ("host"); int64 index arrays are
+ *    device pointers too.  The library never allocates persistent device memory: the caller (PyTorch) owns
+ *    every buffer, including the scratch areas whose size is returned by *_scratch_bytes().
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *  - return value: 0 = ok; >0 = cudaError_t; <0 = argument / capability error.  adil_last_error() returns
+ *    a thread-local description of the last non-zero return.
+ *  - P = C*hw pixels per image (hw = H*W), must be a multiple of 4.  K = atoms (1..256).  D2 is the
+ *    dictionary viewed as [P, K] row-major (atoms innermost, adil.py:148 creates [C,H,W,K]).
+ */
+#ifndef ADIL_B200_H_
+#define ADIL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADIL_VERSION 100
+
+#define ADIL_MAX_CHANNELS 8
+#define ADIL_MAX_ATOMS 256
+
+/* adil_synth flags */
+#define ADIL_SYNTH_NORMALIZE   1 /* out = (out - mean[c]) / std[c]      demo_dL_attack.py:22-25 */
+#define ADIL_SYNTH_CLAMP_DELTA 2 /* delta = clamp(delta, -eps, eps)     adil.py:482             */
+#define ADIL_SYNTH_CLAMP01     4 /* out = clamp(x + delta, 0, 1)        adil.py:484,567,623     */
+
+/* row (coding-vector) projection modes */
+#define ADIL_ROWS_NONE       0
+#define ADIL_ROWS_L1BALL     1 /* utils.py:21-41  project_onto_l1_ball (adil.py:29-31,631-633) */
+#define ADIL_ROWS_L2BALL     2 /* adil.py:626-629 radius * v / max(||v||_2, radius)            */
+#define ADIL_ROWS_SOFTSHRINK 3 /* utils.py:159-161 get_prox_l1 (radius = lambda)               */
+
+/* atom (dictionary) projection modes */
+#define ADIL_ATOMS_NONE     0
+#define ADIL_ATOMS_CLAMP1   1 /* adil.py:33-35,642  clamp(D, -1, 1)                    */
+#define ADIL_ATOMS_L2BALL   2 /* utils.py:52-54     d_k / max(||d_k||_2, 1)            */
+#define ADIL_ATOMS_L2SPHERE 3 /* utils.py:49-51     d_k / ||d_k||_2                    */
+
+/* kernel implementation selector for adil_synth / adil_grad* (adil_set_impl) */
+#define ADIL_IMPL_AUTO 0 /* tcgen05 when the shape qualifies, else FMA */
+#define ADIL_IMPL_FMA  1 /* CUDA-core FMA kernels                       */
+#define ADIL_IMPL_TC   2 /* tcgen05 split-TF32 kernels (error if the shape does not qualify) */
+
+/* AdamW hyper-parameters of ONE update (torch.optim.AdamW as used at adil.py:154,250-251,531,588).
+ * `step` is the 1-based step count t of this update; the bias corrections 1-beta^t are evaluated in double
+ * precision on the host exactly as torch/optim/adam.py does. */
+typedef struct adil_adamw {
+  double lr;
+  double beta1;
+  double beta2;
+  double eps;
+  double weight_decay;
+  long long step;
+} adil_adamw_t;
+
+int adil_version(void);
+const char* adil_last_error(void);
+
+/* Number of SMs / compute capability of the current device (needs a GPU). */
+int adil_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Select the kernel family used by adil_synth / adil_grad / adil_grad_dict_step (process-wide). */
+int adil_set_impl(int impl);
+int adil_get_impl(void);
+/* 1 if the tcgen05 path accepts this shape, else 0. */
+int adil_tc_supported(int B, int P, int K);
+
+/* Perturbation synthesis (replaces adil.py:25-26 tensordot + add, the Normalize module of
+ * demo_dL_attack.py:16-25, and the clamps of adil.py:481-484,563-567,617-623):
+ *     delta[b,:] = sum_k v[v_index ? v_index[b] : b, k] * D2[:, k]
+ *     out[b,:]   = f( x[x_index ? x_index[b] : b, :] + delta[b,:] )   (x == NULL: out = f(delta))
+ * out, delta_out: [B,P] (either may be NULL, not both).  mean/std: HOST arrays of C floats (may be NULL when
+ * NORMALIZE is not set). */
+int adil_synth(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2, const float* v,
+               const int64_t* v_index, int B, int P, int K, int C, int hw, const float* mean_host,
+               const float* std_host, float eps, int flags, void* stream);
+
+/* Scratch (bytes) the grad entry points need for the deterministic cross-CTA reduction of the code gradients. */
+size_t adil_grad_scratch_bytes(int B, int K);
+
+/* Backward contractions (replaces the autograd backward of adil.py:25-26 + Normalize: adil.py:185,281,308,606):
+ *     gx = g / std[c]      (std_host == NULL: gx = g)
+ *     dD2[p,k] = sum_b gx[b,p] * v[v_index[b],k]          (skipped when dD2 == NULL)
+ *     dvb[b,k] = sum_p gx[b,p] * D2[p,k]                  (skipped when dvb == NULL)
+ * g: [B,P] gradient w.r.t. the classifier input.  dvb: [B,K] in batch order (the caller scatters by v_index). */
+int adil_grad(float* dD2, float* dvb, const float* g, const float* D2, const float* v, const int64_t* v_index, int B,
+              int P, int K, int C, int hw, const float* std_host, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Single-GPU fusion of adil_grad with the dictionary AdamW step and projection (adil.py:185-188 for D):
+ * dD2 never touches HBM; D2, m, s are updated in place.  atoms_mode: ADIL_ATOMS_NONE or ADIL_ATOMS_CLAMP1.
+ * dvb is computed against the PRE-update D2, like autograd does. */
+int adil_grad_dict_step(float* D2, float* m, float* s, float* dvb, const float* g, const float* v,
+                        const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host,
+                        const adil_adamw_t* hp, int atoms_mode, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Dictionary AdamW step + elementwise projection on n contiguous elements (a [P_begin,P_end) x K slice):
+ * replaces optimise.step() on d + update_d (adil.py:186,188 ; 310-311).  Used after the dD all-reduce on
+ * multi-GPU runs.  atoms_mode: ADIL_ATOMS_NONE or ADIL_ATOMS_CLAMP1. */
+int adil_dict_step(float* D2, float* m, float* s, const float* dD2, long long n, const adil_adamw_t* hp,
+                   int atoms_mode, void* stream);
+
+/* Code AdamW step over ALL N rows (dense gradient, zero outside the batch -- adil.py:154,186) fused with the
+ * scatter of dvb by v_index (duplicates accumulate, like index_put_(accumulate=True)) and the row projection
+ * (adil.py:187 update_v).  v, m, s: [N,K]; dvb: [B,K] (NULL: zero gradient). */
+int adil_code_step(float* v, float* m, float* s, const float* dvb, const int64_t* v_index, int B, int N, int K,
+                   const adil_adamw_t* hp, int rows_mode, float radius, void* stream);
+
+/* Row projection only (adil.py:625-633 projection_v ; utils.py:21-41 ; utils.py:159-161).  In place. */
+int adil_project_rows(float* v, int N, int K, int rows_mode, float radius, void* stream);
+
+/* Per-atom projection of D2 [P,K] (adil.py:635-642 projection_d ; utils.py:44-57 constraint_dict).
+ * scratch: device buffer of adil_project_atoms_scratch_bytes(K) bytes (unused for CLAMP1). */
+size_t adil_project_atoms_scratch_bytes(int K);
+int adil_project_atoms(float* D2, int P, int K, int atoms_mode, void* scratch, void* stream);
+
+/* Elementwise AdamW + clamp(+-bound) on n elements: the z update of forward_supervised_DDrague
+ * (adil.py:531,554-555).  bound <= 0: no clamp. */
+int adil_adamw_clamp(float* p, float* m, float* s, const float* grad, long long n, const adil_adamw_t* hp,
+                     float bound, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADIL_B200_H_ */

@@ -1,0 +1,87 @@
+"""The C-ABI shared library builds, loads without a GPU and exports every symbol include/adil_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "adil_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(adil_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def library():
+    from dl_attack_on_imagenet_b200.build import build_library
+    path = build_library()
+    return ctypes.CDLL(path)
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("adil_synth", "adil_grad", "adil_grad_dict_step", "adil_dict_step", "adil_code_step",
+                 "adil_project_rows", "adil_project_atoms", "adil_adamw_clamp", "adil_last_error", "adil_version"):
+        assert must in syms
+
+
+def test_every_declared_symbol_is_exported(library):
+    for name in declared_symbols():
+        assert hasattr(library, name), name
+
+
+def test_binding_covers_header_exactly():
+    from dl_attack_on_imagenet_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+
+
+def test_host_only_entry_points(library):
+    from dl_attack_on_imagenet_b200 import _lib
+    lib = _lib.lib()
+    assert lib.adil_version() == 100
+    assert lib.adil_grad_scratch_bytes(100, 50) >= 148 * 100 * 50 * 4
+    assert lib.adil_grad_scratch_bytes(0, 50) == 0
+    assert lib.adil_project_atoms_scratch_bytes(64) > 0
+    assert lib.adil_set_impl(7) != 0 and b"bad impl" in lib.adil_last_error()
+    assert lib.adil_set_impl(0) == 0
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    """Shape validation happens before any CUDA call, so it is checkable on the CPU box."""
+    from dl_attack_on_imagenet_b200 import _lib
+    lib = _lib.lib()
+    one = ctypes.c_void_p(16)
+    rc = lib.adil_synth(one, None, None, None, one, one, None, 4, 10, 3, 1, 10, None, None, 0.0, 0, None)
+    assert rc < 0 and b"multiple of 4" in lib.adil_last_error()
+    rc = lib.adil_synth(one, None, None, None, one, one, None, 4, 12, 300, 1, 12, None, None, 0.0, 0, None)
+    assert rc < 0 and b"ADIL_MAX_ATOMS" in lib.adil_last_error()
+    rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, None, 0, None)
+    assert rc < 0
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected loudly: the product path never computes on the host."""
+    from dl_attack_on_imagenet_b200 import ops
+    D2 = torch.zeros(12, 3)
+    v = torch.zeros(2, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.synth(D2, v, x=torch.zeros(2, 12))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.project_rows(v, ops.ROWS_L1BALL, 0.1)
+    from dl_attack_on_imagenet_b200 import ADIL
+    from oracle.adil_oracle import tiny_classifier
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ADIL(tiny_classifier(), eps=0.03, model_name="cpu_should_fail")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dl_attack_on_imagenet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)

@@ -1,0 +1,203 @@
+"""Class-level parity of the B200 `ADIL` (kernels behind the C ABI) against the CPU oracle -- which is pinned
+bit-exactly to the unmodified reference (tests/test_oracle_golden.py) -- on the same seeds and synthetic inputs.
+
+The classifier here is a smooth (tanh) network evaluated in full fp32 (TF32 off), so free-running trajectories
+can be compared tightly; for ReLU/max-pool ImageNet classifiers the reference itself is chaotic at the 1e-5 level
+ and parity is established teacher-forced in test_kernels_gpu.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import adil_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+EPS = 8.0 / 255.0
+C, H, W, K, N, NVAL, B = 3, 8, 8, 6, 10, 3, 4
+
+
+def tiny_data():
+    g1 = torch.Generator().manual_seed(1)
+    g2 = torch.Generator().manual_seed(2)
+    xtr = torch.rand(N, C, H, W, generator=g1)
+    ytr = torch.randint(0, 10, (N,), generator=g1)
+    xva = torch.rand(NVAL, C, H, W, generator=g2)
+    yva = torch.randint(0, 10, (NVAL,), generator=g2)
+    return xtr, ytr, xva, yva
+
+
+@pytest.fixture(autouse=True)
+def _fp32_classifier(tmp_path, monkeypatch):
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    monkeypatch.chdir(tmp_path)
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def make_attack(monkeypatch, st0, **kw):
+    """ADIL on the GPU starting from the oracle's initial state (the device RNG stream differs from the CPU one)."""
+    from dl_attack_on_imagenet_b200 import ADIL, AdilState, IndexedTensorDataset
+    model = O.tiny_classifier(seed=0).cuda()
+
+    def fixed_init(self, n_img, nc, nx, ny, warm_start, v_zero=False):
+        return AdilState(st0.D().cuda(), st0.v.clone().cuda())
+    monkeypatch.setattr(ADIL, "_init_state", fixed_init)
+    monkeypatch.setattr(ADIL, "verbose", False)
+    xtr, ytr, xva, yva = tiny_data()
+    tr, va = IndexedTensorDataset(xtr, ytr), IndexedTensorDataset(xva, yva)
+    return ADIL(model, eps=EPS, n_atoms=K, batch_size=B, data_train=tr, data_val=va, **kw)
+
+
+def oracle_fit(method, seed, **kw):
+    torch.set_num_threads(1)
+    model = O.tiny_classifier(seed=0)
+    xtr, ytr, xva, yva = tiny_data()
+    tr, va = O.IndexedTensorDataset(xtr, ytr), O.IndexedTensorDataset(xva, yva)
+    norm = kw.get("norm", "linf")
+    torch.manual_seed(seed)
+    st0 = O.init_state(C, H, W, N, K, EPS, norm, v_zero=(method == 'alter'))
+    import copy
+    st = copy.deepcopy(st0)
+    torch.manual_seed(seed + 1)          # shuffling draws come after the init draws in both implementations
+    fn = O.learn_dictionary_a if method == 'gd' else O.learn_dictionary_b
+    st, loss, fool, vf = fn(model, tr, EPS, n_atoms=K, batch_size=B, state=st, val=va, fused_normalize=True, **kw)
+    return st0, st, loss, fool, vf
+
+
+@pytest.mark.parametrize("loss", ["ce", "logits"])
+def test_fit_gd_matches_oracle(monkeypatch, loss):
+    st0, st, loss_all, fool_all, vf = oracle_fit('gd', 100, steps=3, loss=loss)
+    torch.manual_seed(101)
+    atk = make_attack(monkeypatch, st0, steps=3, loss=loss, method='gd', model_name='t_gd_' + loss)
+    D, v, l_gpu, f_gpu, vf_gpu = torch.load(atk.model_file, weights_only=False)
+    assert (D.cpu() - st.D()).abs().max() <= 1e-5            # north-star tolerance on dictionaries
+    assert (v.cpu() - st.v).abs().max() <= 1e-5
+    assert np.allclose(l_gpu, loss_all, rtol=0, atol=1e-5)
+    assert f_gpu == fool_all                                 # fooling rate identical (bound: 0.5 points)
+    assert float(vf_gpu) == pytest.approx(float(vf), abs=1e-9)
+    # perturbations D.v agree to 1e-5
+    assert ((v.cpu() @ D.cpu().reshape(-1, K).t()) - (st.v @ st.D2.t())).abs().max() <= 1e-5
+
+
+def test_fit_alter_matches_oracle(monkeypatch):
+    st0, st, loss_all, fool_all, _ = oracle_fit('alter', 200, steps=4, steps_inner=2)
+    torch.manual_seed(201)
+    atk = make_attack(monkeypatch, st0, steps=4, steps_in=2, method='alter', model_name='t_alter')
+    D, v, l_gpu, f_gpu, _ = torch.load(atk.model_file, weights_only=False)
+    assert (D.cpu() - st.D()).abs().max() <= 1e-5
+    assert (v.cpu() - st.v).abs().max() <= 1e-5
+    assert np.allclose(l_gpu, loss_all, rtol=0, atol=1e-5)
+    assert f_gpu == fool_all
+
+
+def test_fit_without_label_cache_and_resident_data(monkeypatch):
+    """The reference-faithful data path (pinned DataLoader, labels recomputed per batch) gives the same result."""
+    from dl_attack_on_imagenet_b200 import ADIL
+    st0, st, loss_all, _, _ = oracle_fit('gd', 300, steps=2)
+    monkeypatch.setattr(ADIL, "cache_clean_labels", False)
+    monkeypatch.setattr(ADIL, "resident_data", False)
+    torch.manual_seed(301)
+    atk = make_attack(monkeypatch, st0, steps=2, method='gd', model_name='t_faithful')
+    D, v, l_gpu, _, _ = torch.load(atk.model_file, weights_only=False)
+    assert (D.cpu() - st.D()).abs().max() <= 1e-5 and (v.cpu() - st.v).abs().max() <= 1e-5
+    assert np.allclose(l_gpu, loss_all, rtol=0, atol=1e-5)
+
+
+def test_inference_paths_match_oracle(monkeypatch, golden):
+    from dl_attack_on_imagenet_b200 import ADIL
+    monkeypatch.setattr(ADIL, "verbose", False)
+    model_cpu = O.tiny_classifier(seed=0)
+    model = O.tiny_classifier(seed=0).cuda()
+    _, _, xva, yva = tiny_data()
+    D = torch.from_numpy(golden["fit_gd_ce_D"])
+    os.makedirs("trained_dicts", exist_ok=True)
+    torch.save([D, torch.zeros(N, K), [], [], 0.0], "trained_dicts/ImageNet_t_inf.bin")
+    atk = ADIL(model, eps=EPS, n_atoms=K, model_name='t_inf', steps_inference=5)
+    # supervised (DDrague) vs the reference's own output
+    adv = atk(xva, yva)
+    assert (adv.cpu() - torch.from_numpy(golden["ddrague_adv"])).abs().max() <= 1e-5
+    assert adv.min() >= 0 and adv.max() <= 1
+    # validation coder vs the reference's own output
+    adv2 = atk.forward_supervised_AdamW(xva, yva, D.cuda(), 'eval')
+    assert (adv2.cpu() - torch.from_numpy(golden["coder_adv"])).abs().max() <= 1e-5
+    assert int(atk.forward_supervised_AdamW(xva, yva, D.cuda(), 'train')) == int(golden["coder_fooled"])
+    # unsupervised: same CPU RNG draws as the reference
+    atk.attack, atk.trials = 'unsupervised', 3
+    torch.manual_seed(99)
+    advu, dvn = atk(xva, yva)
+    assert (advu.cpu() - torch.from_numpy(golden["unsup_adv"])).abs().max() <= 1e-6
+    assert np.allclose(np.asarray(dvn), golden["unsup_dvnorm"], atol=1e-7)
+    torch.manual_seed(98)
+    assert (atk.sample_sphere(5).cpu() - torch.from_numpy(golden["sample_sphere_linf"])).abs().max() <= 1e-7
+    # perturb alias
+    atk.attack = 'supervised'
+    assert torch.equal(atk.perturb(xva, yva), adv)
+    del model_cpu
+
+
+def test_l2_norm_init_and_projections(monkeypatch):
+    from dl_attack_on_imagenet_b200 import ADIL
+    monkeypatch.setattr(ADIL, "verbose", False)
+    model = O.tiny_classifier(seed=0).cuda()
+    atk = ADIL(model, eps=0.5, norm='L2', n_atoms=7, model_name='t_l2')
+    g = torch.Generator().manual_seed(3)
+    var = torch.randn(3, 6, 6, 7, generator=g)
+    assert (atk.projection_d(var.cuda()).cpu() - O.project_atoms(var, O.ATOMS_L2BALL)).abs().max() <= 1e-6
+    rows = torch.randn(9, 7, generator=g)
+    assert (atk.projection_v(rows.cuda()).cpu() - O.project_rows_l2(rows, 0.5)).abs().max() <= 1e-7
+    torch.manual_seed(97)
+    s = atk.sample_sphere(5)
+    torch.manual_seed(97)
+    assert (s - O.sample_sphere(5, 7, 0.5, 'l2')).abs().max() <= 1e-7
+
+
+def test_attack_dict_model_autograd_bridge():
+    """Attack_dict_model.forward differentiates through the fused synthesis like adil.py:24-27."""
+    from dl_attack_on_imagenet_b200 import Attack_dict_model
+    model = O.tiny_classifier(seed=0).cuda()
+    g = torch.Generator().manual_seed(4)
+    D = -1 + 2 * torch.rand(C, H, W, K, generator=g)
+    v = O.project_rows_l1(torch.rand(N, K, generator=g), EPS)
+    x = torch.rand(B, C, H, W, generator=g)
+    idx = torch.tensor([7, 2, 5, 0])
+    adm = Attack_dict_model(D.cuda(), v.cuda(), EPS)
+    out = adm(x.cuda(), idx, model)
+    out.sum().backward()
+    Dr, vr = D.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    cpu_model = O.tiny_classifier(seed=0)
+    ref = cpu_model(x + torch.tensordot(vr[idx, :], Dr, dims=([1], [3])))
+    ref.sum().backward()
+    assert (out.detach().cpu() - ref.detach()).abs().max() <= 1e-5
+    assert (adm.d.grad.cpu() - Dr.grad).abs().max() <= 1e-5 * Dr.grad.abs().max() + 1e-9
+    assert (adm.v.grad.cpu() - vr.grad).abs().max() <= 1e-5 * vr.grad.abs().max() + 1e-9
+    adm.update_v()
+    adm.update_d()
+    assert adm.d.data.abs().max() <= 1
+
+
+def test_fooling_rate_on_imagenet_classifier(monkeypatch):
+    """Config-1-like smoke at real image size: random-init ResNet-18, 16 images, 10 atoms, l_inf 8/255 -- loss goes
+    down, perturbation respects the budget, fooling rate equals the PyTorch-op evaluation of the same D, v."""
+    from dl_attack_on_imagenet_b200 import ADIL, IndexedTensorDataset, build_classifier, synthetic_images
+    monkeypatch.setattr(ADIL, "verbose", False)
+    monkeypatch.setattr(ADIL, "run_validation", False)
+    model = build_classifier('resnet18', seed=0, device='cuda')
+    x, y = synthetic_images(16, seed=1)
+    torch.manual_seed(1234)
+    atk = ADIL(model, eps=EPS, steps=4, n_atoms=10, batch_size=8, data_train=IndexedTensorDataset(x, y),
+               model_name='t_resnet18', loss='ce', method='gd')
+    D, v, loss_all, fool_all, _ = torch.load(atk.model_file, weights_only=False)
+    assert loss_all[-1] < loss_all[0]
+    assert D.abs().max() <= 1 and (v.abs().sum(1) <= EPS * (1 + 1e-5)).all()
+    dv = torch.tensordot(v, D, dims=([1], [3]))
+    assert dv.abs().max() <= EPS * (1 + 1e-5)
+    with torch.no_grad():
+        clean = model(x.cuda()).argmax(-1)
+        adv = model(x.cuda() + dv).argmax(-1)
+    rate = (clean != adv).float().mean().item()
+    assert 0.0 <= rate <= 1.0

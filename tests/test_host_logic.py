@@ -1,0 +1,138 @@
+"""Host-side logic that needs no GPU: sharding / schedules, Normalize peeling, AdamW scalar packing, and the
+world_size-2 gloo run of the image-sharded step (kernels replaced by the oracle -- test infrastructure only)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dl_attack_on_imagenet_b200 import distributed as dsh
+from dl_attack_on_imagenet_b200 import ops, split_normalize
+from dl_attack_on_imagenet_b200.data import IndexedTensorDataset, Normalize
+from oracle import adil_oracle as O
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 32, 1000, 16384):
+        for world in (1, 2, 3, 8):
+            spans = [dsh.shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans[:-1], spans[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+            for i in range(0, n, max(1, n // 17)):
+                r = dsh.owner_of(i, n, world)
+                assert spans[r][0] <= i < spans[r][1]
+
+
+def test_epoch_schedule_covers_each_shard_once():
+    n, world, bs = 37, 4, 5
+    sched = dsh.epoch_schedule(n, world, bs, epoch=3, seed=11)
+    seen = torch.cat([torch.cat(step) for step in sched])
+    assert sorted(seen.tolist()) == list(range(n))
+    for step in sched:
+        for r, idx in enumerate(step):
+            lo, hi = dsh.shard_bounds(n, world, r)
+            assert idx.numel() <= bs and all(lo <= i < hi for i in idx.tolist())
+    again = dsh.epoch_schedule(n, world, bs, epoch=3, seed=11)
+    assert all(torch.equal(a, b) for sa, sb in zip(sched, again) for a, b in zip(sa, sb))
+    other = dsh.epoch_schedule(n, world, bs, epoch=4, seed=11)
+    assert any(not torch.equal(a, b) for sa, sb in zip(sched, other) for a, b in zip(sa, sb))
+    uni = dsh.union_schedule(n, world, bs, epoch=3, seed=11)
+    assert all(torch.equal(u, torch.cat(s)) for u, s in zip(uni, sched))
+
+
+def test_split_normalize():
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Flatten())
+    model = torch.nn.Sequential(Normalize(), net)
+    rest, mean, std = split_normalize(model)
+    assert rest is net
+    assert mean == pytest.approx([0.485, 0.456, 0.406]) and std == pytest.approx([0.229, 0.224, 0.225])
+    rest2, mean2, _ = split_normalize(net)
+    assert rest2 is net and mean2 is None
+    x = torch.rand(2, 3, 8, 8)
+    assert torch.equal(model(x), rest((x - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)))
+
+
+def test_adamw_params_struct():
+    hp = ops.adamw_params(3, 0.01)
+    assert (hp.lr, hp.beta1, hp.beta2, hp.eps, hp.weight_decay, hp.step) == (0.01, 0.9, 0.999, 1e-8, 1e-2, 3)
+
+
+def test_indexed_dataset_protocol():
+    ds = IndexedTensorDataset(torch.rand(5, 3, 4, 4), torch.arange(5))
+    x, y = ds[2]
+    assert x.shape == (3, 4, 4) and int(y) == 2
+    ds.indexed = True
+    i, x, y = ds[3]
+    assert i == 3 and int(y) == 3
+
+
+# ---- world_size = 2 over gloo: R ranks x B images == one process with the union batch ----------------------
+C, H, W, K, N, B = 3, 8, 8, 5, 12, 3
+EPS = 8.0 / 255.0
+
+
+def _problem():
+    g = torch.Generator().manual_seed(21)
+    D = -1 + 2 * torch.rand(C, H, W, K, generator=g)
+    v = O.project_rows_l1(torch.rand(N, K, generator=g), EPS)
+    x = torch.rand(N, C, H, W, generator=g)
+    return D, v, x
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    model = O.tiny_classifier(seed=0)
+    net, mean, std = O.split_normalize(model)
+    D, v, x = _problem()
+    P = C * H * W
+    lo, hi = dsh.shard_bounds(N, world, rank)
+    st = O.State(D, v[lo:hi])                      # each rank owns its images' code rows only
+    for epoch in range(2):
+        for step in dsh.epoch_schedule(N, world, B, epoch, seed=5):
+            idx = step[rank]
+            if idx.numel():
+                with torch.no_grad():
+                    labels = model(x[idx]).argmax(-1)
+                xin, _ = O.synth(x[idx].reshape(len(idx), P), st.D2, st.v, idx - lo, mean, std, EPS, O.F_NORMALIZE)
+                _, g, _ = O.classifier_grad(net, xin.reshape(-1, C, H, W), labels, 'ce', 50, False, 'sum')
+                dD2, dvb = O.grad(g.reshape(len(idx), P), st.D2, st.v[idx - lo], std)
+            else:
+                dD2, dvb = torch.zeros_like(st.D2), torch.zeros(0, K)
+            dsh.allreduce_sum_(dD2)                # the one data-path collective
+            O.dict_step_(st, dD2, 0.01)
+            O.code_step_(st, dvb, idx - lo, 0.01, EPS)
+    v_all = dsh.gather_rows(st.v, N, world, rank)
+    if rank == 0:
+        torch.save({"D2": st.D2, "v": v_all}, os.path.join(out_dir, "sharded.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "sharded.pt"))
+    # single process, union batches
+    torch.set_num_threads(1)
+    model = O.tiny_classifier(seed=0)
+    net, mean, std = O.split_normalize(model)
+    D, v, x = _problem()
+    P = C * H * W
+    st = O.State(D, v)
+    for epoch in range(2):
+        for idx in dsh.union_schedule(N, world, B, epoch, seed=5):
+            with torch.no_grad():
+                labels = model(x[idx]).argmax(-1)
+            xin, _ = O.synth(x[idx].reshape(len(idx), P), st.D2, st.v, idx, mean, std, EPS, O.F_NORMALIZE)
+            _, g, _ = O.classifier_grad(net, xin.reshape(-1, C, H, W), labels, 'ce', 50, False, 'sum')
+            O.joint_step_(st, g.reshape(len(idx), P), idx, 0.01, EPS, std)
+    assert (got["D2"] - st.D2).abs().max() < 2e-6
+    assert (got["v"] - st.v).abs().max() < 2e-6
