@@ -83,10 +83,9 @@ int check_shape(const char* fn, int B, int P, int K, int C, int hw, bool need_ch
 
 bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
-bool use_tc(int B, int P, int K, int* rc, const char* fn) {
+bool use_tc(bool ok, int B, int P, int K, int* rc, const char* fn) {
   *rc = 0;
   if (g_impl == ADIL_IMPL_FMA) return false;
-  const bool ok = tc_shape_ok(B, P, K);
   if (g_impl == ADIL_IMPL_TC && !ok) {
     *rc = set_error(-4, "%s: ADIL_IMPL_TC requested but shape B=%d P=%d K=%d does not qualify", fn, B, P, K);
     return false;
@@ -124,7 +123,9 @@ extern "C" int adil_set_impl(int impl) {
 
 extern "C" int adil_get_impl(void) { return g_impl; }
 
-extern "C" int adil_tc_supported(int B, int P, int K) { return tc_shape_ok(B, P, K) ? 1 : 0; }
+extern "C" int adil_tc_supported(int B, int P, int K) {
+  return (tc_synth_ok(B, P, K) ? 1 : 0) | (tc_grad_ok(B, P, K) ? 2 : 0);
+}
 
 extern "C" int adil_synth(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
                           const float* v, const int64_t* v_index, int B, int P, int K, int C, int hw,
@@ -139,7 +140,7 @@ extern "C" int adil_synth(float* out, float* delta_out, const float* x, const in
   if (B == 0) return 0;
   ChannelConsts cc = make_consts(C, hw, mean_host, std_host, norm);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(B, P, K, &rc, "adil_synth"))
+  if (use_tc(tc_synth_ok(B, P, K), B, P, K, &rc, "adil_synth"))
     return launch_synth_tc(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
   if (rc) return rc;
   return launch_synth_fma(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
@@ -167,7 +168,7 @@ int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, fl
   memset(&dev, 0, sizeof(dev));
   if (hp) dev = make_adamw(hp);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(B, P, K, &rc, fn))
+  if (use_tc(tc_grad_ok(B, P, K), B, P, K, &rc, fn))
     return launch_grad_tc(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
                           scratch_bytes, st);
   if (rc) return rc;

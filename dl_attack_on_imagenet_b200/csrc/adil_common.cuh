@@ -90,6 +90,8 @@ int launch_grad_fma(float* dD2, float* D2_rw, float* m, float* s, float* dvb, co
 
 // tcgen05-path launchers (adil_tc.cu)
 bool tc_shape_ok(int B, int P, int K);
+bool tc_synth_ok(int B, int P, int K);
+bool tc_grad_ok(int B, int P, int K);
 int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
                     int flags, cudaStream_t st);

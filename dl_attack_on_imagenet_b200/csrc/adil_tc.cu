@@ -1,18 +1,771 @@
-// tcgen05 (5th-gen tensor core) split-TF32 kernels -- placeholder until the FMA path is validated on hardware.
+// tcgen05 (5th-gen tensor core) kernels of the ADiL hot path -- split-TF32 ("3xTF32") contractions with fp32
+// accumulators in TMEM, used when the atom count makes the CUDA-core FFMA pipe the limiter.
+//
+// Every fp32 operand x is split exactly into hi = x & 0xffffe000 (representable in TF32) and lo = x - hi, and each
+// contraction is issued as three tcgen05.mma.kind::tf32 passes  lo*hi + hi*lo + hi*hi  into the same TMEM
+// accumulator: relative error ~2^-21, i.e. fp32-grade (the 1e-5 parity bound of the north star needs it: plain TF32
+// is 2^-11).
+//
+// Operand staging.  All three matrices (dictionary tile D[p][k], gradient tile g[b][p], batch codes v[b][k]) are laid
+// out in shared memory by the CTA's threads in the UMMA no-swizzle canonical form: 128-byte core matrices of
+// 8 "rows" x 16 bytes.  One image serves a matrix in both of its roles because the core matrix of a K-major operand
+// (8 M/N-rows x 4 contiguous K-elements) and of an MN-major operand (8 K-rows x 4 contiguous MN-elements) is the
+// same memory pattern:
+//     img(r, c) = (c/4)*S + (r/8)*128 + (r%8)*16 + (c%4)*4        S = 128*ceil(R/8) + 16  (the +16 de-phases banks)
+//     D tile : r = pixel, c = atom   -> A of synth (K-major, M=pixel)      / B of dv   (MN-major, N=atom)
+//     g tile : r = image, c = pixel  -> A of dD    (MN-major, M=pixel)     / A of dv   (K-major,  M=image)
+//     codes  : r = image, c = atom   -> B of synth (K-major, N=image)      / B of dD   (MN-major, N=atom)
+// The synthesis kernel stages the raw dictionary tile with a 1-D TMA bulk copy (cp.async.bulk + mbarrier,
+// double-buffered) before the split; the gradient kernel prefetches the next tile through registers because its
+// shared memory is taken by the hi/lo images.
+#include <cstdio>
+
 #include "adil_common.cuh"
 
 namespace adil {
 
-bool tc_shape_ok(int, int, int) { return false; }
+int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, cudaStream_t st);
 
-int launch_synth_tc(float*, float*, const float*, const int64_t*, const float*, const float*, const int64_t*, int, int,
-                    int, const ChannelConsts&, float, int, cudaStream_t) {
-  return set_error(-4, "tcgen05 path not built");
+namespace {
+
+constexpr int TC_THREADS = 512;
+constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int TC_TP = 128;                    // pixels per tile = UMMA M
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+__host__ __device__ inline int rup(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+      printf("adil_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-int launch_grad_tc(float*, float*, float*, float*, float*, const float*, const float*, const float*, const int64_t*,
-                   int, int, int, const ChannelConsts&, const AdamwDev*, int, float*, size_t, cudaStream_t) {
-  return set_error(-4, "tcgen05 path not built");
+// UMMA shared-memory matrix descriptor, no swizzle (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
+  return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate (cute/arch/mma_sm100_desc.hpp: InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread (thread t <-> TMEM lane base+t)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = __fsub_rn(x, hi);  // exact
+}
+
+// canonical image offset in floats: r = "8-row" index, c = contiguous index, S = byte stride between c-groups
+__device__ __forceinline__ int img_off(int r, int c, int S_bytes) {
+  return (c >> 2) * (S_bytes >> 2) + (r >> 3) * 32 + (r & 7) * 4 + (c & 3);
+}
+__host__ __device__ inline int img_stride(int R) { return 128 * ((R + 7) / 8) + 16; }
+
+// codes image (hi/lo): rows b < Rz are written (zero beyond B / K), layout img(b, k)
+__device__ void build_code_images(float* Vhi, float* Vlo, const float* v, const int64_t* vidx, int B, int K, int Rz,
+                                  int Kz, int Sv) {
+  for (int e = threadIdx.x; e < Rz * Kz; e += blockDim.x) {
+    const int b = e / Kz, k = e - b * Kz;
+    float val = 0.0f;
+    if (b < B && k < K) {
+      const int64_t row = vidx ? vidx[b] : (int64_t)b;
+      val = v[row * K + k];
+    }
+    float hi, lo;
+    split_tf32(val, hi, lo);
+    const int o = img_off(b, k, Sv);
+    Vhi[o] = hi;
+    Vlo[o] = lo;
+  }
+}
+
+// =========================================================================================================
+// synthesis:  acc[p, b] = sum_k D[p,k] v[b,k]   (M = 128 pixels, N = images, K = atoms)
+// =========================================================================================================
+struct SynthTcArgs {
+  float* out;
+  float* delta;
+  const float* x;
+  const int64_t* xidx;
+  const float* D2;
+  const float* v;
+  const int64_t* vidx;
+  int B, P, K;
+  int Np;      // N of the MMA: round_up(B, 16)
+  int Kp8;     // contraction length: round_up(K, 8)
+  int Sd, Sv;  // image strides (bytes)
+  int raw_floats, dimg_floats, vimg_floats;
+  uint32_t tmem_cols;
+  float eps;
+  int flags;
+  ChannelConsts cc;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) synth_tc_kernel(const SynthTcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);  // [2] raw tile landed
+  uint64_t* bar_mma = bar_full + 2;                            // [1] MMAs of a tile retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 3);
+  float* raw0 = reinterpret_cast<float*>(smem_raw + 128);
+  float* raw1 = raw0 + a.raw_floats;
+  float* Vhi = raw1 + a.raw_floats;
+  float* Vlo = Vhi + a.vimg_floats;
+  float* Dhi = Vlo + a.vimg_floats;
+  float* Dlo = Dhi + a.dimg_floats;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = a.K, P = a.P, B = a.B;
+  const int ntiles = (P + TC_TP - 1) / TC_TP;
+
+  if (tid == 0) {
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
+  // zero the dictionary images once: contraction padding (k in [K, Kp8)) must stay zero
+  for (int e = tid; e < 2 * a.dimg_floats; e += TC_THREADS) Dhi[e] = 0.0f;
+  build_code_images(Vhi, Vlo, a.v, a.vidx, B, K, a.Np, a.Kp8, a.Sv);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int my_first = blockIdx.x;
+  if (tid == 0 && my_first < ntiles) {
+    const int rows = min(TC_TP, P - my_first * TC_TP);
+    mbar_expect_tx(&bar_full[0], (uint32_t)(rows * K * 4));
+    bulk_g2s(raw0, a.D2 + (size_t)my_first * TC_TP * K, (uint32_t)(rows * K * 4), &bar_full[0]);
+  }
+
+  const uint32_t idesc = make_idesc(128, a.Np, false, false);
+  const int ksteps = a.Kp8 / 8;
+  const int quad = warp & 3, cgrp = warp >> 2;          // TMEM lane quadrant / column group of this warp
+  const int nchunks = a.Np / 8;                         // 8-column chunks of the accumulator
+  int it = 0;
+  int prev_tile = -1;
+  for (int tile = my_first;; tile += gridDim.x, ++it) {
+    const bool have = tile < ntiles;
+    if (have) {
+      const int s = it & 1;
+      const int rows = min(TC_TP, P - tile * TC_TP);
+      mbar_wait(&bar_full[s], (it >> 1) & 1);                      // raw tile `it` landed
+      if (it > 0) mbar_wait(bar_mma, (it - 1) & 1);                // MMAs(it-1) retired: images reusable, acc ready
+      tc_fence_after();
+      const float* raw = s ? raw1 : raw0;
+      for (int e = tid; e < TC_TP * K; e += TC_THREADS) {          // split + scatter into the canonical images
+        const int p = e / K, k = e - p * K;
+        const float val = (p < rows) ? raw[e] : 0.0f;
+        float hi, lo;
+        split_tf32(val, hi, lo);
+        const int o = img_off(p, k, a.Sd);
+        Dhi[o] = hi;
+        Dlo[o] = lo;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const int nxt = tile + gridDim.x;
+        if (nxt < ntiles) {                                         // TMA prefetch of the next raw tile
+          const int nrows = min(TC_TP, P - nxt * TC_TP);
+          mbar_expect_tx(&bar_full[s ^ 1], (uint32_t)(nrows * K * 4));
+          bulk_g2s(s ? raw0 : raw1, a.D2 + (size_t)nxt * TC_TP * K, (uint32_t)(nrows * K * 4), &bar_full[s ^ 1]);
+        }
+        const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np);
+        const uint32_t dhi = smem_u32(Dhi), dlo = smem_u32(Dlo), vhi = smem_u32(Vhi), vlo = smem_u32(Vlo);
+        // A (D image, K-major): LBO = Sd between the two 16-byte K chunks, SBO = 128 between 8-pixel groups
+        // B (code image, K-major): LBO = Sv, SBO = 128 between 8-image groups
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t abase = (pass == 0) ? dlo : dhi;            // lo*hi, hi*lo, hi*hi
+          const uint32_t bbase = (pass == 1) ? vlo : vhi;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ad = make_desc(abase + ks * 2 * a.Sd, a.Sd, 128);
+            const uint64_t bd = make_desc(bbase + ks * 2 * a.Sv, a.Sv, 128);
+            mma_tf32(acc, ad, bd, idesc, (pass | ks) ? 1u : 0u);
+          }
+        }
+        mma_commit(bar_mma);
+      }
+    }
+    // epilogue of the previous tile overlaps the MMAs just issued
+    const int etile = prev_tile;
+    if (!have && prev_tile >= 0) {
+      mbar_wait(bar_mma, (it - 1) & 1);
+      tc_fence_after();
+    }
+    if (etile >= 0) {
+      const uint32_t acc = tmem_base + (uint32_t)(((it - 1) & 1) * a.Np) + ((uint32_t)(quad * 32) << 16);
+      const int p = etile * TC_TP + quad * 32 + lane;
+      const bool pok = p < P;
+      int c = 0;
+      float mean = 0.0f, stdv = 1.0f;
+      if (a.cc.use && pok) {
+        c = p / a.cc.hw;
+        mean = a.cc.mean[c];
+        stdv = a.cc.stdv[c];
+      }
+      // this warp's chunks: cgrp, cgrp+4, ... ; x is fetched for all of them first (loads in flight)
+      constexpr int MAXCH = 8;  // Np <= 256 -> at most 32 chunks / 4 groups
+      float xv[MAXCH][8];
+      const bool need_x = (a.x != nullptr) && (a.out != nullptr);
+#pragma unroll
+      for (int ci = 0; ci < MAXCH; ++ci) {
+        const int ch = cgrp + 4 * ci;
+        if (ch < nchunks && need_x && pok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int b = ch * 8 + j;
+            if (b < B) {
+              const int64_t xr = a.xidx ? a.xidx[b] : (int64_t)b;
+              xv[ci][j] = __ldg(a.x + (size_t)xr * P + p);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < MAXCH; ++ci) {
+        const int ch = cgrp + 4 * ci;
+        if (ch < nchunks) {                                      // warp-uniform
+          float d[8];
+          tmem_ld8(acc + (uint32_t)(ch * 8), d);
+          if (pok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int b = ch * 8 + j;
+              if (b < B) {
+                float dv = d[j];
+                if (a.flags & ADIL_SYNTH_CLAMP_DELTA) dv = fminf(fmaxf(dv, -a.eps), a.eps);
+                if (a.delta) a.delta[(size_t)b * P + p] = dv;
+                if (a.out) {
+                  float o = need_x ? __fadd_rn(xv[ci][j], dv) : dv;
+                  if (a.flags & ADIL_SYNTH_CLAMP01) o = fminf(fmaxf(o, 0.0f), 1.0f);
+                  if (a.cc.use) o = __fdiv_rn(__fsub_rn(o, mean), stdv);
+                  a.out[(size_t)b * P + p] = o;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    if (!have) break;
+    prev_tile = tile;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// =========================================================================================================
+// backward contractions (+ optional fused AdamW/clamp), bf16x3 on tcgen05.mma.kind::f16:
+//   dD[p, k] = sum_b gx[b,p] v[b,k]   M = 128 pixels, N = atoms, K = images  (A = g image MN-major, B = code image MN-major)
+//   dv[b, k] = sum_p gx[b,p] D[p,k]   M = images (<=128), N = atoms, K = pixels (A = g image K-major, B = D image MN-major)
+// The gradient tile is needed with the contraction along its contiguous dimension (dv) AND across it (dD).  TF32
+// operands cannot do that from one image (MN-major TF32 exists only in the 128B_BASE32B swizzle, which has no
+// K-major twin -- measured: scripts/umma_probe*.cu), bf16 operands can: an 8x16-byte core matrix is the same bytes
+// for a K-major and an MN-major operand.  So every fp32 value is split exactly into three bf16 terms
+// x = b0 + b1 + b2 (+ O(2^-23 x)) and each contraction is six MMAs: (2,0) (0,2) (1,1) (1,0) (0,1) (0,0); the two
+// dropped cross terms are O(2^-21).  bf16 MMAs run at twice the TF32 rate, so this costs the same tensor time as
+// 3xTF32 while the images take 6 instead of 8 bytes per element.
+// dD accumulators are double-buffered in TMEM and drained by the AdamW epilogue while the next tile's MMAs run;
+// the dv accumulator stays in TMEM across all of the CTA's tiles.
+// =========================================================================================================
+typedef unsigned short bf16_t;
+
+__device__ __forceinline__ void split_bf16x3(float x, bf16_t& b0, bf16_t& b1, bf16_t& b2) {
+  const uint32_t u0 = __float_as_uint(x);
+  b0 = (bf16_t)(u0 >> 16);
+  const float r1 = __fsub_rn(x, __uint_as_float(u0 & 0xffff0000u));  // exact
+  const uint32_t u1 = __float_as_uint(r1);
+  b1 = (bf16_t)(u1 >> 16);
+  const float r2 = __fsub_rn(r1, __uint_as_float(u1 & 0xffff0000u));  // exact
+  const uint32_t u2 = __float_as_uint(r2);
+  b2 = (bf16_t)((u2 + 0x7fffu + ((u2 >> 16) & 1u)) >> 16);            // round to nearest even
+}
+
+// canonical image offset in bf16 elements: r = "8-row" index, c = contiguous index, S = byte stride between 8-c groups
+__device__ __forceinline__ int img16_off(int r, int c, int S_bytes) {
+  return (c >> 3) * (S_bytes >> 1) + (r >> 3) * 64 + (r & 7) * 8 + (c & 7);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct GradTcArgs {
+  float* dD2;
+  float* D2w;
+  float* m;
+  float* s;
+  float* partial;
+  const float* g;
+  const float* D2;
+  const float* v;
+  const int64_t* vidx;
+  int B, P, K;
+  int Bp16;     // contraction length of dD: round_up(B, 16)
+  int Kp16;     // N of both MMAs: round_up(K, 16)
+  int Sg, Sd, Sv;
+  int gimg, dimg, vimg;  // image sizes in bf16 elements (each matrix has three images)
+  uint32_t tmem_cols;
+  int want_dD, want_dv, atoms_mode;
+  ChannelConsts cc;
+  AdamwDev hp;
+};
+
+constexpr int G_MAXQ = 8;    // float4 of g per thread per tile: 128 images x 32 / 512
+constexpr int D_MAXE = 24;   // dictionary elements per thread per tile: 128 x 96 / 512
+
+__global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  bf16_t* Vi = reinterpret_cast<bf16_t*>(smem_raw + 128);  // three code images
+  bf16_t* Di = Vi + 3 * a.vimg;                             // three dictionary images
+  bf16_t* Gi = Di + 3 * a.dimg;                             // three gradient images
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = a.K, P = a.P, B = a.B;
+  const int ntiles = (P + TC_TP - 1) / TC_TP;
+  const int gq_total = B * (TC_TP / 4);  // float4 per g tile
+
+  if (tid == 0) {
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
+  // zero all images once: contraction padding (images in [B, Bp16)) must stay zero, over-read regions stay finite
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(Vi);
+    const int nz = (3 * (a.vimg + a.dimg + a.gimg)) >> 1;
+    for (int e = tid; e < nz; e += TC_THREADS) z[e] = 0u;
+  }
+  __syncthreads();
+  if (a.want_dD) {
+    for (int e = tid; e < B * K; e += TC_THREADS) {
+      const int b = e / K, k = e - b * K;
+      const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
+      bf16_t b0, b1, b2;
+      split_bf16x3(a.v[row * K + k], b0, b1, b2);
+      const int o = img16_off(b, k, a.Sv);
+      Vi[o] = b0;
+      Vi[a.vimg + o] = b1;
+      Vi[2 * a.vimg + o] = b2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_dv = tmem_base + (uint32_t)(2 * a.Kp16);
+
+  const uint32_t idesc_dD = make_idesc_bf16(128, a.Kp16, true, true);
+  const uint32_t idesc_dv = make_idesc_bf16(128, a.Kp16, false, true);
+  const int quad = warp & 3, cgrp = warp >> 2;
+  const int nchunks = a.Kp16 / 8;
+
+  float4 greg[G_MAXQ];
+  float dreg[D_MAXE];
+
+  auto prefetch = [&](int tile) {
+    const int p0 = tile * TC_TP;
+#pragma unroll
+    for (int i = 0; i < G_MAXQ; ++i) {
+      const int q = tid + i * TC_THREADS;
+      greg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < gq_total) {
+        const int b = q >> 5, pq = q & 31;
+        const int p = p0 + 4 * pq;
+        if (p < P) greg[i] = ld_stream4(a.g + (size_t)b * P + p);
+      }
+    }
+    if (a.want_dv) {
+      const int rows = min(TC_TP, P - p0);
+      const float* src = a.D2 + (size_t)p0 * K;
+#pragma unroll
+      for (int i = 0; i < D_MAXE; ++i) {
+        const int e = tid + i * TC_THREADS;
+        dreg[i] = (e < rows * K) ? __ldg(src + e) : 0.0f;
+      }
+    }
+  };
+
+  auto stage = [&](int tile) {
+    const int p0 = tile * TC_TP;
+#pragma unroll
+    for (int i = 0; i < G_MAXQ; ++i) {
+      const int q = tid + i * TC_THREADS;
+      if (q < gq_total) {
+        const int b = q >> 5, pq = q & 31;
+        float val[4] = {greg[i].x, greg[i].y, greg[i].z, greg[i].w};
+        if (a.cc.use) {
+          const int p = p0 + 4 * pq;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) val[j] = __fdiv_rn(val[j], a.cc.stdv[min((p + j) / a.cc.hw, kMaxC - 1)]);
+        }
+        bf16_t t0[4], t1[4], t2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_bf16x3(val[j], t0[j], t1[j], t2[j]);
+        const int o = img16_off(b, 4 * pq, a.Sg);  // 8-byte slot (b, 4pq..4pq+3)
+        *reinterpret_cast<uint2*>(Gi + o) = make_uint2(t0[0] | ((uint32_t)t0[1] << 16), t0[2] | ((uint32_t)t0[3] << 16));
+        *reinterpret_cast<uint2*>(Gi + a.gimg + o) =
+            make_uint2(t1[0] | ((uint32_t)t1[1] << 16), t1[2] | ((uint32_t)t1[3] << 16));
+        *reinterpret_cast<uint2*>(Gi + 2 * a.gimg + o) =
+            make_uint2(t2[0] | ((uint32_t)t2[1] << 16), t2[2] | ((uint32_t)t2[3] << 16));
+      }
+    }
+    if (a.want_dv) {
+#pragma unroll
+      for (int i = 0; i < D_MAXE; ++i) {
+        const int e = tid + i * TC_THREADS;
+        if (e < TC_TP * K) {
+          const int p = e / K, k = e - p * K;
+          bf16_t b0, b1, b2;
+          split_bf16x3(dreg[i], b0, b1, b2);
+          const int o = img16_off(p, k, a.Sd);
+          Di[o] = b0;
+          Di[a.dimg + o] = b1;
+          Di[2 * a.dimg + o] = b2;
+        }
+      }
+    }
+  };
+
+  auto issue = [&](int it) {
+    const uint32_t gb = smem_u32(Gi), vb = smem_u32(Vi), db = smem_u32(Di);
+    const uint32_t gsz = 2u * a.gimg, vsz = 2u * a.vimg, dsz = 2u * a.dimg;  // image sizes in bytes
+    // term order: smallest contributions first
+    const int ta[6] = {2, 0, 1, 1, 0, 0};
+    const int tb[6] = {0, 2, 1, 0, 1, 0};
+    if (a.want_dD) {
+      // A = g image as [M=pixel, K=image] MN-major: SBO = Sg between 8-pixel groups, LBO = 128 between 8-image groups
+      // B = code image as [N=atom, K=image] MN-major: SBO = Sv between 8-atom groups, LBO = 128
+      const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Kp16);
+      const int ksteps = a.Bp16 / 16;
+      for (int t = 0; t < 6; ++t) {
+        const uint32_t abase = gb + ta[t] * gsz, bbase = vb + tb[t] * vsz;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t ad = make_desc(abase + ks * 256, 128, a.Sg);
+          const uint64_t bd = make_desc(bbase + ks * 256, 128, a.Sv);
+          mma_bf16(acc, ad, bd, idesc_dD, (t | ks) ? 1u : 0u);
+        }
+      }
+    }
+    if (a.want_dv) {
+      // A = g image as [M=image, K=pixel] K-major: LBO = Sg between the two 8-pixel chunks, SBO = 128 (8-image groups)
+      // B = D image as [N=atom, K=pixel] MN-major: SBO = Sd between 8-atom groups, LBO = 128 between 8-pixel groups
+      for (int t = 0; t < 6; ++t) {
+        const uint32_t abase = gb + ta[t] * gsz, bbase = db + tb[t] * dsz;
+        for (int ks = 0; ks < TC_TP / 16; ++ks) {
+          const uint64_t ad = make_desc(abase + ks * 2 * a.Sg, a.Sg, 128);
+          const uint64_t bd = make_desc(bbase + ks * 256, 128, a.Sd);
+          mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
+        }
+      }
+    }
+    mma_commit(bar_mma);
+  };
+
+  auto epilogue = [&](int tile, int it) {
+    // accumulator row = pixel (TMEM lane), column = atom
+    const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Kp16) + ((uint32_t)(quad * 32) << 16);
+    const int p = tile * TC_TP + quad * 32 + lane;
+    const bool pok = p < P;
+    const size_t rowoff = (size_t)p * K;
+    for (int ch = cgrp; ch < nchunks; ch += 4) {  // warp-uniform
+      const int k0 = ch * 8;
+      if (k0 >= K) break;
+      float mv[8], sv[8], dv[8];
+      if (a.D2w != nullptr && pok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (k0 + j < K) {
+            mv[j] = a.m[rowoff + k0 + j];
+            sv[j] = a.s[rowoff + k0 + j];
+            dv[j] = a.D2[rowoff + k0 + j];
+          }
+        }
+      }
+      float gacc[8];
+      tmem_ld8(acc + (uint32_t)k0, gacc);
+      if (pok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (k0 + j < K) {
+            if (a.D2w != nullptr) {
+              adamw_update(dv[j], mv[j], sv[j], gacc[j], a.hp);
+              if (a.atoms_mode == ADIL_ATOMS_CLAMP1) dv[j] = clamp1(dv[j]);
+              a.D2w[rowoff + k0 + j] = dv[j];
+              a.m[rowoff + k0 + j] = mv[j];
+              a.s[rowoff + k0 + j] = sv[j];
+            } else {
+              a.dD2[rowoff + k0 + j] = gacc[j];
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  };
+
+  int it = 0, prev_tile = -1;
+  int tile = blockIdx.x;
+  if (tile < ntiles) prefetch(tile);
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    if (it > 0) {
+      mbar_wait(bar_mma, (it - 1) & 1);  // MMAs(it-1) retired: images free, dD accumulator (it-1) complete
+      tc_fence_after();
+    }
+    stage(tile);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue(it);
+    }
+    const int nxt = tile + gridDim.x;
+    if (nxt < ntiles) prefetch(nxt);                    // global loads in flight while the tensor core works
+    if (a.want_dD && prev_tile >= 0) epilogue(prev_tile, it - 1);
+    prev_tile = tile;
+  }
+  if (prev_tile >= 0) {
+    mbar_wait(bar_mma, (it - 1) & 1);
+    tc_fence_after();
+    if (a.want_dD) epilogue(prev_tile, it - 1);
+    if (a.want_dv) {
+      // dv accumulator: row = image (TMEM lane), column = atom -> this CTA's slab of the partial buffer
+      const int b = quad * 32 + lane;
+      float* dst = a.partial + (size_t)blockIdx.x * B * K + (size_t)b * K;
+      for (int ch = cgrp; ch < nchunks; ch += 4) {
+        const int k0 = ch * 8;
+        if (k0 >= K) break;
+        float r[8];
+        tmem_ld8(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)k0, r);
+        if (b < B) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (k0 + j < K) dst[k0 + j] = r[j];
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (a.want_dv) {
+    for (int e = tid; e < B * K; e += TC_THREADS) a.partial[(size_t)blockIdx.x * B * K + e] = 0.0f;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+uint32_t pow2_cols(int need) {
+  uint32_t c = 32;
+  while ((int)c < need) c <<= 1;
+  return c;
+}
+
+struct SynthPlan {
+  int Np, Kp8, Sd, Sv, raw_floats, dimg_floats, vimg_floats;
+  size_t smem;
+  uint32_t tmem_cols;
+  bool ok;
+};
+
+SynthPlan plan_synth(int B, int P, int K) {
+  SynthPlan pl{};
+  pl.ok = false;
+  if (B < 1 || B > 256 || K < 1 || P % 4 != 0) return pl;
+  pl.Np = rup(B, 16);
+  pl.Kp8 = rup(K, 8);
+  pl.Sd = img_stride(TC_TP);
+  pl.Sv = img_stride(pl.Np);
+  pl.raw_floats = rup(TC_TP * K, 32);
+  pl.dimg_floats = (pl.Kp8 / 4) * (pl.Sd / 4) + 64;
+  pl.vimg_floats = (pl.Kp8 / 4) * (pl.Sv / 4) + 64;
+  pl.smem = 128 + sizeof(float) * (2 * (size_t)pl.raw_floats + 2 * (size_t)pl.dimg_floats + 2 * (size_t)pl.vimg_floats);
+  pl.tmem_cols = pow2_cols(2 * pl.Np);
+  pl.ok = pl.smem <= SMEM_LIMIT && pl.tmem_cols <= 512 && pl.Np <= 256;
+  return pl;
+}
+
+struct GradPlan {
+  int Bp16, Kp16, Sg, Sd, Sv, gimg, dimg, vimg;
+  size_t smem;
+  uint32_t tmem_cols;
+  bool ok;
+};
+
+GradPlan plan_grad(int B, int P, int K) {
+  GradPlan pl{};
+  pl.ok = false;
+  if (B < 1 || B > 128 || K < 1 || P % 4 != 0) return pl;
+  pl.Bp16 = rup(B, 16);
+  pl.Kp16 = rup(K, 16);
+  pl.Sg = img_stride(pl.Bp16);
+  pl.Sd = img_stride(TC_TP);
+  pl.Sv = img_stride(pl.Bp16);
+  const int kg = (K + 7) / 8;                             // 8-atom groups actually written
+  pl.vimg = kg * (pl.Sv / 2) + 64;                        // bf16 elements per image
+  pl.dimg = kg * (pl.Sd / 2) + 64;
+  pl.gimg = (TC_TP / 8) * (pl.Sg / 2) + 1024 + 64;        // +2 KB: M = 128 image rows are read even when Bp16 < 128
+  pl.smem = 128 + 2 * 3 * ((size_t)pl.vimg + pl.dimg + pl.gimg);
+  pl.tmem_cols = pow2_cols(3 * pl.Kp16);
+  // the MMAs read N = Kp16 atoms: the code / dictionary images over-read into the buffers that follow them
+  // (codes -> dictionary -> gradient images), which must be large enough to absorb it
+  const size_t over_v = (size_t)(pl.Kp16 / 8) * pl.Sv, over_d = (size_t)(pl.Kp16 / 8) * pl.Sd;
+  const size_t tail_after_v = 2 * (3 * (size_t)pl.dimg + 3 * (size_t)pl.gimg);
+  const size_t tail_after_d = 2 * 3 * (size_t)pl.gimg;
+  pl.ok = pl.smem <= SMEM_LIMIT && pl.tmem_cols <= 512 && over_v <= 2 * (size_t)pl.vimg + tail_after_v &&
+          over_d <= 2 * (size_t)pl.dimg + tail_after_d && B * (TC_TP / 4) <= G_MAXQ * TC_THREADS &&
+          TC_TP * K <= D_MAXE * TC_THREADS;
+  return pl;
+}
+
+}  // namespace
+
+bool tc_synth_ok(int B, int P, int K) { return plan_synth(B, P, K).ok; }
+bool tc_grad_ok(int B, int P, int K) { return plan_grad(B, P, K).ok; }
+bool tc_shape_ok(int B, int P, int K) { return tc_synth_ok(B, P, K) && tc_grad_ok(B, P, K); }
+
+int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
+                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
+                    int flags, cudaStream_t st) {
+  const SynthPlan pl = plan_synth(B, P, K);
+  if (!pl.ok) return set_error(-4, "adil_synth: shape B=%d P=%d K=%d does not qualify for the tcgen05 path", B, P, K);
+  SynthTcArgs a;
+  a.out = out; a.delta = delta_out; a.x = x; a.xidx = x_index; a.D2 = D2; a.v = v; a.vidx = v_index;
+  a.B = B; a.P = P; a.K = K; a.Np = pl.Np; a.Kp8 = pl.Kp8; a.Sd = pl.Sd; a.Sv = pl.Sv;
+  a.raw_floats = pl.raw_floats; a.dimg_floats = pl.dimg_floats; a.vimg_floats = pl.vimg_floats;
+  a.tmem_cols = pl.tmem_cols; a.eps = eps; a.flags = flags; a.cc = cc;
+  a.cc.use = (flags & ADIL_SYNTH_NORMALIZE) ? 1 : 0;
+  int rc = check_cuda(cudaFuncSetAttribute(synth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
+                      "cudaFuncSetAttribute(synth_tc)");
+  if (rc) return rc;
+  const int ntiles = (P + TC_TP - 1) / TC_TP;
+  int grid = sm_count();
+  if (grid > ntiles) grid = ntiles;
+  synth_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(a);
+  return check_cuda(cudaGetLastError(), "synth_tc_kernel launch");
+}
+
+int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
+                   const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
+                   const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, cudaStream_t st) {
+  const GradPlan pl = plan_grad(B, P, K);
+  if (!pl.ok) return set_error(-4, "adil_grad: shape B=%d P=%d K=%d does not qualify for the tcgen05 path", B, P, K);
+  GradTcArgs a;
+  a.dD2 = dD2; a.D2w = D2_rw; a.m = m; a.s = s; a.partial = scratch; a.g = g; a.D2 = D2; a.v = v; a.vidx = v_index;
+  a.B = B; a.P = P; a.K = K; a.Bp16 = pl.Bp16; a.Kp16 = pl.Kp16; a.Sg = pl.Sg; a.Sd = pl.Sd; a.Sv = pl.Sv;
+  a.gimg = pl.gimg; a.dimg = pl.dimg; a.vimg = pl.vimg;
+  a.tmem_cols = pl.tmem_cols;
+  a.want_dD = (dD2 != nullptr || D2_rw != nullptr) ? 1 : 0;
+  a.want_dv = (dvb != nullptr) ? 1 : 0;
+  a.atoms_mode = atoms_mode; a.cc = cc;
+  if (hp) a.hp = *hp;
+  if (!a.want_dD && !a.want_dv) return 0;
+  const int ntiles = (P + TC_TP - 1) / TC_TP;
+  int grid = sm_count();
+  if (grid > ntiles) grid = ntiles;
+  if (grid > kMaxGradCtas) grid = kMaxGradCtas;
+  if (a.want_dv) {
+    const size_t need = (size_t)grid * B * K * sizeof(float);
+    if (scratch == nullptr || scratch_bytes < need)
+      return set_error(-2, "adil_grad: scratch too small (%zu < %zu bytes)", scratch_bytes, need);
+  }
+  int rc = check_cuda(cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
+                      "cudaFuncSetAttribute(grad_tc)");
+  if (rc) return rc;
+  grad_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(a);
+  rc = check_cuda(cudaGetLastError(), "grad_tc_kernel launch");
+  if (rc) return rc;
+  if (a.want_dv) return launch_reduce_partials(dvb, scratch, B * K, grid, st);
+  return 0;
 }
 
 }  // namespace adil

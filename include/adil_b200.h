@@ -75,7 +75,7 @@ int adil_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Select the kernel family used by adil_synth / adil_grad / adil_grad_dict_step (process-wide). */
 int adil_set_impl(int impl);
 int adil_get_impl(void);
-/* 1 if the tcgen05 path accepts this shape, else 0. */
+/* Bit 0: adil_synth runs on the tcgen05 path for this shape; bit 1: adil_grad / adil_grad_dict_step do. */
 int adil_tc_supported(int B, int P, int K);
 
 /* Perturbation synthesis (replaces adil.py:25-26 tensordot + add, the Normalize module of

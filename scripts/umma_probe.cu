@@ -1,0 +1,123 @@
+// Standalone probe of tcgen05.mma.kind::tf32 shared-memory descriptor semantics (no-swizzle), all major-ness combos.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/umma_probe scripts/umma_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cmath>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// A: [128 x 8] (m,k), B: [N x 8] (n,k); images: core matrix of 8 "rows" x 16 bytes.
+//   K-major : rows = m (or n), 4 contiguous = k      : off(r=m, c=k)
+//   MN-major: rows = k,       4 contiguous = m (or n): off(r=k, c=m)
+// off(r,c) = (c/4)*S_c + (r/8)*S_r + (r%8)*16 + (c%4)*4   [bytes]
+struct Cfg { int a_mn, b_mn, N; uint32_t a_lbo, a_sbo, b_lbo, b_sbo; int a_Sc, a_Sr, b_Sc, b_Sr; };
+
+__global__ void probe(const float* A, const float* B, float* out, Cfg c) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = (uint64_t*)smem;
+  uint32_t* slot = (uint32_t*)(smem + 8);
+  float* Ai = (float*)(smem + 128);
+  float* Bi = Ai + 16384 / 4 * 2;   // 32 KB for A image
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < 64 * 1024 / 4; e += blockDim.x) Ai[e] = 0.f;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  __syncthreads();
+  for (int e = tid; e < 128 * 8; e += blockDim.x) {
+    int m = e / 8, k = e % 8;
+    int r = c.a_mn ? k : m, cc = c.a_mn ? m : k;
+    int off = (cc / 4) * c.a_Sc + (r / 8) * c.a_Sr + (r % 8) * 16 + (cc % 4) * 4;
+    Ai[off / 4] = A[e];
+  }
+  for (int e = tid; e < c.N * 8; e += blockDim.x) {
+    int n = e / 8, k = e % 8;
+    int r = c.b_mn ? k : n, cc = c.b_mn ? n : k;
+    int off = (cc / 4) * c.b_Sc + (r / 8) * c.b_Sr + (r % 8) * 16 + (cc % 4) * 4;
+    Bi[off / 4] = B[e];
+  }
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tbase = *slot;
+  if (tid == 0) {
+    uint64_t ad = make_desc(smem_u32(Ai), c.a_lbo, c.a_sbo), bd = make_desc(smem_u32(Bi), c.b_lbo, c.b_sbo);
+    uint32_t idesc = make_idesc(128, c.N, c.a_mn, c.b_mn);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tbase), "l"(ad), "l"(bd), "r"(idesc), "r"(0u) : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  }
+  uint32_t ok = 0; long long t0 = clock64();
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
+    if (clock64() - t0 > 2000000000LL) { if (tid == 0) printf("timeout\n"); break; }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp < 4) {
+    for (int c0 = 0; c0 < c.N; c0 += 8) {
+      uint32_t u[8];
+      uint32_t taddr = tbase + ((uint32_t)(warp * 32) << 16) + c0;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 8; ++j) out[(warp * 32 + lane) * c.N + c0 + j] = __uint_as_float(u[j]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tbase));
+}
+
+int main() {
+  const int N = 16;
+  float hA[128 * 8], hB[N * 8], ref[128 * N], got[128 * N];
+  for (int i = 0; i < 128 * 8; ++i) hA[i] = (float)((i * 7 + 3) % 13) - 6.f;     // small integers: exact in tf32
+  for (int i = 0; i < N * 8; ++i) hB[i] = (float)((i * 5 + 1) % 11) - 5.f;
+  for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) { float s = 0; for (int k = 0; k < 8; ++k) s += hA[m * 8 + k] * hB[n * 8 + k]; ref[m * N + n] = s; }
+  float *dA, *dB, *dO;
+  cudaMalloc(&dA, sizeof(hA)); cudaMalloc(&dB, sizeof(hB)); cudaMalloc(&dO, sizeof(got));
+  cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, sizeof(hB), cudaMemcpyHostToDevice);
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + 64 * 1024);
+  // image strides: group stride along the contiguous (c) dimension and along the 8-row (r) dimension
+  const int SC_A = 2064, SC_B = 272, SR = 128;
+  for (int a_mn = 0; a_mn < 2; ++a_mn) for (int b_mn = 0; b_mn < 2; ++b_mn) for (int variant = 0; variant < 2; ++variant) {
+    Cfg c; c.a_mn = a_mn; c.b_mn = b_mn; c.N = N;
+    // image layout: K-major operand: c=k groups (2 of them) stride Sc, r=m groups stride 128.
+    //               MN-major operand: c=m groups stride Sc, r=k (one group of 8).
+    c.a_Sc = a_mn ? 144 : SC_A; c.a_Sr = SR; c.b_Sc = b_mn ? 144 : SC_B; c.b_Sr = SR;
+    // hypothesis 0 (CUTLASS reading): K-major: LBO = stride between the two k chunks (Sc), SBO = stride between 8-row groups (128)
+    //                                 MN-major: SBO = stride between 4-element MN groups (Sc), LBO = stride between 8-k groups (128)
+    // hypothesis 1: MN-major roles swapped (LBO = MN group stride, SBO = K group stride)
+    if (!a_mn) { c.a_lbo = c.a_Sc; c.a_sbo = SR; } else if (variant == 0) { c.a_sbo = c.a_Sc; c.a_lbo = SR; } else { c.a_lbo = c.a_Sc; c.a_sbo = SR; }
+    if (!b_mn) { c.b_lbo = c.b_Sc; c.b_sbo = SR; } else if (variant == 0) { c.b_sbo = c.b_Sc; c.b_lbo = SR; } else { c.b_lbo = c.b_Sc; c.b_sbo = SR; }
+    if (variant == 1 && !a_mn && !b_mn) continue;
+    cudaMemset(dO, 0xff, sizeof(got));
+    probe<<<1, 128, 128 + 64 * 1024>>>(dA, dB, dO, c);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(got, dO, sizeof(got), cudaMemcpyDeviceToHost);
+    double maxerr = 0; int nz = 0; for (int i = 0; i < 128 * N; ++i) { maxerr = fmax(maxerr, fabs((double)got[i] - ref[i])); nz += got[i] != 0.f; }
+    printf("a_mn=%d b_mn=%d variant=%d : %s maxerr=%g nonzero=%d  got[0..3]=%g %g %g %g ref=%g %g %g %g\n", a_mn, b_mn, variant, cudaGetErrorString(e), maxerr, nz,
+           got[0], got[1], got[2], got[3], ref[0], ref[1], ref[2], ref[3]);
+    if (e != cudaSuccess) return 1;
+  }
+  return 0;
+}

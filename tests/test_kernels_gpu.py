@@ -176,11 +176,11 @@ def test_l1_projection_properties(ops, K):
     ref = O.project_rows_l1(x, EPS)
     got = ops.project_rows(dev(x), ops.ROWS_L1BALL, EPS).cpu()
     assert (got - ref).abs().max() <= 1e-7
-    assert (got.abs().sum(1) <= EPS * (1 + 2e-6)).all()           # feasibility
+    assert (got.double().abs().sum(1) <= EPS * (1 + 2e-5)).all()  # feasibility (fp32 prefix-sum rounding)
     assert (got * x >= 0).all()                                   # sign preserving
     assert torch.equal(got[1], x[1]) and torch.equal(got[0], x[0])  # identity inside the ball
     again = ops.project_rows(dev(got), ops.ROWS_L1BALL, EPS).cpu()
-    assert (again - got).abs().max() <= 1e-8                      # idempotent
+    assert (again - got).abs().max() <= 1e-7                      # idempotent
 
 
 def test_project_atoms(ops, golden):
