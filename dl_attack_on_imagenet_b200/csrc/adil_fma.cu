@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kThreads) synth_fma_kernel(const SynthArgs a) 
   extern __shared__ __align__(16) float smem[];
   float* Dt = smem;                 // [Kp][S_TPS]  Dt[k][p]
   float* vs = smem + a.Kp * S_TPS;  // [bch][Kp]
+  long long* xoff_s = reinterpret_cast<long long*>(vs + a.bch * a.Kp);  // [bch] element offset of each image's x row
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, Kp = a.Kp, P = a.P, B = a.B;
   const int ntiles = (P + S_TP - 1) / S_TP;
@@ -85,6 +86,9 @@ __global__ void __launch_bounds__(kThreads) synth_fma_kernel(const SynthArgs a) 
         }
         vs[e] = val;
       }
+      // x row offsets via shared memory: a dependent global index load per image would serialise the prefetch below
+      for (int r = tid; r < nb; r += kThreads)
+        xoff_s[r] = (a.xidx ? (long long)a.xidx[b0 + r] : (long long)(b0 + r)) * (long long)P;
       __syncthreads();
       const int ngroups = nbp / S_TB;
       const int p = p0 + 4 * lane;
@@ -95,10 +99,7 @@ __global__ void __launch_bounds__(kThreads) synth_fma_kernel(const SynthArgs a) 
 #pragma unroll
           for (int ib = 0; ib < S_TB; ++ib) {
             int b = bbase + ib;
-            if (b < B) {
-              int64_t xr = a.xidx ? a.xidx[b] : (int64_t)b;
-              xv[ib] = ld_stream4(a.x + (size_t)xr * P + p);
-            }
+            if (b < B) xv[ib] = ld_stream4(a.x + xoff_s[b - b0] + p);
           }
         }
         float acc[S_TB][4];
@@ -467,14 +468,14 @@ int launch_synth_fma(float* out, float* delta_out, const float* x, const int64_t
   a.eps = eps; a.flags = flags; a.cc = cc;
   a.cc.use = (flags & ADIL_SYNTH_NORMALIZE) ? 1 : 0;
   const size_t dt_bytes = (size_t)a.Kp * S_TPS * sizeof(float);
-  const size_t budget = 220 * 1024;
+  const size_t budget = 218 * 1024;
   int bch = (int)((budget - dt_bytes) / (a.Kp * sizeof(float)));
   bch = bch / S_TB * S_TB;
   if (bch > 128) bch = 128;
   if (bch > round_up(B, S_TB)) bch = round_up(B, S_TB);
   if (bch < S_TB) return set_error(-3, "adil_synth: K=%d too large for the FMA path", K);
   a.bch = bch;
-  const size_t smem = dt_bytes + (size_t)bch * a.Kp * sizeof(float);
+  const size_t smem = dt_bytes + (size_t)bch * a.Kp * sizeof(float) + (size_t)bch * sizeof(long long);
   int rc = check_cuda(cudaFuncSetAttribute(synth_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "cudaFuncSetAttribute(synth_fma)");
   if (rc) return rc;

@@ -176,25 +176,28 @@ struct SynthTcArgs {
   ChannelConsts cc;
 };
 
+constexpr int S_OS = TC_TP + 4;  // row stride (floats) of the epilogue staging tile [image][pixel]
+constexpr int S_EB = 4;          // float4 per thread per epilogue batch
+
 __global__ void __launch_bounds__(TC_THREADS, 1) synth_tc_kernel(const SynthTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);  // [2] raw tile landed
-  uint64_t* bar_mma = bar_full + 2;                            // [1] MMAs of a tile retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 3);
-  float* raw0 = reinterpret_cast<float*>(smem_raw + 128);
-  float* raw1 = raw0 + a.raw_floats;
-  float* Vhi = raw1 + a.raw_floats;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);  // [1] raw tile landed
+  uint64_t* bar_mma = bar_full + 1;                            // [1] MMAs of a tile retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2);
+  long long* xoff_s = reinterpret_cast<long long*>(smem_raw + 128);  // [256] element offset of each image's x row
+  float* raw = reinterpret_cast<float*>(smem_raw + 128 + 2048);     // TMA landing buffer of the raw D tile
+  float* Vhi = raw + a.raw_floats;
   float* Vlo = Vhi + a.vimg_floats;
   float* Dhi = Vlo + a.vimg_floats;
   float* Dlo = Dhi + a.dimg_floats;
+  float* outs = Dlo + a.dimg_floats;                           // [Np][S_OS] accumulator tile, image-major
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
   const int ntiles = (P + TC_TP - 1) / TC_TP;
 
   if (tid == 0) {
-    mbar_init(&bar_full[0], 1);
-    mbar_init(&bar_full[1], 1);
+    mbar_init(bar_full, 1);
     mbar_init(bar_mma, 1);
     fence_mbar_init();
   }
@@ -202,133 +205,146 @@ __global__ void __launch_bounds__(TC_THREADS, 1) synth_tc_kernel(const SynthTcAr
   // zero the dictionary images once: contraction padding (k in [K, Kp8)) must stay zero
   for (int e = tid; e < 2 * a.dimg_floats; e += TC_THREADS) Dhi[e] = 0.0f;
   build_code_images(Vhi, Vlo, a.v, a.vidx, B, K, a.Np, a.Kp8, a.Sv);
+  // x row offsets in shared memory: a dependent global load per image inside the epilogue would serialise it
+  for (int b = tid; b < B; b += TC_THREADS) xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  int my_first = blockIdx.x;
+  const int my_first = blockIdx.x;
   if (tid == 0 && my_first < ntiles) {
     const int rows = min(TC_TP, P - my_first * TC_TP);
-    mbar_expect_tx(&bar_full[0], (uint32_t)(rows * K * 4));
-    bulk_g2s(raw0, a.D2 + (size_t)my_first * TC_TP * K, (uint32_t)(rows * K * 4), &bar_full[0]);
+    mbar_expect_tx(bar_full, (uint32_t)(rows * K * 4));
+    bulk_g2s(raw, a.D2 + (size_t)my_first * TC_TP * K, (uint32_t)(rows * K * 4), bar_full);
   }
 
   const uint32_t idesc = make_idesc(128, a.Np, false, false);
   const int ksteps = a.Kp8 / 8;
   const int quad = warp & 3, cgrp = warp >> 2;          // TMEM lane quadrant / column group of this warp
   const int nchunks = a.Np / 8;                         // 8-column chunks of the accumulator
-  int it = 0;
-  int prev_tile = -1;
-  for (int tile = my_first;; tile += gridDim.x, ++it) {
-    const bool have = tile < ntiles;
-    if (have) {
-      const int s = it & 1;
-      const int rows = min(TC_TP, P - tile * TC_TP);
-      mbar_wait(&bar_full[s], (it >> 1) & 1);                      // raw tile `it` landed
-      if (it > 0) mbar_wait(bar_mma, (it - 1) & 1);                // MMAs(it-1) retired: images reusable, acc ready
-      tc_fence_after();
-      const float* raw = s ? raw1 : raw0;
-      for (int e = tid; e < TC_TP * K; e += TC_THREADS) {          // split + scatter into the canonical images
-        const int p = e / K, k = e - p * K;
-        const float val = (p < rows) ? raw[e] : 0.0f;
-        float hi, lo;
-        split_tf32(val, hi, lo);
-        const int o = img_off(p, k, a.Sd);
-        Dhi[o] = hi;
-        Dlo[o] = lo;
+  const bool need_x = (a.x != nullptr) && (a.out != nullptr);
+  const bool chan4 = (a.cc.hw & 3) == 0;                // 4 consecutive pixels share a channel
+
+  auto epilogue = [&](int tile, int it) {
+    __syncthreads();  // staging tile free (previous epilogue fully drained)
+    // Phase A: accumulator (row = pixel = TMEM lane, column = image) -> shared memory, image-major
+    {
+      const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np) + ((uint32_t)(quad * 32) << 16);
+      float* col = outs + quad * 32 + lane;
+      for (int ch = cgrp; ch < nchunks; ch += 4) {      // warp-uniform
+        float d[8];
+        tmem_ld8(acc + (uint32_t)(ch * 8), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) col[(ch * 8 + j) * S_OS] = d[j];
       }
-      fence_proxy_async();
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const int nxt = tile + gridDim.x;
-        if (nxt < ntiles) {                                         // TMA prefetch of the next raw tile
-          const int nrows = min(TC_TP, P - nxt * TC_TP);
-          mbar_expect_tx(&bar_full[s ^ 1], (uint32_t)(nrows * K * 4));
-          bulk_g2s(s ? raw0 : raw1, a.D2 + (size_t)nxt * TC_TP * K, (uint32_t)(nrows * K * 4), &bar_full[s ^ 1]);
-        }
-        const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np);
-        const uint32_t dhi = smem_u32(Dhi), dlo = smem_u32(Dlo), vhi = smem_u32(Vhi), vlo = smem_u32(Vlo);
-        // A (D image, K-major): LBO = Sd between the two 16-byte K chunks, SBO = 128 between 8-pixel groups
-        // B (code image, K-major): LBO = Sv, SBO = 128 between 8-image groups
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t abase = (pass == 0) ? dlo : dhi;            // lo*hi, hi*lo, hi*hi
-          const uint32_t bbase = (pass == 1) ? vlo : vhi;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ad = make_desc(abase + ks * 2 * a.Sd, a.Sd, 128);
-            const uint64_t bd = make_desc(bbase + ks * 2 * a.Sv, a.Sv, 128);
-            mma_tf32(acc, ad, bd, idesc, (pass | ks) ? 1u : 0u);
+    }
+    __syncthreads();
+    // Phase B: coalesced 128-bit pass, image rows of 128 pixels: x + delta, clamps, (.-mean)/std, store
+    const int p0 = tile * TC_TP;
+    const int nq = B * (TC_TP / 4);
+    for (int q0 = 0; q0 < nq; q0 += S_EB * TC_THREADS) {
+      float4 xv[S_EB];
+#pragma unroll
+      for (int i = 0; i < S_EB; ++i) {
+        const int q = q0 + tid + i * TC_THREADS;
+        const int b = q >> 5, p = p0 + 4 * (q & 31);
+        if (q < nq && p < P && need_x) xv[i] = ld_stream4(a.x + xoff_s[b] + p);
+      }
+#pragma unroll
+      for (int i = 0; i < S_EB; ++i) {
+        const int q = q0 + tid + i * TC_THREADS;
+        const int b = q >> 5, pq = q & 31, p = p0 + 4 * pq;
+        if (q < nq && p < P) {
+          const float4 d4 = *reinterpret_cast<const float4*>(outs + b * S_OS + 4 * pq);
+          float d[4] = {d4.x, d4.y, d4.z, d4.w};
+          if (a.flags & ADIL_SYNTH_CLAMP_DELTA) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = fminf(fmaxf(d[j], -a.eps), a.eps);
           }
-        }
-        mma_commit(bar_mma);
-      }
-    }
-    // epilogue of the previous tile overlaps the MMAs just issued
-    const int etile = prev_tile;
-    if (!have && prev_tile >= 0) {
-      mbar_wait(bar_mma, (it - 1) & 1);
-      tc_fence_after();
-    }
-    if (etile >= 0) {
-      const uint32_t acc = tmem_base + (uint32_t)(((it - 1) & 1) * a.Np) + ((uint32_t)(quad * 32) << 16);
-      const int p = etile * TC_TP + quad * 32 + lane;
-      const bool pok = p < P;
-      int c = 0;
-      float mean = 0.0f, stdv = 1.0f;
-      if (a.cc.use && pok) {
-        c = p / a.cc.hw;
-        mean = a.cc.mean[c];
-        stdv = a.cc.stdv[c];
-      }
-      // this warp's chunks: cgrp, cgrp+4, ... ; x is fetched for all of them first (loads in flight)
-      constexpr int MAXCH = 8;  // Np <= 256 -> at most 32 chunks / 4 groups
-      float xv[MAXCH][8];
-      const bool need_x = (a.x != nullptr) && (a.out != nullptr);
-#pragma unroll
-      for (int ci = 0; ci < MAXCH; ++ci) {
-        const int ch = cgrp + 4 * ci;
-        if (ch < nchunks && need_x && pok) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int b = ch * 8 + j;
-            if (b < B) {
-              const int64_t xr = a.xidx ? a.xidx[b] : (int64_t)b;
-              xv[ci][j] = __ldg(a.x + (size_t)xr * P + p);
+          if (a.delta) st_stream4(a.delta + (size_t)b * P + p, make_float4(d[0], d[1], d[2], d[3]));
+          if (a.out) {
+            float o[4] = {d[0], d[1], d[2], d[3]};
+            if (need_x) {
+              o[0] = __fadd_rn(xv[i].x, d[0]);
+              o[1] = __fadd_rn(xv[i].y, d[1]);
+              o[2] = __fadd_rn(xv[i].z, d[2]);
+              o[3] = __fadd_rn(xv[i].w, d[3]);
             }
-          }
-        }
-      }
+            if (a.flags & ADIL_SYNTH_CLAMP01) {
 #pragma unroll
-      for (int ci = 0; ci < MAXCH; ++ci) {
-        const int ch = cgrp + 4 * ci;
-        if (ch < nchunks) {                                      // warp-uniform
-          float d[8];
-          tmem_ld8(acc + (uint32_t)(ch * 8), d);
-          if (pok) {
+              for (int j = 0; j < 4; ++j) o[j] = fminf(fmaxf(o[j], 0.0f), 1.0f);
+            }
+            if (a.cc.use) {
+              if (chan4) {
+                const int c = p / a.cc.hw;
+                const float mean = a.cc.mean[c], stdv = a.cc.stdv[c];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int b = ch * 8 + j;
-              if (b < B) {
-                float dv = d[j];
-                if (a.flags & ADIL_SYNTH_CLAMP_DELTA) dv = fminf(fmaxf(dv, -a.eps), a.eps);
-                if (a.delta) a.delta[(size_t)b * P + p] = dv;
-                if (a.out) {
-                  float o = need_x ? __fadd_rn(xv[ci][j], dv) : dv;
-                  if (a.flags & ADIL_SYNTH_CLAMP01) o = fminf(fmaxf(o, 0.0f), 1.0f);
-                  if (a.cc.use) o = __fdiv_rn(__fsub_rn(o, mean), stdv);
-                  a.out[(size_t)b * P + p] = o;
+                for (int j = 0; j < 4; ++j) o[j] = __fdiv_rn(__fsub_rn(o[j], mean), stdv);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int c = (p + j) / a.cc.hw;
+                  o[j] = __fdiv_rn(__fsub_rn(o[j], a.cc.mean[c]), a.cc.stdv[c]);
                 }
               }
             }
+            st_stream4(a.out + (size_t)b * P + p, make_float4(o[0], o[1], o[2], o[3]));
           }
         }
       }
-      tc_fence_before();
     }
-    if (!have) break;
+  };
+
+  int it = 0, prev_tile = -1;
+  for (int tile = my_first; tile < ntiles; tile += gridDim.x, ++it) {
+    const int rows = min(TC_TP, P - tile * TC_TP);
+    mbar_wait(bar_full, it & 1);                                 // raw tile `it` landed
+    if (it > 0) mbar_wait(bar_mma, (it - 1) & 1);                // MMAs(it-1) retired: images reusable, acc ready
+    tc_fence_after();
+    for (int e = tid; e < TC_TP * K; e += TC_THREADS) {          // split + scatter into the canonical images
+      const int p = e / K, k = e - p * K;
+      const float val = (p < rows) ? raw[e] : 0.0f;
+      float hi, lo;
+      split_tf32(val, hi, lo);
+      const int o = img_off(p, k, a.Sd);
+      Dhi[o] = hi;
+      Dlo[o] = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const int nxt = tile + gridDim.x;
+      if (nxt < ntiles) {                                         // TMA prefetch of the next raw tile (raw is consumed)
+        const int nrows = min(TC_TP, P - nxt * TC_TP);
+        mbar_expect_tx(bar_full, (uint32_t)(nrows * K * 4));
+        bulk_g2s(raw, a.D2 + (size_t)nxt * TC_TP * K, (uint32_t)(nrows * K * 4), bar_full);
+      }
+      const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np);
+      const uint32_t dhi = smem_u32(Dhi), dlo = smem_u32(Dlo), vhi = smem_u32(Vhi), vlo = smem_u32(Vlo);
+      // A (D image, K-major): LBO = Sd between the two 16-byte K chunks, SBO = 128 between 8-pixel groups
+      // B (code image, K-major): LBO = Sv, SBO = 128 between 8-image groups
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t abase = (pass == 0) ? dlo : dhi;            // lo*hi, hi*lo, hi*hi
+        const uint32_t bbase = (pass == 1) ? vlo : vhi;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t ad = make_desc(abase + ks * 2 * a.Sd, a.Sd, 128);
+          const uint64_t bd = make_desc(bbase + ks * 2 * a.Sv, a.Sv, 128);
+          mma_tf32(acc, ad, bd, idesc, (pass | ks) ? 1u : 0u);
+        }
+      }
+      mma_commit(bar_mma);
+    }
+    if (prev_tile >= 0) epilogue(prev_tile, it - 1);              // overlaps the MMAs just issued
     prev_tile = tile;
+  }
+  if (prev_tile >= 0) {
+    mbar_wait(bar_mma, (it - 1) & 1);
+    tc_fence_after();
+    epilogue(prev_tile, it - 1);
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
@@ -394,6 +410,7 @@ struct GradTcArgs {
   int Kp16;     // N of both MMAs: round_up(K, 16)
   int Sg, Sd, Sv;
   int gimg, dimg, vimg;  // image sizes in bf16 elements (each matrix has three images)
+  int Ks;                // row stride (floats) of the dD staging tile
   uint32_t tmem_cols;
   int want_dD, want_dv, atoms_mode;
   ChannelConsts cc;
@@ -402,6 +419,8 @@ struct GradTcArgs {
 
 constexpr int G_MAXQ = 8;    // float4 of g per thread per tile: 128 images x 32 / 512
 constexpr int D_MAXE = 24;   // dictionary elements per thread per tile: 128 x 96 / 512
+constexpr int EP_BATCH = 3;  // float4 per thread per epilogue batch
+constexpr int EP_HALVES = 2; // 2 x 3 x 512 float4 = 128 x 96 elements
 
 __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -410,6 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
   bf16_t* Vi = reinterpret_cast<bf16_t*>(smem_raw + 128);  // three code images
   bf16_t* Di = Vi + 3 * a.vimg;                             // three dictionary images
   bf16_t* Gi = Di + 3 * a.dimg;                             // three gradient images
+  float* dDs = reinterpret_cast<float*>(Gi + 3 * a.gimg);   // [128][Ks] dD tile in global layout (epilogue)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
@@ -554,45 +574,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
   };
 
   auto epilogue = [&](int tile, int it) {
-    // accumulator row = pixel (TMEM lane), column = atom
+    // Phase A: accumulator (row = pixel = TMEM lane, column = atom) -> shared memory in the tile's global layout
+    // [pixel][atom] (row stride Ks chosen so the 16-byte stores of a quarter-warp hit distinct banks).
     const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Kp16) + ((uint32_t)(quad * 32) << 16);
-    const int p = tile * TC_TP + quad * 32 + lane;
-    const bool pok = p < P;
-    const size_t rowoff = (size_t)p * K;
+    const int Ks = a.Ks;
+    float* row = dDs + (quad * 32 + lane) * Ks;
+    __syncthreads();  // every thread is done reading the staging tile of the previous epilogue
     for (int ch = cgrp; ch < nchunks; ch += 4) {  // warp-uniform
       const int k0 = ch * 8;
       if (k0 >= K) break;
-      float mv[8], sv[8], dv[8];
-      if (a.D2w != nullptr && pok) {
+      float r[8];
+      tmem_ld8(acc + (uint32_t)k0, r);
+      *reinterpret_cast<float4*>(row + k0) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(row + k0 + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    // Phase B: one coalesced 128-bit pass over the tile's contiguous [rows x K] block of D / m / s (or dD)
+    const int rows = min(TC_TP, P - tile * TC_TP);
+    const int n4 = (rows * K) >> 2;
+    const size_t base = (size_t)tile * TC_TP * K;
+#pragma unroll 1
+    for (int half = 0; half < EP_HALVES; ++half) {
+      float4 Dv[EP_BATCH], Mv[EP_BATCH], Sv[EP_BATCH];
+      if (a.D2w != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (k0 + j < K) {
-            mv[j] = a.m[rowoff + k0 + j];
-            sv[j] = a.s[rowoff + k0 + j];
-            dv[j] = a.D2[rowoff + k0 + j];
+        for (int i = 0; i < EP_BATCH; ++i) {
+          const int e4 = tid + (half * EP_BATCH + i) * TC_THREADS;
+          if (e4 < n4) {
+            Dv[i] = *reinterpret_cast<const float4*>(a.D2 + base + 4 * (size_t)e4);
+            Mv[i] = *reinterpret_cast<const float4*>(a.m + base + 4 * (size_t)e4);
+            Sv[i] = *reinterpret_cast<const float4*>(a.s + base + 4 * (size_t)e4);
           }
         }
       }
-      float gacc[8];
-      tmem_ld8(acc + (uint32_t)k0, gacc);
-      if (pok) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (k0 + j < K) {
-            if (a.D2w != nullptr) {
-              adamw_update(dv[j], mv[j], sv[j], gacc[j], a.hp);
-              if (a.atoms_mode == ADIL_ATOMS_CLAMP1) dv[j] = clamp1(dv[j]);
-              a.D2w[rowoff + k0 + j] = dv[j];
-              a.m[rowoff + k0 + j] = mv[j];
-              a.s[rowoff + k0 + j] = sv[j];
-            } else {
-              a.dD2[rowoff + k0 + j] = gacc[j];
+      for (int i = 0; i < EP_BATCH; ++i) {
+        const int e4 = tid + (half * EP_BATCH + i) * TC_THREADS;
+        if (e4 < n4) {
+          const int e = 4 * e4;
+          int pp = e / K, kk = e - pp * K;
+          float gd[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gd[j] = dDs[pp * Ks + kk];
+            if (++kk == K) { kk = 0; ++pp; }
+          }
+          if (a.D2w != nullptr) {
+            adamw_update(Dv[i].x, Mv[i].x, Sv[i].x, gd[0], a.hp);
+            adamw_update(Dv[i].y, Mv[i].y, Sv[i].y, gd[1], a.hp);
+            adamw_update(Dv[i].z, Mv[i].z, Sv[i].z, gd[2], a.hp);
+            adamw_update(Dv[i].w, Mv[i].w, Sv[i].w, gd[3], a.hp);
+            if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
+              Dv[i].x = clamp1(Dv[i].x); Dv[i].y = clamp1(Dv[i].y); Dv[i].z = clamp1(Dv[i].z); Dv[i].w = clamp1(Dv[i].w);
             }
+            *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv[i];
+            *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mv[i];
+            *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sv[i];
+          } else {
+            *reinterpret_cast<float4*>(a.dD2 + base + 4 * (size_t)e4) = make_float4(gd[0], gd[1], gd[2], gd[3]);
           }
         }
       }
     }
-    tc_fence_before();
   };
 
   int it = 0, prev_tile = -1;
@@ -668,14 +712,15 @@ SynthPlan plan_synth(int B, int P, int K) {
   pl.raw_floats = rup(TC_TP * K, 32);
   pl.dimg_floats = (pl.Kp8 / 4) * (pl.Sd / 4) + 64;
   pl.vimg_floats = (pl.Kp8 / 4) * (pl.Sv / 4) + 64;
-  pl.smem = 128 + sizeof(float) * (2 * (size_t)pl.raw_floats + 2 * (size_t)pl.dimg_floats + 2 * (size_t)pl.vimg_floats);
+  pl.smem = 128 + 2048 + sizeof(float) * ((size_t)pl.raw_floats + 2 * (size_t)pl.dimg_floats + 2 * (size_t)pl.vimg_floats +
+                                          (size_t)pl.Np * S_OS);
   pl.tmem_cols = pow2_cols(2 * pl.Np);
   pl.ok = pl.smem <= SMEM_LIMIT && pl.tmem_cols <= 512 && pl.Np <= 256;
   return pl;
 }
 
 struct GradPlan {
-  int Bp16, Kp16, Sg, Sd, Sv, gimg, dimg, vimg;
+  int Bp16, Kp16, Sg, Sd, Sv, gimg, dimg, vimg, Ks;
   size_t smem;
   uint32_t tmem_cols;
   bool ok;
@@ -694,7 +739,8 @@ GradPlan plan_grad(int B, int P, int K) {
   pl.vimg = kg * (pl.Sv / 2) + 64;                        // bf16 elements per image
   pl.dimg = kg * (pl.Sd / 2) + 64;
   pl.gimg = (TC_TP / 8) * (pl.Sg / 2) + 1024 + 64;        // +2 KB: M = 128 image rows are read even when Bp16 < 128
-  pl.smem = 128 + 2 * 3 * ((size_t)pl.vimg + pl.dimg + pl.gimg);
+  pl.Ks = rup(K, 8) + 4;                                  // Ks % 8 == 4: conflict-free 16-byte row stores
+  pl.smem = 128 + 2 * 3 * ((size_t)pl.vimg + pl.dimg + pl.gimg) + sizeof(float) * TC_TP * (size_t)pl.Ks;
   pl.tmem_cols = pow2_cols(3 * pl.Kp16);
   // the MMAs read N = Kp16 atoms: the code / dictionary images over-read into the buffers that follow them
   // (codes -> dictionary -> gradient images), which must be large enough to absorb it
@@ -703,7 +749,7 @@ GradPlan plan_grad(int B, int P, int K) {
   const size_t tail_after_d = 2 * 3 * (size_t)pl.gimg;
   pl.ok = pl.smem <= SMEM_LIMIT && pl.tmem_cols <= 512 && over_v <= 2 * (size_t)pl.vimg + tail_after_v &&
           over_d <= 2 * (size_t)pl.dimg + tail_after_d && B * (TC_TP / 4) <= G_MAXQ * TC_THREADS &&
-          TC_TP * K <= D_MAXE * TC_THREADS;
+          TC_TP * K <= D_MAXE * TC_THREADS && TC_TP * K <= 4 * EP_BATCH * EP_HALVES * TC_THREADS;
   return pl;
 }
 
@@ -742,7 +788,7 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
   GradTcArgs a;
   a.dD2 = dD2; a.D2w = D2_rw; a.m = m; a.s = s; a.partial = scratch; a.g = g; a.D2 = D2; a.v = v; a.vidx = v_index;
   a.B = B; a.P = P; a.K = K; a.Bp16 = pl.Bp16; a.Kp16 = pl.Kp16; a.Sg = pl.Sg; a.Sd = pl.Sd; a.Sv = pl.Sv;
-  a.gimg = pl.gimg; a.dimg = pl.dimg; a.vimg = pl.vimg;
+  a.gimg = pl.gimg; a.dimg = pl.dimg; a.vimg = pl.vimg; a.Ks = pl.Ks;
   a.tmem_cols = pl.tmem_cols;
   a.want_dD = (dD2 != nullptr || D2_rw != nullptr) ? 1 : 0;
   a.want_dv = (dvb != nullptr) ? 1 : 0;
