@@ -51,6 +51,7 @@ AdamwDev make_adamw(const adil_adamw_t* hp) {
   d.bc2_sqrt = (float)std::sqrt(bc2);
   d.eps = (float)hp->eps;
   d.neg_step = (float)(-(hp->lr / bc1));
+  d.rbc2_sqrt = (float)(1.0 / (double)d.bc2_sqrt);
   d.lerp_hi = std::fabs(1.0 - hp->beta1) >= 0.5 ? 1 : 0;
   return d;
 }
@@ -64,6 +65,7 @@ ChannelConsts make_consts(int C, int hw, const float* mean_host, const float* st
   for (int c = 0; c < kMaxC; ++c) {
     cc.mean[c] = (use && mean_host && c < C) ? mean_host[c] : 0.0f;
     cc.stdv[c] = (use && std_host && c < C) ? std_host[c] : 1.0f;
+    cc.rstd[c] = (float)(1.0 / (double)cc.stdv[c]);
   }
   return cc;
 }

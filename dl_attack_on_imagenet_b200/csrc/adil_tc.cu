@@ -28,8 +28,9 @@ int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, 
 
 namespace {
 
-constexpr int TC_THREADS = 512;
-constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int TC_WARPS = 15;                  // worker warps: staging, prefetch, epilogues
+constexpr int TC_THREADS = TC_WARPS * 32;
+constexpr int TC_BLOCK = TC_THREADS + 32;     // + warp 15, which only issues TMA / tcgen05.mma (512 threads, 128 regs)
 constexpr int TC_TP = 128;                    // pixels per tile = UMMA M
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -74,6 +75,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// named barriers: id 1 = "tile staged" hand-off workers -> issuer warp, id 2 = worker-only barrier
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -177,9 +185,9 @@ struct SynthTcArgs {
 };
 
 constexpr int S_OS = TC_TP + 4;  // row stride (floats) of the epilogue staging tile [image][pixel]
-constexpr int S_EB = 4;          // float4 per thread per epilogue batch
+constexpr int S_EB = 7;          // images per thread per epilogue batch (7 x 16 warps >= 100)
 
-__global__ void __launch_bounds__(TC_THREADS, 1) synth_tc_kernel(const SynthTcArgs a) {
+__global__ void __launch_bounds__(TC_BLOCK, 1) synth_tc_kernel(const SynthTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);  // [1] raw tile landed
   uint64_t* bar_mma = bar_full + 1;                            // [1] MMAs of a tile retired
@@ -203,10 +211,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) synth_tc_kernel(const SynthTcAr
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
   // zero the dictionary images once: contraction padding (k in [K, Kp8)) must stay zero
-  for (int e = tid; e < 2 * a.dimg_floats; e += TC_THREADS) Dhi[e] = 0.0f;
+  for (int e = tid; e < 2 * a.dimg_floats; e += TC_BLOCK) Dhi[e] = 0.0f;
   build_code_images(Vhi, Vlo, a.v, a.vidx, B, K, a.Np, a.Kp8, a.Sv);
   // x row offsets in shared memory: a dependent global load per image inside the epilogue would serialise it
-  for (int b = tid; b < B; b += TC_THREADS) xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
+  for (int b = tid; b < B; b += TC_BLOCK) xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -222,17 +230,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) synth_tc_kernel(const SynthTcAr
   const uint32_t idesc = make_idesc(128, a.Np, false, false);
   const int ksteps = a.Kp8 / 8;
   const int quad = warp & 3, cgrp = warp >> 2;          // TMEM lane quadrant / column group of this warp
+  const int ncg = (quad == 3) ? 3 : 4;                  // quadrant 3 lost warp 15 to the issuer role
   const int nchunks = a.Np / 8;                         // 8-column chunks of the accumulator
   const bool need_x = (a.x != nullptr) && (a.out != nullptr);
-  const bool chan4 = (a.cc.hw & 3) == 0;                // 4 consecutive pixels share a channel
 
   auto epilogue = [&](int tile, int it) {
-    __syncthreads();  // staging tile free (previous epilogue fully drained)
+    bar_sync(2, TC_THREADS);  // staging tile free (previous epilogue fully drained)
     // Phase A: accumulator (row = pixel = TMEM lane, column = image) -> shared memory, image-major
     {
       const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np) + ((uint32_t)(quad * 32) << 16);
       float* col = outs + quad * 32 + lane;
-      for (int ch = cgrp; ch < nchunks; ch += 4) {      // warp-uniform
+      for (int ch = cgrp; ch < nchunks; ch += ncg) {    // warp-uniform
         float d[8];
         tmem_ld8(acc + (uint32_t)(ch * 8), d);
 #pragma unroll
@@ -240,111 +248,122 @@ __global__ void __launch_bounds__(TC_THREADS, 1) synth_tc_kernel(const SynthTcAr
       }
       tc_fence_before();
     }
-    __syncthreads();
-    // Phase B: coalesced 128-bit pass, image rows of 128 pixels: x + delta, clamps, (.-mean)/std, store
-    const int p0 = tile * TC_TP;
-    const int nq = B * (TC_TP / 4);
-    for (int q0 = 0; q0 < nq; q0 += S_EB * TC_THREADS) {
-      float4 xv[S_EB];
+    bar_sync(2, TC_THREADS);
+    // Phase B: coalesced 128-bit pass over image rows of 128 pixels: x + delta, clamps, (.-mean)/std, store.
+    // A thread keeps one 4-pixel column (channel constants hoisted) and walks images b = warp, warp+16, ...
+    const int pq = lane, p = tile * TC_TP + 4 * pq;
+    if (p < P) {
+      float mean[4], stdv[4], rstd[4];
+      if (a.cc.use) {
 #pragma unroll
-      for (int i = 0; i < S_EB; ++i) {
-        const int q = q0 + tid + i * TC_THREADS;
-        const int b = q >> 5, p = p0 + 4 * (q & 31);
-        if (q < nq && p < P && need_x) xv[i] = ld_stream4(a.x + xoff_s[b] + p);
+        for (int j = 0; j < 4; ++j) {
+          const int c = (p + j) / a.cc.hw;
+          mean[j] = a.cc.mean[c]; stdv[j] = a.cc.stdv[c]; rstd[j] = a.cc.rstd[c];
+        }
       }
+      for (int b0 = warp; b0 < B; b0 += S_EB * TC_WARPS) {
+        float4 xv[S_EB];
+        if (need_x) {
 #pragma unroll
-      for (int i = 0; i < S_EB; ++i) {
-        const int q = q0 + tid + i * TC_THREADS;
-        const int b = q >> 5, pq = q & 31, p = p0 + 4 * pq;
-        if (q < nq && p < P) {
-          const float4 d4 = *reinterpret_cast<const float4*>(outs + b * S_OS + 4 * pq);
-          float d[4] = {d4.x, d4.y, d4.z, d4.w};
-          if (a.flags & ADIL_SYNTH_CLAMP_DELTA) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = fminf(fmaxf(d[j], -a.eps), a.eps);
+          for (int i = 0; i < S_EB; ++i) {
+            const int b = b0 + i * TC_WARPS;
+            if (b < B) xv[i] = ld_stream4(a.x + xoff_s[b] + p);
           }
-          if (a.delta) st_stream4(a.delta + (size_t)b * P + p, make_float4(d[0], d[1], d[2], d[3]));
-          if (a.out) {
-            float o[4] = {d[0], d[1], d[2], d[3]};
-            if (need_x) {
-              o[0] = __fadd_rn(xv[i].x, d[0]);
-              o[1] = __fadd_rn(xv[i].y, d[1]);
-              o[2] = __fadd_rn(xv[i].z, d[2]);
-              o[3] = __fadd_rn(xv[i].w, d[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < S_EB; ++i) {
+          const int b = b0 + i * TC_WARPS;
+          if (b < B) {
+            const float4 d4 = *reinterpret_cast<const float4*>(outs + b * S_OS + 4 * pq);
+            float d[4] = {d4.x, d4.y, d4.z, d4.w};
+            if (a.flags & ADIL_SYNTH_CLAMP_DELTA) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) d[j] = fminf(fmaxf(d[j], -a.eps), a.eps);
             }
-            if (a.flags & ADIL_SYNTH_CLAMP01) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = fminf(fmaxf(o[j], 0.0f), 1.0f);
-            }
-            if (a.cc.use) {
-              if (chan4) {
-                const int c = p / a.cc.hw;
-                const float mean = a.cc.mean[c], stdv = a.cc.stdv[c];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = __fdiv_rn(__fsub_rn(o[j], mean), stdv);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int c = (p + j) / a.cc.hw;
-                  o[j] = __fdiv_rn(__fsub_rn(o[j], a.cc.mean[c]), a.cc.stdv[c]);
-                }
+            if (a.delta) st_stream4(a.delta + (size_t)b * P + p, make_float4(d[0], d[1], d[2], d[3]));
+            if (a.out) {
+              float o[4] = {d[0], d[1], d[2], d[3]};
+              if (need_x) {
+                o[0] = __fadd_rn(xv[i].x, d[0]);
+                o[1] = __fadd_rn(xv[i].y, d[1]);
+                o[2] = __fadd_rn(xv[i].z, d[2]);
+                o[3] = __fadd_rn(xv[i].w, d[3]);
               }
+              if (a.flags & ADIL_SYNTH_CLAMP01) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = fminf(fmaxf(o[j], 0.0f), 1.0f);
+              }
+              if (a.cc.use) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = div_by_const(__fsub_rn(o[j], mean[j]), stdv[j], rstd[j]);
+              }
+              st_stream4(a.out + (size_t)b * P + p, make_float4(o[0], o[1], o[2], o[3]));
             }
-            st_stream4(a.out + (size_t)b * P + p, make_float4(o[0], o[1], o[2], o[3]));
           }
         }
       }
     }
   };
 
-  int it = 0, prev_tile = -1;
-  for (int tile = my_first; tile < ntiles; tile += gridDim.x, ++it) {
-    const int rows = min(TC_TP, P - tile * TC_TP);
-    mbar_wait(bar_full, it & 1);                                 // raw tile `it` landed
-    if (it > 0) mbar_wait(bar_mma, (it - 1) & 1);                // MMAs(it-1) retired: images reusable, acc ready
-    tc_fence_after();
-    for (int e = tid; e < TC_TP * K; e += TC_THREADS) {          // split + scatter into the canonical images
-      const int p = e / K, k = e - p * K;
-      const float val = (p < rows) ? raw[e] : 0.0f;
-      float hi, lo;
-      split_tf32(val, hi, lo);
-      const int o = img_off(p, k, a.Sd);
-      Dhi[o] = hi;
-      Dlo[o] = lo;
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+  if (warp == TC_WARPS) {
+    // ===== issuer warp: TMA prefetch of the next raw tile + the 3 x ksteps MMAs of the current one =====
+    const uint64_t dhi = make_desc(smem_u32(Dhi), a.Sd, 128), dlo = make_desc(smem_u32(Dlo), a.Sd, 128);
+    const uint64_t vhi = make_desc(smem_u32(Vhi), a.Sv, 128), vlo = make_desc(smem_u32(Vlo), a.Sv, 128);
+    const uint64_t astep = (uint64_t)((2 * a.Sd) >> 4), bstep = (uint64_t)((2 * a.Sv) >> 4);
+    int it = 0;
+    for (int tile = my_first; tile < ntiles; tile += gridDim.x, ++it) {
+      bar_sync(1, TC_BLOCK);                                       // workers staged tile `it`
       tc_fence_after();
-      const int nxt = tile + gridDim.x;
-      if (nxt < ntiles) {                                         // TMA prefetch of the next raw tile (raw is consumed)
-        const int nrows = min(TC_TP, P - nxt * TC_TP);
-        mbar_expect_tx(bar_full, (uint32_t)(nrows * K * 4));
-        bulk_g2s(raw, a.D2 + (size_t)nxt * TC_TP * K, (uint32_t)(nrows * K * 4), bar_full);
+      if (lane == 0) {
+        const int nxt = tile + gridDim.x;
+        if (nxt < ntiles) {                                         // raw buffer is consumed: prefetch the next tile
+          const int nrows = min(TC_TP, P - nxt * TC_TP);
+          mbar_expect_tx(bar_full, (uint32_t)(nrows * K * 4));
+          bulk_g2s(raw, a.D2 + (size_t)nxt * TC_TP * K, (uint32_t)(nrows * K * 4), bar_full);
+        }
+        const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np);
+        // A (D image, K-major): LBO = Sd between the two 16-byte K chunks, SBO = 128 between 8-pixel groups
+        // B (code image, K-major): LBO = Sv, SBO = 128 between 8-image groups
+        for (int pass = 0; pass < 3; ++pass) {
+          uint64_t ad = (pass == 0) ? dlo : dhi;                    // lo*hi, hi*lo, hi*hi
+          uint64_t bd = (pass == 1) ? vlo : vhi;
+          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, (pass | ks) ? 1u : 0u);
+        }
+        mma_commit(bar_mma);
       }
-      const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np);
-      const uint32_t dhi = smem_u32(Dhi), dlo = smem_u32(Dlo), vhi = smem_u32(Vhi), vlo = smem_u32(Vlo);
-      // A (D image, K-major): LBO = Sd between the two 16-byte K chunks, SBO = 128 between 8-pixel groups
-      // B (code image, K-major): LBO = Sv, SBO = 128 between 8-image groups
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t abase = (pass == 0) ? dlo : dhi;            // lo*hi, hi*lo, hi*hi
-        const uint32_t bbase = (pass == 1) ? vlo : vhi;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t ad = make_desc(abase + ks * 2 * a.Sd, a.Sd, 128);
-          const uint64_t bd = make_desc(bbase + ks * 2 * a.Sv, a.Sv, 128);
-          mma_tf32(acc, ad, bd, idesc, (pass | ks) ? 1u : 0u);
+      __syncwarp();
+    }
+  } else {
+    // ===== worker warps: split/scatter of the raw tile, epilogue of the previous tile =====
+    int it = 0, prev_tile = -1;
+    for (int tile = my_first; tile < ntiles; tile += gridDim.x, ++it) {
+      const int rows = min(TC_TP, P - tile * TC_TP);
+      mbar_wait(bar_full, it & 1);                                 // raw tile `it` landed
+      if (it > 0) mbar_wait(bar_mma, (it - 1) & 1);                // MMAs(it-1) retired: images reusable, acc ready
+      tc_fence_after();
+      for (int p = warp; p < TC_TP; p += TC_WARPS) {                // a warp takes one pixel row, lanes run over atoms
+        const float* rrow = raw + p * K;
+        const int obase = (p >> 3) * 32 + (p & 7) * 4;
+        for (int k = lane; k < K; k += 32) {
+          const float val = (p < rows) ? rrow[k] : 0.0f;
+          float hi, lo;
+          split_tf32(val, hi, lo);
+          const int o = (k >> 2) * (a.Sd >> 2) + obase + (k & 3);
+          Dhi[o] = hi;
+          Dlo[o] = lo;
         }
       }
-      mma_commit(bar_mma);
+      fence_proxy_async();
+      tc_fence_before();
+      bar_arrive(1, TC_BLOCK);                                     // hand the tile to the issuer warp, keep going
+      if (prev_tile >= 0) epilogue(prev_tile, it - 1);             // overlaps the MMAs being issued
+      prev_tile = tile;
     }
-    if (prev_tile >= 0) epilogue(prev_tile, it - 1);              // overlaps the MMAs just issued
-    prev_tile = tile;
-  }
-  if (prev_tile >= 0) {
-    mbar_wait(bar_mma, (it - 1) & 1);
-    tc_fence_after();
-    epilogue(prev_tile, it - 1);
+    if (prev_tile >= 0) {
+      mbar_wait(bar_mma, (it - 1) & 1);
+      tc_fence_after();
+      epilogue(prev_tile, it - 1);
+    }
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
@@ -366,15 +385,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) synth_tc_kernel(const SynthTcAr
 // =========================================================================================================
 typedef unsigned short bf16_t;
 
-__device__ __forceinline__ void split_bf16x3(float x, bf16_t& b0, bf16_t& b1, bf16_t& b2) {
-  const uint32_t u0 = __float_as_uint(x);
-  b0 = (bf16_t)(u0 >> 16);
-  const float r1 = __fsub_rn(x, __uint_as_float(u0 & 0xffff0000u));  // exact
-  const uint32_t u1 = __float_as_uint(r1);
-  b1 = (bf16_t)(u1 >> 16);
-  const float r2 = __fsub_rn(r1, __uint_as_float(u1 & 0xffff0000u));  // exact
-  const uint32_t u2 = __float_as_uint(r2);
-  b2 = (bf16_t)((u2 + 0x7fffu + ((u2 >> 16) & 1u)) >> 16);            // round to nearest even
+// x = t0 + t1 + t2 + O(2^-24 x): t0, t1 are the truncated high halves of x and of the (exact) residuals; the words
+// returned hold the bf16 term in their UPPER 16 bits (ready for PRMT packing).
+__device__ __forceinline__ void split_bf16x3(float x, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  w0 = __float_as_uint(x);
+  const float r1 = __fsub_rn(x, __uint_as_float(w0 & 0xffff0000u));   // exact
+  w1 = __float_as_uint(r1);
+  const float r2 = __fsub_rn(r1, __uint_as_float(w1 & 0xffff0000u));  // exact
+  w2 = __float_as_uint(r2) + 0x8000u;                                  // round the last term to nearest
+}
+__device__ __forceinline__ uint32_t pack_hi16(uint32_t lo_word, uint32_t hi_word) {
+  return __byte_perm(lo_word, hi_word, 0x7632);  // {hi_word[31:16], lo_word[31:16]}
 }
 
 // canonical image offset in bf16 elements: r = "8-row" index, c = contiguous index, S = byte stride between 8-c groups
@@ -411,18 +432,20 @@ struct GradTcArgs {
   int Sg, Sd, Sv;
   int gimg, dimg, vimg;  // image sizes in bf16 elements (each matrix has three images)
   int Ks;                // row stride (floats) of the dD staging tile
+  unsigned kdiv_mul;     // ceil(2^32 / K): e / K == umulhi(e, kdiv_mul) for e < 2^20
   uint32_t tmem_cols;
   int want_dD, want_dv, atoms_mode;
   ChannelConsts cc;
   AdamwDev hp;
 };
 
-constexpr int G_MAXQ = 8;    // float4 of g per thread per tile: 128 images x 32 / 512
-constexpr int D_MAXE = 24;   // dictionary elements per thread per tile: 128 x 96 / 512
-constexpr int EP_BATCH = 3;  // float4 per thread per epilogue batch
-constexpr int EP_HALVES = 2; // 2 x 3 x 512 float4 = 128 x 96 elements
+constexpr int G_MAXQ = 9;    // image rows per worker warp per tile: 9 x 15 >= 128
+constexpr int D_ROWS = (TC_TP + TC_WARPS - 1) / TC_WARPS;  // 9 pixel rows per worker warp per tile
+constexpr int EP_BATCH = 2;  // float4 per thread per epilogue batch
+constexpr int EP_HALVES = 3; // 3 x 2 x 480 float4 >= 128 x 90 elements
 
-__global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs a) {
+template <int D_KJ>  // atoms per lane when staging the dictionary tile: K <= 32 * D_KJ
+__global__ void __launch_bounds__(TC_BLOCK, 1) grad_tc_kernel(const GradTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
@@ -434,7 +457,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
   const int ntiles = (P + TC_TP - 1) / TC_TP;
-  const int gq_total = B * (TC_TP / 4);  // float4 per g tile
 
   if (tid == 0) {
     mbar_init(bar_mma, 1);
@@ -445,19 +467,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
   {
     uint32_t* z = reinterpret_cast<uint32_t*>(Vi);
     const int nz = (3 * (a.vimg + a.dimg + a.gimg)) >> 1;
-    for (int e = tid; e < nz; e += TC_THREADS) z[e] = 0u;
+    for (int e = tid; e < nz; e += TC_BLOCK) z[e] = 0u;
   }
   __syncthreads();
   if (a.want_dD) {
-    for (int e = tid; e < B * K; e += TC_THREADS) {
+    for (int e = tid; e < B * K; e += TC_BLOCK) {
       const int b = e / K, k = e - b * K;
       const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
-      bf16_t b0, b1, b2;
-      split_bf16x3(a.v[row * K + k], b0, b1, b2);
+      uint32_t w0, w1, w2;
+      split_bf16x3(a.v[row * K + k], w0, w1, w2);
       const int o = img16_off(b, k, a.Sv);
-      Vi[o] = b0;
-      Vi[a.vimg + o] = b1;
-      Vi[2 * a.vimg + o] = b2;
+      Vi[o] = (bf16_t)(w0 >> 16);
+      Vi[a.vimg + o] = (bf16_t)(w1 >> 16);
+      Vi[2 * a.vimg + o] = (bf16_t)(w2 >> 16);
     }
   }
   tc_fence_before();
@@ -469,70 +491,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
   const uint32_t idesc_dD = make_idesc_bf16(128, a.Kp16, true, true);
   const uint32_t idesc_dv = make_idesc_bf16(128, a.Kp16, false, true);
   const int quad = warp & 3, cgrp = warp >> 2;
+  const int ncg = (quad == 3) ? 3 : 4;  // quadrant 3 lost warp 15 to the issuer role
   const int nchunks = a.Kp16 / 8;
 
   float4 greg[G_MAXQ];
-  float dreg[D_MAXE];
-
+  float dreg[D_ROWS][D_KJ];
+  // fixed per-thread roles: gradient tile -> image rows b = warp + 16*i, 4-pixel column pq = lane;
+  //                         dictionary tile -> pixel rows p = warp + 16*i, atoms k = lane + 32*j
   auto prefetch = [&](int tile) {
     const int p0 = tile * TC_TP;
+    const int p = p0 + 4 * lane;
 #pragma unroll
     for (int i = 0; i < G_MAXQ; ++i) {
-      const int q = tid + i * TC_THREADS;
+      const int b = warp + i * TC_WARPS;
       greg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q < gq_total) {
-        const int b = q >> 5, pq = q & 31;
-        const int p = p0 + 4 * pq;
-        if (p < P) greg[i] = ld_stream4(a.g + (size_t)b * P + p);
-      }
+      if (b < B && p < P) greg[i] = ld_stream4(a.g + (size_t)b * P + p);
     }
     if (a.want_dv) {
-      const int rows = min(TC_TP, P - p0);
-      const float* src = a.D2 + (size_t)p0 * K;
 #pragma unroll
-      for (int i = 0; i < D_MAXE; ++i) {
-        const int e = tid + i * TC_THREADS;
-        dreg[i] = (e < rows * K) ? __ldg(src + e) : 0.0f;
+      for (int i = 0; i < D_ROWS; ++i) {
+        const int pl = warp + i * TC_WARPS, pr = p0 + pl;
+#pragma unroll
+        for (int j = 0; j < D_KJ; ++j) {
+          const int k = lane + 32 * j;
+          dreg[i][j] = (pl < TC_TP && pr < P && k < K) ? __ldg(a.D2 + (size_t)pr * K + k) : 0.0f;
+        }
       }
     }
   };
 
   auto stage = [&](int tile) {
-    const int p0 = tile * TC_TP;
+    const int p = tile * TC_TP + 4 * lane;
+    float stdv[4], rstd[4];
+    if (a.cc.use) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = min((p + j) / a.cc.hw, kMaxC - 1);
+        stdv[j] = a.cc.stdv[c]; rstd[j] = a.cc.rstd[c];
+      }
+    }
+    const int gcol = (lane >> 1) * (a.Sg >> 1) + (lane & 1) * 4;   // img16_off(b, 4*lane) without the row part
 #pragma unroll
     for (int i = 0; i < G_MAXQ; ++i) {
-      const int q = tid + i * TC_THREADS;
-      if (q < gq_total) {
-        const int b = q >> 5, pq = q & 31;
+      const int b = warp + i * TC_WARPS;
+      if (b < B) {
         float val[4] = {greg[i].x, greg[i].y, greg[i].z, greg[i].w};
         if (a.cc.use) {
-          const int p = p0 + 4 * pq;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) val[j] = __fdiv_rn(val[j], a.cc.stdv[min((p + j) / a.cc.hw, kMaxC - 1)]);
+          for (int j = 0; j < 4; ++j) val[j] = div_by_const(val[j], stdv[j], rstd[j]);
         }
-        bf16_t t0[4], t1[4], t2[4];
+        uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_bf16x3(val[j], t0[j], t1[j], t2[j]);
-        const int o = img16_off(b, 4 * pq, a.Sg);  // 8-byte slot (b, 4pq..4pq+3)
-        *reinterpret_cast<uint2*>(Gi + o) = make_uint2(t0[0] | ((uint32_t)t0[1] << 16), t0[2] | ((uint32_t)t0[3] << 16));
-        *reinterpret_cast<uint2*>(Gi + a.gimg + o) =
-            make_uint2(t1[0] | ((uint32_t)t1[1] << 16), t1[2] | ((uint32_t)t1[3] << 16));
-        *reinterpret_cast<uint2*>(Gi + 2 * a.gimg + o) =
-            make_uint2(t2[0] | ((uint32_t)t2[1] << 16), t2[2] | ((uint32_t)t2[3] << 16));
+        for (int j = 0; j < 4; ++j) split_bf16x3(val[j], w0[j], w1[j], w2[j]);
+        const int o = gcol + (b >> 3) * 64 + (b & 7) * 8;           // 8-byte slot (b, 4*lane .. 4*lane+3)
+        *reinterpret_cast<uint2*>(Gi + o) = make_uint2(pack_hi16(w0[0], w0[1]), pack_hi16(w0[2], w0[3]));
+        *reinterpret_cast<uint2*>(Gi + a.gimg + o) = make_uint2(pack_hi16(w1[0], w1[1]), pack_hi16(w1[2], w1[3]));
+        *reinterpret_cast<uint2*>(Gi + 2 * a.gimg + o) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
       }
     }
     if (a.want_dv) {
 #pragma unroll
-      for (int i = 0; i < D_MAXE; ++i) {
-        const int e = tid + i * TC_THREADS;
-        if (e < TC_TP * K) {
-          const int p = e / K, k = e - p * K;
-          bf16_t b0, b1, b2;
-          split_bf16x3(dreg[i], b0, b1, b2);
-          const int o = img16_off(p, k, a.Sd);
-          Di[o] = b0;
-          Di[a.dimg + o] = b1;
-          Di[2 * a.dimg + o] = b2;
+      for (int i = 0; i < D_ROWS; ++i) {
+        const int pr = warp + i * TC_WARPS;                          // pixel row inside the tile
+        const int obase = (pr >> 3) * 64 + (pr & 7) * 8;
+#pragma unroll
+        for (int j = 0; j < D_KJ; ++j) {
+          const int k = lane + 32 * j;
+          if (k < K && pr < TC_TP) {
+            uint32_t w0, w1, w2;
+            split_bf16x3(dreg[i][j], w0, w1, w2);
+            const int o = (k >> 3) * (a.Sd >> 1) + obase + (k & 7);
+            Di[o] = (bf16_t)(w0 >> 16);
+            Di[a.dimg + o] = (bf16_t)(w1 >> 16);
+            Di[2 * a.dimg + o] = (bf16_t)(w2 >> 16);
+          }
         }
       }
     }
@@ -549,25 +581,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
       // B = code image as [N=atom, K=image] MN-major: SBO = Sv between 8-atom groups, LBO = 128
       const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Kp16);
       const int ksteps = a.Bp16 / 16;
+#pragma unroll 1
       for (int t = 0; t < 6; ++t) {
-        const uint32_t abase = gb + ta[t] * gsz, bbase = vb + tb[t] * vsz;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t ad = make_desc(abase + ks * 256, 128, a.Sg);
-          const uint64_t bd = make_desc(bbase + ks * 256, 128, a.Sv);
-          mma_bf16(acc, ad, bd, idesc_dD, (t | ks) ? 1u : 0u);
-        }
+        uint64_t ad = make_desc(gb + ta[t] * gsz, 128, a.Sg);
+        uint64_t bd = make_desc(vb + tb[t] * vsz, 128, a.Sv);
+        for (int ks = 0; ks < ksteps; ++ks, ad += 16, bd += 16) mma_bf16(acc, ad, bd, idesc_dD, (t | ks) ? 1u : 0u);
       }
     }
     if (a.want_dv) {
       // A = g image as [M=image, K=pixel] K-major: LBO = Sg between the two 8-pixel chunks, SBO = 128 (8-image groups)
       // B = D image as [N=atom, K=pixel] MN-major: SBO = Sd between 8-atom groups, LBO = 128 between 8-pixel groups
+      const uint64_t astep = (uint64_t)((2 * a.Sg) >> 4);
+#pragma unroll 1
       for (int t = 0; t < 6; ++t) {
-        const uint32_t abase = gb + ta[t] * gsz, bbase = db + tb[t] * dsz;
-        for (int ks = 0; ks < TC_TP / 16; ++ks) {
-          const uint64_t ad = make_desc(abase + ks * 2 * a.Sg, a.Sg, 128);
-          const uint64_t bd = make_desc(bbase + ks * 256, 128, a.Sd);
+        uint64_t ad = make_desc(gb + ta[t] * gsz, a.Sg, 128);
+        uint64_t bd = make_desc(db + tb[t] * dsz, 128, a.Sd);
+        for (int ks = 0; ks < TC_TP / 16; ++ks, ad += astep, bd += 16)
           mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
-        }
       }
     }
     mma_commit(bar_mma);
@@ -579,8 +609,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
     const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Kp16) + ((uint32_t)(quad * 32) << 16);
     const int Ks = a.Ks;
     float* row = dDs + (quad * 32 + lane) * Ks;
-    __syncthreads();  // every thread is done reading the staging tile of the previous epilogue
-    for (int ch = cgrp; ch < nchunks; ch += 4) {  // warp-uniform
+    bar_sync(2, TC_THREADS);  // every worker is done reading the staging tile of the previous epilogue
+    for (int ch = cgrp; ch < nchunks; ch += ncg) {  // warp-uniform
       const int k0 = ch * 8;
       if (k0 >= K) break;
       float r[8];
@@ -589,7 +619,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
       *reinterpret_cast<float4*>(row + k0 + 4) = make_float4(r[4], r[5], r[6], r[7]);
     }
     tc_fence_before();
-    __syncthreads();
+    bar_sync(2, TC_THREADS);
     // Phase B: one coalesced 128-bit pass over the tile's contiguous [rows x K] block of D / m / s (or dD)
     const int rows = min(TC_TP, P - tile * TC_TP);
     const int n4 = (rows * K) >> 2;
@@ -613,7 +643,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
         const int e4 = tid + (half * EP_BATCH + i) * TC_THREADS;
         if (e4 < n4) {
           const int e = 4 * e4;
-          int pp = e / K, kk = e - pp * K;
+          int pp = a.kdiv_mul ? (int)__umulhi((unsigned)e, a.kdiv_mul) : e;      // e / K (exact for e < 2^20; 0: K == 1)
+          int kk = e - pp * K;
           float gd[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -639,50 +670,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(const GradTcArgs
     }
   };
 
-  int it = 0, prev_tile = -1;
-  int tile = blockIdx.x;
-  if (tile < ntiles) prefetch(tile);
-  for (; tile < ntiles; tile += gridDim.x, ++it) {
-    if (it > 0) {
-      mbar_wait(bar_mma, (it - 1) & 1);  // MMAs(it-1) retired: images free, dD accumulator (it-1) complete
+  if (warp == TC_WARPS) {
+    // ===== issuer warp: waits for "tile staged", issues the 6-term MMAs of both contractions, commits =====
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      bar_sync(1, TC_BLOCK);
       tc_fence_after();
+      if (lane == 0) issue(it);
+      __syncwarp();
     }
-    stage(tile);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue(it);
-    }
-    const int nxt = tile + gridDim.x;
-    if (nxt < ntiles) prefetch(nxt);                    // global loads in flight while the tensor core works
-    if (a.want_dD && prev_tile >= 0) epilogue(prev_tile, it - 1);
-    prev_tile = tile;
-  }
-  if (prev_tile >= 0) {
-    mbar_wait(bar_mma, (it - 1) & 1);
-    tc_fence_after();
-    if (a.want_dD) epilogue(prev_tile, it - 1);
-    if (a.want_dv) {
-      // dv accumulator: row = image (TMEM lane), column = atom -> this CTA's slab of the partial buffer
-      const int b = quad * 32 + lane;
-      float* dst = a.partial + (size_t)blockIdx.x * B * K + (size_t)b * K;
-      for (int ch = cgrp; ch < nchunks; ch += 4) {
-        const int k0 = ch * 8;
-        if (k0 >= K) break;
-        float r[8];
-        tmem_ld8(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)k0, r);
-        if (b < B) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (k0 + j < K) dst[k0 + j] = r[j];
-        }
+  } else {
+    int it = 0, prev_tile = -1;
+    int tile = blockIdx.x;
+    if (tile < ntiles) prefetch(tile);
+    for (; tile < ntiles; tile += gridDim.x, ++it) {
+      if (it > 0) {
+        mbar_wait(bar_mma, (it - 1) & 1);  // MMAs(it-1) retired: images free, dD accumulator (it-1) complete
+        tc_fence_after();
       }
+      stage(tile);
+      fence_proxy_async();
       tc_fence_before();
+      bar_arrive(1, TC_BLOCK);                            // hand the tile to the issuer warp, keep going
+      const int nxt = tile + gridDim.x;
+      if (nxt < ntiles) prefetch(nxt);                    // global loads in flight while the tensor core works
+      if (a.want_dD && prev_tile >= 0) epilogue(prev_tile, it - 1);
+      prev_tile = tile;
     }
-  } else if (a.want_dv) {
-    for (int e = tid; e < B * K; e += TC_THREADS) a.partial[(size_t)blockIdx.x * B * K + e] = 0.0f;
+    if (prev_tile >= 0) {
+      mbar_wait(bar_mma, (it - 1) & 1);
+      tc_fence_after();
+      if (a.want_dD) epilogue(prev_tile, it - 1);
+      if (a.want_dv) {
+        // dv accumulator: row = image (TMEM lane), column = atom -> this CTA's slab of the partial buffer
+        const int b = quad * 32 + lane;
+        float* dst = a.partial + (size_t)blockIdx.x * B * K + (size_t)b * K;
+        for (int ch = cgrp; ch < nchunks; ch += ncg) {
+          const int k0 = ch * 8;
+          if (k0 >= K) break;
+          float r[8];
+          tmem_ld8(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)k0, r);
+          if (b < B) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (k0 + j < K) dst[k0 + j] = r[j];
+          }
+        }
+        tc_fence_before();
+      }
+    } else if (a.want_dv) {
+      for (int e = tid; e < B * K; e += TC_THREADS) a.partial[(size_t)blockIdx.x * B * K + e] = 0.0f;
+    }
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
@@ -748,8 +786,8 @@ GradPlan plan_grad(int B, int P, int K) {
   const size_t tail_after_v = 2 * (3 * (size_t)pl.dimg + 3 * (size_t)pl.gimg);
   const size_t tail_after_d = 2 * 3 * (size_t)pl.gimg;
   pl.ok = pl.smem <= SMEM_LIMIT && pl.tmem_cols <= 512 && over_v <= 2 * (size_t)pl.vimg + tail_after_v &&
-          over_d <= 2 * (size_t)pl.dimg + tail_after_d && B * (TC_TP / 4) <= G_MAXQ * TC_THREADS &&
-          TC_TP * K <= D_MAXE * TC_THREADS && TC_TP * K <= 4 * EP_BATCH * EP_HALVES * TC_THREADS;
+          over_d <= 2 * (size_t)pl.dimg + tail_after_d && B <= G_MAXQ * TC_WARPS && K <= 96 &&
+          TC_TP * K <= 4 * EP_BATCH * EP_HALVES * TC_THREADS;
   return pl;
 }
 
@@ -776,7 +814,7 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
   const int ntiles = (P + TC_TP - 1) / TC_TP;
   int grid = sm_count();
   if (grid > ntiles) grid = ntiles;
-  synth_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(a);
+  synth_tc_kernel<<<grid, TC_BLOCK, pl.smem, st>>>(a);
   return check_cuda(cudaGetLastError(), "synth_tc_kernel launch");
 }
 
@@ -789,6 +827,7 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
   a.dD2 = dD2; a.D2w = D2_rw; a.m = m; a.s = s; a.partial = scratch; a.g = g; a.D2 = D2; a.v = v; a.vidx = v_index;
   a.B = B; a.P = P; a.K = K; a.Bp16 = pl.Bp16; a.Kp16 = pl.Kp16; a.Sg = pl.Sg; a.Sd = pl.Sd; a.Sv = pl.Sv;
   a.gimg = pl.gimg; a.dimg = pl.dimg; a.vimg = pl.vimg; a.Ks = pl.Ks;
+  a.kdiv_mul = K == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned long long)K - 1) / (unsigned long long)K);
   a.tmem_cols = pl.tmem_cols;
   a.want_dD = (dD2 != nullptr || D2_rw != nullptr) ? 1 : 0;
   a.want_dv = (dvb != nullptr) ? 1 : 0;
@@ -804,10 +843,11 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
     if (scratch == nullptr || scratch_bytes < need)
       return set_error(-2, "adil_grad: scratch too small (%zu < %zu bytes)", scratch_bytes, need);
   }
-  int rc = check_cuda(cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
+  auto kern = K <= 32 ? grad_tc_kernel<1> : (K <= 64 ? grad_tc_kernel<2> : grad_tc_kernel<3>);
+  int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
                       "cudaFuncSetAttribute(grad_tc)");
   if (rc) return rc;
-  grad_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(a);
+  kern<<<grid, TC_BLOCK, pl.smem, st>>>(a);
   rc = check_cuda(cudaGetLastError(), "grad_tc_kernel launch");
   if (rc) return rc;
   if (a.want_dv) return launch_reduce_partials(dvb, scratch, B * K, grid, st);
