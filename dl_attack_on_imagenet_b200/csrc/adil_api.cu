@@ -126,7 +126,8 @@ extern "C" int adil_set_impl(int impl) {
 extern "C" int adil_get_impl(void) { return g_impl; }
 
 extern "C" int adil_tc_supported(int B, int P, int K) {
-  return (tc_synth_ok(B, P, K) ? 1 : 0) | (tc_grad_ok(B, P, K) ? 2 : 0);
+  const int hw = (P % 3 == 0) ? P / 3 : P;
+  return (tc_synth_ok(B, P, K, hw) ? 1 : 0) | (tc_grad_ok(B, P, K, hw, true, true, true) ? 2 : 0);
 }
 
 extern "C" int adil_synth(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
@@ -142,7 +143,7 @@ extern "C" int adil_synth(float* out, float* delta_out, const float* x, const in
   if (B == 0) return 0;
   ChannelConsts cc = make_consts(C, hw, mean_host, std_host, norm);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(tc_synth_ok(B, P, K), B, P, K, &rc, "adil_synth"))
+  if (use_tc(tc_synth_ok(B, P, K, norm ? hw : P), B, P, K, &rc, "adil_synth"))
     return launch_synth_tc(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
   if (rc) return rc;
   return launch_synth_fma(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
@@ -170,7 +171,8 @@ int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, fl
   memset(&dev, 0, sizeof(dev));
   if (hp) dev = make_adamw(hp);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(tc_grad_ok(B, P, K), B, P, K, &rc, fn))
+  if (use_tc(tc_grad_ok(B, P, K, scale ? hw : P, dD2 != nullptr || D2_rw != nullptr, dvb != nullptr, D2_rw != nullptr), B, P,
+             K, &rc, fn))
     return launch_grad_tc(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
                           scratch_bytes, st);
   if (rc) return rc;

@@ -243,7 +243,7 @@ __device__ __forceinline__ void dict_epilogue(const GradArgs& a, const float (&a
 #pragma unroll
         for (int c = 0; c < VK; ++c) {
           dv[c] = Ds ? Ds[(4 * pg + j) * Kp + k + c] : a.D2[idx + c];
-          adamw_update(dv[c], mv[c], sv[c], acc[j][c0 + c], a.hp);
+          adamw_update_fast(dv[c], mv[c], sv[c], acc[j][c0 + c], a.hp);
           if (a.atoms_mode == ADIL_ATOMS_CLAMP1) dv[c] = clamp1(dv[c]);
         }
         if (VK == 4) {
@@ -428,12 +428,33 @@ __global__ void __launch_bounds__(kThreads) grad_fma_kernel(const GradArgs a) {
   }
 }
 
-__global__ void reduce_partials_kernel(float* __restrict__ dvb, const float* __restrict__ partial, int n, int nslabs) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  float acc = 0.0f;
-  for (int c = 0; c < nslabs; ++c) acc += partial[(size_t)c * n + e];  // fixed order: deterministic
-  dvb[e] = acc;
+// Second stage of the deterministic dv reduction: dvb[e] = sum over the per-CTA slabs, in a fixed order.  A block owns
+// 32 consecutive outputs; warp w adds slabs w, w+8, ... (independent coalesced 128-byte loads), then the eight partial
+// sums are combined in warp order -- the summation tree depends only on nslabs, so results are bit-reproducible.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(float* __restrict__ dvb, const float* __restrict__ partial,
+                                                              int n, int nslabs) {
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  if (e < n) {
+    int c = warp;
+    for (; c + 24 < nslabs; c += 32) {
+      a0 += partial[(size_t)c * n + e];
+      a1 += partial[(size_t)(c + 8) * n + e];
+      a2 += partial[(size_t)(c + 16) * n + e];
+      a3 += partial[(size_t)(c + 24) * n + e];
+    }
+    for (; c < nslabs; c += 8) a0 += partial[(size_t)c * n + e];
+  }
+  part[warp][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (warp == 0 && e < n) {
+    float acc = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) acc += part[w][lane];
+    dvb[e] = acc;
+  }
 }
 
 size_t grad_smem_bytes(int TP, int B, int Kp, bool want_dD, bool want_dv) {
@@ -455,7 +476,7 @@ int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
 }  // namespace
 
 int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, cudaStream_t st) {
-  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(dvb, partial, n, nslabs);
+  reduce_partials_kernel<<<(n + 31) / 32, 256, 0, st>>>(dvb, partial, n, nslabs);
   return check_cuda(cudaGetLastError(), "reduce_partials_kernel launch");
 }
 

@@ -12,6 +12,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // elementwise AdamW (+ clamp) -- 128-bit vectorised, grid-stride, 7 arrays touched once each
 // ---------------------------------------------------------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(256) adamw_elem_kernel(float* __restrict__ p, float* __restrict__ m,
                                                          float* __restrict__ s, const float* __restrict__ g,
                                                          long long n, AdamwDev hp, float bound) {
@@ -22,10 +23,17 @@ __global__ void __launch_bounds__(256) adamw_elem_kernel(float* __restrict__ p, 
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 sv = reinterpret_cast<float4*>(s)[i];
     const float4 gv = ld_stream4(g + 4 * i);
-    adamw_update(pv.x, mv.x, sv.x, gv.x, hp);
-    adamw_update(pv.y, mv.y, sv.y, gv.y, hp);
-    adamw_update(pv.z, mv.z, sv.z, gv.z, hp);
-    adamw_update(pv.w, mv.w, sv.w, gv.w, hp);
+    if (FAST) {
+      adamw_update_fast(pv.x, mv.x, sv.x, gv.x, hp);
+      adamw_update_fast(pv.y, mv.y, sv.y, gv.y, hp);
+      adamw_update_fast(pv.z, mv.z, sv.z, gv.z, hp);
+      adamw_update_fast(pv.w, mv.w, sv.w, gv.w, hp);
+    } else {
+      adamw_update(pv.x, mv.x, sv.x, gv.x, hp);
+      adamw_update(pv.y, mv.y, sv.y, gv.y, hp);
+      adamw_update(pv.z, mv.z, sv.z, gv.z, hp);
+      adamw_update(pv.w, mv.w, sv.w, gv.w, hp);
+    }
     if (bound > 0.0f) {
       pv.x = fminf(fmaxf(pv.x, -bound), bound);
       pv.y = fminf(fmaxf(pv.y, -bound), bound);
@@ -40,7 +48,8 @@ __global__ void __launch_bounds__(256) adamw_elem_kernel(float* __restrict__ p, 
   const long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) {
     float pv = p[t], mv = m[t], sv = s[t];
-    adamw_update(pv, mv, sv, g[t], hp);
+    if (FAST) adamw_update_fast(pv, mv, sv, g[t], hp);
+    else adamw_update(pv, mv, sv, g[t], hp);
     if (bound > 0.0f) pv = fminf(fmaxf(pv, -bound), bound);
     p[t] = pv; m[t] = mv; s[t] = sv;
   }
@@ -307,7 +316,7 @@ extern "C" int adil_dict_step(float* D2, float* m, float* s, const float* dD2, l
   if (n <= 0) return 0;
   if ((((uintptr_t)D2 | (uintptr_t)m | (uintptr_t)s | (uintptr_t)dD2) & 15) != 0)
     return set_error(-1, "adil_dict_step: pointers must be 16-byte aligned");
-  adamw_elem_kernel<<<elem_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(
+  adamw_elem_kernel<true><<<elem_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(
       D2, m, s, dD2, n, make_adamw(hp), atoms_mode == ADIL_ATOMS_CLAMP1 ? 1.0f : 0.0f);
   return check_cuda(cudaGetLastError(), "adamw_elem_kernel launch");
 }
@@ -318,7 +327,7 @@ extern "C" int adil_adamw_clamp(float* p, float* m, float* s, const float* grad,
   if (n <= 0) return 0;
   if ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)s | (uintptr_t)grad) & 15) != 0)
     return set_error(-1, "adil_adamw_clamp: pointers must be 16-byte aligned");
-  adamw_elem_kernel<<<elem_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(p, m, s, grad, n, make_adamw(hp), bound);
+  adamw_elem_kernel<false><<<elem_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(p, m, s, grad, n, make_adamw(hp), bound);
   return check_cuda(cudaGetLastError(), "adamw_elem_kernel launch");
 }
 

@@ -1,23 +1,30 @@
-// tcgen05 (5th-gen tensor core) kernels of the ADiL hot path -- split-TF32 ("3xTF32") contractions with fp32
-// accumulators in TMEM, used when the atom count makes the CUDA-core FFMA pipe the limiter.
+// tcgen05 (5th-gen tensor core) kernels of the ADiL hot path: warp-specialised, persistent, TMA-fed pipelines.
 //
-// Every fp32 operand x is split exactly into hi = x & 0xffffe000 (representable in TF32) and lo = x - hi, and each
-// contraction is issued as three tcgen05.mma.kind::tf32 passes  lo*hi + hi*lo + hi*hi  into the same TMEM
-// accumulator: relative error ~2^-21, i.e. fp32-grade (the 1e-5 parity bound of the north star needs it: plain TF32
-// is 2^-11).
+//   synth_kernel  out[b,p] = f(x[b,p] + sum_k v[b,k] D[p,k])                        (adil.py:24-27, demo:22-25)
+//   grad_kernel   dD[p,k]  = sum_b gx[b,p] v[b,k] ;  dv[b,k] = sum_p gx[b,p] D[p,k]   (autograd of the above)
+//                 optionally fused with AdamW(D) + clamp                             (adil.py:186,188)
 //
-// Operand staging.  All three matrices (dictionary tile D[p][k], gradient tile g[b][p], batch codes v[b][k]) are laid
-// out in shared memory by the CTA's threads in the UMMA no-swizzle canonical form: 128-byte core matrices of
-// 8 "rows" x 16 bytes.  One image serves a matrix in both of its roles because the core matrix of a K-major operand
-// (8 M/N-rows x 4 contiguous K-elements) and of an MN-major operand (8 K-rows x 4 contiguous MN-elements) is the
-// same memory pattern:
-//     img(r, c) = (c/4)*S + (r/8)*128 + (r%8)*16 + (c%4)*4        S = 128*ceil(R/8) + 16  (the +16 de-phases banks)
-//     D tile : r = pixel, c = atom   -> A of synth (K-major, M=pixel)      / B of dv   (MN-major, N=atom)
-//     g tile : r = image, c = pixel  -> A of dD    (MN-major, M=pixel)     / A of dv   (K-major,  M=image)
-//     codes  : r = image, c = atom   -> B of synth (K-major, N=image)      / B of dD   (MN-major, N=atom)
-// The synthesis kernel stages the raw dictionary tile with a 1-D TMA bulk copy (cp.async.bulk + mbarrier,
-// double-buffered) before the split; the gradient kernel prefetches the next tile through registers because its
-// shared memory is taken by the hi/lo images.
+// Numerics.  The contractions run on the tensor cores with fp32-grade split operands and fp32 accumulators in TMEM:
+//   synthesis : 3xTF32.  x = hi + lo, hi = x & 0xffffe000 (exact in TF32), lo = x - hi; MMAs lo*hi + hi*lo + hi*hi.
+//   backward  : bf16x3.  x = b0 + b1 + b2 (exact residual split, last term rounded); six MMAs (2,0)(0,2)(1,1)(1,0)
+//               (0,1)(0,0).  bf16 because the gradient tile is contracted over images for dD and over pixels for dv:
+//               one shared-memory image of a 16-bit operand can be read in both majors, a TF32 operand cannot.
+//
+// Roles (one CTA per SM, 18 warps):
+//   warps 0..15  workers: operand split (fp32 -> hi/lo or bf16x3 images in the UMMA canonical no-swizzle layout),
+//                epilogues (TMEM -> registers -> shared-memory staging -> coalesced 128-bit global stores), AdamW
+//   warp 16      MMA issuer: one lane issues tcgen05.mma and commits to an mbarrier
+//   warp 17      loader: 1-D TMA bulk copies (cp.async.bulk + mbarrier expect_tx) of the contiguous D / m / s tiles
+//                and cp.async (LDGSTS) of the image rows, running up to three tiles ahead of the workers
+// Tiles of TP pixels are assigned round-robin (tile = blockIdx.x + i * gridDim.x).  Per tile the workers stage the
+// operands of tile i, hand them to the issuer, and run the epilogue of tile i-1 while the MMAs of tile i execute;
+// accumulators are double-buffered in TMEM.
+//
+// Shared-memory operand images (no swizzle): 128-byte core matrices of 8 "rows" x 16 bytes,
+//     off(r, c) = (c / E) * S + (r / 8) * 128 + (r % 8) * 16 + (c % E) * sizeof(elem)      E = 16 / sizeof(elem)
+// r = index along which 8 rows form a core matrix, c = contiguous index.  The same image serves a K-major operand
+// (r = M/N index, c = contraction index: LBO = S, SBO = 128) and an MN-major operand (r = contraction index,
+// c = M/N index: LBO = 128, SBO = S).
 #include <cstdio>
 
 #include "adil_common.cuh"
@@ -28,11 +35,15 @@ int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, 
 
 namespace {
 
-constexpr int TC_WARPS = 15;                  // worker warps: staging, prefetch, epilogues
-constexpr int TC_THREADS = TC_WARPS * 32;
-constexpr int TC_BLOCK = TC_THREADS + 32;     // + warp 15, which only issues TMA / tcgen05.mma (512 threads, 128 regs)
-constexpr int TC_TP = 128;                    // pixels per tile = UMMA M
+constexpr int NW = 16;              // worker warps
+constexpr int NT = NW * 32;         // worker threads
+constexpr int WARP_MMA = NW;        // issuer warp
+constexpr int WARP_LOAD = NW + 1;   // loader warp
+constexpr int NTHREADS = NT + 64;   // 576 threads -> at most 112 registers each
+constexpr int NS = 3;               // stages of the raw dictionary tiles
+constexpr int NSX = 3;              // stages of the image-row tiles (synthesis)
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int HDR_BYTES = 256 + 1024;  // barriers + tmem slot | per-image row offsets
 
 __host__ __device__ inline int rup(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -48,6 +59,9 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -60,11 +74,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.
+// try_wait suspends the warp in hardware for a while before it returns false, so the loop is cheap.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+    if (++spins > (1u << 24)) {
       printf("adil_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
@@ -75,6 +89,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// the mbarrier receives one arrival once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // named barriers: id 1 = "tile staged" hand-off workers -> issuer warp, id 2 = worker-only barrier
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
@@ -104,9 +125,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
   return d;
 }
-// instruction descriptor for kind::tf32, fp32 accumulate (cute/arch/mma_sm100_desc.hpp: InstrDescriptor)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
+// instruction descriptors, fp32 accumulate (cute/arch/mma_sm100_desc.hpp: InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -118,273 +143,36 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread (thread t <-> TMEM lane base+t)
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
-  uint32_t u[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-               : "r"(taddr));
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread t <-> TMEM lane base+t)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+  uint32_t u[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+  for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
   lo = __fsub_rn(x, hi);  // exact
 }
-
-// canonical image offset in floats: r = "8-row" index, c = contiguous index, S = byte stride between c-groups
-__device__ __forceinline__ int img_off(int r, int c, int S_bytes) {
-  return (c >> 2) * (S_bytes >> 2) + (r >> 3) * 32 + (r & 7) * 4 + (c & 3);
-}
-__host__ __device__ inline int img_stride(int R) { return 128 * ((R + 7) / 8) + 16; }
-
-// codes image (hi/lo): rows b < Rz are written (zero beyond B / K), layout img(b, k)
-__device__ void build_code_images(float* Vhi, float* Vlo, const float* v, const int64_t* vidx, int B, int K, int Rz,
-                                  int Kz, int Sv) {
-  for (int e = threadIdx.x; e < Rz * Kz; e += blockDim.x) {
-    const int b = e / Kz, k = e - b * Kz;
-    float val = 0.0f;
-    if (b < B && k < K) {
-      const int64_t row = vidx ? vidx[b] : (int64_t)b;
-      val = v[row * K + k];
-    }
-    float hi, lo;
-    split_tf32(val, hi, lo);
-    const int o = img_off(b, k, Sv);
-    Vhi[o] = hi;
-    Vlo[o] = lo;
-  }
-}
-
-// =========================================================================================================
-// synthesis:  acc[p, b] = sum_k D[p,k] v[b,k]   (M = 128 pixels, N = images, K = atoms)
-// =========================================================================================================
-struct SynthTcArgs {
-  float* out;
-  float* delta;
-  const float* x;
-  const int64_t* xidx;
-  const float* D2;
-  const float* v;
-  const int64_t* vidx;
-  int B, P, K;
-  int Np;      // N of the MMA: round_up(B, 16)
-  int Kp8;     // contraction length: round_up(K, 8)
-  int Sd, Sv;  // image strides (bytes)
-  int raw_floats, dimg_floats, vimg_floats;
-  uint32_t tmem_cols;
-  float eps;
-  int flags;
-  ChannelConsts cc;
-};
-
-constexpr int S_OS = TC_TP + 4;  // row stride (floats) of the epilogue staging tile [image][pixel]
-constexpr int S_EB = 7;          // images per thread per epilogue batch (7 x 16 warps >= 100)
-
-__global__ void __launch_bounds__(TC_BLOCK, 1) synth_tc_kernel(const SynthTcArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);  // [1] raw tile landed
-  uint64_t* bar_mma = bar_full + 1;                            // [1] MMAs of a tile retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2);
-  long long* xoff_s = reinterpret_cast<long long*>(smem_raw + 128);  // [256] element offset of each image's x row
-  float* raw = reinterpret_cast<float*>(smem_raw + 128 + 2048);     // TMA landing buffer of the raw D tile
-  float* Vhi = raw + a.raw_floats;
-  float* Vlo = Vhi + a.vimg_floats;
-  float* Dhi = Vlo + a.vimg_floats;
-  float* Dlo = Dhi + a.dimg_floats;
-  float* outs = Dlo + a.dimg_floats;                           // [Np][S_OS] accumulator tile, image-major
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = a.K, P = a.P, B = a.B;
-  const int ntiles = (P + TC_TP - 1) / TC_TP;
-
-  if (tid == 0) {
-    mbar_init(bar_full, 1);
-    mbar_init(bar_mma, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  // zero the dictionary images once: contraction padding (k in [K, Kp8)) must stay zero
-  for (int e = tid; e < 2 * a.dimg_floats; e += TC_BLOCK) Dhi[e] = 0.0f;
-  build_code_images(Vhi, Vlo, a.v, a.vidx, B, K, a.Np, a.Kp8, a.Sv);
-  // x row offsets in shared memory: a dependent global load per image inside the epilogue would serialise it
-  for (int b = tid; b < B; b += TC_BLOCK) xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int my_first = blockIdx.x;
-  if (tid == 0 && my_first < ntiles) {
-    const int rows = min(TC_TP, P - my_first * TC_TP);
-    mbar_expect_tx(bar_full, (uint32_t)(rows * K * 4));
-    bulk_g2s(raw, a.D2 + (size_t)my_first * TC_TP * K, (uint32_t)(rows * K * 4), bar_full);
-  }
-
-  const uint32_t idesc = make_idesc(128, a.Np, false, false);
-  const int ksteps = a.Kp8 / 8;
-  const int quad = warp & 3, cgrp = warp >> 2;          // TMEM lane quadrant / column group of this warp
-  const int ncg = (quad == 3) ? 3 : 4;                  // quadrant 3 lost warp 15 to the issuer role
-  const int nchunks = a.Np / 8;                         // 8-column chunks of the accumulator
-  const bool need_x = (a.x != nullptr) && (a.out != nullptr);
-
-  auto epilogue = [&](int tile, int it) {
-    bar_sync(2, TC_THREADS);  // staging tile free (previous epilogue fully drained)
-    // Phase A: accumulator (row = pixel = TMEM lane, column = image) -> shared memory, image-major
-    {
-      const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np) + ((uint32_t)(quad * 32) << 16);
-      float* col = outs + quad * 32 + lane;
-      for (int ch = cgrp; ch < nchunks; ch += ncg) {    // warp-uniform
-        float d[8];
-        tmem_ld8(acc + (uint32_t)(ch * 8), d);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) col[(ch * 8 + j) * S_OS] = d[j];
-      }
-      tc_fence_before();
-    }
-    bar_sync(2, TC_THREADS);
-    // Phase B: coalesced 128-bit pass over image rows of 128 pixels: x + delta, clamps, (.-mean)/std, store.
-    // A thread keeps one 4-pixel column (channel constants hoisted) and walks images b = warp, warp+16, ...
-    const int pq = lane, p = tile * TC_TP + 4 * pq;
-    if (p < P) {
-      float mean[4], stdv[4], rstd[4];
-      if (a.cc.use) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = (p + j) / a.cc.hw;
-          mean[j] = a.cc.mean[c]; stdv[j] = a.cc.stdv[c]; rstd[j] = a.cc.rstd[c];
-        }
-      }
-      for (int b0 = warp; b0 < B; b0 += S_EB * TC_WARPS) {
-        float4 xv[S_EB];
-        if (need_x) {
-#pragma unroll
-          for (int i = 0; i < S_EB; ++i) {
-            const int b = b0 + i * TC_WARPS;
-            if (b < B) xv[i] = ld_stream4(a.x + xoff_s[b] + p);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < S_EB; ++i) {
-          const int b = b0 + i * TC_WARPS;
-          if (b < B) {
-            const float4 d4 = *reinterpret_cast<const float4*>(outs + b * S_OS + 4 * pq);
-            float d[4] = {d4.x, d4.y, d4.z, d4.w};
-            if (a.flags & ADIL_SYNTH_CLAMP_DELTA) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) d[j] = fminf(fmaxf(d[j], -a.eps), a.eps);
-            }
-            if (a.delta) st_stream4(a.delta + (size_t)b * P + p, make_float4(d[0], d[1], d[2], d[3]));
-            if (a.out) {
-              float o[4] = {d[0], d[1], d[2], d[3]};
-              if (need_x) {
-                o[0] = __fadd_rn(xv[i].x, d[0]);
-                o[1] = __fadd_rn(xv[i].y, d[1]);
-                o[2] = __fadd_rn(xv[i].z, d[2]);
-                o[3] = __fadd_rn(xv[i].w, d[3]);
-              }
-              if (a.flags & ADIL_SYNTH_CLAMP01) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = fminf(fmaxf(o[j], 0.0f), 1.0f);
-              }
-              if (a.cc.use) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = div_by_const(__fsub_rn(o[j], mean[j]), stdv[j], rstd[j]);
-              }
-              st_stream4(a.out + (size_t)b * P + p, make_float4(o[0], o[1], o[2], o[3]));
-            }
-          }
-        }
-      }
-    }
-  };
-
-  if (warp == TC_WARPS) {
-    // ===== issuer warp: TMA prefetch of the next raw tile + the 3 x ksteps MMAs of the current one =====
-    const uint64_t dhi = make_desc(smem_u32(Dhi), a.Sd, 128), dlo = make_desc(smem_u32(Dlo), a.Sd, 128);
-    const uint64_t vhi = make_desc(smem_u32(Vhi), a.Sv, 128), vlo = make_desc(smem_u32(Vlo), a.Sv, 128);
-    const uint64_t astep = (uint64_t)((2 * a.Sd) >> 4), bstep = (uint64_t)((2 * a.Sv) >> 4);
-    int it = 0;
-    for (int tile = my_first; tile < ntiles; tile += gridDim.x, ++it) {
-      bar_sync(1, TC_BLOCK);                                       // workers staged tile `it`
-      tc_fence_after();
-      if (lane == 0) {
-        const int nxt = tile + gridDim.x;
-        if (nxt < ntiles) {                                         // raw buffer is consumed: prefetch the next tile
-          const int nrows = min(TC_TP, P - nxt * TC_TP);
-          mbar_expect_tx(bar_full, (uint32_t)(nrows * K * 4));
-          bulk_g2s(raw, a.D2 + (size_t)nxt * TC_TP * K, (uint32_t)(nrows * K * 4), bar_full);
-        }
-        const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Np);
-        // A (D image, K-major): LBO = Sd between the two 16-byte K chunks, SBO = 128 between 8-pixel groups
-        // B (code image, K-major): LBO = Sv, SBO = 128 between 8-image groups
-        for (int pass = 0; pass < 3; ++pass) {
-          uint64_t ad = (pass == 0) ? dlo : dhi;                    // lo*hi, hi*lo, hi*hi
-          uint64_t bd = (pass == 1) ? vlo : vhi;
-          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, (pass | ks) ? 1u : 0u);
-        }
-        mma_commit(bar_mma);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===== worker warps: split/scatter of the raw tile, epilogue of the previous tile =====
-    int it = 0, prev_tile = -1;
-    for (int tile = my_first; tile < ntiles; tile += gridDim.x, ++it) {
-      const int rows = min(TC_TP, P - tile * TC_TP);
-      mbar_wait(bar_full, it & 1);                                 // raw tile `it` landed
-      if (it > 0) mbar_wait(bar_mma, (it - 1) & 1);                // MMAs(it-1) retired: images reusable, acc ready
-      tc_fence_after();
-      for (int p = warp; p < TC_TP; p += TC_WARPS) {                // a warp takes one pixel row, lanes run over atoms
-        const float* rrow = raw + p * K;
-        const int obase = (p >> 3) * 32 + (p & 7) * 4;
-        for (int k = lane; k < K; k += 32) {
-          const float val = (p < rows) ? rrow[k] : 0.0f;
-          float hi, lo;
-          split_tf32(val, hi, lo);
-          const int o = (k >> 2) * (a.Sd >> 2) + obase + (k & 3);
-          Dhi[o] = hi;
-          Dlo[o] = lo;
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      bar_arrive(1, TC_BLOCK);                                     // hand the tile to the issuer warp, keep going
-      if (prev_tile >= 0) epilogue(prev_tile, it - 1);             // overlaps the MMAs being issued
-      prev_tile = tile;
-    }
-    if (prev_tile >= 0) {
-      mbar_wait(bar_mma, (it - 1) & 1);
-      tc_fence_after();
-      epilogue(prev_tile, it - 1);
-    }
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
-}
-
-// =========================================================================================================
-// backward contractions (+ optional fused AdamW/clamp), bf16x3 on tcgen05.mma.kind::f16:
-//   dD[p, k] = sum_b gx[b,p] v[b,k]   M = 128 pixels, N = atoms, K = images  (A = g image MN-major, B = code image MN-major)
-//   dv[b, k] = sum_p gx[b,p] D[p,k]   M = images (<=128), N = atoms, K = pixels (A = g image K-major, B = D image MN-major)
-// The gradient tile is needed with the contraction along its contiguous dimension (dv) AND across it (dD).  TF32
-// operands cannot do that from one image (MN-major TF32 exists only in the 128B_BASE32B swizzle, which has no
-// K-major twin -- measured: scripts/umma_probe*.cu), bf16 operands can: an 8x16-byte core matrix is the same bytes
-// for a K-major and an MN-major operand.  So every fp32 value is split exactly into three bf16 terms
-// x = b0 + b1 + b2 (+ O(2^-23 x)) and each contraction is six MMAs: (2,0) (0,2) (1,1) (1,0) (0,1) (0,0); the two
-// dropped cross terms are O(2^-21).  bf16 MMAs run at twice the TF32 rate, so this costs the same tensor time as
-// 3xTF32 while the images take 6 instead of 8 bytes per element.
-// dD accumulators are double-buffered in TMEM and drained by the AdamW epilogue while the next tile's MMAs run;
-// the dv accumulator stays in TMEM across all of the CTA's tiles.
-// =========================================================================================================
-typedef unsigned short bf16_t;
-
 // x = t0 + t1 + t2 + O(2^-24 x): t0, t1 are the truncated high halves of x and of the (exact) residuals; the words
 // returned hold the bf16 term in their UPPER 16 bits (ready for PRMT packing).
 __device__ __forceinline__ void split_bf16x3(float x, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
@@ -398,25 +186,299 @@ __device__ __forceinline__ uint32_t pack_hi16(uint32_t lo_word, uint32_t hi_word
   return __byte_perm(lo_word, hi_word, 0x7632);  // {hi_word[31:16], lo_word[31:16]}
 }
 
-// canonical image offset in bf16 elements: r = "8-row" index, c = contiguous index, S = byte stride between 8-c groups
-__device__ __forceinline__ int img16_off(int r, int c, int S_bytes) {
-  return (c >> 3) * (S_bytes >> 1) + (r >> 3) * 64 + (r & 7) * 8 + (c & 7);
-}
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+// e / d for the loop-invariant divisor d whose magic is `mul` = ceil(2^32 / d) (0: d == 1); exact for e * d < 2^32
+__device__ __forceinline__ int div_magic_dev(int e, unsigned mul) { return mul ? (int)__umulhi((unsigned)e, mul) : e; }
+
+__host__ __device__ inline int img_stride(int R) { return 128 * ((R + 7) / 8) + 16; }  // +16 de-phases the banks
+
+// channel constants of a tile that spans at most two channels: pixels [0, bnd) of the tile are channel c0
+struct TileChan {
+  int bnd;
+  float mean0, std0, rstd0, mean1, std1, rstd1;
+};
+__device__ __forceinline__ TileChan tile_chan(const ChannelConsts& cc, int p0) {
+  TileChan t;
+  const int c0 = p0 / cc.hw;
+  const int c1 = min(c0 + 1, kMaxC - 1);
+  t.bnd = (c0 + 1) * cc.hw - p0;
+  t.mean0 = cc.mean[c0]; t.std0 = cc.stdv[c0]; t.rstd0 = cc.rstd[c0];
+  t.mean1 = cc.mean[c1]; t.std1 = cc.stdv[c1]; t.rstd1 = cc.rstd[c1];
+  return t;
 }
 
-struct GradTcArgs {
+// =========================================================================================================
+// synthesis:  acc[b, p] = sum_k v[b,k] D[p,k]      M = 128 image lanes, N = TP pixels, contraction over atoms
+//   A = code images (hi/lo)  r = image, c = atom   K-major      (built once per CTA)
+//   B = D tile images        r = pixel, c = atom   K-major      (rebuilt per tile from the TMA-landed raw tile)
+// The image-row tile x[b, p0:p0+TP] lands by cp.async in a padded [B][TP+4] buffer; the epilogue thread of image b
+// reads its accumulator row, applies +x / clamps / Normalize in place, and the finished tile goes out as coalesced
+// 128-bit streaming stores.
+// =========================================================================================================
+struct SynthArgs {
+  float* out;
+  float* delta;
+  const float* x;
+  const int64_t* xidx;
+  const float* D2;
+  const float* v;
+  const int64_t* vidx;
+  int B, P, K;
+  int Kp8;               // contraction length: round_up(K, 8)
+  int Sv, Sd;            // byte strides between 4-atom groups of the code / dictionary images
+  int vimg, dimg;        // floats per code image (incl. over-read pad) / per dictionary image
+  int raw_floats;        // floats per raw stage
+  int vk;                // vector width of the dictionary split: 4, 2 or 1 (K % vk == 0)
+  unsigned kdiv;         // ceil(2^32 / (K / vk))
+  uint32_t tmem_cols;
+  float eps;
+  int flags;
+  ChannelConsts cc;
+};
+
+template <int TP>
+__global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
+  constexpr int XP = TP + 4;       // floats per staged image row (pitch 16 bytes off a multiple of 128)
+  constexpr int Q4 = TP / 4;       // float4 per image row
+  constexpr int NCG = TP / 16;     // 16-column groups of the accumulator
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS]
+  uint64_t* empty_raw = full_raw + NS;                         // [NS]
+  uint64_t* full_x = empty_raw + NS;                           // [NSX]
+  uint64_t* empty_x = full_x + NSX;                            // [NSX]
+  uint64_t* mma_done = empty_x + NSX;                          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  long long* xoff_s = reinterpret_cast<long long*>(smem_raw + 256);  // [128]
+  float* raw = reinterpret_cast<float*>(smem_raw + HDR_BYTES);       // [NS][raw_floats]
+  float* Vhi = raw + NS * a.raw_floats;
+  float* Vlo = Vhi + a.vimg;
+  float* Dhi = Vlo + a.vimg;
+  float* Dlo = Dhi + a.dimg;
+  float* xs = Dlo + a.dimg;                                          // [NSX][B][XP]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = a.K, P = a.P, B = a.B;
+  const int ntiles = (P + TP - 1) / TP;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool need_x = (a.x != nullptr) && (a.out != nullptr);
+  const int xstage = B * XP;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
+    for (int i = 0; i < NSX; ++i) { mbar_init(full_x + i, 32); mbar_init(empty_x + i, NW); }
+    mbar_init(mma_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
+  // zero the operand images (contraction padding k in [K, Kp8) and image rows >= B must be zero / finite) and the
+  // raw stages (a partial last tile leaves stale rows behind, which must stay finite)
+  {
+    const int nz = NS * a.raw_floats + 2 * a.vimg + 2 * a.dimg;
+    for (int e = tid; e < nz; e += NTHREADS) raw[e] = 0.0f;
+  }
+  for (int b = tid; b < B; b += NTHREADS) xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
+  __syncthreads();
+  for (int e = tid; e < B * K; e += NTHREADS) {
+    const int b = e / K, k = e - b * K;
+    const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
+    float hi, lo;
+    split_tf32(a.v[row * K + k], hi, lo);
+    const int o = (k >> 2) * (a.Sv >> 2) + (b >> 3) * 32 + (b & 7) * 4 + (k & 3);
+    Vhi[o] = hi;
+    Vlo[o] = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == WARP_LOAD) {
+    // ===== loader: raw dictionary tiles by TMA bulk copy, image rows by cp.async, up to NS / NSX tiles ahead =====
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int p0 = tile * TP;
+      const int rows = min(TP, P - p0);
+      const int s = it % NS;
+      if (lane == 0) {
+        if (it >= NS) mbar_wait(empty_raw + s, ((it / NS) - 1) & 1);
+        const uint32_t bytes = (uint32_t)(rows * K * 4);
+        mbar_expect_tx(full_raw + s, bytes);
+        bulk_g2s(raw + s * a.raw_floats, a.D2 + (size_t)p0 * K, bytes, full_raw + s);
+      }
+      if (need_x) {
+        const int sx = it % NSX;
+        if (it >= NSX) mbar_wait(empty_x + sx, ((it / NSX) - 1) & 1);
+        float* dst = xs + sx * xstage;
+        for (int e = lane; e < B * Q4; e += 32) {
+          const int b = e / Q4, c4 = e - b * Q4;
+          const int p = p0 + 4 * c4;
+          if (p < P) cp_async16(dst + b * XP + 4 * c4, a.x + xoff_s[b] + p);
+        }
+        cp_async_arrive_noinc(full_x + sx);
+      }
+      __syncwarp();
+    }
+  } else if (warp == WARP_MMA) {
+    // ===== issuer: 3 x ksteps MMAs per tile into the accumulator buffer (it & 1) =====
+    const uint32_t idesc = make_idesc_tf32(128, TP, false, false);
+    const uint64_t vhi = make_desc(smem_u32(Vhi), a.Sv, 128), vlo = make_desc(smem_u32(Vlo), a.Sv, 128);
+    const uint64_t dhi = make_desc(smem_u32(Dhi), a.Sd, 128), dlo = make_desc(smem_u32(Dlo), a.Sd, 128);
+    const uint64_t astep = (uint64_t)((2 * a.Sv) >> 4), bstep = (uint64_t)((2 * a.Sd) >> 4);
+    const int ksteps = a.Kp8 / 8;
+    for (int it = 0; it < my_tiles; ++it) {
+      bar_sync(1, NT + 32);  // workers staged tile `it`
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
+        for (int pass = 0; pass < 3; ++pass) {  // lo*hi, hi*lo, hi*hi
+          uint64_t ad = (pass == 0) ? vlo : vhi;
+          uint64_t bd = (pass == 1) ? dlo : dhi;
+          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, (pass | ks) ? 1u : 0u);
+        }
+        mma_commit(mma_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== workers =====
+    const int quad = warp & 3, cg = warp >> 2;
+    const int nitems = TP * (K / a.vk);  // vector items of the raw tile
+    const int kv = K / a.vk;
+
+    auto epilogue = [&](int j) {
+      const int tile = blockIdx.x + j * gridDim.x;
+      const int p0 = tile * TP;
+      const int sx = j % NSX;
+      float* xt = xs + sx * xstage;
+      if (need_x) mbar_wait(full_x + sx, (j / NSX) & 1);
+      // phase 1: thread <-> image row b; 16 accumulator columns per warp
+      if (cg < NCG) {
+        const int b = quad * 32 + lane;
+        float r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((j & 1) * TP + cg * 16), r);
+        if (b < B) {
+          TileChan tc;
+          if (a.cc.use) tc = tile_chan(a.cc, p0);
+          float* xrow = xt + b * XP + cg * 16;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float d[4] = {r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]};
+            if (a.flags & ADIL_SYNTH_CLAMP_DELTA) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d[i] = fminf(fmaxf(d[i], -a.eps), a.eps);
+            }
+            float o[4] = {d[0], d[1], d[2], d[3]};
+            if (a.out != nullptr) {
+              if (a.delta != nullptr) {  // secondary output: written straight from the accumulator row
+                const int p = p0 + cg * 16 + 4 * c;
+                if (p < P) st_stream4(a.delta + (size_t)b * P + p, make_float4(d[0], d[1], d[2], d[3]));
+              }
+              if (need_x) {
+                const float4 xv = *reinterpret_cast<const float4*>(xrow + 4 * c);
+                o[0] = __fadd_rn(xv.x, d[0]); o[1] = __fadd_rn(xv.y, d[1]);
+                o[2] = __fadd_rn(xv.z, d[2]); o[3] = __fadd_rn(xv.w, d[3]);
+              }
+              if (a.flags & ADIL_SYNTH_CLAMP01) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = fminf(fmaxf(o[i], 0.0f), 1.0f);
+              }
+              if (a.cc.use) {
+                const bool hi_c = (cg * 16 + 4 * c) >= tc.bnd;
+                const float mean = hi_c ? tc.mean1 : tc.mean0, stdv = hi_c ? tc.std1 : tc.std0,
+                            rstd = hi_c ? tc.rstd1 : tc.rstd0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = div_by_const(__fsub_rn(o[i], mean), stdv, rstd);
+              }
+            }
+            *reinterpret_cast<float4*>(xrow + 4 * c) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        tc_fence_before();
+      }
+      bar_sync(2, NT);
+      // phase 2: coalesced 128-bit stores of the finished [B][TP] tile
+      float* dst = a.out != nullptr ? a.out : a.delta;
+      for (int e = tid; e < B * Q4; e += NT) {
+        const int b = e / Q4, c4 = e - b * Q4;
+        const int p = p0 + 4 * c4;
+        if (p < P) st_stream4(dst + (size_t)b * P + p, *reinterpret_cast<const float4*>(xt + b * XP + 4 * c4));
+      }
+      if (need_x) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_x + sx);
+      }
+    };
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % NS;
+      if (it > 0) {
+        mbar_wait(mma_done, (it - 1) & 1);  // MMAs(it-1) retired: dictionary images reusable, accumulator ready
+        tc_fence_after();
+      }
+      mbar_wait(full_raw + s, (it / NS) & 1);
+      const float* rt = raw + s * a.raw_floats;
+      if (a.vk == 4) {
+        for (int e = tid; e < nitems; e += NT) {
+          const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 4;
+          const float4 val = *reinterpret_cast<const float4*>(rt + 4 * e);
+          float4 hi, lo;
+          split_tf32(val.x, hi.x, lo.x); split_tf32(val.y, hi.y, lo.y);
+          split_tf32(val.z, hi.z, lo.z); split_tf32(val.w, hi.w, lo.w);
+          const int o = (k >> 2) * (a.Sd >> 2) + (p >> 3) * 32 + (p & 7) * 4;
+          *reinterpret_cast<float4*>(Dhi + o) = hi;
+          *reinterpret_cast<float4*>(Dlo + o) = lo;
+        }
+      } else if (a.vk == 2) {
+        for (int e = tid; e < nitems; e += NT) {
+          const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 2;
+          const float2 val = *reinterpret_cast<const float2*>(rt + 2 * e);
+          float2 hi, lo;
+          split_tf32(val.x, hi.x, lo.x); split_tf32(val.y, hi.y, lo.y);
+          const int o = (k >> 2) * (a.Sd >> 2) + (p >> 3) * 32 + (p & 7) * 4 + (k & 3);
+          *reinterpret_cast<float2*>(Dhi + o) = hi;
+          *reinterpret_cast<float2*>(Dlo + o) = lo;
+        }
+      } else {
+        for (int e = tid; e < nitems; e += NT) {
+          const int p = div_magic_dev(e, a.kdiv), k = e - p * kv;
+          float hi, lo;
+          split_tf32(rt[e], hi, lo);
+          const int o = (k >> 2) * (a.Sd >> 2) + (p >> 3) * 32 + (p & 7) * 4 + (k & 3);
+          Dhi[o] = hi;
+          Dlo[o] = lo;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_raw + s);
+      bar_arrive(1, NT + 32);            // hand the tile to the issuer warp, keep going
+      if (it > 0) epilogue(it - 1);      // overlaps the MMAs being issued
+    }
+    if (my_tiles > 0) {
+      mbar_wait(mma_done, (my_tiles - 1) & 1);
+      tc_fence_after();
+      epilogue(my_tiles - 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// =========================================================================================================
+// backward contractions (+ optional fused AdamW / clamp), bf16x3:
+//   dD^T[k, p] = sum_b v[b,k] gx[b,p]   M = MA atom lanes, N = TP pixels, contraction over images
+//                A = code images   r = image, c = atom   MN-major       B = gradient images  r = image, c = pixel  MN-major
+//   dv[b, k]   = sum_p gx[b,p] D[p,k]   M = 128 image lanes, N = atoms, contraction over pixels (accumulated in TMEM
+//                over all tiles of the CTA)
+//                A = gradient images  (the same bytes, read K-major)    B = D tile images  r = pixel, c = atom  MN-major
+// gx = g / std[c] is folded into the operands' consumers: dD accumulators are divided by std on their way out and
+// the dictionary tile of the dv contraction is divided by std while it is split.
+// The raw D (and m, s) tiles land by TMA; the dD tile is transposed through shared memory into the flat [p][k]
+// layout of the dictionary, where AdamW + clamp run as one 128-bit vectorised pass that stores D, m, s coalesced.
+// =========================================================================================================
+struct GradArgs {
   float* dD2;
   float* D2w;
   float* m;
@@ -427,430 +489,524 @@ struct GradTcArgs {
   const float* v;
   const int64_t* vidx;
   int B, P, K;
-  int Bp16;     // contraction length of dD: round_up(B, 16)
-  int Kp16;     // N of both MMAs: round_up(K, 16)
-  int Sg, Sd, Sv;
-  int gimg, dimg, vimg;  // image sizes in bf16 elements (each matrix has three images)
-  int Ks;                // row stride (floats) of the dD staging tile
-  unsigned kdiv_mul;     // ceil(2^32 / K): e / K == umulhi(e, kdiv_mul) for e < 2^20
+  int Bp;             // contraction length of dD: round_up(B, 16)
+  int Kp;             // N of the dv MMA: round_up(K, 16)
+  int Sg, Sd;         // byte strides between column groups of the gradient (= code) / dictionary images
+  int vimg, dimg, gimg;  // bf16 elements per image term
+  int raw_floats;     // floats per raw stage
+  int nraw;           // arrays per raw stage: 3 (D, m, s: fused), 1 (D only) or 0
+  int vk;             // vector width of the dictionary split
+  unsigned kdiv;      // ceil(2^32 / (K / vk))
   uint32_t tmem_cols;
   int want_dD, want_dv, atoms_mode;
   ChannelConsts cc;
   AdamwDev hp;
 };
 
-constexpr int G_MAXQ = 9;    // image rows per worker warp per tile: 9 x 15 >= 128
-constexpr int D_ROWS = (TC_TP + TC_WARPS - 1) / TC_WARPS;  // 9 pixel rows per worker warp per tile
-constexpr int EP_BATCH = 2;  // float4 per thread per epilogue batch
-constexpr int EP_HALVES = 3; // 3 x 2 x 480 float4 >= 128 x 90 elements
-
-template <int D_KJ>  // atoms per lane when staging the dictionary tile: K <= 32 * D_KJ
-__global__ void __launch_bounds__(TC_BLOCK, 1) grad_tc_kernel(const GradTcArgs a) {
+template <int TP, int MA>
+__global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
+  constexpr int Q4 = TP / 4;                           // float4 per gradient row
+  constexpr int GJ = (128 * Q4 + NT - 1) / NT;         // float4 per worker thread (B <= 128)
+  constexpr int NCG = TP / 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
-  bf16_t* Vi = reinterpret_cast<bf16_t*>(smem_raw + 128);  // three code images
-  bf16_t* Di = Vi + 3 * a.vimg;                             // three dictionary images
-  bf16_t* Gi = Di + 3 * a.dimg;                             // three gradient images
-  float* dDs = reinterpret_cast<float*>(Gi + 3 * a.gimg);   // [128][Ks] dD tile in global layout (epilogue)
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS]
+  uint64_t* empty_raw = full_raw + NS;                         // [NS]
+  uint64_t* mma_done = empty_raw + NS;                         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  typedef unsigned short bf16_t;
+  bf16_t* Vi = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);  // three code images
+  bf16_t* Di = Vi + 3 * a.vimg;                                   // three dictionary images
+  bf16_t* Gi = Di + 3 * a.dimg;                                   // three gradient images (+ 2 KB over-read pad)
+  float* dDs = reinterpret_cast<float*>(Gi + 3 * a.gimg + 1024);  // [TP*K] dD tile, flat like the dictionary
+  float* raw = dDs + (a.want_dD ? TP * a.K : 0);                  // [NS][raw_floats]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
-  const int ntiles = (P + TC_TP - 1) / TC_TP;
+  const int ntiles = (P + TP - 1) / TP;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool fused = a.D2w != nullptr;
+  const int tile_elems = TP * K;
 
   if (tid == 0) {
-    mbar_init(bar_mma, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
+    mbar_init(mma_done, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  // zero all images once: contraction padding (images in [B, Bp16)) must stay zero, over-read regions stay finite
   {
+    // zero everything once: contraction padding must be zero, over-read regions and stale rows finite
     uint32_t* z = reinterpret_cast<uint32_t*>(Vi);
-    const int nz = (3 * (a.vimg + a.dimg + a.gimg)) >> 1;
-    for (int e = tid; e < nz; e += TC_BLOCK) z[e] = 0u;
+    const int nz = ((3 * (a.vimg + a.dimg + a.gimg) + 1024) >> 1) + (a.want_dD ? tile_elems : 0) + NS * a.raw_floats;
+    for (int e = tid; e < nz; e += NTHREADS) z[e] = 0u;
   }
   __syncthreads();
   if (a.want_dD) {
-    for (int e = tid; e < B * K; e += TC_BLOCK) {
+    for (int e = tid; e < B * K; e += NTHREADS) {
       const int b = e / K, k = e - b * K;
       const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
       uint32_t w0, w1, w2;
       split_bf16x3(a.v[row * K + k], w0, w1, w2);
-      const int o = img16_off(b, k, a.Sv);
+      const int o = (k >> 3) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (k & 7);
       Vi[o] = (bf16_t)(w0 >> 16);
       Vi[a.vimg + o] = (bf16_t)(w1 >> 16);
       Vi[2 * a.vimg + o] = (bf16_t)(w2 >> 16);
     }
   }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc_dv = tmem_base + (uint32_t)(2 * a.Kp16);
+  const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
 
-  const uint32_t idesc_dD = make_idesc_bf16(128, a.Kp16, true, true);
-  const uint32_t idesc_dv = make_idesc_bf16(128, a.Kp16, false, true);
-  const int quad = warp & 3, cgrp = warp >> 2;
-  const int ncg = (quad == 3) ? 3 : 4;  // quadrant 3 lost warp 15 to the issuer role
-  const int nchunks = a.Kp16 / 8;
-
-  float4 greg[G_MAXQ];
-  float dreg[D_ROWS][D_KJ];
-  // fixed per-thread roles: gradient tile -> image rows b = warp + 16*i, 4-pixel column pq = lane;
-  //                         dictionary tile -> pixel rows p = warp + 16*i, atoms k = lane + 32*j
-  auto prefetch = [&](int tile) {
-    const int p0 = tile * TC_TP;
-    const int p = p0 + 4 * lane;
-#pragma unroll
-    for (int i = 0; i < G_MAXQ; ++i) {
-      const int b = warp + i * TC_WARPS;
-      greg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < B && p < P) greg[i] = ld_stream4(a.g + (size_t)b * P + p);
-    }
-    if (a.want_dv) {
-#pragma unroll
-      for (int i = 0; i < D_ROWS; ++i) {
-        const int pl = warp + i * TC_WARPS, pr = p0 + pl;
-#pragma unroll
-        for (int j = 0; j < D_KJ; ++j) {
-          const int k = lane + 32 * j;
-          dreg[i][j] = (pl < TC_TP && pr < P && k < K) ? __ldg(a.D2 + (size_t)pr * K + k) : 0.0f;
+  if (warp == WARP_LOAD) {
+    // ===== loader: contiguous D (, m, s) tiles by TMA bulk copy =====
+    if (lane == 0 && a.nraw > 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int p0 = tile * TP;
+        const int rows = min(TP, P - p0);
+        const int s = it % NS;
+        if (it >= NS) mbar_wait(empty_raw + s, ((it / NS) - 1) & 1);
+        const uint32_t bytes = (uint32_t)(rows * K * 4);
+        float* dst = raw + s * a.raw_floats;
+        const size_t off = (size_t)p0 * K;
+        mbar_expect_tx(full_raw + s, bytes * (uint32_t)a.nraw);
+        bulk_g2s(dst, a.D2 + off, bytes, full_raw + s);
+        if (a.nraw == 3) {
+          bulk_g2s(dst + tile_elems, a.m + off, bytes, full_raw + s);
+          bulk_g2s(dst + 2 * tile_elems, a.s + off, bytes, full_raw + s);
         }
       }
     }
-  };
-
-  auto stage = [&](int tile) {
-    const int p = tile * TC_TP + 4 * lane;
-    float stdv[4], rstd[4];
-    if (a.cc.use) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = min((p + j) / a.cc.hw, kMaxC - 1);
-        stdv[j] = a.cc.stdv[c]; rstd[j] = a.cc.rstd[c];
-      }
-    }
-    const int gcol = (lane >> 1) * (a.Sg >> 1) + (lane & 1) * 4;   // img16_off(b, 4*lane) without the row part
-#pragma unroll
-    for (int i = 0; i < G_MAXQ; ++i) {
-      const int b = warp + i * TC_WARPS;
-      if (b < B) {
-        float val[4] = {greg[i].x, greg[i].y, greg[i].z, greg[i].w};
-        if (a.cc.use) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) val[j] = div_by_const(val[j], stdv[j], rstd[j]);
-        }
-        uint32_t w0[4], w1[4], w2[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split_bf16x3(val[j], w0[j], w1[j], w2[j]);
-        const int o = gcol + (b >> 3) * 64 + (b & 7) * 8;           // 8-byte slot (b, 4*lane .. 4*lane+3)
-        *reinterpret_cast<uint2*>(Gi + o) = make_uint2(pack_hi16(w0[0], w0[1]), pack_hi16(w0[2], w0[3]));
-        *reinterpret_cast<uint2*>(Gi + a.gimg + o) = make_uint2(pack_hi16(w1[0], w1[1]), pack_hi16(w1[2], w1[3]));
-        *reinterpret_cast<uint2*>(Gi + 2 * a.gimg + o) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
-      }
-    }
-    if (a.want_dv) {
-#pragma unroll
-      for (int i = 0; i < D_ROWS; ++i) {
-        const int pr = warp + i * TC_WARPS;                          // pixel row inside the tile
-        const int obase = (pr >> 3) * 64 + (pr & 7) * 8;
-#pragma unroll
-        for (int j = 0; j < D_KJ; ++j) {
-          const int k = lane + 32 * j;
-          if (k < K && pr < TC_TP) {
-            uint32_t w0, w1, w2;
-            split_bf16x3(dreg[i][j], w0, w1, w2);
-            const int o = (k >> 3) * (a.Sd >> 1) + obase + (k & 7);
-            Di[o] = (bf16_t)(w0 >> 16);
-            Di[a.dimg + o] = (bf16_t)(w1 >> 16);
-            Di[2 * a.dimg + o] = (bf16_t)(w2 >> 16);
-          }
-        }
-      }
-    }
-  };
-
-  auto issue = [&](int it) {
+  } else if (warp == WARP_MMA) {
+    // ===== issuer =====
+    const uint32_t idesc_dD = make_idesc_bf16(MA, TP, true, true);
+    const uint32_t idesc_dv = make_idesc_bf16(128, a.Kp, false, true);
     const uint32_t gb = smem_u32(Gi), vb = smem_u32(Vi), db = smem_u32(Di);
     const uint32_t gsz = 2u * a.gimg, vsz = 2u * a.vimg, dsz = 2u * a.dimg;  // image sizes in bytes
-    // term order: smallest contributions first
-    const int ta[6] = {2, 0, 1, 1, 0, 0};
-    const int tb[6] = {0, 2, 1, 0, 1, 0};
-    if (a.want_dD) {
-      // A = g image as [M=pixel, K=image] MN-major: SBO = Sg between 8-pixel groups, LBO = 128 between 8-image groups
-      // B = code image as [N=atom, K=image] MN-major: SBO = Sv between 8-atom groups, LBO = 128
-      const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Kp16);
-      const int ksteps = a.Bp16 / 16;
-#pragma unroll 1
-      for (int t = 0; t < 6; ++t) {
-        uint64_t ad = make_desc(gb + ta[t] * gsz, 128, a.Sg);
-        uint64_t bd = make_desc(vb + tb[t] * vsz, 128, a.Sv);
-        for (int ks = 0; ks < ksteps; ++ks, ad += 16, bd += 16) mma_bf16(acc, ad, bd, idesc_dD, (t | ks) ? 1u : 0u);
-      }
-    }
-    if (a.want_dv) {
-      // A = g image as [M=image, K=pixel] K-major: LBO = Sg between the two 8-pixel chunks, SBO = 128 (8-image groups)
-      // B = D image as [N=atom, K=pixel] MN-major: SBO = Sd between 8-atom groups, LBO = 128 between 8-pixel groups
-      const uint64_t astep = (uint64_t)((2 * a.Sg) >> 4);
-#pragma unroll 1
-      for (int t = 0; t < 6; ++t) {
-        uint64_t ad = make_desc(gb + ta[t] * gsz, a.Sg, 128);
-        uint64_t bd = make_desc(db + tb[t] * dsz, 128, a.Sd);
-        for (int ks = 0; ks < TC_TP / 16; ++ks, ad += astep, bd += 16)
-          mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
-      }
-    }
-    mma_commit(bar_mma);
-  };
-
-  auto epilogue = [&](int tile, int it) {
-    // Phase A: accumulator (row = pixel = TMEM lane, column = atom) -> shared memory in the tile's global layout
-    // [pixel][atom] (row stride Ks chosen so the 16-byte stores of a quarter-warp hit distinct banks).
-    const uint32_t acc = tmem_base + (uint32_t)((it & 1) * a.Kp16) + ((uint32_t)(quad * 32) << 16);
-    const int Ks = a.Ks;
-    float* row = dDs + (quad * 32 + lane) * Ks;
-    bar_sync(2, TC_THREADS);  // every worker is done reading the staging tile of the previous epilogue
-    for (int ch = cgrp; ch < nchunks; ch += ncg) {  // warp-uniform
-      const int k0 = ch * 8;
-      if (k0 >= K) break;
-      float r[8];
-      tmem_ld8(acc + (uint32_t)k0, r);
-      *reinterpret_cast<float4*>(row + k0) = make_float4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<float4*>(row + k0 + 4) = make_float4(r[4], r[5], r[6], r[7]);
-    }
-    tc_fence_before();
-    bar_sync(2, TC_THREADS);
-    // Phase B: one coalesced 128-bit pass over the tile's contiguous [rows x K] block of D / m / s (or dD)
-    const int rows = min(TC_TP, P - tile * TC_TP);
-    const int n4 = (rows * K) >> 2;
-    const size_t base = (size_t)tile * TC_TP * K;
-#pragma unroll 1
-    for (int half = 0; half < EP_HALVES; ++half) {
-      float4 Dv[EP_BATCH], Mv[EP_BATCH], Sv[EP_BATCH];
-      if (a.D2w != nullptr) {
-#pragma unroll
-        for (int i = 0; i < EP_BATCH; ++i) {
-          const int e4 = tid + (half * EP_BATCH + i) * TC_THREADS;
-          if (e4 < n4) {
-            Dv[i] = *reinterpret_cast<const float4*>(a.D2 + base + 4 * (size_t)e4);
-            Mv[i] = *reinterpret_cast<const float4*>(a.m + base + 4 * (size_t)e4);
-            Sv[i] = *reinterpret_cast<const float4*>(a.s + base + 4 * (size_t)e4);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < EP_BATCH; ++i) {
-        const int e4 = tid + (half * EP_BATCH + i) * TC_THREADS;
-        if (e4 < n4) {
-          const int e = 4 * e4;
-          int pp = a.kdiv_mul ? (int)__umulhi((unsigned)e, a.kdiv_mul) : e;      // e / K (exact for e < 2^20; 0: K == 1)
-          int kk = e - pp * K;
-          float gd[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            gd[j] = dDs[pp * Ks + kk];
-            if (++kk == K) { kk = 0; ++pp; }
-          }
-          if (a.D2w != nullptr) {
-            adamw_update(Dv[i].x, Mv[i].x, Sv[i].x, gd[0], a.hp);
-            adamw_update(Dv[i].y, Mv[i].y, Sv[i].y, gd[1], a.hp);
-            adamw_update(Dv[i].z, Mv[i].z, Sv[i].z, gd[2], a.hp);
-            adamw_update(Dv[i].w, Mv[i].w, Sv[i].w, gd[3], a.hp);
-            if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
-              Dv[i].x = clamp1(Dv[i].x); Dv[i].y = clamp1(Dv[i].y); Dv[i].z = clamp1(Dv[i].z); Dv[i].w = clamp1(Dv[i].w);
-            }
-            *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv[i];
-            *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mv[i];
-            *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sv[i];
-          } else {
-            *reinterpret_cast<float4*>(a.dD2 + base + 4 * (size_t)e4) = make_float4(gd[0], gd[1], gd[2], gd[3]);
-          }
-        }
-      }
-    }
-  };
-
-  if (warp == TC_WARPS) {
-    // ===== issuer warp: waits for "tile staged", issues the 6-term MMAs of both contractions, commits =====
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      bar_sync(1, TC_BLOCK);
+    const int ta[6] = {2, 0, 1, 1, 0, 0};  // term of the gradient operand; smallest contributions first
+    const int tb[6] = {0, 2, 1, 0, 1, 0};  // term of the code / dictionary operand
+    for (int it = 0; it < my_tiles; ++it) {
+      bar_sync(1, NT + 32);
       tc_fence_after();
-      if (lane == 0) issue(it);
+      if (lane == 0) {
+        if (a.want_dD) {
+          // A = code image [M = atom, K = image] MN-major: LBO = 128 (8-image groups), SBO = Sg (8-atom groups)
+          // B = gradient image [N = pixel, K = image] MN-major: LBO = 128, SBO = Sg (8-pixel groups)
+          const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
+          const int ksteps = a.Bp / 16;
+#pragma unroll 1
+          for (int t = 0; t < 6; ++t) {
+            uint64_t ad = make_desc(vb + tb[t] * vsz, 128, a.Sg);
+            uint64_t bd = make_desc(gb + ta[t] * gsz, 128, a.Sg);
+            for (int ks = 0; ks < ksteps; ++ks, ad += 16, bd += 16) mma_bf16(acc, ad, bd, idesc_dD, (t | ks) ? 1u : 0u);
+          }
+        }
+        if (a.want_dv) {
+          // A = gradient image [M = image, K = pixel] K-major: LBO = Sg (8-pixel chunks), SBO = 128 (8-image groups)
+          // B = D image [N = atom, K = pixel] MN-major: LBO = 128 (8-pixel groups), SBO = Sd (8-atom groups)
+          const uint64_t astep = (uint64_t)((2 * a.Sg) >> 4);
+#pragma unroll 1
+          for (int t = 0; t < 6; ++t) {
+            uint64_t ad = make_desc(gb + ta[t] * gsz, a.Sg, 128);
+            uint64_t bd = make_desc(db + tb[t] * dsz, 128, a.Sd);
+            for (int ks = 0; ks < TP / 16; ++ks, ad += astep, bd += 16)
+              mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
+          }
+        }
+        mma_commit(mma_done);
+      }
       __syncwarp();
     }
   } else {
-    int it = 0, prev_tile = -1;
-    int tile = blockIdx.x;
-    if (tile < ntiles) prefetch(tile);
-    for (; tile < ntiles; tile += gridDim.x, ++it) {
-      if (it > 0) {
-        mbar_wait(bar_mma, (it - 1) & 1);  // MMAs(it-1) retired: images free, dD accumulator (it-1) complete
-        tc_fence_after();
-      }
-      stage(tile);
-      fence_proxy_async();
-      tc_fence_before();
-      bar_arrive(1, TC_BLOCK);                            // hand the tile to the issuer warp, keep going
-      const int nxt = tile + gridDim.x;
-      if (nxt < ntiles) prefetch(nxt);                    // global loads in flight while the tensor core works
-      if (a.want_dD && prev_tile >= 0) epilogue(prev_tile, it - 1);
-      prev_tile = tile;
-    }
-    if (prev_tile >= 0) {
-      mbar_wait(bar_mma, (it - 1) & 1);
-      tc_fence_after();
-      if (a.want_dD) epilogue(prev_tile, it - 1);
-      if (a.want_dv) {
-        // dv accumulator: row = image (TMEM lane), column = atom -> this CTA's slab of the partial buffer
-        const int b = quad * 32 + lane;
-        float* dst = a.partial + (size_t)blockIdx.x * B * K + (size_t)b * K;
-        for (int ch = cgrp; ch < nchunks; ch += ncg) {
-          const int k0 = ch * 8;
-          if (k0 >= K) break;
-          float r[8];
-          tmem_ld8(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)k0, r);
-          if (b < B) {
+    // ===== workers =====
+    const int quad = warp & 3, cg = warp >> 2;
+    const int kv = K / a.vk;
+    const int nitems = TP * kv;
+
+    // fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q
+    int gsrc[GJ], gdst[GJ];  // gsrc: b * P + 4q as an element offset (-1: none); gdst: bf16 offset inside an image
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (k0 + j < K) dst[k0 + j] = r[j];
+    for (int j = 0; j < GJ; ++j) {
+      const int e = tid + j * NT;
+      const int b = e / Q4, q = e - b * Q4;
+      gsrc[j] = (b < B) ? 4 * q : -1;
+      gdst[j] = (q >> 1) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (q & 1) * 4;
+    }
+    float4 greg[GJ];
+    auto prefetch = [&](int it) {
+      const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+#pragma unroll
+      for (int j = 0; j < GJ; ++j) {
+        greg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int b = (tid + j * NT) / Q4;
+        if (gsrc[j] >= 0 && p0 + gsrc[j] < P) greg[j] = ld_stream4(a.g + (size_t)b * P + p0 + gsrc[j]);
+      }
+    };
+
+    auto epilogue = [&](int j) {
+      const int tile = blockIdx.x + j * gridDim.x;
+      const int p0 = tile * TP;
+      const int rows = min(TP, P - p0);
+      const int sj = j % NS;
+      bar_sync(2, NT);  // every worker is done with the dD staging tile of the previous epilogue
+      // phase A: accumulator (lane = atom, column = pixel) -> flat [pixel][atom] staging tile, divided by std
+      if (cg < NCG) {
+        float r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((j & 1) * TP + cg * 16), r);
+        const int k = (MA == 64) ? (lane < 16 ? quad * 16 + lane : K) : quad * 32 + lane;
+        if (k < K) {
+          float* col = dDs + (cg * 16) * K + k;
+          if (a.cc.use) {
+            const TileChan tc = tile_chan(a.cc, p0);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool hi_c = (cg * 16 + i) >= tc.bnd;
+              col[i * K] = div_by_const(r[i], hi_c ? tc.std1 : tc.std0, hi_c ? tc.rstd1 : tc.rstd0);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) col[i * K] = r[i];
           }
         }
         tc_fence_before();
       }
-    } else if (a.want_dv) {
-      for (int e = tid; e < B * K; e += TC_THREADS) a.partial[(size_t)blockIdx.x * B * K + e] = 0.0f;
+      bar_sync(2, NT);
+      // phase B: one flat 128-bit pass over the tile's contiguous [rows x K] block
+      const int n4 = (rows * K) >> 2;
+      const size_t base = (size_t)p0 * K;
+      if (fused) {
+        mbar_wait(full_raw + sj, (j / NS) & 1);
+        const float* rt = raw + sj * a.raw_floats;
+        for (int e4 = tid; e4 < n4; e4 += NT) {
+          float4 Dv = *reinterpret_cast<const float4*>(rt + 4 * e4);
+          float4 Mv = *reinterpret_cast<const float4*>(rt + tile_elems + 4 * e4);
+          float4 Sv = *reinterpret_cast<const float4*>(rt + 2 * tile_elems + 4 * e4);
+          const float4 gd = *reinterpret_cast<const float4*>(dDs + 4 * e4);
+          adamw_update_fast(Dv.x, Mv.x, Sv.x, gd.x, a.hp);
+          adamw_update_fast(Dv.y, Mv.y, Sv.y, gd.y, a.hp);
+          adamw_update_fast(Dv.z, Mv.z, Sv.z, gd.z, a.hp);
+          adamw_update_fast(Dv.w, Mv.w, Sv.w, gd.w, a.hp);
+          if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
+            Dv.x = clamp1(Dv.x); Dv.y = clamp1(Dv.y); Dv.z = clamp1(Dv.z); Dv.w = clamp1(Dv.w);
+          }
+          *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv;
+          *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mv;
+          *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sv;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_raw + sj);
+      } else {
+        for (int e4 = tid; e4 < n4; e4 += NT)
+          *reinterpret_cast<float4*>(a.dD2 + base + 4 * (size_t)e4) = *reinterpret_cast<const float4*>(dDs + 4 * e4);
+      }
+    };
+
+    if (my_tiles > 0) prefetch(0);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+      const int s = it % NS;
+      if (it > 0) {
+        mbar_wait(mma_done, (it - 1) & 1);  // MMAs(it-1) retired: images free, dD accumulator (it-1) complete
+        tc_fence_after();
+      }
+      // gradient tile: registers -> three bf16 images
+#pragma unroll
+      for (int j = 0; j < GJ; ++j) {
+        if (gsrc[j] >= 0) {
+          const float val[4] = {greg[j].x, greg[j].y, greg[j].z, greg[j].w};
+          uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_bf16x3(val[i], w0[i], w1[i], w2[i]);
+          bf16_t* dst = Gi + gdst[j];
+          *reinterpret_cast<uint2*>(dst) = make_uint2(pack_hi16(w0[0], w0[1]), pack_hi16(w0[2], w0[3]));
+          *reinterpret_cast<uint2*>(dst + a.gimg) = make_uint2(pack_hi16(w1[0], w1[1]), pack_hi16(w1[2], w1[3]));
+          *reinterpret_cast<uint2*>(dst + 2 * a.gimg) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
+        }
+      }
+      if (a.want_dv) {
+        // dictionary tile (pre-update values): TMA-landed raw rows -> three bf16 images of D / std
+        mbar_wait(full_raw + s, (it / NS) & 1);
+        const float* rt = raw + s * a.raw_floats;
+        TileChan tc;
+        tc.bnd = TP; tc.std0 = tc.std1 = tc.rstd0 = tc.rstd1 = 1.0f;
+        if (a.cc.use) tc = tile_chan(a.cc, p0);
+        if (a.vk == 4) {
+          for (int e = tid; e < nitems; e += NT) {
+            const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 4;
+            const float4 raw4 = *reinterpret_cast<const float4*>(rt + 4 * e);
+            float val[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+            if (a.cc.use) {
+              const float sd = p >= tc.bnd ? tc.std1 : tc.std0, rs = p >= tc.bnd ? tc.rstd1 : tc.rstd0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) val[i] = div_by_const(val[i], sd, rs);
+            }
+            uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_bf16x3(val[i], w0[i], w1[i], w2[i]);
+            bf16_t* dst = Di + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_hi16(w0[0], w0[1]), pack_hi16(w0[2], w0[3]));
+            *reinterpret_cast<uint2*>(dst + a.dimg) = make_uint2(pack_hi16(w1[0], w1[1]), pack_hi16(w1[2], w1[3]));
+            *reinterpret_cast<uint2*>(dst + 2 * a.dimg) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
+          }
+        } else if (a.vk == 2) {
+          for (int e = tid; e < nitems; e += NT) {
+            const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 2;
+            const float2 raw2 = *reinterpret_cast<const float2*>(rt + 2 * e);
+            float val[2] = {raw2.x, raw2.y};
+            if (a.cc.use) {
+              const float sd = p >= tc.bnd ? tc.std1 : tc.std0, rs = p >= tc.bnd ? tc.rstd1 : tc.rstd0;
+              val[0] = div_by_const(val[0], sd, rs);
+              val[1] = div_by_const(val[1], sd, rs);
+            }
+            uint32_t w0[2], w1[2], w2[2];
+            split_bf16x3(val[0], w0[0], w1[0], w2[0]);
+            split_bf16x3(val[1], w0[1], w1[1], w2[1]);
+            bf16_t* dst = Di + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
+            *reinterpret_cast<uint32_t*>(dst) = pack_hi16(w0[0], w0[1]);
+            *reinterpret_cast<uint32_t*>(dst + a.dimg) = pack_hi16(w1[0], w1[1]);
+            *reinterpret_cast<uint32_t*>(dst + 2 * a.dimg) = pack_hi16(w2[0], w2[1]);
+          }
+        } else {
+          for (int e = tid; e < nitems; e += NT) {
+            const int p = div_magic_dev(e, a.kdiv), k = e - p * kv;
+            float val = rt[e];
+            if (a.cc.use) val = div_by_const(val, p >= tc.bnd ? tc.std1 : tc.std0, p >= tc.bnd ? tc.rstd1 : tc.rstd0);
+            uint32_t w0, w1, w2;
+            split_bf16x3(val, w0, w1, w2);
+            bf16_t* dst = Di + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
+            dst[0] = (bf16_t)(w0 >> 16);
+            dst[a.dimg] = (bf16_t)(w1 >> 16);
+            dst[2 * a.dimg] = (bf16_t)(w2 >> 16);
+          }
+        }
+        if (!fused) {  // the raw stage held D only and is consumed
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_raw + s);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      bar_arrive(1, NT + 32);                       // hand the tile to the issuer warp, keep going
+      if (it + 1 < my_tiles) prefetch(it + 1);      // global loads in flight while the tensor core works
+      if (a.want_dD && it > 0) epilogue(it - 1);
+    }
+    if (my_tiles > 0) {
+      mbar_wait(mma_done, (my_tiles - 1) & 1);
+      tc_fence_after();
+      if (a.want_dD) epilogue(my_tiles - 1);
+      if (a.want_dv) {
+        // dv accumulator: lane = image, column = atom -> this CTA's slab of the partial buffer
+        const int b = quad * 32 + lane;
+        float* dst = a.partial + (size_t)blockIdx.x * B * K + (size_t)b * K;
+        for (int c0 = cg * 16; c0 < a.Kp; c0 += 64) {  // warp-uniform
+          float r[16];
+          tmem_ld16(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+          if (b < B) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < K) dst[c0 + i] = r[i];
+          }
+        }
+        tc_fence_before();
+      }
     }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// host side: tile-size selection by shared-memory fit, launches
+// ---------------------------------------------------------------------------------------------------------
 uint32_t pow2_cols(int need) {
   uint32_t c = 32;
   while ((int)c < need) c <<= 1;
   return c;
 }
 
+int vec_width(int K) { return (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1); }
+unsigned div_magic(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned long long)d - 1) / (unsigned long long)d); }
+
 struct SynthPlan {
-  int Np, Kp8, Sd, Sv, raw_floats, dimg_floats, vimg_floats;
+  int TP, Kp8, Sv, Sd, vimg, dimg, raw_floats;
   size_t smem;
   uint32_t tmem_cols;
   bool ok;
 };
 
-SynthPlan plan_synth(int B, int P, int K) {
+SynthPlan plan_synth(int B, int P, int K, int hw) {
   SynthPlan pl{};
   pl.ok = false;
-  if (B < 1 || B > 256 || K < 1 || P % 4 != 0) return pl;
-  pl.Np = rup(B, 16);
-  pl.Kp8 = rup(K, 8);
-  pl.Sd = img_stride(TC_TP);
-  pl.Sv = img_stride(pl.Np);
-  pl.raw_floats = rup(TC_TP * K, 32);
-  pl.dimg_floats = (pl.Kp8 / 4) * (pl.Sd / 4) + 64;
-  pl.vimg_floats = (pl.Kp8 / 4) * (pl.Sv / 4) + 64;
-  pl.smem = 128 + 2048 + sizeof(float) * ((size_t)pl.raw_floats + 2 * (size_t)pl.dimg_floats + 2 * (size_t)pl.vimg_floats +
-                                          (size_t)pl.Np * S_OS);
-  pl.tmem_cols = pow2_cols(2 * pl.Np);
-  pl.ok = pl.smem <= SMEM_LIMIT && pl.tmem_cols <= 512 && pl.Np <= 256;
+  if (B < 1 || B > 128 || K < 1 || K > 128 || P % 4 != 0 || hw % 4 != 0) return pl;
+  const int tps[4] = {64, 48, 32, 16};
+  for (int i = 0; i < 4; ++i) {
+    const int TP = tps[i];
+    if (hw < TP) continue;  // a tile may span at most two channels
+    pl.TP = TP;
+    pl.Kp8 = rup(K, 8);
+    pl.Sv = img_stride(rup(B, 8));
+    pl.Sd = img_stride(TP);
+    pl.vimg = (pl.Kp8 / 4) * (pl.Sv / 4) + 512;  // + 2 KB: the MMA reads M = 128 image rows
+    pl.dimg = (pl.Kp8 / 4) * (pl.Sd / 4);
+    pl.raw_floats = rup(TP * K, 32);
+    pl.smem = HDR_BYTES + sizeof(float) * ((size_t)NS * pl.raw_floats + 2 * (size_t)pl.vimg + 2 * (size_t)pl.dimg +
+                                           (size_t)NSX * B * (TP + 4));
+    pl.tmem_cols = pow2_cols(2 * TP);
+    if (pl.smem <= (size_t)SMEM_LIMIT) { pl.ok = true; return pl; }
+  }
   return pl;
 }
 
 struct GradPlan {
-  int Bp16, Kp16, Sg, Sd, Sv, gimg, dimg, vimg, Ks;
+  int TP, MA, Bp, Kp, Sg, Sd, vimg, dimg, gimg, raw_floats, nraw;
   size_t smem;
   uint32_t tmem_cols;
   bool ok;
 };
 
-GradPlan plan_grad(int B, int P, int K) {
+GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool fused) {
   GradPlan pl{};
   pl.ok = false;
-  if (B < 1 || B > 128 || K < 1 || P % 4 != 0) return pl;
-  pl.Bp16 = rup(B, 16);
-  pl.Kp16 = rup(K, 16);
-  pl.Sg = img_stride(pl.Bp16);
-  pl.Sd = img_stride(TC_TP);
-  pl.Sv = img_stride(pl.Bp16);
-  const int kg = (K + 7) / 8;                             // 8-atom groups actually written
-  pl.vimg = kg * (pl.Sv / 2) + 64;                        // bf16 elements per image
-  pl.dimg = kg * (pl.Sd / 2) + 64;
-  pl.gimg = (TC_TP / 8) * (pl.Sg / 2) + 1024 + 64;        // +2 KB: M = 128 image rows are read even when Bp16 < 128
-  pl.Ks = rup(K, 8) + 4;                                  // Ks % 8 == 4: conflict-free 16-byte row stores
-  pl.smem = 128 + 2 * 3 * ((size_t)pl.vimg + pl.dimg + pl.gimg) + sizeof(float) * TC_TP * (size_t)pl.Ks;
-  pl.tmem_cols = pow2_cols(3 * pl.Kp16);
-  // the MMAs read N = Kp16 atoms: the code / dictionary images over-read into the buffers that follow them
-  // (codes -> dictionary -> gradient images), which must be large enough to absorb it
-  const size_t over_v = (size_t)(pl.Kp16 / 8) * pl.Sv, over_d = (size_t)(pl.Kp16 / 8) * pl.Sd;
-  const size_t tail_after_v = 2 * (3 * (size_t)pl.dimg + 3 * (size_t)pl.gimg);
-  const size_t tail_after_d = 2 * 3 * (size_t)pl.gimg;
-  pl.ok = pl.smem <= SMEM_LIMIT && pl.tmem_cols <= 512 && over_v <= 2 * (size_t)pl.vimg + tail_after_v &&
-          over_d <= 2 * (size_t)pl.dimg + tail_after_d && B <= G_MAXQ * TC_WARPS && K <= 96 &&
-          TC_TP * K <= 4 * EP_BATCH * EP_HALVES * TC_THREADS;
+  if (B < 1 || B > 128 || K < 1 || K > 128 || P % 4 != 0 || hw % 4 != 0) return pl;
+  if (!want_dD && !want_dv) return pl;
+  const int tps[4] = {64, 48, 32, 16};
+  for (int i = 0; i < 4; ++i) {
+    const int TP = tps[i];
+    if (hw < TP) continue;
+    pl.TP = TP;
+    pl.MA = K <= 64 ? 64 : 128;
+    pl.Bp = rup(B, 16);
+    pl.Kp = rup(K, 16);
+    pl.Sg = img_stride(pl.Bp);
+    pl.Sd = img_stride(TP);
+    pl.vimg = want_dD ? (pl.MA / 8) * (pl.Sg / 2) : 0;
+    pl.dimg = want_dv ? (pl.Kp / 8) * (pl.Sd / 2) : 0;
+    pl.gimg = (TP / 8) * (pl.Sg / 2);
+    pl.nraw = fused ? 3 : (want_dv ? 1 : 0);
+    pl.raw_floats = pl.nraw * TP * K;
+    pl.smem = HDR_BYTES + 2 * (3 * ((size_t)pl.vimg + pl.dimg + pl.gimg) + 1024) +
+              sizeof(float) * ((want_dD ? (size_t)TP * K : 0) + (size_t)NS * pl.raw_floats);
+    pl.tmem_cols = pow2_cols(2 * TP + pl.Kp);
+    if (pl.smem <= (size_t)SMEM_LIMIT && pl.tmem_cols <= 512) { pl.ok = true; return pl; }
+  }
   return pl;
+}
+
+template <typename KernelT>
+int set_smem(KernelT kern, size_t smem, const char* what) {
+  return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), what);
 }
 
 }  // namespace
 
-bool tc_synth_ok(int B, int P, int K) { return plan_synth(B, P, K).ok; }
-bool tc_grad_ok(int B, int P, int K) { return plan_grad(B, P, K).ok; }
-bool tc_shape_ok(int B, int P, int K) { return tc_synth_ok(B, P, K) && tc_grad_ok(B, P, K); }
+bool tc_synth_ok(int B, int P, int K, int hw) { return plan_synth(B > 128 ? 128 : B, P, K, hw).ok; }
+bool tc_grad_ok(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool fused) {
+  return plan_grad(B, P, K, hw, want_dD, want_dv, fused).ok;
+}
 
 int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
                     int flags, cudaStream_t st) {
-  const SynthPlan pl = plan_synth(B, P, K);
-  if (!pl.ok) return set_error(-4, "adil_synth: shape B=%d P=%d K=%d does not qualify for the tcgen05 path", B, P, K);
-  SynthTcArgs a;
-  a.out = out; a.delta = delta_out; a.x = x; a.xidx = x_index; a.D2 = D2; a.v = v; a.vidx = v_index;
-  a.B = B; a.P = P; a.K = K; a.Np = pl.Np; a.Kp8 = pl.Kp8; a.Sd = pl.Sd; a.Sv = pl.Sv;
-  a.raw_floats = pl.raw_floats; a.dimg_floats = pl.dimg_floats; a.vimg_floats = pl.vimg_floats;
-  a.tmem_cols = pl.tmem_cols; a.eps = eps; a.flags = flags; a.cc = cc;
-  a.cc.use = (flags & ADIL_SYNTH_NORMALIZE) ? 1 : 0;
-  int rc = check_cuda(cudaFuncSetAttribute(synth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
-                      "cudaFuncSetAttribute(synth_tc)");
-  if (rc) return rc;
-  const int ntiles = (P + TC_TP - 1) / TC_TP;
-  int grid = sm_count();
-  if (grid > ntiles) grid = ntiles;
-  synth_tc_kernel<<<grid, TC_BLOCK, pl.smem, st>>>(a);
-  return check_cuda(cudaGetLastError(), "synth_tc_kernel launch");
+  const bool norm = (flags & ADIL_SYNTH_NORMALIZE) != 0;
+  const int hw = norm ? cc.hw : P;
+  // images beyond 128 go through further launches (M = 128 image lanes per pass)
+  for (int b0 = 0; b0 < B; b0 += 128) {
+    const int nb = B - b0 < 128 ? B - b0 : 128;
+    const SynthPlan pl = plan_synth(nb, P, K, hw);
+    if (!pl.ok) return set_error(-4, "adil_synth: shape B=%d P=%d K=%d does not qualify for the tcgen05 path", B, P, K);
+    SynthArgs a;
+    a.out = out ? out + (size_t)b0 * P : nullptr;
+    a.delta = delta_out ? delta_out + (size_t)b0 * P : nullptr;
+    a.x = x ? (x_index ? x : x + (size_t)b0 * P) : nullptr;
+    a.xidx = x_index ? x_index + b0 : nullptr;
+    a.D2 = D2;
+    a.v = v_index ? v : v + (size_t)b0 * K;
+    a.vidx = v_index ? v_index + b0 : nullptr;
+    a.B = nb; a.P = P; a.K = K; a.Kp8 = pl.Kp8; a.Sv = pl.Sv; a.Sd = pl.Sd; a.vimg = pl.vimg; a.dimg = pl.dimg;
+    a.raw_floats = pl.raw_floats; a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.tmem_cols = pl.tmem_cols;
+    a.eps = eps; a.flags = flags; a.cc = cc;
+    a.cc.use = norm ? 1 : 0;
+    const int ntiles = (P + pl.TP - 1) / pl.TP;
+    int grid = sm_count();
+    if (grid > ntiles) grid = ntiles;
+    int rc = 0;
+    switch (pl.TP) {
+      case 64:
+        rc = set_smem(synth_kernel<64>, pl.smem, "cudaFuncSetAttribute(synth_kernel)");
+        if (!rc) synth_kernel<64><<<grid, NTHREADS, pl.smem, st>>>(a);
+        break;
+      case 48:
+        rc = set_smem(synth_kernel<48>, pl.smem, "cudaFuncSetAttribute(synth_kernel)");
+        if (!rc) synth_kernel<48><<<grid, NTHREADS, pl.smem, st>>>(a);
+        break;
+      case 32:
+        rc = set_smem(synth_kernel<32>, pl.smem, "cudaFuncSetAttribute(synth_kernel)");
+        if (!rc) synth_kernel<32><<<grid, NTHREADS, pl.smem, st>>>(a);
+        break;
+      default:
+        rc = set_smem(synth_kernel<16>, pl.smem, "cudaFuncSetAttribute(synth_kernel)");
+        if (!rc) synth_kernel<16><<<grid, NTHREADS, pl.smem, st>>>(a);
+        break;
+    }
+    if (rc) return rc;
+    rc = check_cuda(cudaGetLastError(), "synth_kernel launch");
+    if (rc) return rc;
+  }
+  return 0;
 }
+
+namespace {
+template <int TP>
+int launch_grad_tp(const GradArgs& a, int MA, size_t smem, int grid, cudaStream_t st) {
+  int rc;
+  if (MA == 64) {
+    rc = set_smem(grad_kernel<TP, 64>, smem, "cudaFuncSetAttribute(grad_kernel)");
+    if (!rc) grad_kernel<TP, 64><<<grid, NTHREADS, smem, st>>>(a);
+  } else {
+    rc = set_smem(grad_kernel<TP, 128>, smem, "cudaFuncSetAttribute(grad_kernel)");
+    if (!rc) grad_kernel<TP, 128><<<grid, NTHREADS, smem, st>>>(a);
+  }
+  if (rc) return rc;
+  return check_cuda(cudaGetLastError(), "grad_kernel launch");
+}
+}  // namespace
 
 int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, cudaStream_t st) {
-  const GradPlan pl = plan_grad(B, P, K);
+  const bool want_dD = dD2 != nullptr || D2_rw != nullptr, want_dv = dvb != nullptr, fused = D2_rw != nullptr;
+  if (!want_dD && !want_dv) return 0;
+  const int hw = cc.use ? cc.hw : P;
+  const GradPlan pl = plan_grad(B, P, K, hw, want_dD, want_dv, fused);
   if (!pl.ok) return set_error(-4, "adil_grad: shape B=%d P=%d K=%d does not qualify for the tcgen05 path", B, P, K);
-  GradTcArgs a;
+  GradArgs a;
   a.dD2 = dD2; a.D2w = D2_rw; a.m = m; a.s = s; a.partial = scratch; a.g = g; a.D2 = D2; a.v = v; a.vidx = v_index;
-  a.B = B; a.P = P; a.K = K; a.Bp16 = pl.Bp16; a.Kp16 = pl.Kp16; a.Sg = pl.Sg; a.Sd = pl.Sd; a.Sv = pl.Sv;
-  a.gimg = pl.gimg; a.dimg = pl.dimg; a.vimg = pl.vimg; a.Ks = pl.Ks;
-  a.kdiv_mul = K == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned long long)K - 1) / (unsigned long long)K);
-  a.tmem_cols = pl.tmem_cols;
-  a.want_dD = (dD2 != nullptr || D2_rw != nullptr) ? 1 : 0;
-  a.want_dv = (dvb != nullptr) ? 1 : 0;
-  a.atoms_mode = atoms_mode; a.cc = cc;
+  a.B = B; a.P = P; a.K = K; a.Bp = pl.Bp; a.Kp = pl.Kp; a.Sg = pl.Sg; a.Sd = pl.Sd;
+  a.vimg = pl.vimg; a.dimg = pl.dimg; a.gimg = pl.gimg; a.raw_floats = pl.raw_floats; a.nraw = pl.nraw;
+  a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.tmem_cols = pl.tmem_cols;
+  a.want_dD = want_dD ? 1 : 0; a.want_dv = want_dv ? 1 : 0; a.atoms_mode = atoms_mode; a.cc = cc;
   if (hp) a.hp = *hp;
-  if (!a.want_dD && !a.want_dv) return 0;
-  const int ntiles = (P + TC_TP - 1) / TC_TP;
+  const int ntiles = (P + pl.TP - 1) / pl.TP;
   int grid = sm_count();
   if (grid > ntiles) grid = ntiles;
   if (grid > kMaxGradCtas) grid = kMaxGradCtas;
-  if (a.want_dv) {
+  if (want_dv) {
     const size_t need = (size_t)grid * B * K * sizeof(float);
     if (scratch == nullptr || scratch_bytes < need)
       return set_error(-2, "adil_grad: scratch too small (%zu < %zu bytes)", scratch_bytes, need);
   }
-  auto kern = K <= 32 ? grad_tc_kernel<1> : (K <= 64 ? grad_tc_kernel<2> : grad_tc_kernel<3>);
-  int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
-                      "cudaFuncSetAttribute(grad_tc)");
+  int rc;
+  switch (pl.TP) {
+    case 64: rc = launch_grad_tp<64>(a, pl.MA, pl.smem, grid, st); break;
+    case 48: rc = launch_grad_tp<48>(a, pl.MA, pl.smem, grid, st); break;
+    case 32: rc = launch_grad_tp<32>(a, pl.MA, pl.smem, grid, st); break;
+    default: rc = launch_grad_tp<16>(a, pl.MA, pl.smem, grid, st); break;
+  }
   if (rc) return rc;
-  kern<<<grid, TC_BLOCK, pl.smem, st>>>(a);
-  rc = check_cuda(cudaGetLastError(), "grad_tc_kernel launch");
-  if (rc) return rc;
-  if (a.want_dv) return launch_reduce_partials(dvb, scratch, B * K, grid, st);
+  if (want_dv) return launch_reduce_partials(dvb, scratch, B * K, grid, st);
   return 0;
 }
 

@@ -113,7 +113,9 @@ def test_fused_grad_dict_step(ops, B, hw, K, impl):
             dD_gpu, dv_gpu = ops.grad(dev(g), Dd.clone(), dev(v), dev(idx), STD)
             dvb = ops.grad_dict_step(Dd, md, sd, dev(g), dev(v), dev(idx), ops.adamw_params(t, 0.01), STD,
                                      ops.ATOMS_CLAMP1)
-            assert torch.equal(dvb, dv_gpu)                      # dv uses the pre-update dictionary
+            # dv uses the pre-update dictionary (the post-update one differs by lr = 1e-2); the fused and unfused
+            # launches may tile the pixels differently, so the sums agree to rounding, not bit for bit
+            assert (dvb - dv_gpu).abs().max() <= 2e-6 * dv_gpu.abs().max()
             p, m, s = (D2 * 1.2).clone(), m0.clone(), s0.clone()
             O.adamw_step_(p, dD_gpu.cpu(), m, s, t, 0.01)
             p = p.clamp(-1, 1)
