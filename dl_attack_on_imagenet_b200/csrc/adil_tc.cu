@@ -52,6 +52,15 @@ __host__ __device__ inline int rup(int a, int b) { return (a + b - 1) / b * b; }
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  tcgen05.mma / cp.async.bulk are warp-uniform instructions (operands in uniform
+// registers): under `elect.sync` ptxas issues them once, under a `lane == 0` test it wraps each one in a per-thread
+// "waterfall" loop that costs ~100 cycles per instruction (measured: scripts/umma_speed*.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p mov.u32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -299,12 +308,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
       const int p0 = tile * TP;
       const int rows = min(TP, P - p0);
       const int s = it % NS;
-      if (lane == 0) {
-        if (it >= NS) mbar_wait(empty_raw + s, ((it / NS) - 1) & 1);
+      if (it >= NS) mbar_wait(empty_raw + s, ((it / NS) - 1) & 1);
+      if (elect_one()) {
         const uint32_t bytes = (uint32_t)(rows * K * 4);
         mbar_expect_tx(full_raw + s, bytes);
         bulk_g2s(raw + s * a.raw_floats, a.D2 + (size_t)p0 * K, bytes, full_raw + s);
       }
+      __syncwarp();
       if (need_x) {
         const int sx = it % NSX;
         if (it >= NSX) mbar_wait(empty_x + sx, ((it / NSX) - 1) & 1);
@@ -328,12 +338,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
     for (int it = 0; it < my_tiles; ++it) {
       bar_sync(1, NT + 32);  // workers staged tile `it`
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
-        for (int pass = 0; pass < 3; ++pass) {  // lo*hi, hi*lo, hi*hi
-          uint64_t ad = (pass == 0) ? vlo : vhi;
-          uint64_t bd = (pass == 1) ? dlo : dhi;
-          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, (pass | ks) ? 1u : 0u);
+        {  // lo*hi
+          uint64_t ad = vlo, bd = dhi;
+          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, ks ? 1u : 0u);
+        }
+        {  // hi*lo
+          uint64_t ad = vhi, bd = dlo;
+          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, 1u);
+        }
+        {  // hi*hi
+          uint64_t ad = vhi, bd = dhi;
+          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, 1u);
         }
         mma_commit(mma_done);
       }
@@ -561,22 +578,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
 
   if (warp == WARP_LOAD) {
     // ===== loader: contiguous D (, m, s) tiles by TMA bulk copy =====
-    if (lane == 0 && a.nraw > 0) {
+    if (a.nraw > 0) {
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int p0 = tile * TP;
         const int rows = min(TP, P - p0);
         const int s = it % NS;
         if (it >= NS) mbar_wait(empty_raw + s, ((it / NS) - 1) & 1);
-        const uint32_t bytes = (uint32_t)(rows * K * 4);
-        float* dst = raw + s * a.raw_floats;
-        const size_t off = (size_t)p0 * K;
-        mbar_expect_tx(full_raw + s, bytes * (uint32_t)a.nraw);
-        bulk_g2s(dst, a.D2 + off, bytes, full_raw + s);
-        if (a.nraw == 3) {
-          bulk_g2s(dst + tile_elems, a.m + off, bytes, full_raw + s);
-          bulk_g2s(dst + 2 * tile_elems, a.s + off, bytes, full_raw + s);
+        if (elect_one()) {
+          const uint32_t bytes = (uint32_t)(rows * K * 4);
+          float* dst = raw + s * a.raw_floats;
+          const size_t off = (size_t)p0 * K;
+          mbar_expect_tx(full_raw + s, bytes * (uint32_t)a.nraw);
+          bulk_g2s(dst, a.D2 + off, bytes, full_raw + s);
+          if (a.nraw == 3) {
+            bulk_g2s(dst + tile_elems, a.m + off, bytes, full_raw + s);
+            bulk_g2s(dst + 2 * tile_elems, a.s + off, bytes, full_raw + s);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == WARP_MMA) {
@@ -585,32 +605,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     const uint32_t idesc_dv = make_idesc_bf16(128, a.Kp, false, true);
     const uint32_t gb = smem_u32(Gi), vb = smem_u32(Vi), db = smem_u32(Di);
     const uint32_t gsz = 2u * a.gimg, vsz = 2u * a.vimg, dsz = 2u * a.dimg;  // image sizes in bytes
-    const int ta[6] = {2, 0, 1, 1, 0, 0};  // term of the gradient operand; smallest contributions first
-    const int tb[6] = {0, 2, 1, 0, 1, 0};  // term of the code / dictionary operand
+    // term pairs (gradient term, code / dictionary term), smallest contributions first: (2,0)(0,2)(1,1)(1,0)(0,1)(0,0)
+    // A = code image [M = atom, K = image] MN-major: LBO = 128 (8-image groups), SBO = Sg (8-atom groups)
+    // B = gradient image [N = pixel, K = image] MN-major: LBO = 128, SBO = Sg (8-pixel groups)
+    const uint64_t dD_a0 = make_desc(vb, 128, a.Sg), dD_b0 = make_desc(gb, 128, a.Sg);
+    // A = gradient image [M = image, K = pixel] K-major: LBO = Sg (8-pixel chunks), SBO = 128 (8-image groups)
+    // B = D image [N = atom, K = pixel] MN-major: LBO = 128 (8-pixel groups), SBO = Sd (8-atom groups)
+    const uint64_t dv_a0 = make_desc(gb, a.Sg, 128), dv_b0 = make_desc(db, 128, a.Sd);
+    const uint64_t gs16 = (uint64_t)(gsz >> 4), vs16 = (uint64_t)(vsz >> 4), ds16 = (uint64_t)(dsz >> 4);
+    const uint64_t astep = (uint64_t)((2 * a.Sg) >> 4);
+    const int ksteps_dD = a.Bp / 16;
     for (int it = 0; it < my_tiles; ++it) {
       bar_sync(1, NT + 32);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         if (a.want_dD) {
-          // A = code image [M = atom, K = image] MN-major: LBO = 128 (8-image groups), SBO = Sg (8-atom groups)
-          // B = gradient image [N = pixel, K = image] MN-major: LBO = 128, SBO = Sg (8-pixel groups)
           const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
-          const int ksteps = a.Bp / 16;
-#pragma unroll 1
+#pragma unroll
           for (int t = 0; t < 6; ++t) {
-            uint64_t ad = make_desc(vb + tb[t] * vsz, 128, a.Sg);
-            uint64_t bd = make_desc(gb + ta[t] * gsz, 128, a.Sg);
-            for (int ks = 0; ks < ksteps; ++ks, ad += 16, bd += 16) mma_bf16(acc, ad, bd, idesc_dD, (t | ks) ? 1u : 0u);
+            constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, tv[6] = {0, 2, 1, 0, 1, 0};
+            uint64_t ad = dD_a0 + (uint64_t)tv[t] * vs16, bd = dD_b0 + (uint64_t)tg[t] * gs16;
+#pragma unroll 1
+            for (int ks = 0; ks < ksteps_dD; ++ks, ad += 16, bd += 16) mma_bf16(acc, ad, bd, idesc_dD, (t | ks) ? 1u : 0u);
           }
         }
         if (a.want_dv) {
-          // A = gradient image [M = image, K = pixel] K-major: LBO = Sg (8-pixel chunks), SBO = 128 (8-image groups)
-          // B = D image [N = atom, K = pixel] MN-major: LBO = 128 (8-pixel groups), SBO = Sd (8-atom groups)
-          const uint64_t astep = (uint64_t)((2 * a.Sg) >> 4);
-#pragma unroll 1
+#pragma unroll
           for (int t = 0; t < 6; ++t) {
-            uint64_t ad = make_desc(gb + ta[t] * gsz, a.Sg, 128);
-            uint64_t bd = make_desc(db + tb[t] * dsz, 128, a.Sd);
+            constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, td[6] = {0, 2, 1, 0, 1, 0};
+            uint64_t ad = dv_a0 + (uint64_t)tg[t] * gs16, bd = dv_b0 + (uint64_t)td[t] * ds16;
+#pragma unroll
             for (int ks = 0; ks < TP / 16; ++ks, ad += astep, bd += 16)
               mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
           }
