@@ -75,10 +75,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint (ns): idle warps must not eat issue slots
       : "memory");
   return ok != 0;
 }
@@ -207,7 +207,8 @@ struct TileChan {
 };
 __device__ __forceinline__ TileChan tile_chan(const ChannelConsts& cc, int p0) {
   TileChan t;
-  const int c0 = p0 / cc.hw;
+  int c0 = 0;
+  for (int c = 1; c < cc.C; ++c) c0 += (p0 >= c * cc.hw) ? 1 : 0;
   const int c1 = min(c0 + 1, kMaxC - 1);
   t.bnd = (c0 + 1) * cc.hw - p0;
   t.mean0 = cc.mean[c0]; t.std0 = cc.stdv[c0]; t.rstd0 = cc.rstd[c0];
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
-    for (int i = 0; i < NSX; ++i) { mbar_init(full_x + i, 32); mbar_init(empty_x + i, NW); }
+    for (int i = 0; i < NSX; ++i) { mbar_init(full_x + i, NT); mbar_init(empty_x + i, NW); }
     mbar_init(mma_done, 1);
     fence_mbar_init();
   }
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == WARP_LOAD) {
-    // ===== loader: raw dictionary tiles by TMA bulk copy, image rows by cp.async, up to NS / NSX tiles ahead =====
+    // ===== loader: raw dictionary tiles by TMA bulk copy, up to NS tiles ahead =====
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int p0 = tile * TP;
@@ -313,18 +314,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
         const uint32_t bytes = (uint32_t)(rows * K * 4);
         mbar_expect_tx(full_raw + s, bytes);
         bulk_g2s(raw + s * a.raw_floats, a.D2 + (size_t)p0 * K, bytes, full_raw + s);
-      }
-      __syncwarp();
-      if (need_x) {
-        const int sx = it % NSX;
-        if (it >= NSX) mbar_wait(empty_x + sx, ((it / NSX) - 1) & 1);
-        float* dst = xs + sx * xstage;
-        for (int e = lane; e < B * Q4; e += 32) {
-          const int b = e / Q4, c4 = e - b * Q4;
-          const int p = p0 + 4 * c4;
-          if (p < P) cp_async16(dst + b * XP + 4 * c4, a.x + xoff_s[b] + p);
-        }
-        cp_async_arrive_noinc(full_x + sx);
       }
       __syncwarp();
     }
@@ -361,6 +350,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
     const int quad = warp & 3, cg = warp >> 2;
     const int nitems = TP * (K / a.vk);  // vector items of the raw tile
     const int kv = K / a.vk;
+
+    // fixed per-thread share of an image-row tile: float4 e = tid + i*NT -> image b = e / Q4, 4-pixel column c4
+    constexpr int XJ = (128 * Q4 + NT - 1) / NT;
+    int xdst[XJ];         // float offset inside a stage, -1: none
+    long long odst[XJ];   // element offset of out[b, 4*c4]
+#pragma unroll
+    for (int i = 0; i < XJ; ++i) {
+      const int e = tid + i * NT;
+      const int b = e / Q4, c4 = e - b * Q4;
+      xdst[i] = (b < B) ? b * XP + 4 * c4 : -1;
+      odst[i] = (long long)b * P + 4 * c4;
+    }
+    // image rows of tile j -> stage j % NSX by cp.async; every worker arrives on full_x once its copies have landed
+    auto load_x = [&](int j) {
+      const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+      float* dst = xs + (j % NSX) * xstage;
+#pragma unroll
+      for (int i = 0; i < XJ; ++i) {
+        const int b = (tid + i * NT) / Q4, col = ((tid + i * NT) % Q4) * 4;
+        if (xdst[i] >= 0 && p0 + col < P) cp_async16(dst + xdst[i], a.x + xoff_s[b] + p0 + col);
+      }
+      cp_async_arrive_noinc(full_x + (j % NSX));
+    };
+    if (need_x)
+      for (int j = 0; j < NSX && j < my_tiles; ++j) load_x(j);
 
     auto epilogue = [&](int j) {
       const int tile = blockIdx.x + j * gridDim.x;
@@ -413,17 +427,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
         tc_fence_before();
       }
       bar_sync(2, NT);
+      // every worker has finished the stores of tile j-1: its stage can take the rows of tile j-1+NSX
+      if (need_x && j >= 1 && j - 1 + NSX < my_tiles) load_x(j - 1 + NSX);
       // phase 2: coalesced 128-bit stores of the finished [B][TP] tile
       float* dst = a.out != nullptr ? a.out : a.delta;
-      for (int e = tid; e < B * Q4; e += NT) {
-        const int b = e / Q4, c4 = e - b * Q4;
-        const int p = p0 + 4 * c4;
-        if (p < P) st_stream4(dst + (size_t)b * P + p, *reinterpret_cast<const float4*>(xt + b * XP + 4 * c4));
-      }
-      if (need_x) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_x + sx);
-      }
+#pragma unroll
+      for (int i = 0; i < XJ; ++i)
+        if (xdst[i] >= 0 && p0 + ((tid + i * NT) % Q4) * 4 < P)
+          st_stream4(dst + odst[i] + p0, *reinterpret_cast<const float4*>(xt + xdst[i]));
     };
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -650,12 +661,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     const int nitems = TP * kv;
 
     // fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q
-    int gsrc[GJ], gdst[GJ];  // gsrc: b * P + 4q as an element offset (-1: none); gdst: bf16 offset inside an image
+    int gsrc[GJ], gdst[GJ];  // gsrc: 4q, the pixel column (-1: none); gdst: bf16 offset inside an image
+    const float* grow[GJ];   // &g[b, 4q]
 #pragma unroll
     for (int j = 0; j < GJ; ++j) {
       const int e = tid + j * NT;
       const int b = e / Q4, q = e - b * Q4;
       gsrc[j] = (b < B) ? 4 * q : -1;
+      grow[j] = a.g + (size_t)min(b, B - 1) * P + 4 * q;
       gdst[j] = (q >> 1) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (q & 1) * 4;
     }
     float4 greg[GJ];
@@ -664,8 +677,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
 #pragma unroll
       for (int j = 0; j < GJ; ++j) {
         greg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int b = (tid + j * NT) / Q4;
-        if (gsrc[j] >= 0 && p0 + gsrc[j] < P) greg[j] = ld_stream4(a.g + (size_t)b * P + p0 + gsrc[j]);
+        if (gsrc[j] >= 0 && p0 + gsrc[j] < P) greg[j] = ld_stream4(grow[j] + p0);
       }
     };
 
@@ -684,10 +696,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
           float* col = dDs + (cg * 16) * K + k;
           if (a.cc.use) {
             const TileChan tc = tile_chan(a.cc, p0);
+            if (tc.bnd >= TP) {  // the whole tile lies in one channel (warp-uniform)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const bool hi_c = (cg * 16 + i) >= tc.bnd;
-              col[i * K] = div_by_const(r[i], hi_c ? tc.std1 : tc.std0, hi_c ? tc.rstd1 : tc.rstd0);
+              for (int i = 0; i < 16; ++i) col[i * K] = div_by_const(r[i], tc.std0, tc.rstd0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool hi_c = (cg * 16 + i) >= tc.bnd;
+                col[i * K] = div_by_const(r[i], hi_c ? tc.std1 : tc.std0, hi_c ? tc.rstd1 : tc.rstd0);
+              }
             }
           } else {
 #pragma unroll
