@@ -200,20 +200,31 @@ __device__ __forceinline__ int div_magic_dev(int e, unsigned mul) { return mul ?
 
 __host__ __device__ inline int img_stride(int R) { return 128 * ((R + 7) / 8) + 16; }  // +16 de-phases the banks
 
-// channel constants of a tile that spans at most two channels: pixels [0, bnd) of the tile are channel c0
+// Channel constants of a tile that spans at most two channels: pixels [0, bnd) of the tile are channel c0.  Tiles are
+// visited in increasing order, so the constants are cached in registers and reloaded only when a tile leaves the
+// cached channel (twice per launch for 3 channels) -- a per-tile integer division or a scan over the channels costs
+// more than 10 % of the kernel's instructions.
 struct TileChan {
+  int lo, hi;  // absolute pixel range [lo, hi) of channel c0; tile-local boundary bnd = hi - p0
   int bnd;
   float mean0, std0, rstd0, mean1, std1, rstd1;
 };
-__device__ __forceinline__ TileChan tile_chan(const ChannelConsts& cc, int p0) {
-  TileChan t;
-  int c0 = 0;
-  for (int c = 1; c < cc.C; ++c) c0 += (p0 >= c * cc.hw) ? 1 : 0;
-  const int c1 = min(c0 + 1, kMaxC - 1);
-  t.bnd = (c0 + 1) * cc.hw - p0;
-  t.mean0 = cc.mean[c0]; t.std0 = cc.stdv[c0]; t.rstd0 = cc.rstd[c0];
-  t.mean1 = cc.mean[c1]; t.std1 = cc.stdv[c1]; t.rstd1 = cc.rstd[c1];
-  return t;
+__device__ __forceinline__ void tile_chan_init(TileChan& t) {
+  t.lo = 0; t.hi = 0; t.bnd = 0;
+  t.mean0 = t.mean1 = 0.0f;
+  t.std0 = t.std1 = t.rstd0 = t.rstd1 = 1.0f;
+}
+__device__ __forceinline__ void tile_chan_update(TileChan& t, const ChannelConsts& cc, int p0) {
+  if (p0 < t.lo || p0 >= t.hi) {
+    int c0 = 0;
+    for (int c = 1; c < cc.C; ++c) c0 += (p0 >= c * cc.hw) ? 1 : 0;
+    const int c1 = min(c0 + 1, kMaxC - 1);
+    t.lo = c0 * cc.hw;
+    t.hi = t.lo + cc.hw;
+    t.mean0 = cc.mean[c0]; t.std0 = cc.stdv[c0]; t.rstd0 = cc.rstd[c0];
+    t.mean1 = cc.mean[c1]; t.std1 = cc.stdv[c1]; t.rstd1 = cc.rstd[c1];
+  }
+  t.bnd = t.hi - p0;
 }
 
 // =========================================================================================================
@@ -324,10 +335,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
     const uint64_t dhi = make_desc(smem_u32(Dhi), a.Sd, 128), dlo = make_desc(smem_u32(Dlo), a.Sd, 128);
     const uint64_t astep = (uint64_t)((2 * a.Sv) >> 4), bstep = (uint64_t)((2 * a.Sd) >> 4);
     const int ksteps = a.Kp8 / 8;
+    const bool leader = elect_one();
     for (int it = 0; it < my_tiles; ++it) {
       bar_sync(1, NT + 32);  // workers staged tile `it`
       tc_fence_after();
-      if (elect_one()) {
+      if (leader) {
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
         {  // lo*hi
           uint64_t ad = vlo, bd = dhi;
@@ -351,6 +363,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
     const int nitems = TP * (K / a.vk);  // vector items of the raw tile
     const int kv = K / a.vk;
 
+    TileChan tc;
+    tile_chan_init(tc);
     // fixed per-thread share of an image-row tile: float4 e = tid + i*NT -> image b = e / Q4, 4-pixel column c4
     constexpr int XJ = (128 * Q4 + NT - 1) / NT;
     int xdst[XJ];         // float offset inside a stage, -1: none
@@ -388,8 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
         float r[16];
         tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((j & 1) * TP + cg * 16), r);
         if (b < B) {
-          TileChan tc;
-          if (a.cc.use) tc = tile_chan(a.cc, p0);
+          if (a.cc.use) tile_chan_update(tc, a.cc, p0);
           float* xrow = xt + b * XP + cg * 16;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -626,10 +639,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     const uint64_t gs16 = (uint64_t)(gsz >> 4), vs16 = (uint64_t)(vsz >> 4), ds16 = (uint64_t)(dsz >> 4);
     const uint64_t astep = (uint64_t)((2 * a.Sg) >> 4);
     const int ksteps_dD = a.Bp / 16;
+    const bool leader = elect_one();
     for (int it = 0; it < my_tiles; ++it) {
       bar_sync(1, NT + 32);
       tc_fence_after();
-      if (elect_one()) {
+      if (leader) {
         if (a.want_dD) {
           const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
 #pragma unroll
@@ -660,6 +674,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     const int kv = K / a.vk;
     const int nitems = TP * kv;
 
+    TileChan tc;
+    tile_chan_init(tc);
     // fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q
     int gsrc[GJ], gdst[GJ];  // gsrc: 4q, the pixel column (-1: none); gdst: bf16 offset inside an image
     const float* grow[GJ];   // &g[b, 4q]
@@ -695,7 +711,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         if (k < K) {
           float* col = dDs + (cg * 16) * K + k;
           if (a.cc.use) {
-            const TileChan tc = tile_chan(a.cc, p0);
+            tile_chan_update(tc, a.cc, p0);
             if (tc.bnd >= TP) {  // the whole tile lies in one channel (warp-uniform)
 #pragma unroll
               for (int i = 0; i < 16; ++i) col[i * K] = div_by_const(r[i], tc.std0, tc.rstd0);
@@ -770,9 +786,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         // dictionary tile (pre-update values): TMA-landed raw rows -> three bf16 images of D / std
         mbar_wait(full_raw + s, (it / NS) & 1);
         const float* rt = raw + s * a.raw_floats;
-        TileChan tc;
-        tc.bnd = TP; tc.std0 = tc.std1 = tc.rstd0 = tc.rstd1 = 1.0f;
-        if (a.cc.use) tc = tile_chan(a.cc, p0);
+        if (a.cc.use) tile_chan_update(tc, a.cc, p0);
         if (a.vk == 4) {
           for (int e = tid; e < nitems; e += NT) {
             const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 4;
