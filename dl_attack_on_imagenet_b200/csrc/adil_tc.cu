@@ -208,10 +208,11 @@ struct TileChan {
   int lo, hi;  // absolute pixel range [lo, hi) of channel c0; tile-local boundary bnd = hi - p0
   int bnd;
   float mean0, std0, rstd0, mean1, std1, rstd1;
+  float nmr0, nmr1;  // -mean * (1/std): Normalize as one FFMA, x * rstd + nmr
 };
 __device__ __forceinline__ void tile_chan_init(TileChan& t) {
   t.lo = 0; t.hi = 0; t.bnd = 0;
-  t.mean0 = t.mean1 = 0.0f;
+  t.mean0 = t.mean1 = t.nmr0 = t.nmr1 = 0.0f;
   t.std0 = t.std1 = t.rstd0 = t.rstd1 = 1.0f;
 }
 __device__ __forceinline__ void tile_chan_update(TileChan& t, const ChannelConsts& cc, int p0) {
@@ -223,6 +224,8 @@ __device__ __forceinline__ void tile_chan_update(TileChan& t, const ChannelConst
     t.hi = t.lo + cc.hw;
     t.mean0 = cc.mean[c0]; t.std0 = cc.stdv[c0]; t.rstd0 = cc.rstd[c0];
     t.mean1 = cc.mean[c1]; t.std1 = cc.stdv[c1]; t.rstd1 = cc.rstd[c1];
+    t.nmr0 = -t.mean0 * t.rstd0;
+    t.nmr1 = -t.mean1 * t.rstd1;
   }
   t.bnd = t.hi - p0;
 }
@@ -256,7 +259,8 @@ struct SynthArgs {
   ChannelConsts cc;
 };
 
-template <int TP>
+// TRAIN = the learning-loop configuration (x and out given, no delta output, no clamps): those branches vanish.
+template <int TP, bool TRAIN>
 __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
   constexpr int XP = TP + 4;       // floats per staged image row (pitch 16 bytes off a multiple of 128)
   constexpr int Q4 = TP / 4;       // float4 per image row
@@ -297,21 +301,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
     for (int e = tid; e < nz; e += NTHREADS) raw[e] = 0.0f;
   }
   for (int b = tid; b < B; b += NTHREADS) xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
-  __syncthreads();
-  for (int e = tid; e < B * K; e += NTHREADS) {
-    const int b = e / K, k = e - b * K;
-    const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
-    float hi, lo;
-    split_tf32(a.v[row * K + k], hi, lo);
-    const int o = (k >> 2) * (a.Sv >> 2) + (b >> 3) * 32 + (b & 7) * 4 + (k & 3);
-    Vhi[o] = hi;
-    Vlo[o] = lo;
-  }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // From here the roles run free: the loader starts fetching at once, the workers first put their image rows in
+  // flight and then build the code images (the issuer cannot start before every worker has arrived on barrier 1).
 
   if (warp == WARP_LOAD) {
     // ===== loader: raw dictionary tiles by TMA bulk copy, up to NS tiles ahead =====
@@ -389,6 +384,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
     };
     if (need_x)
       for (int j = 0; j < NSX && j < my_tiles; ++j) load_x(j);
+    // code images (hi / lo), once per CTA
+    for (int e = tid; e < B * K; e += NT) {
+      const int b = e / K, k = e - b * K;
+      const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
+      float hi, lo;
+      split_tf32(a.v[row * K + k], hi, lo);
+      const int o = (k >> 2) * (a.Sv >> 2) + (b >> 3) * 32 + (b & 7) * 4 + (k & 3);
+      Vhi[o] = hi;
+      Vlo[o] = lo;
+    }
 
     auto epilogue = [&](int j) {
       const int tile = blockIdx.x + j * gridDim.x;
@@ -407,31 +412,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float d[4] = {r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]};
-            if (a.flags & ADIL_SYNTH_CLAMP_DELTA) {
+            if (!TRAIN && (a.flags & ADIL_SYNTH_CLAMP_DELTA)) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) d[i] = fminf(fmaxf(d[i], -a.eps), a.eps);
             }
             float o[4] = {d[0], d[1], d[2], d[3]};
-            if (a.out != nullptr) {
-              if (a.delta != nullptr) {  // secondary output: written straight from the accumulator row
+            if (TRAIN || a.out != nullptr) {
+              if (!TRAIN && a.delta != nullptr) {  // secondary output: written straight from the accumulator row
                 const int p = p0 + cg * 16 + 4 * c;
                 if (p < P) st_stream4(a.delta + (size_t)b * P + p, make_float4(d[0], d[1], d[2], d[3]));
               }
-              if (need_x) {
+              if (TRAIN || need_x) {
                 const float4 xv = *reinterpret_cast<const float4*>(xrow + 4 * c);
                 o[0] = __fadd_rn(xv.x, d[0]); o[1] = __fadd_rn(xv.y, d[1]);
                 o[2] = __fadd_rn(xv.z, d[2]); o[3] = __fadd_rn(xv.w, d[3]);
               }
-              if (a.flags & ADIL_SYNTH_CLAMP01) {
+              if (!TRAIN && (a.flags & ADIL_SYNTH_CLAMP01)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = fminf(fmaxf(o[i], 0.0f), 1.0f);
               }
               if (a.cc.use) {
+                // Normalize (demo_dL_attack.py:22-25) as one FFMA: (o - mean) / std == o * rstd - mean * rstd up to
+                // 1.5 ulp of the result (|result| < 3: < 4e-7)
                 const bool hi_c = (cg * 16 + 4 * c) >= tc.bnd;
-                const float mean = hi_c ? tc.mean1 : tc.mean0, stdv = hi_c ? tc.std1 : tc.std0,
-                            rstd = hi_c ? tc.rstd1 : tc.rstd0;
+                const float rstd = hi_c ? tc.rstd1 : tc.rstd0, nmr = hi_c ? tc.nmr1 : tc.nmr0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) o[i] = div_by_const(__fsub_rn(o[i], mean), stdv, rstd);
+                for (int i = 0; i < 4; ++i) o[i] = __fmaf_rn(o[i], rstd, nmr);
               }
             }
             *reinterpret_cast<float4*>(xrow + 4 * c) = make_float4(o[0], o[1], o[2], o[3]);
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
 //   dv[b, k]   = sum_p gx[b,p] D[p,k]   M = 128 image lanes, N = atoms, contraction over pixels (accumulated in TMEM
 //                over all tiles of the CTA)
 //                A = gradient images  (the same bytes, read K-major)    B = D tile images  r = pixel, c = atom  MN-major
-// gx = g / std[c] is folded into the operands' consumers: dD accumulators are divided by std on their way out and
+// gx = g / std[c] is folded into the operands' consumers: dD accumulators are multiplied by 1/std on their way out and
 // the dictionary tile of the dv contraction is divided by std while it is split.
 // The raw D (and m, s) tiles land by TMA; the dD tile is transposed through shared memory into the flat [p][k]
 // layout of the dictionary, where AdamW + clamp run as one 128-bit vectorised pass that stores D, m, s coalesced.
@@ -580,20 +586,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     const int nz = ((3 * (a.vimg + a.dimg + a.gimg) + 1024) >> 1) + (a.want_dD ? tile_elems : 0) + NS * a.raw_floats;
     for (int e = tid; e < nz; e += NTHREADS) z[e] = 0u;
   }
-  __syncthreads();
-  if (a.want_dD) {
-    for (int e = tid; e < B * K; e += NTHREADS) {
-      const int b = e / K, k = e - b * K;
-      const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
-      uint32_t w0, w1, w2;
-      split_bf16x3(a.v[row * K + k], w0, w1, w2);
-      const int o = (k >> 3) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (k & 7);
-      Vi[o] = (bf16_t)(w0 >> 16);
-      Vi[a.vimg + o] = (bf16_t)(w1 >> 16);
-      Vi[2 * a.vimg + o] = (bf16_t)(w2 >> 16);
-    }
-  }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -714,12 +706,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
             tile_chan_update(tc, a.cc, p0);
             if (tc.bnd >= TP) {  // the whole tile lies in one channel (warp-uniform)
 #pragma unroll
-              for (int i = 0; i < 16; ++i) col[i * K] = div_by_const(r[i], tc.std0, tc.rstd0);
+              for (int i = 0; i < 16; ++i) col[i * K] = __fmul_rn(r[i], tc.rstd0);
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const bool hi_c = (cg * 16 + i) >= tc.bnd;
-                col[i * K] = div_by_const(r[i], hi_c ? tc.std1 : tc.std0, hi_c ? tc.rstd1 : tc.rstd0);
+                col[i * K] = __fmul_rn(r[i], hi_c ? tc.rstd1 : tc.rstd0);
               }
             }
           } else {
@@ -761,6 +753,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     };
 
     if (my_tiles > 0) prefetch(0);
+    if (a.want_dD) {
+      // code images (three bf16 terms), once per CTA, while the first gradient rows are in flight
+      for (int e = tid; e < B * K; e += NT) {
+        const int b = e / K, k = e - b * K;
+        const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
+        uint32_t w0, w1, w2;
+        split_bf16x3(a.v[row * K + k], w0, w1, w2);
+        const int o = (k >> 3) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (k & 7);
+        Vi[o] = (bf16_t)(w0 >> 16);
+        Vi[a.vimg + o] = (bf16_t)(w1 >> 16);
+        Vi[2 * a.vimg + o] = (bf16_t)(w2 >> 16);
+      }
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const int p0 = (blockIdx.x + it * gridDim.x) * TP;
       const int s = it % NS;
@@ -955,6 +960,14 @@ int set_smem(KernelT kern, size_t smem, const char* what) {
   return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), what);
 }
 
+template <int TP, bool TRAIN>
+int launch_synth_tp(const SynthArgs& a, size_t smem, int grid, cudaStream_t st) {
+  int rc = set_smem(synth_kernel<TP, TRAIN>, smem, "cudaFuncSetAttribute(synth_kernel)");
+  if (rc) return rc;
+  synth_kernel<TP, TRAIN><<<grid, NTHREADS, smem, st>>>(a);
+  return 0;
+}
+
 }  // namespace
 
 bool tc_synth_ok(int B, int P, int K, int hw) { return plan_synth(B > 128 ? 128 : B, P, K, hw).ok; }
@@ -987,24 +1000,14 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     const int ntiles = (P + pl.TP - 1) / pl.TP;
     int grid = sm_count();
     if (grid > ntiles) grid = ntiles;
+    const bool train = a.out != nullptr && a.x != nullptr && a.delta == nullptr &&
+                       (flags & (ADIL_SYNTH_CLAMP_DELTA | ADIL_SYNTH_CLAMP01)) == 0;
     int rc = 0;
     switch (pl.TP) {
-      case 64:
-        rc = set_smem(synth_kernel<64>, pl.smem, "cudaFuncSetAttribute(synth_kernel)");
-        if (!rc) synth_kernel<64><<<grid, NTHREADS, pl.smem, st>>>(a);
-        break;
-      case 48:
-        rc = set_smem(synth_kernel<48>, pl.smem, "cudaFuncSetAttribute(synth_kernel)");
-        if (!rc) synth_kernel<48><<<grid, NTHREADS, pl.smem, st>>>(a);
-        break;
-      case 32:
-        rc = set_smem(synth_kernel<32>, pl.smem, "cudaFuncSetAttribute(synth_kernel)");
-        if (!rc) synth_kernel<32><<<grid, NTHREADS, pl.smem, st>>>(a);
-        break;
-      default:
-        rc = set_smem(synth_kernel<16>, pl.smem, "cudaFuncSetAttribute(synth_kernel)");
-        if (!rc) synth_kernel<16><<<grid, NTHREADS, pl.smem, st>>>(a);
-        break;
+      case 64: rc = train ? launch_synth_tp<64, true>(a, pl.smem, grid, st) : launch_synth_tp<64, false>(a, pl.smem, grid, st); break;
+      case 48: rc = train ? launch_synth_tp<48, true>(a, pl.smem, grid, st) : launch_synth_tp<48, false>(a, pl.smem, grid, st); break;
+      case 32: rc = train ? launch_synth_tp<32, true>(a, pl.smem, grid, st) : launch_synth_tp<32, false>(a, pl.smem, grid, st); break;
+      default: rc = train ? launch_synth_tp<16, true>(a, pl.smem, grid, st) : launch_synth_tp<16, false>(a, pl.smem, grid, st); break;
     }
     if (rc) return rc;
     rc = check_cuda(cudaGetLastError(), "synth_kernel launch");
