@@ -429,31 +429,26 @@ __global__ void __launch_bounds__(kThreads) grad_fma_kernel(const GradArgs a) {
 }
 
 // Second stage of the deterministic dv reduction: dvb[e] = sum over the per-CTA slabs, in a fixed order.  A block owns
-// 32 consecutive outputs; warp w adds slabs w, w+8, ... (independent coalesced 128-byte loads), then the eight partial
-// sums are combined in warp order -- the summation tree depends only on nslabs, so results are bit-reproducible.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(float* __restrict__ dvb, const float* __restrict__ partial,
-                                                              int n, int nslabs) {
-  __shared__ float part[8][32];
+// 32 consecutive outputs; warp w of 32 adds slabs w, w+32, ... (at most 19 independent coalesced 128-byte loads, all
+// in flight together), then the 32 partial sums are combined in warp order -- the summation tree depends only on
+// nslabs, so results are bit-reproducible.
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(float* __restrict__ dvb, const float* __restrict__ partial,
+                                                               int n, int nslabs) {
+  __shared__ float part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
-  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  float acc = 0.0f;
   if (e < n) {
-    int c = warp;
-    for (; c + 24 < nslabs; c += 32) {
-      a0 += partial[(size_t)c * n + e];
-      a1 += partial[(size_t)(c + 8) * n + e];
-      a2 += partial[(size_t)(c + 16) * n + e];
-      a3 += partial[(size_t)(c + 24) * n + e];
-    }
-    for (; c < nslabs; c += 8) a0 += partial[(size_t)c * n + e];
+#pragma unroll 4
+    for (int c = warp; c < nslabs; c += 32) acc += partial[(size_t)c * n + e];
   }
-  part[warp][lane] = (a0 + a1) + (a2 + a3);
+  part[warp][lane] = acc;
   __syncthreads();
   if (warp == 0 && e < n) {
-    float acc = part[0][lane];
+    float t = part[0][lane];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) acc += part[w][lane];
-    dvb[e] = acc;
+    for (int w = 1; w < 32; ++w) t += part[w][lane];
+    dvb[e] = t;
   }
 }
 
@@ -476,7 +471,7 @@ int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
 }  // namespace
 
 int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, cudaStream_t st) {
-  reduce_partials_kernel<<<(n + 31) / 32, 256, 0, st>>>(dvb, partial, n, nslabs);
+  reduce_partials_kernel<<<(n + 31) / 32, 1024, 0, st>>>(dvb, partial, n, nslabs);
   return check_cuda(cudaGetLastError(), "reduce_partials_kernel launch");
 }
 

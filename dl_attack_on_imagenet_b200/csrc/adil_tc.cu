@@ -35,15 +35,31 @@ int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, 
 
 namespace {
 
+// Phase timing (debug builds only, -DADIL_TIMING): thread 0 of every CTA accumulates clock64 deltas per pipeline phase;
+// the launchers print the per-CTA-tile averages to stderr.  Never compiled into the product library.
+#ifdef ADIL_TIMING
+__device__ long long g_tim[16];
+#define TIM_DECL long long tim_last = clock64(); long long tim_acc[12] = {0}
+#define TIM(i) do { if (tid == 0) { const long long t_ = clock64(); tim_acc[i] += t_ - tim_last; tim_last = t_; } } while (0)
+#define TIM_FLUSH(n) do { if (tid == 0) { for (int i_ = 0; i_ < 12; ++i_) atomicAdd((unsigned long long*)&g_tim[i_], (unsigned long long)tim_acc[i_]); atomicAdd((unsigned long long*)&g_tim[12], (unsigned long long)(n)); } } while (0)
+#else
+#define TIM_DECL
+#define TIM(i)
+#define TIM_FLUSH(n)
+#endif
+
 constexpr int NW = 16;              // worker warps
 constexpr int NT = NW * 32;         // worker threads
 constexpr int WARP_MMA = NW;        // issuer warp
 constexpr int WARP_LOAD = NW + 1;   // loader warp
 constexpr int NTHREADS = NT + 64;   // 576 threads -> at most 112 registers each
+constexpr int NIO = 4;              // synthesis: warps 17..20 move the image rows (cp.async in, coalesced stores out)
+constexpr int NTIO = NIO * 32;
+constexpr int NTHREADS_SYNTH = NT + 32 + NTIO;  // 672 threads -> at most 96 registers each
 constexpr int NS = 3;               // stages of the raw dictionary tiles
 constexpr int NSX = 3;              // stages of the image-row tiles (synthesis)
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int HDR_BYTES = 256 + 1024;  // barriers + tmem slot | per-image row offsets
+constexpr int HDR_BYTES = 256 + 2048;  // barriers + tmem slot | per-image x row offsets | per-image code rows
 
 __host__ __device__ inline int rup(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -261,18 +277,19 @@ struct SynthArgs {
 
 // TRAIN = the learning-loop configuration (x and out given, no delta output, no clamps): those branches vanish.
 template <int TP, bool TRAIN>
-__global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
+__global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArgs a) {
   constexpr int XP = TP + 4;       // floats per staged image row (pitch 16 bytes off a multiple of 128)
   constexpr int Q4 = TP / 4;       // float4 per image row
   constexpr int NCG = TP / 16;     // 16-column groups of the accumulator
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS]
   uint64_t* empty_raw = full_raw + NS;                         // [NS]
-  uint64_t* full_x = empty_raw + NS;                           // [NSX]
-  uint64_t* empty_x = full_x + NSX;                            // [NSX]
-  uint64_t* mma_done = empty_x + NSX;                          // [1]
+  uint64_t* full_x = empty_raw + NS;                           // [NSX] rows landed / stage free (I/O warps -> workers)
+  uint64_t* out_ready = full_x + NSX;                          // [NSX] finished tile staged (workers -> I/O warps)
+  uint64_t* mma_done = out_ready + NSX;                        // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
   long long* xoff_s = reinterpret_cast<long long*>(smem_raw + 256);  // [128]
+  long long* vrow_s = xoff_s + 128;                                   // [128] row of v of each image
   float* raw = reinterpret_cast<float*>(smem_raw + HDR_BYTES);       // [NS][raw_floats]
   float* Vhi = raw + NS * a.raw_floats;
   float* Vlo = Vhi + a.vimg;
@@ -289,7 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
-    for (int i = 0; i < NSX; ++i) { mbar_init(full_x + i, NT); mbar_init(empty_x + i, NW); }
+    for (int i = 0; i < NSX; ++i) { mbar_init(full_x + i, NTIO); mbar_init(out_ready + i, NW); }
     mbar_init(mma_done, 1);
     fence_mbar_init();
   }
@@ -298,9 +315,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
   // raw stages (a partial last tile leaves stale rows behind, which must stay finite)
   {
     const int nz = NS * a.raw_floats + 2 * a.vimg + 2 * a.dimg;
-    for (int e = tid; e < nz; e += NTHREADS) raw[e] = 0.0f;
+    for (int e = tid; e < nz; e += NTHREADS_SYNTH) raw[e] = 0.0f;
   }
-  for (int b = tid; b < B; b += NTHREADS) xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
+  for (int b = tid; b < B; b += NTHREADS_SYNTH) {
+    xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
+    vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -308,20 +328,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
   // From here the roles run free: the loader starts fetching at once, the workers first put their image rows in
   // flight and then build the code images (the issuer cannot start before every worker has arrived on barrier 1).
 
-  if (warp == WARP_LOAD) {
-    // ===== loader: raw dictionary tiles by TMA bulk copy, up to NS tiles ahead =====
-    for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int p0 = tile * TP;
-      const int rows = min(TP, P - p0);
-      const int s = it % NS;
-      if (it >= NS) mbar_wait(empty_raw + s, ((it / NS) - 1) & 1);
-      if (elect_one()) {
-        const uint32_t bytes = (uint32_t)(rows * K * 4);
-        mbar_expect_tx(full_raw + s, bytes);
-        bulk_g2s(raw + s * a.raw_floats, a.D2 + (size_t)p0 * K, bytes, full_raw + s);
+  if (warp >= WARP_LOAD) {
+    // ===== I/O warps: every global access of the image rows, so that the workers only ever touch shared memory and
+    // TMEM.  Per tile j: wait until the workers have staged the finished tile, store it with coalesced 128-bit
+    // streaming stores, and refill the stage with the rows of tile j+NSX by cp.async (each thread overwrites exactly
+    // the elements it has just read). =====
+    const int iot = tid - WARP_LOAD * 32;
+    float* dstg = a.out != nullptr ? a.out : a.delta;
+    auto load_x = [&](int j) {
+      if (need_x && j < my_tiles) {
+        const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+        float* dst = xs + (j % NSX) * xstage;
+        for (int e = iot; e < B * Q4; e += NTIO) {
+          const int b = e / Q4, col = (e - b * Q4) * 4;
+          if (p0 + col < P) cp_async16(dst + b * XP + col, a.x + xoff_s[b] + p0 + col);
+        }
       }
-      __syncwarp();
+      cp_async_arrive_noinc(full_x + (j % NSX));  // rows landed (or, without x, simply: stage free)
+    };
+    for (int j = 0; j < NSX; ++j) load_x(j);
+    for (int j = 0; j < my_tiles; ++j) {
+      const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+      const int sx = j % NSX;
+      const float* xt = xs + sx * xstage;
+      mbar_wait(out_ready + sx, (j / NSX) & 1);
+#pragma unroll 4
+      for (int e = iot; e < B * Q4; e += NTIO) {
+        const int b = e / Q4, col = (e - b * Q4) * 4;
+        if (p0 + col < P) st_stream4(dstg + (size_t)b * P + p0 + col, *reinterpret_cast<const float4*>(xt + b * XP + col));
+      }
+      load_x(j + NSX);
     }
   } else if (warp == WARP_MMA) {
     // ===== issuer: 3 x ksteps MMAs per tile into the accumulator buffer (it & 1) =====
@@ -331,10 +367,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
     const uint64_t astep = (uint64_t)((2 * a.Sv) >> 4), bstep = (uint64_t)((2 * a.Sd) >> 4);
     const int ksteps = a.Kp8 / 8;
     const bool leader = elect_one();
+    // raw dictionary tile `it` -> stage it % NS by one TMA bulk copy.  The stage is known to be free: the copy for
+    // tile it is issued right after barrier 1 of tile it-NS, i.e. after every worker has finished splitting that tile.
+    auto load_D = [&](int it) {
+      const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+      const uint32_t bytes = (uint32_t)(min(TP, P - p0) * K * 4);
+      mbar_expect_tx(full_raw + it % NS, bytes);
+      bulk_g2s(raw + (it % NS) * a.raw_floats, a.D2 + (size_t)p0 * K, bytes, full_raw + it % NS);
+    };
+    if (leader)
+      for (int it = 0; it < NS && it < my_tiles; ++it) load_D(it);
     for (int it = 0; it < my_tiles; ++it) {
       bar_sync(1, NT + 32);  // workers staged tile `it`
       tc_fence_after();
       if (leader) {
+        if (it + NS < my_tiles) load_D(it + NS);
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
         {  // lo*hi
           uint64_t ad = vlo, bd = dhi;
@@ -360,39 +407,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
 
     TileChan tc;
     tile_chan_init(tc);
-    // fixed per-thread share of an image-row tile: float4 e = tid + i*NT -> image b = e / Q4, 4-pixel column c4
-    constexpr int XJ = (128 * Q4 + NT - 1) / NT;
-    int xdst[XJ];         // float offset inside a stage, -1: none
-    long long odst[XJ];   // element offset of out[b, 4*c4]
+    TIM_DECL;
+    // code images (hi / lo), once per CTA: warp w takes the rows b = w, w+16, ...; all of its loads are issued before
+    // the first use (a dependent index -> row -> element chain per element costs ~10 us of latency per launch)
+    {
+      float vv[128 / NW][4];
 #pragma unroll
-    for (int i = 0; i < XJ; ++i) {
-      const int e = tid + i * NT;
-      const int b = e / Q4, c4 = e - b * Q4;
-      xdst[i] = (b < B) ? b * XP + 4 * c4 : -1;
-      odst[i] = (long long)b * P + 4 * c4;
-    }
-    // image rows of tile j -> stage j % NSX by cp.async; every worker arrives on full_x once its copies have landed
-    auto load_x = [&](int j) {
-      const int p0 = (blockIdx.x + j * gridDim.x) * TP;
-      float* dst = xs + (j % NSX) * xstage;
+      for (int r = 0; r < 128 / NW; ++r) {
+        const int b = warp + r * NW;
 #pragma unroll
-      for (int i = 0; i < XJ; ++i) {
-        const int b = (tid + i * NT) / Q4, col = ((tid + i * NT) % Q4) * 4;
-        if (xdst[i] >= 0 && p0 + col < P) cp_async16(dst + xdst[i], a.x + xoff_s[b] + p0 + col);
+        for (int j = 0; j < 4; ++j) {
+          const int k = lane + 32 * j;
+          vv[r][j] = (b < B && k < K) ? __ldg(a.v + vrow_s[b] * K + k) : 0.0f;
+        }
       }
-      cp_async_arrive_noinc(full_x + (j % NSX));
-    };
-    if (need_x)
-      for (int j = 0; j < NSX && j < my_tiles; ++j) load_x(j);
-    // code images (hi / lo), once per CTA
-    for (int e = tid; e < B * K; e += NT) {
-      const int b = e / K, k = e - b * K;
-      const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
-      float hi, lo;
-      split_tf32(a.v[row * K + k], hi, lo);
-      const int o = (k >> 2) * (a.Sv >> 2) + (b >> 3) * 32 + (b & 7) * 4 + (k & 3);
-      Vhi[o] = hi;
-      Vlo[o] = lo;
+#pragma unroll
+      for (int r = 0; r < 128 / NW; ++r) {
+        const int b = warp + r * NW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = lane + 32 * j;
+          if (b < B && k < K) {
+            float hi, lo;
+            split_tf32(vv[r][j], hi, lo);
+            const int o = (k >> 2) * (a.Sv >> 2) + (b >> 3) * 32 + (b & 7) * 4 + (k & 3);
+            Vhi[o] = hi;
+            Vlo[o] = lo;
+          }
+        }
+      }
     }
 
     auto epilogue = [&](int j) {
@@ -400,12 +443,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
       const int p0 = tile * TP;
       const int sx = j % NSX;
       float* xt = xs + sx * xstage;
-      if (need_x) mbar_wait(full_x + sx, (j / NSX) & 1);
+      mbar_wait(full_x + sx, (j / NSX) & 1);  // rows landed / the I/O warps are done with this stage
+      TIM(3);
       // phase 1: thread <-> image row b; 16 accumulator columns per warp
       if (cg < NCG) {
         const int b = quad * 32 + lane;
         float r[16];
         tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((j & 1) * TP + cg * 16), r);
+        TIM(4);
         if (b < B) {
           if (a.cc.use) tile_chan_update(tc, a.cc, p0);
           float* xrow = xt + b * XP + cg * 16;
@@ -445,15 +490,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
         }
         tc_fence_before();
       }
-      bar_sync(2, NT);
-      // every worker has finished the stores of tile j-1: its stage can take the rows of tile j-1+NSX
-      if (need_x && j >= 1 && j - 1 + NSX < my_tiles) load_x(j - 1 + NSX);
-      // phase 2: coalesced 128-bit stores of the finished [B][TP] tile
-      float* dst = a.out != nullptr ? a.out : a.delta;
-#pragma unroll
-      for (int i = 0; i < XJ; ++i)
-        if (xdst[i] >= 0 && p0 + ((tid + i * NT) % Q4) * 4 < P)
-          st_stream4(dst + odst[i] + p0, *reinterpret_cast<const float4*>(xt + xdst[i]));
+      TIM(5);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_ready + sx);  // this warp's part of the finished tile is staged
+      TIM(8);
     };
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -462,7 +502,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
         mbar_wait(mma_done, (it - 1) & 1);  // MMAs(it-1) retired: dictionary images reusable, accumulator ready
         tc_fence_after();
       }
+      TIM(0);
       mbar_wait(full_raw + s, (it / NS) & 1);
+      TIM(1);
       const float* rt = raw + s * a.raw_floats;
       if (a.vk == 4) {
         for (int e = tid; e < nitems; e += NT) {
@@ -497,16 +539,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) synth_kernel(const SynthArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_raw + s);
-      bar_arrive(1, NT + 32);            // hand the tile to the issuer warp, keep going
+      bar_arrive(1, NT + 32);            // hand the tile (and the consumed raw stage) to the issuer warp, keep going
+      TIM(2);
       if (it > 0) epilogue(it - 1);      // overlaps the MMAs being issued
     }
     if (my_tiles > 0) {
       mbar_wait(mma_done, (my_tiles - 1) & 1);
       tc_fence_after();
+      TIM(9);
       epilogue(my_tiles - 1);
     }
+    TIM_FLUSH(my_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -560,6 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   uint64_t* empty_raw = full_raw + NS;                         // [NS]
   uint64_t* mma_done = empty_raw + NS;                         // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  long long* vrow_s = reinterpret_cast<long long*>(smem_raw + 256 + 1024);  // [128] row of v of each image
   typedef unsigned short bf16_t;
   bf16_t* Vi = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);  // three code images
   bf16_t* Di = Vi + 3 * a.vimg;                                   // three dictionary images
@@ -586,6 +630,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     const int nz = ((3 * (a.vimg + a.dimg + a.gimg) + 1024) >> 1) + (a.want_dD ? tile_elems : 0) + NS * a.raw_floats;
     for (int e = tid; e < nz; e += NTHREADS) z[e] = 0u;
   }
+  for (int b = tid; b < B; b += NTHREADS) vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -754,16 +799,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
 
     if (my_tiles > 0) prefetch(0);
     if (a.want_dD) {
-      // code images (three bf16 terms), once per CTA, while the first gradient rows are in flight
-      for (int e = tid; e < B * K; e += NT) {
-        const int b = e / K, k = e - b * K;
-        const int64_t row = a.vidx ? a.vidx[b] : (int64_t)b;
-        uint32_t w0, w1, w2;
-        split_bf16x3(a.v[row * K + k], w0, w1, w2);
-        const int o = (k >> 3) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (k & 7);
-        Vi[o] = (bf16_t)(w0 >> 16);
-        Vi[a.vimg + o] = (bf16_t)(w1 >> 16);
-        Vi[2 * a.vimg + o] = (bf16_t)(w2 >> 16);
+      // code images (three bf16 terms), once per CTA, while the first gradient rows are in flight: warp w takes the
+      // rows b = w, w+16, ...; all of its loads are issued before the first use
+      float vv[128 / NW][4];
+#pragma unroll
+      for (int r = 0; r < 128 / NW; ++r) {
+        const int b = warp + r * NW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = lane + 32 * j;
+          vv[r][j] = (b < B && k < K) ? __ldg(a.v + vrow_s[b] * K + k) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 128 / NW; ++r) {
+        const int b = warp + r * NW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = lane + 32 * j;
+          if (b < B && k < K) {
+            uint32_t w0, w1, w2;
+            split_bf16x3(vv[r][j], w0, w1, w2);
+            const int o = (k >> 3) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (k & 7);
+            Vi[o] = (bf16_t)(w0 >> 16);
+            Vi[a.vimg + o] = (bf16_t)(w1 >> 16);
+            Vi[2 * a.vimg + o] = (bf16_t)(w2 >> 16);
+          }
+        }
       }
     }
     for (int it = 0; it < my_tiles; ++it) {
@@ -964,7 +1026,7 @@ template <int TP, bool TRAIN>
 int launch_synth_tp(const SynthArgs& a, size_t smem, int grid, cudaStream_t st) {
   int rc = set_smem(synth_kernel<TP, TRAIN>, smem, "cudaFuncSetAttribute(synth_kernel)");
   if (rc) return rc;
-  synth_kernel<TP, TRAIN><<<grid, NTHREADS, smem, st>>>(a);
+  synth_kernel<TP, TRAIN><<<grid, NTHREADS_SYNTH, smem, st>>>(a);
   return 0;
 }
 
@@ -1012,6 +1074,20 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     if (rc) return rc;
     rc = check_cuda(cudaGetLastError(), "synth_kernel launch");
     if (rc) return rc;
+#ifdef ADIL_TIMING
+    {
+      cudaDeviceSynchronize();
+      long long h[16];
+      cudaMemcpyFromSymbol(h, g_tim, sizeof(h));
+      long long z[16] = {0};
+      cudaMemcpyToSymbol(g_tim, z, sizeof(z));
+      fprintf(stderr, "synth TP=%d tiles=%lld cycles/tile:", pl.TP, h[12]);
+      const char* nm[10] = {"wait_mma", "wait_raw", "split+arrive", "wait_x", "tmem_ld", "phase1", "bar", "load_x", "store", "tail_wait"};
+      long long tot = 0;
+      for (int i = 0; i < 10; ++i) { fprintf(stderr, " %s=%.0f", nm[i], (double)h[i] / (double)h[12]); tot += h[i]; }
+      fprintf(stderr, " | total=%.0f\n", (double)tot / (double)h[12]);
+    }
+#endif
   }
   return 0;
 }
