@@ -159,15 +159,25 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
+// A operand in TMEM (lane = M row, one 32-bit column per TF32 element), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 32 lanes x 8 consecutive 32-bit columns <- 8 registers per thread (thread t <-> TMEM lane base+t)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])),
+               "r"(__float_as_uint(r[3])), "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])),
+               "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
@@ -248,8 +258,11 @@ __device__ __forceinline__ void tile_chan_update(TileChan& t, const ChannelConst
 
 // =========================================================================================================
 // synthesis:  acc[b, p] = sum_k v[b,k] D[p,k]      M = 128 image lanes, N = TP pixels, contraction over atoms
-//   A = code images (hi/lo)  r = image, c = atom   K-major      (built once per CTA)
-//   B = D tile images        r = pixel, c = atom   K-major      (rebuilt per tile from the TMA-landed raw tile)
+//   A = batch codes (hi/lo) in TENSOR MEMORY: lane = image, column = atom (written once per CTA with tcgen05.st) --
+//       a loop-invariant operand read from shared memory would cost 4 KB of shared-memory bandwidth per MMA
+//       (measured: 48.7 -> 32.8 cycles per M=128,N=64 MMA, scripts/umma_probe_ts.cu) and 50 KB of capacity
+//   B = D tile images        r = pixel, c = atom   K-major      (rebuilt per tile from the TMA-landed raw tile,
+//       double-buffered so that the split of tile i+1 overlaps the MMAs of tile i)
 // The image-row tile x[b, p0:p0+TP] lands by cp.async in a padded [B][TP+4] buffer; the epilogue thread of image b
 // reads its accumulator row, applies +x / clamps / Normalize in place, and the finished tile goes out as coalesced
 // 128-bit streaming stores.
@@ -264,8 +277,8 @@ struct SynthArgs {
   const int64_t* vidx;
   int B, P, K;
   int Kp8;               // contraction length: round_up(K, 8)
-  int Sv, Sd;            // byte strides between 4-atom groups of the code / dictionary images
-  int vimg, dimg;        // floats per code image (incl. over-read pad) / per dictionary image
+  int Sd;                // byte stride between 4-atom groups of a dictionary image
+  int dimg;              // floats per dictionary image
   int raw_floats;        // floats per raw stage
   int vk;                // vector width of the dictionary split: 4, 2 or 1 (K % vk == 0)
   unsigned kdiv;         // ceil(2^32 / (K / vk))
@@ -286,16 +299,14 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   uint64_t* empty_raw = full_raw + NS;                         // [NS]
   uint64_t* full_x = empty_raw + NS;                           // [NSX] rows landed / stage free (I/O warps -> workers)
   uint64_t* out_ready = full_x + NSX;                          // [NSX] finished tile staged (workers -> I/O warps)
-  uint64_t* mma_done = out_ready + NSX;                        // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  uint64_t* mma_done = out_ready + NSX;                        // [2] MMAs of the tiles using buffer 0 / 1 retired
+  uint64_t* staged = mma_done + 2;                             // [2] dictionary images of buffer 0 / 1 written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
   long long* xoff_s = reinterpret_cast<long long*>(smem_raw + 256);  // [128]
   long long* vrow_s = xoff_s + 128;                                   // [128] row of v of each image
   float* raw = reinterpret_cast<float*>(smem_raw + HDR_BYTES);       // [NS][raw_floats]
-  float* Vhi = raw + NS * a.raw_floats;
-  float* Vlo = Vhi + a.vimg;
-  float* Dhi = Vlo + a.vimg;
-  float* Dlo = Dhi + a.dimg;
-  float* xs = Dlo + a.dimg;                                          // [NSX][B][XP]
+  float* Dimg = raw + NS * a.raw_floats;                             // [2 buffers][hi, lo][dimg]
+  float* xs = Dimg + 4 * a.dimg;                                     // [NSX][B][XP]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
@@ -308,19 +319,23 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
     for (int i = 0; i < NSX; ++i) { mbar_init(full_x + i, NTIO); mbar_init(out_ready + i, NW); }
     mbar_init(mma_done, 1);
+    mbar_init(mma_done + 1, 1);
+    mbar_init(staged, NW);
+    mbar_init(staged + 1, NW);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  // zero the operand images (contraction padding k in [K, Kp8) and image rows >= B must be zero / finite) and the
-  // raw stages (a partial last tile leaves stale rows behind, which must stay finite)
+  // zero the dictionary images (contraction padding k in [K, Kp8) must be zero) and the raw stages (a partial last
+  // tile leaves stale rows behind, which must stay finite)
   {
-    const int nz = NS * a.raw_floats + 2 * a.vimg + 2 * a.dimg;
+    const int nz = NS * a.raw_floats + 4 * a.dimg;
     for (int e = tid; e < nz; e += NTHREADS_SYNTH) raw[e] = 0.0f;
   }
   for (int b = tid; b < B; b += NTHREADS_SYNTH) {
     xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
     vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
   }
+  fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes into the same stages
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -362,13 +377,14 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   } else if (warp == WARP_MMA) {
     // ===== issuer: 3 x ksteps MMAs per tile into the accumulator buffer (it & 1) =====
     const uint32_t idesc = make_idesc_tf32(128, TP, false, false);
-    const uint64_t vhi = make_desc(smem_u32(Vhi), a.Sv, 128), vlo = make_desc(smem_u32(Vlo), a.Sv, 128);
-    const uint64_t dhi = make_desc(smem_u32(Dhi), a.Sd, 128), dlo = make_desc(smem_u32(Dlo), a.Sd, 128);
-    const uint64_t astep = (uint64_t)((2 * a.Sv) >> 4), bstep = (uint64_t)((2 * a.Sd) >> 4);
+    const uint32_t a_hi = tmem_base + (uint32_t)(2 * TP), a_lo = a_hi + (uint32_t)a.Kp8;  // codes: columns after the accumulators
+    const uint64_t dhi0 = make_desc(smem_u32(Dimg), a.Sd, 128);
+    const uint64_t dlo_off = (uint64_t)((a.dimg * 4) >> 4), buf_off = 2 * dlo_off;
+    const uint64_t bstep = (uint64_t)((2 * a.Sd) >> 4);
     const int ksteps = a.Kp8 / 8;
     const bool leader = elect_one();
     // raw dictionary tile `it` -> stage it % NS by one TMA bulk copy.  The stage is known to be free: the copy for
-    // tile it is issued right after barrier 1 of tile it-NS, i.e. after every worker has finished splitting that tile.
+    // tile it is issued right after the hand-off of tile it-NS, i.e. after every worker has finished splitting it.
     auto load_D = [&](int it) {
       const int p0 = (blockIdx.x + it * gridDim.x) * TP;
       const uint32_t bytes = (uint32_t)(min(TP, P - p0) * K * 4);
@@ -378,24 +394,31 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     if (leader)
       for (int it = 0; it < NS && it < my_tiles; ++it) load_D(it);
     for (int it = 0; it < my_tiles; ++it) {
-      bar_sync(1, NT + 32);  // workers staged tile `it`
+      // Workers staged tile `it`.  An mbarrier per image buffer, not a named barrier: with double-buffered images a
+      // fast warp reaches the hand-off of tile it+1 before a slow warp has arrived for tile it, and a second
+      // bar.arrive of the same warp would complete the named barrier early.
+      mbar_wait(staged + (it & 1), (it >> 1) & 1);
       tc_fence_after();
       if (leader) {
         if (it + NS < my_tiles) load_D(it + NS);
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
+        const uint64_t dhi = dhi0 + (uint64_t)(it & 1) * buf_off, dlo = dhi + dlo_off;
         {  // lo*hi
-          uint64_t ad = vlo, bd = dhi;
-          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, ks ? 1u : 0u);
+          uint32_t at = a_lo;
+          uint64_t bd = dhi;
+          for (int ks = 0; ks < ksteps; ++ks, at += 8, bd += bstep) mma_tf32_ts(acc, at, bd, idesc, ks ? 1u : 0u);
         }
         {  // hi*lo
-          uint64_t ad = vhi, bd = dlo;
-          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, 1u);
+          uint32_t at = a_hi;
+          uint64_t bd = dlo;
+          for (int ks = 0; ks < ksteps; ++ks, at += 8, bd += bstep) mma_tf32_ts(acc, at, bd, idesc, 1u);
         }
         {  // hi*hi
-          uint64_t ad = vhi, bd = dhi;
-          for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_tf32(acc, ad, bd, idesc, 1u);
+          uint32_t at = a_hi;
+          uint64_t bd = dhi;
+          for (int ks = 0; ks < ksteps; ++ks, at += 8, bd += bstep) mma_tf32_ts(acc, at, bd, idesc, 1u);
         }
-        mma_commit(mma_done);
+        mma_commit(mma_done + (it & 1));
       }
       __syncwarp();
     }
@@ -408,34 +431,32 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     TileChan tc;
     tile_chan_init(tc);
     TIM_DECL;
-    // code images (hi / lo), once per CTA: warp w takes the rows b = w, w+16, ...; all of its loads are issued before
-    // the first use (a dependent index -> row -> element chain per element costs ~10 us of latency per launch)
+    // batch codes (hi / lo) -> tensor memory, once per CTA: thread <-> image b = 32*quad + lane (its TMEM lane), the
+    // warps of a quadrant share the 8-atom column chunks.  All global loads are issued before the first use.
     {
-      float vv[128 / NW][4];
+      const int b = quad * 32 + lane;
+      const int nchunks = a.Kp8 / 8;
+      const float* vrow = a.v + vrow_s[min(b, B - 1)] * K;
+      float vv[4][8];
 #pragma unroll
-      for (int r = 0; r < 128 / NW; ++r) {
-        const int b = warp + r * NW;
+      for (int ci = 0; ci < 4; ++ci) {
+        const int k0 = 8 * (cg + 4 * ci);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = lane + 32 * j;
-          vv[r][j] = (b < B && k < K) ? __ldg(a.v + vrow_s[b] * K + k) : 0.0f;
+        for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+      }
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * TP);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = cg + 4 * ci;
+        if (c < nchunks) {  // warp-uniform
+          float hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_tf32(vv[ci][i], hi[i], lo[i]);
+          tmem_st8(lane_base + (uint32_t)(8 * c), hi);
+          tmem_st8(lane_base + (uint32_t)(a.Kp8 + 8 * c), lo);
         }
       }
-#pragma unroll
-      for (int r = 0; r < 128 / NW; ++r) {
-        const int b = warp + r * NW;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = lane + 32 * j;
-          if (b < B && k < K) {
-            float hi, lo;
-            split_tf32(vv[r][j], hi, lo);
-            const int o = (k >> 2) * (a.Sv >> 2) + (b >> 3) * 32 + (b & 7) * 4 + (k & 3);
-            Vhi[o] = hi;
-            Vlo[o] = lo;
-          }
-        }
-      }
+      tmem_st_wait();
     }
 
     auto epilogue = [&](int j) {
@@ -443,7 +464,10 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       const int p0 = tile * TP;
       const int sx = j % NSX;
       float* xt = xs + sx * xstage;
-      mbar_wait(full_x + sx, (j / NSX) & 1);  // rows landed / the I/O warps are done with this stage
+      mbar_wait(mma_done + (j & 1), (j >> 1) & 1);  // accumulator of tile j complete
+      tc_fence_after();
+      TIM(9);
+      mbar_wait(full_x + sx, (j / NSX) & 1);        // rows landed / the I/O warps are done with this stage
       TIM(3);
       // phase 1: thread <-> image row b; 16 accumulator columns per warp
       if (cg < NCG) {
@@ -498,14 +522,16 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
 
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % NS;
-      if (it > 0) {
-        mbar_wait(mma_done, (it - 1) & 1);  // MMAs(it-1) retired: dictionary images reusable, accumulator ready
+      if (it >= 2) {
+        mbar_wait(mma_done + (it & 1), ((it - 2) >> 1) & 1);  // MMAs(it-2) retired: this image buffer is free again
         tc_fence_after();
       }
       TIM(0);
       mbar_wait(full_raw + s, (it / NS) & 1);
       TIM(1);
       const float* rt = raw + s * a.raw_floats;
+      float* Dhi = Dimg + (it & 1) * 2 * a.dimg;
+      float* Dlo = Dhi + a.dimg;
       if (a.vk == 4) {
         for (int e = tid; e < nitems; e += NT) {
           const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 4;
@@ -539,16 +565,12 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       }
       fence_proxy_async();
       tc_fence_before();
-      bar_arrive(1, NT + 32);            // hand the tile (and the consumed raw stage) to the issuer warp, keep going
+      __syncwarp();                      // the ragged last split iteration of every lane is over
+      if (lane == 0) mbar_arrive(staged + (it & 1));  // hand the tile (and the consumed raw stage) to the issuer
       TIM(2);
       if (it > 0) epilogue(it - 1);      // overlaps the MMAs being issued
     }
-    if (my_tiles > 0) {
-      mbar_wait(mma_done, (my_tiles - 1) & 1);
-      tc_fence_after();
-      TIM(9);
-      epilogue(my_tiles - 1);
-    }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
     TIM_FLUSH(my_tiles);
   }
   tc_fence_before();
@@ -631,6 +653,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     for (int e = tid; e < nz; e += NTHREADS) z[e] = 0u;
   }
   for (int b = tid; b < B; b += NTHREADS) vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
+  fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes into the same stages
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -910,6 +933,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
+      __syncwarp();                                 // bar.arrive is warp-collective: reconverge after the ragged loops
       bar_arrive(1, NT + 32);                       // hand the tile to the issuer warp, keep going
       if (it + 1 < my_tiles) prefetch(it + 1);      // global loads in flight while the tensor core works
       if (a.want_dD && it > 0) epilogue(it - 1);
@@ -953,7 +977,7 @@ int vec_width(int K) { return (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1); }
 unsigned div_magic(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned long long)d - 1) / (unsigned long long)d); }
 
 struct SynthPlan {
-  int TP, Kp8, Sv, Sd, vimg, dimg, raw_floats;
+  int TP, Kp8, Sd, dimg, raw_floats;
   size_t smem;
   uint32_t tmem_cols;
   bool ok;
@@ -969,15 +993,12 @@ SynthPlan plan_synth(int B, int P, int K, int hw) {
     if (hw < TP) continue;  // a tile may span at most two channels
     pl.TP = TP;
     pl.Kp8 = rup(K, 8);
-    pl.Sv = img_stride(rup(B, 8));
     pl.Sd = img_stride(TP);
-    pl.vimg = (pl.Kp8 / 4) * (pl.Sv / 4) + 512;  // + 2 KB: the MMA reads M = 128 image rows
     pl.dimg = (pl.Kp8 / 4) * (pl.Sd / 4);
     pl.raw_floats = rup(TP * K, 32);
-    pl.smem = HDR_BYTES + sizeof(float) * ((size_t)NS * pl.raw_floats + 2 * (size_t)pl.vimg + 2 * (size_t)pl.dimg +
-                                           (size_t)NSX * B * (TP + 4));
-    pl.tmem_cols = pow2_cols(2 * TP);
-    if (pl.smem <= (size_t)SMEM_LIMIT) { pl.ok = true; return pl; }
+    pl.smem = HDR_BYTES + sizeof(float) * ((size_t)NS * pl.raw_floats + 4 * (size_t)pl.dimg + (size_t)NSX * B * (TP + 4));
+    pl.tmem_cols = pow2_cols(2 * TP + 2 * pl.Kp8);  // two accumulators + the codes (hi, lo)
+    if (pl.smem <= (size_t)SMEM_LIMIT && pl.tmem_cols <= 512) { pl.ok = true; return pl; }
   }
   return pl;
 }
@@ -1055,7 +1076,7 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     a.D2 = D2;
     a.v = v_index ? v : v + (size_t)b0 * K;
     a.vidx = v_index ? v_index + b0 : nullptr;
-    a.B = nb; a.P = P; a.K = K; a.Kp8 = pl.Kp8; a.Sv = pl.Sv; a.Sd = pl.Sd; a.vimg = pl.vimg; a.dimg = pl.dimg;
+    a.B = nb; a.P = P; a.K = K; a.Kp8 = pl.Kp8; a.Sd = pl.Sd; a.dimg = pl.dimg;
     a.raw_floats = pl.raw_floats; a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.tmem_cols = pl.tmem_cols;
     a.eps = eps; a.flags = flags; a.cc = cc;
     a.cc.use = norm ? 1 : 0;
