@@ -23,4 +23,9 @@ for hw in (64 * 148 // 3 * 3 // 3, 12544, 25088, 50176, 100352):
     idx = torch.randperm(N, device=dev)[:B]; out = torch.empty(B, P, device=dev); dvb = torch.empty(B, K, device=dev)
     ts = timeit(lambda: ops.synth(D2, v, idx, x=x, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE, out=out))
     tg = timeit(lambda: ops.grad_dict_step(D2, m, s, g, v, idx, ops.adamw_params(3, 0.01), STD, dvb=dvb))
+    tg2 = timeit(lambda: ops.grad_dict_step(D2, m, s, g, v, idx, ops.adamw_params(3, 0.01), STD, want_dv=False))
+    dD = torch.empty(P, K, device=dev)
+    tg3 = timeit(lambda: ops.grad(g, D2, v, idx, STD, dD2=dD, want_dv=False))
+    tg4 = timeit(lambda: ops.grad(g, D2, v, idx, STD, dvb=dvb, want_dD=False))
+    print(f"      fused no-dv {tg2:7.1f}   unfused dD only {tg3:7.1f}   dv only {tg4:7.1f}")
     print(f"P={P:7d} tiles64={P//64:5d} ({P/64/148:5.2f}/SM)  synth {ts:7.1f} us   grad_dict_step {tg:7.1f} us", flush=True)
