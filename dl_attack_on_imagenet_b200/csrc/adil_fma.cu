@@ -437,6 +437,9 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(float* __restrict
   __shared__ float part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
+  // launched with programmatic stream serialisation: the grid may be resident before the contraction kernel has
+  // finished; this waits for its completion and for the visibility of its slabs
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   float acc = 0.0f;
   if (e < n) {
 #pragma unroll 4
@@ -471,8 +474,17 @@ int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
 }  // namespace
 
 int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, cudaStream_t st) {
-  reduce_partials_kernel<<<(n + 31) / 32, 1024, 0, st>>>(dvb, partial, n, nslabs);
-  return check_cuda(cudaGetLastError(), "reduce_partials_kernel launch");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((n + 31) / 32));
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, dvb, partial, n, nslabs), "reduce_partials_kernel launch");
 }
 
 int launch_synth_fma(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,

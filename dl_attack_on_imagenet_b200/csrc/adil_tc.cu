@@ -943,19 +943,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
       tc_fence_after();
       if (a.want_dD) epilogue(my_tiles - 1);
       if (a.want_dv) {
-        // dv accumulator: lane = image, column = atom -> this CTA's slab of the partial buffer
+        // dv accumulator (lane = image, column = atom) -> this CTA's slab of the partial buffer.  The slab is first
+        // laid out flat in shared memory (the operand images are dead by now) so that it leaves as coalesced stores:
+        // 148 CTAs writing 4-byte pieces at a 4K-byte stride cost several microseconds at the end of the kernel.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the reduction kernel may start launching
+        float* stg = reinterpret_cast<float*>(Vi);
+        bar_sync(2, NT);
         const int b = quad * 32 + lane;
-        float* dst = a.partial + (size_t)blockIdx.x * B * K + (size_t)b * K;
         for (int c0 = cg * 16; c0 < a.Kp; c0 += 64) {  // warp-uniform
           float r[16];
           tmem_ld16(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
           if (b < B) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (c0 + i < K) dst[c0 + i] = r[i];
+              if (c0 + i < K) stg[b * K + c0 + i] = r[i];
           }
         }
         tc_fence_before();
+        bar_sync(2, NT);
+        float* dst = a.partial + (size_t)blockIdx.x * B * K;
+        const int n = B * K;
+        if ((n & 3) == 0) {
+          for (int e = tid; e < (n >> 2); e += NT)
+            reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(stg)[e];
+        } else {
+          for (int e = tid; e < n; e += NT) dst[e] = stg[e];
+        }
       }
     }
   }
@@ -1032,6 +1045,7 @@ GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool
     pl.raw_floats = pl.nraw * TP * K;
     pl.smem = HDR_BYTES + 2 * (3 * ((size_t)pl.vimg + pl.dimg + pl.gimg) + 1024) +
               sizeof(float) * ((want_dD ? (size_t)TP * K : 0) + (size_t)NS * pl.raw_floats);
+    if (want_dv && pl.smem < HDR_BYTES + sizeof(float) * (size_t)B * K) pl.smem = HDR_BYTES + sizeof(float) * (size_t)B * K;
     pl.tmem_cols = pow2_cols(2 * TP + pl.Kp);
     if (pl.smem <= (size_t)SMEM_LIMIT && pl.tmem_cols <= 512) { pl.ok = true; return pl; }
   }
