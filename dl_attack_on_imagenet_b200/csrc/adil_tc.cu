@@ -122,12 +122,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// named barriers: id 1 = "tile staged" hand-off workers -> issuer warp, id 2 = worker-only barrier
+// named barrier id 2 = worker-only barrier (hand-offs between roles use mbarriers)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -186,6 +183,21 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// A operand in TMEM (lane = M row, one 32-bit column per PAIR of bf16 contraction elements, even element low)
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -580,8 +592,10 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
 
 // =========================================================================================================
 // backward contractions (+ optional fused AdamW / clamp), bf16x3:
-//   dD^T[k, p] = sum_b v[b,k] gx[b,p]   M = MA atom lanes, N = TP pixels, contraction over images
-//                A = code images   r = image, c = atom   MN-major       B = gradient images  r = image, c = pixel  MN-major
+//   dD^T[k, p] = sum_b v[b,k] gx[b,p]   M = 128 atom lanes, N = TP pixels, contraction over images
+//                A = batch codes (three bf16 terms) in TENSOR MEMORY: lane = atom, column = image pair (loop
+//                    invariant: written once per CTA with tcgen05.st; saves 2 KB of shared-memory reads per MMA)
+//                B = gradient images  r = image, c = pixel  MN-major
 //   dv[b, k]   = sum_p gx[b,p] D[p,k]   M = 128 image lanes, N = atoms, contraction over pixels (accumulated in TMEM
 //                over all tiles of the CTA)
 //                A = gradient images  (the same bytes, read K-major)    B = D tile images  r = pixel, c = atom  MN-major
@@ -589,6 +603,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
 // the dictionary tile of the dv contraction is divided by std while it is split.
 // The raw D (and m, s) tiles land by TMA; the dD tile is transposed through shared memory into the flat [p][k]
 // layout of the dictionary, where AdamW + clamp run as one 128-bit vectorised pass that stores D, m, s coalesced.
+// The gradient and dictionary images are double-buffered: the workers stage tile i+1 while the MMAs of tile i run.
 // =========================================================================================================
 struct GradArgs {
   float* dD2;
@@ -604,7 +619,7 @@ struct GradArgs {
   int Bp;             // contraction length of dD: round_up(B, 16)
   int Kp;             // N of the dv MMA: round_up(K, 16)
   int Sg, Sd;         // byte strides between column groups of the gradient (= code) / dictionary images
-  int vimg, dimg, gimg;  // bf16 elements per image term
+  int dimg, gimg;     // bf16 elements per image term
   int raw_floats;     // floats per raw stage
   int nraw;           // arrays per raw stage: 3 (D, m, s: fused), 1 (D only) or 0
   int vk;             // vector width of the dictionary split
@@ -615,7 +630,7 @@ struct GradArgs {
   AdamwDev hp;
 };
 
-template <int TP, int MA>
+template <int TP>
 __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   constexpr int Q4 = TP / 4;                           // float4 per gradient row
   constexpr int GJ = (128 * Q4 + NT - 1) / NT;         // float4 per worker thread (B <= 128)
@@ -623,14 +638,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS]
   uint64_t* empty_raw = full_raw + NS;                         // [NS]
-  uint64_t* mma_done = empty_raw + NS;                         // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  uint64_t* mma_done = empty_raw + NS;                         // [2] MMAs of the tiles using image buffer 0 / 1 retired
+  uint64_t* staged = mma_done + 2;                             // [2] images of buffer 0 / 1 written (workers -> issuer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
   long long* vrow_s = reinterpret_cast<long long*>(smem_raw + 256 + 1024);  // [128] row of v of each image
   typedef unsigned short bf16_t;
-  bf16_t* Vi = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);  // three code images
-  bf16_t* Di = Vi + 3 * a.vimg;                                   // three dictionary images
-  bf16_t* Gi = Di + 3 * a.dimg;                                   // three gradient images (+ 2 KB over-read pad)
-  float* dDs = reinterpret_cast<float*>(Gi + 3 * a.gimg + 1024);  // [TP*K] dD tile, flat like the dictionary
+  const int dbuf = 3 * a.dimg, gbuf = 3 * a.gimg + 1024;          // bf16 elements per buffer (gradient: + 2 KB pad)
+  bf16_t* Di = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);   // [2 buffers][3 terms] dictionary images
+  bf16_t* Gi = Di + 2 * dbuf;                                     // [2 buffers][3 terms (+ over-read pad)] gradient images
+  float* dDs = reinterpret_cast<float*>(Gi + 2 * gbuf);           // [TP*K] dD tile, flat like the dictionary
   float* raw = dDs + (a.want_dD ? TP * a.K : 0);                  // [NS][raw_floats]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -642,14 +658,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
-    mbar_init(mma_done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(mma_done + i, 1); mbar_init(staged + i, NW); }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
   {
     // zero everything once: contraction padding must be zero, over-read regions and stale rows finite
-    uint32_t* z = reinterpret_cast<uint32_t*>(Vi);
-    const int nz = ((3 * (a.vimg + a.dimg + a.gimg) + 1024) >> 1) + (a.want_dD ? tile_elems : 0) + NS * a.raw_floats;
+    uint32_t* z = reinterpret_cast<uint32_t*>(Di);
+    const int nz = (dbuf + gbuf) + (a.want_dD ? tile_elems : 0) + NS * a.raw_floats;
     for (int e = tid; e < nz; e += NTHREADS) z[e] = 0u;
   }
   for (int b = tid; b < B; b += NTHREADS) vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
@@ -658,7 +674,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // tensor memory: [0, 2 TP) two dD^T accumulators | [2 TP, 2 TP + Kp) dv accumulator | then the codes, 3 x Bp/2 columns
   const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
+  const uint32_t codes = acc_dv + (uint32_t)a.Kp;
 
   if (warp == WARP_LOAD) {
     // ===== loader: contiguous D (, m, s) tiles by TMA bulk copy =====
@@ -685,46 +703,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     }
   } else if (warp == WARP_MMA) {
     // ===== issuer =====
-    const uint32_t idesc_dD = make_idesc_bf16(MA, TP, true, true);
+    const uint32_t idesc_dD = make_idesc_bf16(128, TP, false, true);
     const uint32_t idesc_dv = make_idesc_bf16(128, a.Kp, false, true);
-    const uint32_t gb = smem_u32(Gi), vb = smem_u32(Vi), db = smem_u32(Di);
-    const uint32_t gsz = 2u * a.gimg, vsz = 2u * a.vimg, dsz = 2u * a.dimg;  // image sizes in bytes
+    const uint32_t gb = smem_u32(Gi), db = smem_u32(Di);
     // term pairs (gradient term, code / dictionary term), smallest contributions first: (2,0)(0,2)(1,1)(1,0)(0,1)(0,0)
-    // A = code image [M = atom, K = image] MN-major: LBO = 128 (8-image groups), SBO = Sg (8-atom groups)
-    // B = gradient image [N = pixel, K = image] MN-major: LBO = 128, SBO = Sg (8-pixel groups)
-    const uint64_t dD_a0 = make_desc(vb, 128, a.Sg), dD_b0 = make_desc(gb, 128, a.Sg);
-    // A = gradient image [M = image, K = pixel] K-major: LBO = Sg (8-pixel chunks), SBO = 128 (8-image groups)
-    // B = D image [N = atom, K = pixel] MN-major: LBO = 128 (8-pixel groups), SBO = Sd (8-atom groups)
+    // dD^T: A = codes in TMEM (term tv at column offset tv * Bp/2, 8 columns per 16-image k-step)
+    //       B = gradient image [N = pixel, K = image] MN-major: LBO = 128 (8-image groups), SBO = Sg (8-pixel groups)
+    // dv:   A = gradient image [M = image, K = pixel] K-major: LBO = Sg (8-pixel chunks), SBO = 128 (8-image groups)
+    //       B = D image [N = atom, K = pixel] MN-major: LBO = 128 (8-pixel groups), SBO = Sd (8-atom groups)
+    const uint64_t dD_b0 = make_desc(gb, 128, a.Sg);
     const uint64_t dv_a0 = make_desc(gb, a.Sg, 128), dv_b0 = make_desc(db, 128, a.Sd);
-    const uint64_t gs16 = (uint64_t)(gsz >> 4), vs16 = (uint64_t)(vsz >> 4), ds16 = (uint64_t)(dsz >> 4);
+    const uint64_t gs16 = (uint64_t)((2u * a.gimg) >> 4), ds16 = (uint64_t)((2u * a.dimg) >> 4);  // term strides
+    const uint64_t gb16 = (uint64_t)((2u * gbuf) >> 4), db16 = (uint64_t)((2u * dbuf) >> 4);      // buffer strides
     const uint64_t astep = (uint64_t)((2 * a.Sg) >> 4);
     const int ksteps_dD = a.Bp / 16;
+    const uint32_t cterm = (uint32_t)(a.Bp / 2);
     const bool leader = elect_one();
     for (int it = 0; it < my_tiles; ++it) {
-      bar_sync(1, NT + 32);
+      const int buf = it & 1;
+      mbar_wait(staged + buf, (it >> 1) & 1);  // workers staged tile `it` (mbarrier: fast warps run one tile ahead)
       tc_fence_after();
       if (leader) {
         if (a.want_dD) {
-          const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
+          const uint32_t acc = tmem_base + (uint32_t)(buf * TP);
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
             constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, tv[6] = {0, 2, 1, 0, 1, 0};
-            uint64_t ad = dD_a0 + (uint64_t)tv[t] * vs16, bd = dD_b0 + (uint64_t)tg[t] * gs16;
+            uint32_t at = codes + (uint32_t)tv[t] * cterm;
+            uint64_t bd = dD_b0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
 #pragma unroll 1
-            for (int ks = 0; ks < ksteps_dD; ++ks, ad += 16, bd += 16) mma_bf16(acc, ad, bd, idesc_dD, (t | ks) ? 1u : 0u);
+            for (int ks = 0; ks < ksteps_dD; ++ks, at += 8, bd += 16) mma_bf16_ts(acc, at, bd, idesc_dD, (t | ks) ? 1u : 0u);
           }
         }
         if (a.want_dv) {
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
             constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, td[6] = {0, 2, 1, 0, 1, 0};
-            uint64_t ad = dv_a0 + (uint64_t)tg[t] * gs16, bd = dv_b0 + (uint64_t)td[t] * ds16;
+            uint64_t ad = dv_a0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
+            uint64_t bd = dv_b0 + (uint64_t)buf * db16 + (uint64_t)td[t] * ds16;
 #pragma unroll
             for (int ks = 0; ks < TP / 16; ++ks, ad += astep, bd += 16)
               mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
           }
         }
-        mma_commit(mma_done);
+        mma_commit(mma_done + buf);
       }
       __syncwarp();
     }
@@ -736,6 +758,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
 
     TileChan tc;
     tile_chan_init(tc);
+    TIM_DECL;
     // fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q
     int gsrc[GJ], gdst[GJ];  // gsrc: 4q, the pixel column (-1: none); gdst: bf16 offset inside an image
     const float* grow[GJ];   // &g[b, 4q]
@@ -762,12 +785,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
       const int p0 = tile * TP;
       const int rows = min(TP, P - p0);
       const int sj = j % NS;
+      mbar_wait(mma_done + (j & 1), (j >> 1) & 1);  // MMAs of tile j retired: its dD accumulator is complete
+      tc_fence_after();
+      TIM(4);
       bar_sync(2, NT);  // every worker is done with the dD staging tile of the previous epilogue
+      TIM(5);
       // phase A: accumulator (lane = atom, column = pixel) -> flat [pixel][atom] staging tile, divided by std
       if (cg < NCG) {
         float r[16];
         tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((j & 1) * TP + cg * 16), r);
-        const int k = (MA == 64) ? (lane < 16 ? quad * 16 + lane : K) : quad * 32 + lane;
+        const int k = quad * 32 + lane;
         if (k < K) {
           float* col = dDs + (cg * 16) * K + k;
           if (a.cc.use) {
@@ -789,12 +816,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         }
         tc_fence_before();
       }
+      TIM(6);
       bar_sync(2, NT);
+      TIM(7);
       // phase B: one flat 128-bit pass over the tile's contiguous [rows x K] block
       const int n4 = (rows * K) >> 2;
       const size_t base = (size_t)p0 * K;
       if (fused) {
         mbar_wait(full_raw + sj, (j / NS) & 1);
+        TIM(8);
         const float* rt = raw + sj * a.raw_floats;
         for (int e4 = tid; e4 < n4; e4 += NT) {
           float4 Dv = *reinterpret_cast<const float4*>(rt + 4 * e4);
@@ -818,46 +848,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         for (int e4 = tid; e4 < n4; e4 += NT)
           *reinterpret_cast<float4*>(a.dD2 + base + 4 * (size_t)e4) = *reinterpret_cast<const float4*>(dDs + 4 * e4);
       }
+      TIM(9);
     };
 
     if (my_tiles > 0) prefetch(0);
     if (a.want_dD) {
-      // code images (three bf16 terms), once per CTA, while the first gradient rows are in flight: warp w takes the
-      // rows b = w, w+16, ...; all of its loads are issued before the first use
-      float vv[128 / NW][4];
+      // batch codes (three bf16 terms) -> tensor memory, once per CTA, while the first gradient rows are in flight.
+      // thread <-> atom m = 32*quad + lane (its TMEM lane); a column holds the image pair (2c, 2c+1); the warps of a
+      // quadrant share the 16-image chunks.  All global loads are issued before the first use.
+      const int m = quad * 32 + lane;
+      const int nchunks = a.Bp / 16;  // 8-column chunks per term
+      float vv[2][16];
 #pragma unroll
-      for (int r = 0; r < 128 / NW; ++r) {
-        const int b = warp + r * NW;
+      for (int ci = 0; ci < 2; ++ci) {
+        const int b0 = 16 * (cg + 4 * ci);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = lane + 32 * j;
-          vv[r][j] = (b < B && k < K) ? __ldg(a.v + vrow_s[b] * K + k) : 0.0f;
+        for (int i = 0; i < 16; ++i) {
+          const int b = b0 + i;
+          vv[ci][i] = (b < B && m < K) ? __ldg(a.v + vrow_s[b] * K + m) : 0.0f;
         }
       }
+      const uint32_t lane_base = codes + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
-      for (int r = 0; r < 128 / NW; ++r) {
-        const int b = warp + r * NW;
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = cg + 4 * ci;
+        if (c < nchunks) {  // warp-uniform
+          uint32_t t0[8], t1[8], t2[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = lane + 32 * j;
-          if (b < B && k < K) {
-            uint32_t w0, w1, w2;
-            split_bf16x3(vv[r][j], w0, w1, w2);
-            const int o = (k >> 3) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (k & 7);
-            Vi[o] = (bf16_t)(w0 >> 16);
-            Vi[a.vimg + o] = (bf16_t)(w1 >> 16);
-            Vi[2 * a.vimg + o] = (bf16_t)(w2 >> 16);
+          for (int i = 0; i < 8; ++i) {
+            uint32_t a0, a1, a2, b0w, b1w, b2w;
+            split_bf16x3(vv[ci][2 * i], a0, a1, a2);
+            split_bf16x3(vv[ci][2 * i + 1], b0w, b1w, b2w);
+            t0[i] = pack_hi16(a0, b0w);
+            t1[i] = pack_hi16(a1, b1w);
+            t2[i] = pack_hi16(a2, b2w);
           }
+          tmem_st8u(lane_base + (uint32_t)(8 * c), t0);
+          tmem_st8u(lane_base + (uint32_t)(a.Bp / 2 + 8 * c), t1);
+          tmem_st8u(lane_base + (uint32_t)(a.Bp + 8 * c), t2);
         }
       }
+      tmem_st_wait();
     }
     for (int it = 0; it < my_tiles; ++it) {
       const int p0 = (blockIdx.x + it * gridDim.x) * TP;
       const int s = it % NS;
-      if (it > 0) {
-        mbar_wait(mma_done, (it - 1) & 1);  // MMAs(it-1) retired: images free, dD accumulator (it-1) complete
+      const int buf = it & 1;
+      bf16_t* Gb = Gi + buf * gbuf;
+      bf16_t* Db = Di + buf * dbuf;
+      if (it >= 2) {
+        mbar_wait(mma_done + buf, ((it - 2) >> 1) & 1);  // MMAs(it-2) retired: this image buffer is free again
         tc_fence_after();
       }
+      TIM(0);
       // gradient tile: registers -> three bf16 images
 #pragma unroll
       for (int j = 0; j < GJ; ++j) {
@@ -866,15 +909,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
           uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) split_bf16x3(val[i], w0[i], w1[i], w2[i]);
-          bf16_t* dst = Gi + gdst[j];
+          bf16_t* dst = Gb + gdst[j];
           *reinterpret_cast<uint2*>(dst) = make_uint2(pack_hi16(w0[0], w0[1]), pack_hi16(w0[2], w0[3]));
           *reinterpret_cast<uint2*>(dst + a.gimg) = make_uint2(pack_hi16(w1[0], w1[1]), pack_hi16(w1[2], w1[3]));
           *reinterpret_cast<uint2*>(dst + 2 * a.gimg) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
         }
       }
+      TIM(1);
       if (a.want_dv) {
         // dictionary tile (pre-update values): TMA-landed raw rows -> three bf16 images of D / std
         mbar_wait(full_raw + s, (it / NS) & 1);
+        TIM(2);
         const float* rt = raw + s * a.raw_floats;
         if (a.cc.use) tile_chan_update(tc, a.cc, p0);
         if (a.vk == 4) {
@@ -890,7 +935,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
             uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_bf16x3(val[i], w0[i], w1[i], w2[i]);
-            bf16_t* dst = Di + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
+            bf16_t* dst = Db + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
             *reinterpret_cast<uint2*>(dst) = make_uint2(pack_hi16(w0[0], w0[1]), pack_hi16(w0[2], w0[3]));
             *reinterpret_cast<uint2*>(dst + a.dimg) = make_uint2(pack_hi16(w1[0], w1[1]), pack_hi16(w1[2], w1[3]));
             *reinterpret_cast<uint2*>(dst + 2 * a.dimg) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
@@ -908,7 +953,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
             uint32_t w0[2], w1[2], w2[2];
             split_bf16x3(val[0], w0[0], w1[0], w2[0]);
             split_bf16x3(val[1], w0[1], w1[1], w2[1]);
-            bf16_t* dst = Di + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
+            bf16_t* dst = Db + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
             *reinterpret_cast<uint32_t*>(dst) = pack_hi16(w0[0], w0[1]);
             *reinterpret_cast<uint32_t*>(dst + a.dimg) = pack_hi16(w1[0], w1[1]);
             *reinterpret_cast<uint32_t*>(dst + 2 * a.dimg) = pack_hi16(w2[0], w2[1]);
@@ -920,7 +965,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
             if (a.cc.use) val = div_by_const(val, p >= tc.bnd ? tc.std1 : tc.std0, p >= tc.bnd ? tc.rstd1 : tc.rstd0);
             uint32_t w0, w1, w2;
             split_bf16x3(val, w0, w1, w2);
-            bf16_t* dst = Di + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
+            bf16_t* dst = Db + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
             dst[0] = (bf16_t)(w0 >> 16);
             dst[a.dimg] = (bf16_t)(w1 >> 16);
             dst[2 * a.dimg] = (bf16_t)(w2 >> 16);
@@ -933,21 +978,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
-      __syncwarp();                                 // bar.arrive is warp-collective: reconverge after the ragged loops
-      bar_arrive(1, NT + 32);                       // hand the tile to the issuer warp, keep going
+      __syncwarp();                                 // the ragged loops of every lane are over
+      if (lane == 0) mbar_arrive(staged + buf);     // hand the tile to the issuer warp, keep going
+      TIM(3);
       if (it + 1 < my_tiles) prefetch(it + 1);      // global loads in flight while the tensor core works
       if (a.want_dD && it > 0) epilogue(it - 1);
     }
     if (my_tiles > 0) {
-      mbar_wait(mma_done, (my_tiles - 1) & 1);
-      tc_fence_after();
       if (a.want_dD) epilogue(my_tiles - 1);
+      mbar_wait(mma_done + ((my_tiles - 1) & 1), ((my_tiles - 1) >> 1) & 1);  // (dv only: nobody has waited yet)
+      tc_fence_after();
       if (a.want_dv) {
         // dv accumulator (lane = image, column = atom) -> this CTA's slab of the partial buffer.  The slab is first
         // laid out flat in shared memory (the operand images are dead by now) so that it leaves as coalesced stores:
         // 148 CTAs writing 4-byte pieces at a 4K-byte stride cost several microseconds at the end of the kernel.
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the reduction kernel may start launching
-        float* stg = reinterpret_cast<float*>(Vi);
+        float* stg = reinterpret_cast<float*>(Di);
         bar_sync(2, NT);
         const int b = quad * 32 + lane;
         for (int c0 = cg * 16; c0 < a.Kp; c0 += 64) {  // warp-uniform
@@ -971,6 +1017,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         }
       }
     }
+    TIM_FLUSH(my_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -1017,7 +1064,7 @@ SynthPlan plan_synth(int B, int P, int K, int hw) {
 }
 
 struct GradPlan {
-  int TP, MA, Bp, Kp, Sg, Sd, vimg, dimg, gimg, raw_floats, nraw;
+  int TP, Bp, Kp, Sg, Sd, dimg, gimg, raw_floats, nraw;
   size_t smem;
   uint32_t tmem_cols;
   bool ok;
@@ -1033,20 +1080,18 @@ GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool
     const int TP = tps[i];
     if (hw < TP) continue;
     pl.TP = TP;
-    pl.MA = K <= 64 ? 64 : 128;
     pl.Bp = rup(B, 16);
     pl.Kp = rup(K, 16);
     pl.Sg = img_stride(pl.Bp);
     pl.Sd = img_stride(TP);
-    pl.vimg = want_dD ? (pl.MA / 8) * (pl.Sg / 2) : 0;
     pl.dimg = want_dv ? (pl.Kp / 8) * (pl.Sd / 2) : 0;
     pl.gimg = (TP / 8) * (pl.Sg / 2);
     pl.nraw = fused ? 3 : (want_dv ? 1 : 0);
     pl.raw_floats = pl.nraw * TP * K;
-    pl.smem = HDR_BYTES + 2 * (3 * ((size_t)pl.vimg + pl.dimg + pl.gimg) + 1024) +
+    pl.smem = HDR_BYTES + 2 * 2 * (3 * ((size_t)pl.dimg + pl.gimg) + 1024) +  // two buffers of bf16 images
               sizeof(float) * ((want_dD ? (size_t)TP * K : 0) + (size_t)NS * pl.raw_floats);
     if (want_dv && pl.smem < HDR_BYTES + sizeof(float) * (size_t)B * K) pl.smem = HDR_BYTES + sizeof(float) * (size_t)B * K;
-    pl.tmem_cols = pow2_cols(2 * TP + pl.Kp);
+    pl.tmem_cols = pow2_cols(2 * TP + pl.Kp + 3 * (pl.Bp / 2));  // accumulators + the codes
     if (pl.smem <= (size_t)SMEM_LIMIT && pl.tmem_cols <= 512) { pl.ok = true; return pl; }
   }
   return pl;
@@ -1129,16 +1174,10 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
 
 namespace {
 template <int TP>
-int launch_grad_tp(const GradArgs& a, int MA, size_t smem, int grid, cudaStream_t st) {
-  int rc;
-  if (MA == 64) {
-    rc = set_smem(grad_kernel<TP, 64>, smem, "cudaFuncSetAttribute(grad_kernel)");
-    if (!rc) grad_kernel<TP, 64><<<grid, NTHREADS, smem, st>>>(a);
-  } else {
-    rc = set_smem(grad_kernel<TP, 128>, smem, "cudaFuncSetAttribute(grad_kernel)");
-    if (!rc) grad_kernel<TP, 128><<<grid, NTHREADS, smem, st>>>(a);
-  }
+int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
+  int rc = set_smem(grad_kernel<TP>, smem, "cudaFuncSetAttribute(grad_kernel)");
   if (rc) return rc;
+  grad_kernel<TP><<<grid, NTHREADS, smem, st>>>(a);
   return check_cuda(cudaGetLastError(), "grad_kernel launch");
 }
 }  // namespace
@@ -1154,7 +1193,7 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
   GradArgs a;
   a.dD2 = dD2; a.D2w = D2_rw; a.m = m; a.s = s; a.partial = scratch; a.g = g; a.D2 = D2; a.v = v; a.vidx = v_index;
   a.B = B; a.P = P; a.K = K; a.Bp = pl.Bp; a.Kp = pl.Kp; a.Sg = pl.Sg; a.Sd = pl.Sd;
-  a.vimg = pl.vimg; a.dimg = pl.dimg; a.gimg = pl.gimg; a.raw_floats = pl.raw_floats; a.nraw = pl.nraw;
+  a.dimg = pl.dimg; a.gimg = pl.gimg; a.raw_floats = pl.raw_floats; a.nraw = pl.nraw;
   a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.tmem_cols = pl.tmem_cols;
   a.want_dD = want_dD ? 1 : 0; a.want_dv = want_dv ? 1 : 0; a.atoms_mode = atoms_mode; a.cc = cc;
   if (hp) a.hp = *hp;
@@ -1169,12 +1208,26 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
   }
   int rc;
   switch (pl.TP) {
-    case 64: rc = launch_grad_tp<64>(a, pl.MA, pl.smem, grid, st); break;
-    case 48: rc = launch_grad_tp<48>(a, pl.MA, pl.smem, grid, st); break;
-    case 32: rc = launch_grad_tp<32>(a, pl.MA, pl.smem, grid, st); break;
-    default: rc = launch_grad_tp<16>(a, pl.MA, pl.smem, grid, st); break;
+    case 64: rc = launch_grad_tp<64>(a, pl.smem, grid, st); break;
+    case 48: rc = launch_grad_tp<48>(a, pl.smem, grid, st); break;
+    case 32: rc = launch_grad_tp<32>(a, pl.smem, grid, st); break;
+    default: rc = launch_grad_tp<16>(a, pl.smem, grid, st); break;
   }
   if (rc) return rc;
+#ifdef ADIL_TIMING
+  {
+    cudaDeviceSynchronize();
+    long long h[16];
+    cudaMemcpyFromSymbol(h, g_tim, sizeof(h));
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_tim, z, sizeof(z));
+    const char* nm[10] = {"wait_mma", "g_split", "wait_raw", "D_split+arrive", "prefetch", "bar1", "phaseA", "bar2", "wait_raw2", "phaseB"};
+    fprintf(stderr, "grad TP=%d tiles=%lld cycles/tile:", pl.TP, h[12]);
+    long long tot = 0;
+    for (int i = 0; i < 10; ++i) { fprintf(stderr, " %s=%.0f", nm[i], (double)h[i] / (double)h[12]); tot += h[i]; }
+    fprintf(stderr, " | total=%.0f\n", (double)tot / (double)h[12]);
+  }
+#endif
   if (want_dv) return launch_reduce_partials(dvb, scratch, B * K, grid, st);
   return 0;
 }
