@@ -44,7 +44,21 @@ def parse_args():
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "fma", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cudnn-autotune", action="store_true",
+                    help="cudnn.benchmark off (profiling runs: fewer trial kernels in the launch list)")
     return ap.parse_args()
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json):
+    dram__bytes_read.sum + dram__bytes_write.sum.  None when no capture is recorded for it."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)[kernel]
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -196,7 +210,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = not args.no_cudnn_autotune
     ops.set_impl({"auto": ops.IMPL_AUTO, "fma": ops.IMPL_FMA, "tc": ops.IMPL_TC}[args.kernel_impl])
 
     B, K, N = args.batch, args.atoms, args.images
@@ -345,8 +359,9 @@ def run_ours(args):
     if kt["grad"]:
         ach = alg_bytes / (kt["grad"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "alg_bytes": alg_bytes, "kernel_ms": kt["grad"],
-                    "peak_source": peak_src}
+                    "frac": ach / hbm_peak,
+                    "traffic": measured_traffic("adil_grad_dict_step" if world == 1 else "adil_grad"),
+                    "alg_bytes": alg_bytes, "kernel_ms": kt["grad"], "peak_source": peak_src}
         kernels["grad"] = {"ms": kt["grad"], "GBps": ach, "frac": ach / hbm_peak}
     if kt["synth"]:
         ach = synth_bytes / (kt["synth"] * 1e-3) / 1e9
@@ -376,7 +391,8 @@ def run_ours(args):
                             "random-init %s, %d synthetic 3x224x224 images per GPU, %d atoms, minibatch %d per GPU, "
                             "l_inf eps=8/255, AdamW lr 0.01, CE loss" % (args.model, N, K, B),
                 "classifier_math": "cuDNN TF32 allowed" if args.tf32 else "strict fp32 (TF32 off)",
-                "adil_kernels": "fp32 FMA / split-TF32 tcgen05 (impl=%s)" % args.kernel_impl,
+                "adil_kernels": "tcgen05 split precision (3xTF32 synthesis, bf16x3 backward), fp32 accumulate; FMA "
+                                "fallback for shapes outside B<=128, K<=128 (impl=%s)" % args.kernel_impl,
                 "l2": "inputs larger than L2: each step touches >150 MB of ADiL state + GBs of activations",
                 "parallelism": "image-sharded x%d, dD SUM all-reduce (NCCL)" % world if world > 1 else "single GPU",
             },
