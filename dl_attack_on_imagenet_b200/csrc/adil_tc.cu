@@ -42,10 +42,14 @@ __device__ long long g_tim[16];
 #define TIM_DECL long long tim_last = clock64(); long long tim_acc[12] = {0}
 #define TIM(i) do { if (tid == 0) { const long long t_ = clock64(); tim_acc[i] += t_ - tim_last; tim_last = t_; } } while (0)
 #define TIM_FLUSH(n) do { if (tid == 0) { for (int i_ = 0; i_ < 12; ++i_) atomicAdd((unsigned long long*)&g_tim[i_], (unsigned long long)tim_acc[i_]); atomicAdd((unsigned long long*)&g_tim[12], (unsigned long long)(n)); } } while (0)
+__device__ long long g_stamp[8];
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_stamp[i] = gtime(); } while (0)
 #else
 #define TIM_DECL
 #define TIM(i)
 #define TIM_FLUSH(n)
+#define STAMP(i)
 #endif
 
 constexpr int NW = 16;              // worker warps
@@ -337,23 +341,39 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  // zero the dictionary images (contraction padding k in [K, Kp8) must be zero) and the raw stages (a partial last
-  // tile leaves stale rows behind, which must stay finite)
-  {
-    const int nz = NS * a.raw_floats + 4 * a.dimg;
-    for (int e = tid; e < nz; e += NTHREADS_SYNTH) raw[e] = 0.0f;
-  }
   for (int b = tid; b < B; b += NTHREADS_SYNTH) {
     xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
     vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
   }
-  fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes into the same stages
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // From here the roles run free: the loader starts fetching at once, the workers first put their image rows in
-  // flight and then build the code images (the issuer cannot start before every worker has arrived on barrier 1).
+  // The batch codes are the first thing on the critical path of tile 0: their loads go out BEFORE any bulk prefetch of
+  // dictionary tiles and image rows (which would queue megabytes ahead of them) and fly during the zero fill.
+  // worker thread <-> image b = 32*quad + lane (its TMEM lane); the warps of a quadrant share the 8-atom chunks.
+  float vv[4][8];
+  if (warp < NW) {
+    const int b = (warp & 3) * 32 + lane;
+    const float* vrow = a.v + vrow_s[min(b, B - 1)] * K;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      const int k0 = 8 * ((warp >> 2) + 4 * ci);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+    }
+  }
+  // zero the dictionary images (contraction padding k in [K, Kp8) must be zero) and the raw stages (a partial last
+  // tile leaves stale rows behind, which must stay finite)
+  {
+    float4* z = reinterpret_cast<float4*>(raw);
+    const int nz = (NS * a.raw_floats + 4 * a.dimg) >> 2;
+    for (int e = tid; e < nz; e += NTHREADS_SYNTH) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes into the same stages
+  __syncthreads();
+  // From here the roles run free: the issuer and the I/O warps start fetching at once, the workers write the codes to
+  // tensor memory (the issuer cannot start before every worker has handed over tile 0).
 
   if (warp >= WARP_LOAD) {
     // ===== I/O warps: every global access of the image rows, so that the workers only ever touch shared memory and
@@ -443,19 +463,9 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     TileChan tc;
     tile_chan_init(tc);
     TIM_DECL;
-    // batch codes (hi / lo) -> tensor memory, once per CTA: thread <-> image b = 32*quad + lane (its TMEM lane), the
-    // warps of a quadrant share the 8-atom column chunks.  All global loads are issued before the first use.
+    // batch codes (hi / lo) -> tensor memory, once per CTA
     {
-      const int b = quad * 32 + lane;
       const int nchunks = a.Kp8 / 8;
-      const float* vrow = a.v + vrow_s[min(b, B - 1)] * K;
-      float vv[4][8];
-#pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int k0 = 8 * (cg + 4 * ci);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
-      }
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * TP);
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
@@ -655,6 +665,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool fused = a.D2w != nullptr;
   const int tile_elems = TP * K;
+  STAMP(0);
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
@@ -662,14 +673,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  {
-    // zero everything once: contraction padding must be zero, over-read regions and stale rows finite
-    uint32_t* z = reinterpret_cast<uint32_t*>(Di);
-    const int nz = (dbuf + gbuf) + (a.want_dD ? tile_elems : 0) + NS * a.raw_floats;
-    for (int e = tid; e < nz; e += NTHREADS) z[e] = 0u;
-  }
   for (int b = tid; b < B; b += NTHREADS) vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
-  fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes into the same stages
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -677,6 +681,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   // tensor memory: [0, 2 TP) two dD^T accumulators | [2 TP, 2 TP + Kp) dv accumulator | then the codes, 3 x Bp/2 columns
   const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
   const uint32_t codes = acc_dv + (uint32_t)a.Kp;
+  // The batch codes are the first thing on the critical path of tile 0.  Their loads go out BEFORE any bulk prefetch
+  // (148 CTAs x 3 stages of D/m/s tiles would queue ~13 MB ahead of them: measured 4 us) and fly during the zero fill.
+  // worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
+  float vv[2][16];
+  if (warp < NW && a.want_dD) {
+    const int m = (warp & 3) * 32 + lane;
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      const int b0 = 16 * ((warp >> 2) + 4 * ci);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int b = b0 + i;
+        vv[ci][i] = (b < B && m < K) ? __ldg(a.v + vrow_s[b] * K + m) : 0.0f;
+      }
+    }
+  }
+  {
+    // zero everything once: contraction padding must be zero, over-read regions and stale rows finite
+    uint4* z = reinterpret_cast<uint4*>(Di);
+    const int nz = ((dbuf + gbuf) + (a.want_dD ? tile_elems : 0) + NS * a.raw_floats) >> 2;
+    for (int e = tid; e < nz; e += NTHREADS) z[e] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes into the same stages
+  __syncthreads();
+  STAMP(1);
 
   if (warp == WARP_LOAD) {
     // ===== loader: contiguous D (, m, s) tiles by TMA bulk copy =====
@@ -852,22 +881,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     };
 
     if (my_tiles > 0) prefetch(0);
+    STAMP(3);
     if (a.want_dD) {
-      // batch codes (three bf16 terms) -> tensor memory, once per CTA, while the first gradient rows are in flight.
-      // thread <-> atom m = 32*quad + lane (its TMEM lane); a column holds the image pair (2c, 2c+1); the warps of a
-      // quadrant share the 16-image chunks.  All global loads are issued before the first use.
-      const int m = quad * 32 + lane;
+      // batch codes (three bf16 terms) -> tensor memory, once per CTA: a column holds the image pair (2c, 2c+1)
       const int nchunks = a.Bp / 16;  // 8-column chunks per term
-      float vv[2][16];
-#pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int b0 = 16 * (cg + 4 * ci);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int b = b0 + i;
-          vv[ci][i] = (b < B && m < K) ? __ldg(a.v + vrow_s[b] * K + m) : 0.0f;
-        }
-      }
       const uint32_t lane_base = codes + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
@@ -888,8 +905,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
           tmem_st8u(lane_base + (uint32_t)(a.Bp + 8 * c), t2);
         }
       }
+      STAMP(7);
       tmem_st_wait();
     }
+    STAMP(2);
     for (int it = 0; it < my_tiles; ++it) {
       const int p0 = (blockIdx.x + it * gridDim.x) * TP;
       const int s = it % NS;
@@ -984,10 +1003,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
       if (it + 1 < my_tiles) prefetch(it + 1);      // global loads in flight while the tensor core works
       if (a.want_dD && it > 0) epilogue(it - 1);
     }
+    STAMP(4);
     if (my_tiles > 0) {
       if (a.want_dD) epilogue(my_tiles - 1);
       mbar_wait(mma_done + ((my_tiles - 1) & 1), ((my_tiles - 1) >> 1) & 1);  // (dv only: nobody has waited yet)
       tc_fence_after();
+      STAMP(5);
       if (a.want_dv) {
         // dv accumulator (lane = image, column = atom) -> this CTA's slab of the partial buffer.  The slab is first
         // laid out flat in shared memory (the operand images are dead by now) so that it leaves as coalesced stores:
@@ -1022,6 +1043,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+  STAMP(6);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1226,6 +1248,10 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
     long long tot = 0;
     for (int i = 0; i < 10; ++i) { fprintf(stderr, " %s=%.0f", nm[i], (double)h[i] / (double)h[12]); tot += h[i]; }
     fprintf(stderr, " | total=%.0f\n", (double)tot / (double)h[12]);
+    long long st8[8];
+    cudaMemcpyFromSymbol(st8, g_stamp, sizeof(st8));
+    fprintf(stderr, "grad CTA0 stamps (ns from entry): sync=%lld prefetched=%lld codes_stored=%lld codes_built=%lld loop_end=%lld last_epi=%lld exit=%lld\n",
+            st8[1] - st8[0], st8[3] - st8[0], st8[7] - st8[0], st8[2] - st8[0], st8[4] - st8[0], st8[5] - st8[0], st8[6] - st8[0]);
   }
 #endif
   if (want_dv) return launch_reduce_partials(dvb, scratch, B * K, grid, st);
