@@ -555,25 +555,47 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       float* Dhi = Dimg + (it & 1) * 2 * a.dimg;
       float* Dlo = Dhi + a.dimg;
       if (a.vk == 4) {
-        for (int e = tid; e < nitems; e += NT) {
-          const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 4;
-          const float4 val = *reinterpret_cast<const float4*>(rt + 4 * e);
-          float4 hi, lo;
-          split_tf32(val.x, hi.x, lo.x); split_tf32(val.y, hi.y, lo.y);
-          split_tf32(val.z, hi.z, lo.z); split_tf32(val.w, hi.w, lo.w);
-          const int o = (k >> 2) * (a.Sd >> 2) + (p >> 3) * 32 + (p & 7) * 4;
-          *reinterpret_cast<float4*>(Dhi + o) = hi;
-          *reinterpret_cast<float4*>(Dlo + o) = lo;
+        for (int e0 = tid; e0 < nitems; e0 += 4 * NT) {  // four items per thread in flight
+          float4 rawv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * NT;
+            rawv[u] = e < nitems ? *reinterpret_cast<const float4*>(rt + 4 * e) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * NT;
+            if (e < nitems) {
+              const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 4;
+              float4 hi, lo;
+              split_tf32(rawv[u].x, hi.x, lo.x); split_tf32(rawv[u].y, hi.y, lo.y);
+              split_tf32(rawv[u].z, hi.z, lo.z); split_tf32(rawv[u].w, hi.w, lo.w);
+              const int o = (k >> 2) * (a.Sd >> 2) + (p >> 3) * 32 + (p & 7) * 4;
+              *reinterpret_cast<float4*>(Dhi + o) = hi;
+              *reinterpret_cast<float4*>(Dlo + o) = lo;
+            }
+          }
         }
       } else if (a.vk == 2) {
-        for (int e = tid; e < nitems; e += NT) {
-          const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 2;
-          const float2 val = *reinterpret_cast<const float2*>(rt + 2 * e);
-          float2 hi, lo;
-          split_tf32(val.x, hi.x, lo.x); split_tf32(val.y, hi.y, lo.y);
-          const int o = (k >> 2) * (a.Sd >> 2) + (p >> 3) * 32 + (p & 7) * 4 + (k & 3);
-          *reinterpret_cast<float2*>(Dhi + o) = hi;
-          *reinterpret_cast<float2*>(Dlo + o) = lo;
+        for (int e0 = tid; e0 < nitems; e0 += 4 * NT) {
+          float2 rawv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * NT;
+            rawv[u] = e < nitems ? *reinterpret_cast<const float2*>(rt + 2 * e) : make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * NT;
+            if (e < nitems) {
+              const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 2;
+              float2 hi, lo;
+              split_tf32(rawv[u].x, hi.x, lo.x); split_tf32(rawv[u].y, hi.y, lo.y);
+              const int o = (k >> 2) * (a.Sd >> 2) + (p >> 3) * 32 + (p & 7) * 4 + (k & 3);
+              *reinterpret_cast<float2*>(Dhi + o) = hi;
+              *reinterpret_cast<float2*>(Dlo + o) = lo;
+            }
+          }
         }
       } else {
         for (int e = tid; e < nitems; e += NT) {
@@ -852,7 +874,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
       const int n4 = (rows * K) >> 2;
       const size_t base = (size_t)p0 * K;
       if (fused) {
-        mbar_wait(full_raw + sj, (j / NS) & 1);
+        if (!a.want_dv) mbar_wait(full_raw + sj, (j / NS) & 1);  // (with dv, every thread already waited for this stage)
         TIM(8);
         const float* rt = raw + sj * a.raw_floats;
         for (int e4 = tid; e4 < n4; e4 += NT) {
@@ -942,40 +964,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         const float* rt = raw + s * a.raw_floats;
         if (a.cc.use) tile_chan_update(tc, a.cc, p0);
         if (a.vk == 4) {
-          for (int e = tid; e < nitems; e += NT) {
-            const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 4;
-            const float4 raw4 = *reinterpret_cast<const float4*>(rt + 4 * e);
-            float val[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
-            if (a.cc.use) {
-              const float sd = p >= tc.bnd ? tc.std1 : tc.std0, rs = p >= tc.bnd ? tc.rstd1 : tc.rstd0;
+          // four items per thread in flight: the loads first, then four independent split chains
+          for (int e0 = tid; e0 < nitems; e0 += 4 * NT) {
+            float4 rawv[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) val[i] = div_by_const(val[i], sd, rs);
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + u * NT;
+              rawv[u] = e < nitems ? *reinterpret_cast<const float4*>(rt + 4 * e) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_bf16x3(val[i], w0[i], w1[i], w2[i]);
-            bf16_t* dst = Db + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
-            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_hi16(w0[0], w0[1]), pack_hi16(w0[2], w0[3]));
-            *reinterpret_cast<uint2*>(dst + a.dimg) = make_uint2(pack_hi16(w1[0], w1[1]), pack_hi16(w1[2], w1[3]));
-            *reinterpret_cast<uint2*>(dst + 2 * a.dimg) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + u * NT;
+              if (e < nitems) {
+                const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 4;
+                float val[4] = {rawv[u].x, rawv[u].y, rawv[u].z, rawv[u].w};
+                if (a.cc.use) {
+                  const float sd = p >= tc.bnd ? tc.std1 : tc.std0, rs = p >= tc.bnd ? tc.rstd1 : tc.rstd0;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) val[i] = div_by_const(val[i], sd, rs);
+                }
+                uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_bf16x3(val[i], w0[i], w1[i], w2[i]);
+                bf16_t* dst = Db + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_hi16(w0[0], w0[1]), pack_hi16(w0[2], w0[3]));
+                *reinterpret_cast<uint2*>(dst + a.dimg) = make_uint2(pack_hi16(w1[0], w1[1]), pack_hi16(w1[2], w1[3]));
+                *reinterpret_cast<uint2*>(dst + 2 * a.dimg) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
+              }
+            }
           }
         } else if (a.vk == 2) {
-          for (int e = tid; e < nitems; e += NT) {
-            const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 2;
-            const float2 raw2 = *reinterpret_cast<const float2*>(rt + 2 * e);
-            float val[2] = {raw2.x, raw2.y};
-            if (a.cc.use) {
-              const float sd = p >= tc.bnd ? tc.std1 : tc.std0, rs = p >= tc.bnd ? tc.rstd1 : tc.rstd0;
-              val[0] = div_by_const(val[0], sd, rs);
-              val[1] = div_by_const(val[1], sd, rs);
+          for (int e0 = tid; e0 < nitems; e0 += 4 * NT) {
+            float2 rawv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + u * NT;
+              rawv[u] = e < nitems ? *reinterpret_cast<const float2*>(rt + 2 * e) : make_float2(0.f, 0.f);
             }
-            uint32_t w0[2], w1[2], w2[2];
-            split_bf16x3(val[0], w0[0], w1[0], w2[0]);
-            split_bf16x3(val[1], w0[1], w1[1], w2[1]);
-            bf16_t* dst = Db + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
-            *reinterpret_cast<uint32_t*>(dst) = pack_hi16(w0[0], w0[1]);
-            *reinterpret_cast<uint32_t*>(dst + a.dimg) = pack_hi16(w1[0], w1[1]);
-            *reinterpret_cast<uint32_t*>(dst + 2 * a.dimg) = pack_hi16(w2[0], w2[1]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + u * NT;
+              if (e < nitems) {
+                const int p = div_magic_dev(e, a.kdiv), k = (e - p * kv) * 2;
+                float val[2] = {rawv[u].x, rawv[u].y};
+                if (a.cc.use) {
+                  const float sd = p >= tc.bnd ? tc.std1 : tc.std0, rs = p >= tc.bnd ? tc.rstd1 : tc.rstd0;
+                  val[0] = div_by_const(val[0], sd, rs);
+                  val[1] = div_by_const(val[1], sd, rs);
+                }
+                uint32_t w0[2], w1[2], w2[2];
+                split_bf16x3(val[0], w0[0], w1[0], w2[0]);
+                split_bf16x3(val[1], w0[1], w1[1], w2[1]);
+                bf16_t* dst = Db + (k >> 3) * (a.Sd >> 1) + (p >> 3) * 64 + (p & 7) * 8 + (k & 7);
+                *reinterpret_cast<uint32_t*>(dst) = pack_hi16(w0[0], w0[1]);
+                *reinterpret_cast<uint32_t*>(dst + a.dimg) = pack_hi16(w1[0], w1[1]);
+                *reinterpret_cast<uint32_t*>(dst + 2 * a.dimg) = pack_hi16(w2[0], w2[1]);
+              }
+            }
           }
         } else {
           for (int e = tid; e < nitems; e += NT) {
