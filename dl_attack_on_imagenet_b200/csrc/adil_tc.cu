@@ -695,7 +695,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  for (int b = tid; b < B; b += NTHREADS) vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
+  for (int b = tid; b < 128; b += NTHREADS)  // element offset of the code row of image b (rows >= B: row of image B-1)
+    vrow_s[b] = (a.vidx ? (long long)a.vidx[min(b, B - 1)] : (long long)min(b, B - 1)) * (long long)K;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -707,16 +708,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   // (148 CTAs x 3 stages of D/m/s tiles would queue ~13 MB ahead of them: measured 4 us) and fly during the zero fill.
   // worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
   float vv[2][16];
-  if (warp < NW && a.want_dD) {
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) vv[ci][i] = 0.0f;
+  if (warp < NW && a.want_dD && (warp & 3) * 32 < K) {  // (a quadrant whose 32 atoms are all padding keeps zeros)
     const int m = (warp & 3) * 32 + lane;
+    const float* vcol = a.v + min(m, K - 1);
+    const float keep = m < K ? 1.0f : 0.0f;
 #pragma unroll
     for (int ci = 0; ci < 2; ++ci) {
       const int b0 = 16 * ((warp >> 2) + 4 * ci);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int b = b0 + i;
-        vv[ci][i] = (b < B && m < K) ? __ldg(a.v + vrow_s[b] * K + m) : 0.0f;
-      }
+      for (int i = 0; i < 16; ++i) vv[ci][i] = __ldg(vcol + vrow_s[b0 + i]) * ((b0 + i < B) ? keep : 0.0f);
     }
   }
   {
