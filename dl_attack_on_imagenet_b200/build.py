@@ -9,7 +9,8 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libadil_b200.so")
+# ADIL_B200_LIB: load an alternative build (e.g. the -DADIL_TIMING debug build of scripts/build_timing.sh)
+LIB_PATH = os.environ.get("ADIL_B200_LIB") or os.path.join(PKG_DIR, "libadil_b200.so")
 SOURCES = ["adil_api.cu", "adil_fma.cu", "adil_steps.cu", "adil_tc.cu"]
 HEADERS = [os.path.join(CSRC, "adil_common.cuh"), os.path.join(ROOT, "include", "adil_b200.h")]
 

@@ -41,22 +41,44 @@ namespace {
 __device__ long long g_tim[16];
 #define TIM_DECL long long tim_last = clock64(); long long tim_acc[12] = {0}
 #define TIM(i) do { if (tid == 0) { const long long t_ = clock64(); tim_acc[i] += t_ - tim_last; tim_last = t_; } } while (0)
+#define ETIM_DECL long long etim_last = clock64(); long long etim_acc[4] = {0}
+#define ETIM(i) do { if (tid == WARP_EPI * 32) { const long long t_ = clock64(); etim_acc[i] += t_ - etim_last; etim_last = t_; } } while (0)
+#define ETIM_FLUSH() do { if (tid == WARP_EPI * 32) { for (int i_ = 0; i_ < 4; ++i_) atomicAdd((unsigned long long*)&g_tim[4 + i_], (unsigned long long)etim_acc[i_]); } } while (0)
 #define TIM_FLUSH(n) do { if (tid == 0) { for (int i_ = 0; i_ < 12; ++i_) atomicAdd((unsigned long long*)&g_tim[i_], (unsigned long long)tim_acc[i_]); atomicAdd((unsigned long long*)&g_tim[12], (unsigned long long)(n)); } } while (0)
 __device__ long long g_stamp[8];
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_stamp[i] = gtime(); } while (0)
+
 #else
 #define TIM_DECL
 #define TIM(i)
 #define TIM_FLUSH(n)
+#define ETIM_DECL
+#define ETIM(i)
+#define ETIM_FLUSH()
 #define STAMP(i)
+#endif
+// Hand-off chain of one tile (debug builds only, -DADIL_CHAIN; cheap enough not to disturb the schedule): global-timer
+// stamps of CTA 5, tile 6, written by lane 0 of whichever warp passes the probe.
+#ifdef ADIL_CHAIN
+__device__ long long g_chain[16];
+__device__ __forceinline__ long long gtime2() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CHAIN(i, tile) do { if (blockIdx.x == 5 && (tile) == 6 && (threadIdx.x & 31) == 0) g_chain[i] = gtime2(); } while (0)
+#else
+#define CHAIN(i, tile)
 #endif
 
 constexpr int NW = 16;              // worker warps
 constexpr int NT = NW * 32;         // worker threads
 constexpr int WARP_MMA = NW;        // issuer warp
 constexpr int WARP_LOAD = NW + 1;   // loader warp
-constexpr int NTHREADS = NT + 64;   // 576 threads -> at most 112 registers each
+constexpr int NE = 8;               // backward: epilogue warps 16..23 (TMEM quadrant = warp & 3, pixel half = (warp - 16) / 4)
+constexpr int WARP_EPI = NW;
+// The active epilogue warps sit on schedulers 0 and 1 (quadrant = warp % 4 = scheduler) whenever K <= 64; the issuer
+// and the loader go to schedulers 2 and 3 so that they do not queue behind them for issue slots.
+constexpr int WARP_MMA_G = NW + NE + 2;   // backward: issuer warp (26)
+constexpr int WARP_LOAD_G = NW + NE + 3;  // backward: loader warp (27)
+constexpr int NTHREADS_GRAD = (NW + NE + 4) * 32;  // 896 threads -> at most 72 registers each
 constexpr int NIO = 4;              // synthesis: warps 17..20 move the image rows (cp.async in, coalesced stores out)
 constexpr int NTIO = NIO * 32;
 constexpr int NTHREADS_SYNTH = NT + 32 + NTIO;  // 672 threads -> at most 96 registers each
@@ -119,6 +141,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// shared -> global bulk copy (TMA store): full-line writes whatever the row pitch of the tile
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -207,6 +237,24 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* r) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread t <-> TMEM lane base+t)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
   uint32_t u[16];
@@ -663,23 +711,25 @@ struct GradArgs {
 };
 
 template <int TP>
-__global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
+__global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a) {
   constexpr int Q4 = TP / 4;                           // float4 per gradient row
   constexpr int GJ = (128 * Q4 + NT - 1) / NT;         // float4 per worker thread (B <= 128)
-  constexpr int NCG = TP / 16;
+  constexpr int HALF = TP / 2;                         // accumulator columns per epilogue warp
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS]
-  uint64_t* empty_raw = full_raw + NS;                         // [NS]
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS] D (, m, s) tile landed
+  uint64_t* empty_raw = full_raw + NS;                         // [NS] stage consumed (workers: split, epilogue warps: AdamW)
   uint64_t* mma_done = empty_raw + NS;                         // [2] MMAs of the tiles using image buffer 0 / 1 retired
   uint64_t* staged = mma_done + 2;                             // [2] images of buffer 0 / 1 written (workers -> issuer)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
+  uint64_t* acc_empty = staged + 2;                            // [2] dD accumulator 0 / 1 read out (epilogue warps -> issuer)
+  uint64_t* epi_done = acc_empty + 2;                          // [NS] output tile written into the stage (epilogue warps -> loader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + NS);
   long long* vrow_s = reinterpret_cast<long long*>(smem_raw + 256 + 1024);  // [128] row of v of each image
   typedef unsigned short bf16_t;
   const int dbuf = 3 * a.dimg, gbuf = 3 * a.gimg + 1024;          // bf16 elements per buffer (gradient: + 2 KB pad)
   bf16_t* Di = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);   // [2 buffers][3 terms] dictionary images
   bf16_t* Gi = Di + 2 * dbuf;                                     // [2 buffers][3 terms (+ over-read pad)] gradient images
-  float* dDs = reinterpret_cast<float*>(Gi + 2 * gbuf);           // [TP*K] dD tile, flat like the dictionary
-  float* raw = dDs + (a.want_dD ? TP * a.K : 0);                  // [NS][raw_floats]
+  float* dDs = reinterpret_cast<float*>(Gi + 2 * gbuf);           // [2][TP*K] dD tiles, flat like the dictionary (fused step)
+  float* raw = dDs + (a.D2w != nullptr ? 2 * TP * a.K : 0);       // [NS][raw_floats]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
@@ -687,15 +737,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool fused = a.D2w != nullptr;
   const int tile_elems = TP * K;
+  const uint32_t ne_tmem = 2u * (uint32_t)((K + 31) / 32);  // epilogue warps whose TMEM quadrant holds atoms
   STAMP(0);
 
   if (tid == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
-    for (int i = 0; i < 2; ++i) { mbar_init(mma_done + i, 1); mbar_init(staged + i, NW); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); mbar_init(epi_done + i, fused ? NE : ne_tmem); }
+    for (int i = 0; i < 2; ++i) { mbar_init(mma_done + i, 1); mbar_init(staged + i, NW); mbar_init(acc_empty + i, ne_tmem); }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  for (int b = tid; b < 128; b += NTHREADS)  // element offset of the code row of image b (rows >= B: row of image B-1)
+  for (int b = tid; b < 128; b += NTHREADS_GRAD)  // element offset of the code row of image b (rows >= B: row of image B-1)
     vrow_s[b] = (a.vidx ? (long long)a.vidx[min(b, B - 1)] : (long long)min(b, B - 1)) * (long long)K;
   tc_fence_before();
   __syncthreads();
@@ -704,8 +755,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
   // tensor memory: [0, 2 TP) two dD^T accumulators | [2 TP, 2 TP + Kp) dv accumulator | then the codes, 3 x Bp/2 columns
   const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
   const uint32_t codes = acc_dv + (uint32_t)a.Kp;
-  // The batch codes are the first thing on the critical path of tile 0.  Their loads go out BEFORE any bulk prefetch
-  // (148 CTAs x 3 stages of D/m/s tiles would queue ~13 MB ahead of them: measured 4 us) and fly during the zero fill.
+
+  // D (, m, s) tile `it` -> raw stage it % NS: contiguous runs, one TMA bulk copy each.  The raw stages are written
+  // by the async proxy only (never zero-filled), so tile 0 is requested right here; the deeper prefetches wait until
+  // the latency-critical code loads are out (148 CTAs x 3 stages would queue ~13 MB ahead of them: measured 4 us).
+  auto load_raw = [&](int it) {
+    const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+    const int rows = min(TP, P - p0);
+    const int s = it % NS;
+    const uint32_t bytes = (uint32_t)(rows * K * 4);
+    float* dst = raw + s * a.raw_floats;
+    const size_t off = (size_t)p0 * K;
+    mbar_expect_tx(full_raw + s, bytes * (uint32_t)a.nraw);
+    bulk_g2s(dst, a.D2 + off, bytes, full_raw + s);
+    if (a.nraw == 3) {
+      bulk_g2s(dst + tile_elems, a.m + off, bytes, full_raw + s);
+      bulk_g2s(dst + 2 * tile_elems, a.s + off, bytes, full_raw + s);
+    }
+  };
+  if (warp == WARP_LOAD_G && a.nraw > 0) {
+    if (elect_one() && my_tiles > 0) load_raw(0);
+    __syncwarp();
+  }
+
+  // workers: fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q.
+  // The rows of tile 0 are requested before the batch codes (both are on the critical path of the first tile).
+  int gsrc[GJ], gdst[GJ];  // gsrc: 4q, the pixel column (-1: none); gdst: bf16 offset inside an image
+  const float* grow[GJ];   // &g[b, 4q]
+  float4 greg[GJ];
+  auto prefetch = [&](int it) {
+    const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+      greg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gsrc[j] >= 0 && p0 + gsrc[j] < P) greg[j] = ld_stream4(grow[j] + p0);
+    }
+  };
+  if (warp < NW) {
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+      const int e = tid + j * NT;
+      const int b = e / Q4, q = e - b * Q4;
+      gsrc[j] = (b < B) ? 4 * q : -1;
+      grow[j] = a.g + (size_t)min(b, B - 1) * P + 4 * q;
+      gdst[j] = (q >> 1) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (q & 1) * 4;
+    }
+    if (my_tiles > 0) prefetch(0);
+  }
+  // The batch codes: loads go out now and fly during the zero fill.
   // worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
   float vv[2][16];
 #pragma unroll
@@ -724,39 +821,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     }
   }
   {
-    // zero everything once: contraction padding must be zero, over-read regions and stale rows finite
+    // zero the operand images once: contraction padding must be zero, over-read regions finite
     uint4* z = reinterpret_cast<uint4*>(Di);
-    const int nz = ((dbuf + gbuf) + (a.want_dD ? tile_elems : 0) + NS * a.raw_floats) >> 2;
-    for (int e = tid; e < nz; e += NTHREADS) z[e] = make_uint4(0u, 0u, 0u, 0u);
+    const int nz = (2 * (dbuf + gbuf)) >> 3;
+    for (int e = tid; e < nz; e += NTHREADS_GRAD) z[e] = make_uint4(0u, 0u, 0u, 0u);
   }
-  fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes into the same stages
+  fence_proxy_async();  // the zero fill (generic proxy) is ordered before the tensor core's (async proxy) reads
   __syncthreads();
   STAMP(1);
 
-  if (warp == WARP_LOAD) {
-    // ===== loader: contiguous D (, m, s) tiles by TMA bulk copy =====
-    if (a.nraw > 0) {
-      for (int it = 0; it < my_tiles; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int p0 = tile * TP;
-        const int rows = min(TP, P - p0);
-        const int s = it % NS;
-        if (it >= NS) mbar_wait(empty_raw + s, ((it / NS) - 1) & 1);
-        if (elect_one()) {
-          const uint32_t bytes = (uint32_t)(rows * K * 4);
-          float* dst = raw + s * a.raw_floats;
-          const size_t off = (size_t)p0 * K;
-          mbar_expect_tx(full_raw + s, bytes * (uint32_t)a.nraw);
-          bulk_g2s(dst, a.D2 + off, bytes, full_raw + s);
-          if (a.nraw == 3) {
-            bulk_g2s(dst + tile_elems, a.m + off, bytes, full_raw + s);
-            bulk_g2s(dst + 2 * tile_elems, a.s + off, bytes, full_raw + s);
+  if (warp == WARP_LOAD_G) {
+    // ===== loader: the remaining D (, m, s) tiles, each as soon as its stage has been recycled; and the output side:
+    // once the epilogue warps have rewritten the stage of tile jt in place (D, m, s after AdamW, or dD), it leaves
+    // as TMA bulk stores -- contiguous runs of the [p][k] arrays, written as full lines -- and the stage is reused
+    // when the copy engine has read it. =====
+    const bool leader = elect_one();
+    for (int it = 1; it < my_tiles + NS; ++it) {
+      const int jt = it - NS;  // the tile whose stage is recycled now
+      if (jt >= 0) {
+        const int sj = jt % NS;
+        if (a.want_dD) {
+          mbar_wait(epi_done + sj, (jt / NS) & 1);
+          if (leader) {
+            const int p0 = (blockIdx.x + jt * gridDim.x) * TP;
+            const uint32_t bytes = (uint32_t)(min(TP, P - p0) * K * 4);
+            const float* src = raw + sj * a.raw_floats;
+            const size_t off = (size_t)p0 * K;
+            if (fused) {
+              bulk_s2g(a.D2w + off, src, bytes);
+              bulk_s2g(a.m + off, src + tile_elems, bytes);
+              bulk_s2g(a.s + off, src + 2 * tile_elems, bytes);
+            } else {
+              bulk_s2g(a.dD2 + off, src, bytes);
+            }
+            bulk_commit();
+            if (it < my_tiles) {  // the stage is about to be refilled
+              bulk_wait_read0();
+              if (a.nraw == 0) mbar_arrive(full_raw + sj);  // (no loads: hand the staging buffer back directly)
+            }
           }
+          __syncwarp();
         }
+        if (a.want_dv && it < my_tiles) mbar_wait(empty_raw + sj, (jt / NS) & 1);  // the workers have split its D rows
+      }
+      if (it < my_tiles && a.nraw > 0) {
+        if (leader) load_raw(it);
         __syncwarp();
       }
     }
-  } else if (warp == WARP_MMA) {
+    if (leader) bulk_wait0();  // every output tile has been written before the CTA retires
+    __syncwarp();
+  } else if (warp == WARP_MMA_G) {
     // ===== issuer =====
     const uint32_t idesc_dD = make_idesc_bf16(128, TP, false, true);
     const uint32_t idesc_dv = make_idesc_bf16(128, a.Kp, false, true);
@@ -776,10 +891,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     const bool leader = elect_one();
     for (int it = 0; it < my_tiles; ++it) {
       const int buf = it & 1;
+      if (a.want_dD && it >= 2) mbar_wait(acc_empty + buf, ((it - 2) >> 1) & 1);  // accumulator of tile it-2 read out
+      CHAIN(0, it);
       mbar_wait(staged + buf, (it >> 1) & 1);  // workers staged tile `it` (mbarrier: fast warps run one tile ahead)
       tc_fence_after();
+      CHAIN(1, it);
       if (leader) {
+#ifdef ADIL_EXP_NO_DDMMA
+        if (false) {
+#else
         if (a.want_dD) {
+#endif
           const uint32_t acc = tmem_base + (uint32_t)(buf * TP);
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
@@ -790,7 +912,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
             for (int ks = 0; ks < ksteps_dD; ++ks, at += 8, bd += 16) mma_bf16_ts(acc, at, bd, idesc_dD, (t | ks) ? 1u : 0u);
           }
         }
+#ifdef ADIL_EXP_NO_DVMMA
+        if (false) {
+#else
         if (a.want_dv) {
+#endif
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
             constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, td[6] = {0, 2, 1, 0, 1, 0};
@@ -804,9 +930,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         mma_commit(mma_done + buf);
       }
       __syncwarp();
+      CHAIN(2, it);
+    }
+  } else if (warp >= WARP_EPI + NE) {
+    // (warps 24, 25: idle filler so that the issuer and the loader land on schedulers 2 and 3)
+  } else if (warp >= WARP_EPI) {
+    // ===== epilogue warps (8, two per scheduler).  Phase A: the warps whose TMEM quadrant holds atoms (quadrant q,
+    // pixel half h: atoms [32q, 32q+32) of pixels [h TP/2, (h+1) TP/2)) read the dD^T accumulator (lane = atom,
+    // column = pixel), release it to the tensor core, multiply by 1/std and write it flat -- [pixel][atom], like the
+    // dictionary -- into shared memory: per pixel a warp writes 32 consecutive floats, conflict-free.  Fused step:
+    // into a double-buffered gradient tile; then (phase B) all eight warps run AdamW + clamp as one 128-bit pass over
+    // the TMA-landed D / m / s rows IN PLACE.  Plain dD output: straight into the stage.  Either way the finished
+    // stage leaves through the loader warp as TMA bulk stores. =====
+    const int quad = warp & 3, half = (warp - WARP_EPI) >> 2;
+    const bool has_atoms = quad * 32 < K;
+    if (a.want_dD && (fused || has_atoms)) {  // (plain dD output: a quadrant without atoms has nothing to do)
+      const int k = quad * 32 + lane;
+      const bool k_ok = k < K;
+      const int etid = tid - WARP_EPI * 32;
+      TileChan tc;
+      tile_chan_init(tc);
+      ETIM_DECL;
+      for (int j = 0; j < my_tiles; ++j) {
+        const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+        const int rows = min(TP, P - p0);
+        const int sj = j % NS, buf = j & 1;
+        float* stage = raw + sj * a.raw_floats;
+        float* gtile = fused ? dDs + buf * tile_elems : stage;
+        if (has_atoms) {
+          if (a.cc.use) tile_chan_update(tc, a.cc, p0);
+          mbar_wait(mma_done + buf, (j >> 1) & 1);  // MMAs of tile j retired: its dD accumulator is complete
+          tc_fence_after();
+          ETIM(0);
+          if (warp == WARP_EPI) CHAIN(3, j);
+          float r[HALF];
+          {
+            const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TP + half * HALF);
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 8) tmem_ld8_nowait(tcol + (uint32_t)c0, &r[c0]);
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + buf);  // the accumulator is in registers: the tensor core may reuse it
+          ETIM(1);
+          if (warp == WARP_EPI) CHAIN(4, j);
+          // (plain dD output with dv: the stage held the D rows of the dictionary split, which every worker finished
+          // before the MMAs of this tile were issued; without dv it is a staging buffer handed back by the loader)
+          if (!fused && a.nraw == 0 && j >= NS) mbar_wait(full_raw + sj, ((j / NS) - 1) & 1);
+          if (k_ok) {
+            float* col = gtile + (half * HALF) * K + k;
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+              const float sc = a.cc.use ? ((half * HALF + i) >= tc.bnd ? tc.rstd1 : tc.rstd0) : 1.0f;
+              col[i * K] = __fmul_rn(r[i], sc);  // (rows past a ragged end are written too: never stored)
+            }
+          }
+        }
+        if (fused) {
+          bar_sync(3, NE * 32);  // gradient tile complete (and every warp is done with the tile two steps back)
+          ETIM(2);
+          mbar_wait(full_raw + sj, (j / NS) & 1);
+          const int n4 = (rows * K) >> 2;
+#ifndef ADIL_EXP_NO_EPI
+#pragma unroll 2
+          for (int e4 = etid; e4 < n4; e4 += NE * 32) {
+            float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
+            float4 Mv = *reinterpret_cast<const float4*>(stage + tile_elems + 4 * e4);
+            float4 Sv = *reinterpret_cast<const float4*>(stage + 2 * tile_elems + 4 * e4);
+            const float4 gd = *reinterpret_cast<const float4*>(gtile + 4 * e4);
+            adamw_update_fast(Dv.x, Mv.x, Sv.x, gd.x, a.hp);
+            adamw_update_fast(Dv.y, Mv.y, Sv.y, gd.y, a.hp);
+            adamw_update_fast(Dv.z, Mv.z, Sv.z, gd.z, a.hp);
+            adamw_update_fast(Dv.w, Mv.w, Sv.w, gd.w, a.hp);
+            if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
+              Dv.x = clamp1(Dv.x); Dv.y = clamp1(Dv.y); Dv.z = clamp1(Dv.z); Dv.w = clamp1(Dv.w);
+            }
+            *reinterpret_cast<float4*>(stage + 4 * e4) = Dv;
+            *reinterpret_cast<float4*>(stage + tile_elems + 4 * e4) = Mv;
+            *reinterpret_cast<float4*>(stage + 2 * tile_elems + 4 * e4) = Sv;
+          }
+#endif
+        }
+        fence_proxy_async();  // the rewritten stage is read by the copy engine
+        __syncwarp();
+        if (lane == 0) mbar_arrive(epi_done + sj);
+        ETIM(3);
+        if (warp == WARP_EPI) CHAIN(5, j);
+      }
+      ETIM_FLUSH();
     }
   } else {
-    // ===== workers =====
+    // ===== workers: stage the operand images of tile `it` while the MMAs of tile it-1 run =====
     const int quad = warp & 3, cg = warp >> 2;
     const int kv = K / a.vk;
     const int nitems = TP * kv;
@@ -814,99 +1029,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
     TileChan tc;
     tile_chan_init(tc);
     TIM_DECL;
-    // fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q
-    int gsrc[GJ], gdst[GJ];  // gsrc: 4q, the pixel column (-1: none); gdst: bf16 offset inside an image
-    const float* grow[GJ];   // &g[b, 4q]
-#pragma unroll
-    for (int j = 0; j < GJ; ++j) {
-      const int e = tid + j * NT;
-      const int b = e / Q4, q = e - b * Q4;
-      gsrc[j] = (b < B) ? 4 * q : -1;
-      grow[j] = a.g + (size_t)min(b, B - 1) * P + 4 * q;
-      gdst[j] = (q >> 1) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (q & 1) * 4;
-    }
-    float4 greg[GJ];
-    auto prefetch = [&](int it) {
-      const int p0 = (blockIdx.x + it * gridDim.x) * TP;
-#pragma unroll
-      for (int j = 0; j < GJ; ++j) {
-        greg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gsrc[j] >= 0 && p0 + gsrc[j] < P) greg[j] = ld_stream4(grow[j] + p0);
-      }
-    };
-
-    auto epilogue = [&](int j) {
-      const int tile = blockIdx.x + j * gridDim.x;
-      const int p0 = tile * TP;
-      const int rows = min(TP, P - p0);
-      const int sj = j % NS;
-      mbar_wait(mma_done + (j & 1), (j >> 1) & 1);  // MMAs of tile j retired: its dD accumulator is complete
-      tc_fence_after();
-      TIM(4);
-      bar_sync(2, NT);  // every worker is done with the dD staging tile of the previous epilogue
-      TIM(5);
-      // phase A: accumulator (lane = atom, column = pixel) -> flat [pixel][atom] staging tile, divided by std
-      if (cg < NCG) {
-        float r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((j & 1) * TP + cg * 16), r);
-        const int k = quad * 32 + lane;
-        if (k < K) {
-          float* col = dDs + (cg * 16) * K + k;
-          if (a.cc.use) {
-            tile_chan_update(tc, a.cc, p0);
-            if (tc.bnd >= TP) {  // the whole tile lies in one channel (warp-uniform)
-#pragma unroll
-              for (int i = 0; i < 16; ++i) col[i * K] = __fmul_rn(r[i], tc.rstd0);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const bool hi_c = (cg * 16 + i) >= tc.bnd;
-                col[i * K] = __fmul_rn(r[i], hi_c ? tc.rstd1 : tc.rstd0);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) col[i * K] = r[i];
-          }
-        }
-        tc_fence_before();
-      }
-      TIM(6);
-      bar_sync(2, NT);
-      TIM(7);
-      // phase B: one flat 128-bit pass over the tile's contiguous [rows x K] block
-      const int n4 = (rows * K) >> 2;
-      const size_t base = (size_t)p0 * K;
-      if (fused) {
-        if (!a.want_dv) mbar_wait(full_raw + sj, (j / NS) & 1);  // (with dv, every thread already waited for this stage)
-        TIM(8);
-        const float* rt = raw + sj * a.raw_floats;
-        for (int e4 = tid; e4 < n4; e4 += NT) {
-          float4 Dv = *reinterpret_cast<const float4*>(rt + 4 * e4);
-          float4 Mv = *reinterpret_cast<const float4*>(rt + tile_elems + 4 * e4);
-          float4 Sv = *reinterpret_cast<const float4*>(rt + 2 * tile_elems + 4 * e4);
-          const float4 gd = *reinterpret_cast<const float4*>(dDs + 4 * e4);
-          adamw_update_fast(Dv.x, Mv.x, Sv.x, gd.x, a.hp);
-          adamw_update_fast(Dv.y, Mv.y, Sv.y, gd.y, a.hp);
-          adamw_update_fast(Dv.z, Mv.z, Sv.z, gd.z, a.hp);
-          adamw_update_fast(Dv.w, Mv.w, Sv.w, gd.w, a.hp);
-          if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
-            Dv.x = clamp1(Dv.x); Dv.y = clamp1(Dv.y); Dv.z = clamp1(Dv.z); Dv.w = clamp1(Dv.w);
-          }
-          *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv;
-          *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mv;
-          *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sv;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_raw + sj);
-      } else {
-        for (int e4 = tid; e4 < n4; e4 += NT)
-          *reinterpret_cast<float4*>(a.dD2 + base + 4 * (size_t)e4) = *reinterpret_cast<const float4*>(dDs + 4 * e4);
-      }
-      TIM(9);
-    };
-
-    if (my_tiles > 0) prefetch(0);
     STAMP(3);
     if (a.want_dD) {
       // batch codes (three bf16 terms) -> tensor memory, once per CTA: a column holds the image pair (2c, 2c+1)
@@ -960,12 +1082,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
           *reinterpret_cast<uint2*>(dst + 2 * a.gimg) = make_uint2(pack_hi16(w2[0], w2[1]), pack_hi16(w2[2], w2[3]));
         }
       }
+      if (it + 1 < my_tiles) prefetch(it + 1);      // the registers are free again: next tile's rows fly from here on
       TIM(1);
       if (a.want_dv) {
-        // dictionary tile (pre-update values): TMA-landed raw rows -> three bf16 images of D / std
+        // dictionary tile (pre-update values): TMA-landed raw rows -> three bf16 images of D / std.  Rows past the end
+        // of the array (ragged last tile) were never written: they are staged as zeros.
+        if (warp == 0) { CHAIN(7, it - NS); CHAIN(10, it); }
         mbar_wait(full_raw + s, (it / NS) & 1);
         TIM(2);
+        if (warp == 0) CHAIN(8, it - NS);
         const float* rt = raw + s * a.raw_floats;
+        const int nvalid = min(TP, P - p0) * kv;
         if (a.cc.use) tile_chan_update(tc, a.cc, p0);
         if (a.vk == 4) {
           // four items per thread in flight: the loads first, then four independent split chains
@@ -974,7 +1101,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int e = e0 + u * NT;
-              rawv[u] = e < nitems ? *reinterpret_cast<const float4*>(rt + 4 * e) : make_float4(0.f, 0.f, 0.f, 0.f);
+              rawv[u] = e < nvalid ? *reinterpret_cast<const float4*>(rt + 4 * e) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -1003,7 +1130,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int e = e0 + u * NT;
-              rawv[u] = e < nitems ? *reinterpret_cast<const float2*>(rt + 2 * e) : make_float2(0.f, 0.f);
+              rawv[u] = e < nvalid ? *reinterpret_cast<const float2*>(rt + 2 * e) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -1029,7 +1156,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         } else {
           for (int e = tid; e < nitems; e += NT) {
             const int p = div_magic_dev(e, a.kdiv), k = e - p * kv;
-            float val = rt[e];
+            float val = e < nvalid ? rt[e] : 0.0f;
             if (a.cc.use) val = div_by_const(val, p >= tc.bnd ? tc.std1 : tc.std0, p >= tc.bnd ? tc.rstd1 : tc.rstd0);
             uint32_t w0, w1, w2;
             split_bf16x3(val, w0, w1, w2);
@@ -1039,23 +1166,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
             dst[2 * a.dimg] = (bf16_t)(w2 >> 16);
           }
         }
-        if (!fused) {  // the raw stage held D only and is consumed
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty_raw + s);
-        }
       }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();                                 // the ragged loops of every lane are over
-      if (lane == 0) mbar_arrive(staged + buf);     // hand the tile to the issuer warp, keep going
+      if (lane == 0) {
+        mbar_arrive(staged + buf);                  // hand the tile to the issuer warp, keep going
+        if (a.want_dv) mbar_arrive(empty_raw + s);  // this warp is done with the raw dictionary rows
+      }
       TIM(3);
-      if (it + 1 < my_tiles) prefetch(it + 1);      // global loads in flight while the tensor core works
-      if (a.want_dD && it > 0) epilogue(it - 1);
+      if (warp == 0) CHAIN(9, it);
     }
     STAMP(4);
     if (my_tiles > 0) {
-      if (a.want_dD) epilogue(my_tiles - 1);
-      mbar_wait(mma_done + ((my_tiles - 1) & 1), ((my_tiles - 1) >> 1) & 1);  // (dv only: nobody has waited yet)
+      mbar_wait(mma_done + ((my_tiles - 1) & 1), ((my_tiles - 1) >> 1) & 1);  // every MMA of this CTA has retired
       tc_fence_after();
       STAMP(5);
       if (a.want_dv) {
@@ -1064,7 +1188,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) grad_kernel(const GradArgs a) {
         // 148 CTAs writing 4-byte pieces at a 4K-byte stride cost several microseconds at the end of the kernel.
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the reduction kernel may start launching
         float* stg = reinterpret_cast<float*>(Di);
-        bar_sync(2, NT);
         const int b = quad * 32 + lane;
         for (int c0 = cg * 16; c0 < a.Kp; c0 += 64) {  // warp-uniform
           float r[16];
@@ -1158,9 +1281,9 @@ GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool
     pl.dimg = want_dv ? (pl.Kp / 8) * (pl.Sd / 2) : 0;
     pl.gimg = (TP / 8) * (pl.Sg / 2);
     pl.nraw = fused ? 3 : (want_dv ? 1 : 0);
-    pl.raw_floats = pl.nraw * TP * K;
+    pl.raw_floats = (pl.nraw > 0 ? pl.nraw : 1) * TP * K;  // (dD only: the stage is the staging buffer of the output tile)
     pl.smem = HDR_BYTES + 2 * 2 * (3 * ((size_t)pl.dimg + pl.gimg) + 1024) +  // two buffers of bf16 images
-              sizeof(float) * ((want_dD ? (size_t)TP * K : 0) + (size_t)NS * pl.raw_floats);
+              sizeof(float) * ((fused ? 2 * (size_t)TP * K : 0) + (size_t)NS * pl.raw_floats);
     if (want_dv && pl.smem < HDR_BYTES + sizeof(float) * (size_t)B * K) pl.smem = HDR_BYTES + sizeof(float) * (size_t)B * K;
     pl.tmem_cols = pow2_cols(2 * TP + pl.Kp + 3 * (pl.Bp / 2));  // accumulators + the codes
     if (pl.smem <= (size_t)SMEM_LIMIT && pl.tmem_cols <= 512) { pl.ok = true; return pl; }
@@ -1248,7 +1371,7 @@ template <int TP>
 int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
   int rc = set_smem(grad_kernel<TP>, smem, "cudaFuncSetAttribute(grad_kernel)");
   if (rc) return rc;
-  grad_kernel<TP><<<grid, NTHREADS, smem, st>>>(a);
+  grad_kernel<TP><<<grid, NTHREADS_GRAD, smem, st>>>(a);
   return check_cuda(cudaGetLastError(), "grad_kernel launch");
 }
 }  // namespace
@@ -1292,11 +1415,23 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
     cudaMemcpyFromSymbol(h, g_tim, sizeof(h));
     long long z[16] = {0};
     cudaMemcpyToSymbol(g_tim, z, sizeof(z));
-    const char* nm[10] = {"wait_mma", "g_split", "wait_raw", "D_split+arrive", "prefetch", "bar1", "phaseA", "bar2", "wait_raw2", "phaseB"};
+    const char* nm[10] = {"wait_mma", "g_split+prefetch", "wait_raw", "D_split+arrive", "E:wait_mma", "E:tmem_ld", "E:wait_raw", "E:adamw+store", "-", "-"};
     fprintf(stderr, "grad TP=%d tiles=%lld cycles/tile:", pl.TP, h[12]);
     long long tot = 0;
     for (int i = 0; i < 10; ++i) { fprintf(stderr, " %s=%.0f", nm[i], (double)h[i] / (double)h[12]); tot += h[i]; }
     fprintf(stderr, " | total=%.0f\n", (double)tot / (double)h[12]);
+#endif
+#ifdef ADIL_CHAIN
+  {
+    cudaDeviceSynchronize();
+    long long ch[16];
+    cudaMemcpyFromSymbol(ch, g_chain, sizeof(ch));
+    fprintf(stderr, "grad CTA5 tile 6 chain (ns after worker D-split start of tile 6): issuer_waits=%lld staged=%lld mma_issued=%lld E_sees_done=%lld E_ld_done=%lld E_adamw_done=%lld loader_sees_empty=%lld | worker_staged6=%lld worker_at_raw9=%lld raw9_landed=%lld\n",
+            ch[0] - ch[10], ch[1] - ch[10], ch[2] - ch[10], ch[3] - ch[10], ch[4] - ch[10], ch[5] - ch[10], ch[6] - ch[10], ch[9] - ch[10], ch[7] - ch[10], ch[8] - ch[10]);
+  }
+#endif
+#ifdef ADIL_TIMING
+  {
     long long st8[8];
     cudaMemcpyFromSymbol(st8, g_stamp, sizeof(st8));
     fprintf(stderr, "grad CTA0 stamps (ns from entry): sync=%lld prefetched=%lld codes_stored=%lld codes_built=%lld loop_end=%lld last_epi=%lld exit=%lld\n",
