@@ -102,6 +102,15 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
                : "l"(p));
   return r;
 }
+// 128-bit load of data this kernel also writes (no .nc), not kept in L1
+__device__ __forceinline__ float4 ld_global4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
 __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)

@@ -26,6 +26,7 @@
 // (r = M/N index, c = contraction index: LBO = S, SBO = 128) and an MN-major operand (r = contraction index,
 // c = M/N index: LBO = 128, SBO = S).
 #include <cstdio>
+#include <cstdlib>
 
 #include "adil_common.cuh"
 
@@ -701,7 +702,7 @@ struct GradArgs {
   int Sg, Sd;         // byte strides between column groups of the gradient (= code) / dictionary images
   int dimg, gimg;     // bf16 elements per image term
   int raw_floats;     // floats per raw stage
-  int nraw;           // arrays per raw stage: 3 (D, m, s: fused), 1 (D only) or 0
+  int nraw;           // 1: the stages receive the D rows of each tile by TMA; 0: no loads (dD only: staging buffers)
   int vk;             // vector width of the dictionary split
   unsigned kdiv;      // ceil(2^32 / (K / vk))
   uint32_t tmem_cols;
@@ -715,6 +716,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   constexpr int Q4 = TP / 4;                           // float4 per gradient row
   constexpr int GJ = (128 * Q4 + NT - 1) / NT;         // float4 per worker thread (B <= 128)
   constexpr int HALF = TP / 2;                         // accumulator columns per epilogue warp
+  constexpr int NPF = 4;                               // float4 items per epilogue thread whose moments are prefetched
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS] D (, m, s) tile landed
   uint64_t* empty_raw = full_raw + NS;                         // [NS] stage consumed (workers: split, epilogue warps: AdamW)
@@ -741,7 +743,8 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   STAMP(0);
 
   if (tid == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); mbar_init(epi_done + i, fused ? NE : ne_tmem); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, (a.want_dv ? NW : 0) + (fused ? NE : 0) + ((a.want_dv || fused) ? 0 : 1));
+                                   mbar_init(epi_done + i, ne_tmem); }
     for (int i = 0; i < 2; ++i) { mbar_init(mma_done + i, 1); mbar_init(staged + i, NW); mbar_init(acc_empty + i, ne_tmem); }
     fence_mbar_init();
   }
@@ -766,12 +769,8 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     const uint32_t bytes = (uint32_t)(rows * K * 4);
     float* dst = raw + s * a.raw_floats;
     const size_t off = (size_t)p0 * K;
-    mbar_expect_tx(full_raw + s, bytes * (uint32_t)a.nraw);
+    mbar_expect_tx(full_raw + s, bytes);
     bulk_g2s(dst, a.D2 + off, bytes, full_raw + s);
-    if (a.nraw == 3) {
-      bulk_g2s(dst + tile_elems, a.m + off, bytes, full_raw + s);
-      bulk_g2s(dst + 2 * tile_elems, a.s + off, bytes, full_raw + s);
-    }
   };
   if (warp == WARP_LOAD_G && a.nraw > 0) {
     if (elect_one() && my_tiles > 0) load_raw(0);
@@ -831,29 +830,21 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   STAMP(1);
 
   if (warp == WARP_LOAD_G) {
-    // ===== loader: the remaining D (, m, s) tiles, each as soon as its stage has been recycled; and the output side:
-    // once the epilogue warps have rewritten the stage of tile jt in place (D, m, s after AdamW, or dD), it leaves
-    // as TMA bulk stores -- contiguous runs of the [p][k] arrays, written as full lines -- and the stage is reused
-    // when the copy engine has read it. =====
+    // ===== loader: the remaining D tiles, each as soon as its stage has been recycled (by the workers' dictionary split
+    // and, in the fused step, by the AdamW pass of the epilogue warps).  Plain dD output: the epilogue warps write
+    // the dD tile into the stage and it leaves here as one TMA bulk store (full-line writes whatever the row pitch);
+    // the stage is reused when the copy engine has read it. =====
     const bool leader = elect_one();
+    const bool dD_out = a.want_dD && !fused;
     for (int it = 1; it < my_tiles + NS; ++it) {
       const int jt = it - NS;  // the tile whose stage is recycled now
       if (jt >= 0) {
         const int sj = jt % NS;
-        if (a.want_dD) {
+        if (dD_out) {
           mbar_wait(epi_done + sj, (jt / NS) & 1);
           if (leader) {
             const int p0 = (blockIdx.x + jt * gridDim.x) * TP;
-            const uint32_t bytes = (uint32_t)(min(TP, P - p0) * K * 4);
-            const float* src = raw + sj * a.raw_floats;
-            const size_t off = (size_t)p0 * K;
-            if (fused) {
-              bulk_s2g(a.D2w + off, src, bytes);
-              bulk_s2g(a.m + off, src + tile_elems, bytes);
-              bulk_s2g(a.s + off, src + 2 * tile_elems, bytes);
-            } else {
-              bulk_s2g(a.dD2 + off, src, bytes);
-            }
+            bulk_s2g(a.dD2 + (size_t)p0 * K, raw + sj * a.raw_floats, (uint32_t)(min(TP, P - p0) * K * 4));
             bulk_commit();
             if (it < my_tiles) {  // the stage is about to be refilled
               bulk_wait_read0();
@@ -862,14 +853,14 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           }
           __syncwarp();
         }
-        if (a.want_dv && it < my_tiles) mbar_wait(empty_raw + sj, (jt / NS) & 1);  // the workers have split its D rows
+        if ((a.want_dv || fused) && it < my_tiles) mbar_wait(empty_raw + sj, (jt / NS) & 1);  // D rows consumed
       }
       if (it < my_tiles && a.nraw > 0) {
         if (leader) load_raw(it);
         __syncwarp();
       }
     }
-    if (leader) bulk_wait0();  // every output tile has been written before the CTA retires
+    if (leader && dD_out) bulk_wait0();  // every output tile has been written before the CTA retires
     __syncwarp();
   } else if (warp == WARP_MMA_G) {
     // ===== issuer =====
@@ -951,6 +942,22 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       TileChan tc;
       tile_chan_init(tc);
       ETIM_DECL;
+      // AdamW moments: straight from global memory into registers, one tile ahead (they never need shared memory)
+      float4 Mp[NPF], Sp[NPF];
+      auto prefetch_ms = [&](int j) {
+        const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+        const int n4 = (min(TP, P - p0) * K) >> 2;
+        const size_t base = (size_t)p0 * K;
+#pragma unroll
+        for (int u = 0; u < NPF; ++u) {
+          const int e4 = etid + u * (NE * 32);
+          if (e4 < n4) {
+            Mp[u] = ld_global4(a.m + base + 4 * (size_t)e4);
+            Sp[u] = ld_global4(a.s + base + 4 * (size_t)e4);
+          }
+        }
+      };
+      if (fused && my_tiles > 0) prefetch_ms(0);
       for (int j = 0; j < my_tiles; ++j) {
         const int p0 = (blockIdx.x + j * gridDim.x) * TP;
         const int rows = min(TP, P - p0);
@@ -963,41 +970,59 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           tc_fence_after();
           ETIM(0);
           if (warp == WARP_EPI) CHAIN(3, j);
-          float r[HALF];
-          {
-            const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TP + half * HALF);
-#pragma unroll
-            for (int c0 = 0; c0 < HALF; c0 += 8) tmem_ld8_nowait(tcol + (uint32_t)c0, &r[c0]);
-            tmem_ld_wait();
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + buf);  // the accumulator is in registers: the tensor core may reuse it
-          ETIM(1);
-          if (warp == WARP_EPI) CHAIN(4, j);
           // (plain dD output with dv: the stage held the D rows of the dictionary split, which every worker finished
           // before the MMAs of this tile were issued; without dv it is a staging buffer handed back by the loader)
           if (!fused && a.nraw == 0 && j >= NS) mbar_wait(full_raw + sj, ((j / NS) - 1) & 1);
-          if (k_ok) {
-            float* col = gtile + (half * HALF) * K + k;
+          const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TP + half * HALF);
 #pragma unroll
-            for (int i = 0; i < HALF; ++i) {
-              const float sc = a.cc.use ? ((half * HALF + i) >= tc.bnd ? tc.rstd1 : tc.rstd0) : 1.0f;
-              col[i * K] = __fmul_rn(r[i], sc);  // (rows past a ragged end are written too: never stored)
+          for (int c0 = 0; c0 < HALF; c0 += 8) {  // eight columns at a time: low register pressure
+            float r[8];
+            tmem_ld8_nowait(tcol + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (k_ok) {
+              float* col = gtile + (half * HALF + c0) * K + k;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float sc = a.cc.use ? ((half * HALF + c0 + i) >= tc.bnd ? tc.rstd1 : tc.rstd0) : 1.0f;
+                col[i * K] = __fmul_rn(r[i], sc);  // (rows past a ragged end are written too: never stored)
+              }
             }
           }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + buf);  // the accumulator has been read: the tensor core may reuse it
+          ETIM(1);
+          if (warp == WARP_EPI) CHAIN(4, j);
         }
         if (fused) {
           bar_sync(3, NE * 32);  // gradient tile complete (and every warp is done with the tile two steps back)
           ETIM(2);
-          mbar_wait(full_raw + sj, (j / NS) & 1);
+          mbar_wait(full_raw + sj, (j / NS) & 1);  // D rows landed
           const int n4 = (rows * K) >> 2;
+          const size_t base = (size_t)p0 * K;
 #ifndef ADIL_EXP_NO_EPI
-#pragma unroll 2
-          for (int e4 = etid; e4 < n4; e4 += NE * 32) {
+#pragma unroll
+          for (int u = 0; u < NPF; ++u) {
+            const int e4 = etid + u * (NE * 32);
+            if (e4 < n4) {
+              float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
+              const float4 gd = *reinterpret_cast<const float4*>(gtile + 4 * e4);
+              adamw_update_fast(Dv.x, Mp[u].x, Sp[u].x, gd.x, a.hp);
+              adamw_update_fast(Dv.y, Mp[u].y, Sp[u].y, gd.y, a.hp);
+              adamw_update_fast(Dv.z, Mp[u].z, Sp[u].z, gd.z, a.hp);
+              adamw_update_fast(Dv.w, Mp[u].w, Sp[u].w, gd.w, a.hp);
+              if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
+                Dv.x = clamp1(Dv.x); Dv.y = clamp1(Dv.y); Dv.z = clamp1(Dv.z); Dv.w = clamp1(Dv.w);
+              }
+              *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv;
+              *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mp[u];
+              *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sp[u];
+            }
+          }
+          for (int e4 = etid + NPF * (NE * 32); e4 < n4; e4 += NE * 32) {  // (large K: beyond the prefetched part)
             float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
-            float4 Mv = *reinterpret_cast<const float4*>(stage + tile_elems + 4 * e4);
-            float4 Sv = *reinterpret_cast<const float4*>(stage + 2 * tile_elems + 4 * e4);
+            float4 Mv = ld_global4(a.m + base + 4 * (size_t)e4);
+            float4 Sv = ld_global4(a.s + base + 4 * (size_t)e4);
             const float4 gd = *reinterpret_cast<const float4*>(gtile + 4 * e4);
             adamw_update_fast(Dv.x, Mv.x, Sv.x, gd.x, a.hp);
             adamw_update_fast(Dv.y, Mv.y, Sv.y, gd.y, a.hp);
@@ -1006,15 +1031,19 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
             if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
               Dv.x = clamp1(Dv.x); Dv.y = clamp1(Dv.y); Dv.z = clamp1(Dv.z); Dv.w = clamp1(Dv.w);
             }
-            *reinterpret_cast<float4*>(stage + 4 * e4) = Dv;
-            *reinterpret_cast<float4*>(stage + tile_elems + 4 * e4) = Mv;
-            *reinterpret_cast<float4*>(stage + 2 * tile_elems + 4 * e4) = Sv;
+            *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv;
+            *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mv;
+            *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sv;
           }
 #endif
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_raw + sj);  // this warp is done with the D rows of the stage
+          if (j + 1 < my_tiles) prefetch_ms(j + 1);    // the moments of the next tile fly while its MMAs run
+        } else {
+          fence_proxy_async();  // the dD tile in the stage is read by the copy engine
+          __syncwarp();
+          if (lane == 0) mbar_arrive(epi_done + sj);
         }
-        fence_proxy_async();  // the rewritten stage is read by the copy engine
-        __syncwarp();
-        if (lane == 0) mbar_arrive(epi_done + sj);
         ETIM(3);
         if (warp == WARP_EPI) CHAIN(5, j);
       }
@@ -1270,9 +1299,10 @@ GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool
   if (B < 1 || B > 128 || K < 1 || K > 128 || P % 4 != 0 || hw % 4 != 0) return pl;
   if (!want_dD && !want_dv) return pl;
   const int tps[4] = {64, 48, 32, 16};
+  static const int max_tp = getenv("ADIL_GRAD_MAX_TP") ? atoi(getenv("ADIL_GRAD_MAX_TP")) : 64;  // tuning knob
   for (int i = 0; i < 4; ++i) {
     const int TP = tps[i];
-    if (hw < TP) continue;
+    if (hw < TP || TP > max_tp) continue;
     pl.TP = TP;
     pl.Bp = rup(B, 16);
     pl.Kp = rup(K, 16);
@@ -1280,7 +1310,7 @@ GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool
     pl.Sd = img_stride(TP);
     pl.dimg = want_dv ? (pl.Kp / 8) * (pl.Sd / 2) : 0;
     pl.gimg = (TP / 8) * (pl.Sg / 2);
-    pl.nraw = fused ? 3 : (want_dv ? 1 : 0);
+    pl.nraw = (fused || want_dv) ? 1 : 0;
     pl.raw_floats = (pl.nraw > 0 ? pl.nraw : 1) * TP * K;  // (dD only: the stage is the staging buffer of the output tile)
     pl.smem = HDR_BYTES + 2 * 2 * (3 * ((size_t)pl.dimg + pl.gimg) + 1024) +  // two buffers of bf16 images
               sizeof(float) * ((fused ? 2 * (size_t)TP * K : 0) + (size_t)NS * pl.raw_floats);
