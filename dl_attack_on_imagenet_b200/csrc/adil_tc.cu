@@ -57,7 +57,6 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #define ETIM_DECL
 #define ETIM(i)
 #define ETIM_FLUSH()
-#define STAMP(i)
 #endif
 // Hand-off chain of one tile (debug builds only, -DADIL_CHAIN; cheap enough not to disturb the schedule): global-timer
 // stamps of CTA 5, tile 6, written by lane 0 of whichever warp passes the probe.
@@ -65,8 +64,11 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 __device__ long long g_chain[16];
 __device__ __forceinline__ long long gtime2() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define CHAIN(i, tile) do { if (blockIdx.x == 5 && (tile) == 6 && (threadIdx.x & 31) == 0) g_chain[i] = gtime2(); } while (0)
+__device__ long long g_stamp[8];
+#define STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_stamp[i] = gtime2(); } while (0)
 #else
 #define CHAIN(i, tile)
+#define STAMP(i)
 #endif
 
 constexpr int NW = 16;              // worker warps
@@ -114,14 +116,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait WITHOUT a suspend-time hint: the instruction itself blocks in hardware for an implementation-defined
+// time.  With a hint ptxas emits PHASECHK + NANOSLEEP.SYNCS, which returns at once: measured 3.0 M spin iterations per
+// launch -- 36 % of all executed instructions and 76 % utilisation of the XU pipe that AdamW's sqrt / rcp need.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint (ns): idle warps must not eat issue slots
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
@@ -164,6 +169,15 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// register rebalancing between warpgroups (all four warps of an aligned group of four must execute it)
+#ifndef ADIL_V_SETMAXNREG  // (measured: no gain here -- the issuer spills at 24 registers, the epilogue warps do not need 96)
+template <int R> __device__ __forceinline__ void reg_alloc() {}
+template <int R> __device__ __forceinline__ void reg_dealloc() {}
+#else
+template <int R> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+#endif
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
@@ -759,9 +773,8 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
   const uint32_t codes = acc_dv + (uint32_t)a.Kp;
 
-  // D (, m, s) tile `it` -> raw stage it % NS: contiguous runs, one TMA bulk copy each.  The raw stages are written
-  // by the async proxy only (never zero-filled), so tile 0 is requested right here; the deeper prefetches wait until
-  // the latency-critical code loads are out (148 CTAs x 3 stages would queue ~13 MB ahead of them: measured 4 us).
+  // D tile `it` -> raw stage it % NS: a contiguous run, one TMA bulk copy (the stages are never zero-filled: a ragged
+  // last tile is handled by the consumers).
   auto load_raw = [&](int it) {
     const int p0 = (blockIdx.x + it * gridDim.x) * TP;
     const int rows = min(TP, P - p0);
@@ -772,11 +785,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     mbar_expect_tx(full_raw + s, bytes);
     bulk_g2s(dst, a.D2 + off, bytes, full_raw + s);
   };
-  if (warp == WARP_LOAD_G && a.nraw > 0) {
-    if (elect_one() && my_tiles > 0) load_raw(0);
-    __syncwarp();
-  }
-
   // workers: fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q.
   // The rows of tile 0 are requested before the batch codes (both are on the critical path of the first tile).
   int gsrc[GJ], gdst[GJ];  // gsrc: 4q, the pixel column (-1: none); gdst: bf16 offset inside an image
@@ -799,9 +807,11 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       grow[j] = a.g + (size_t)min(b, B - 1) * P + 4 * q;
       gdst[j] = (q >> 1) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (q & 1) * 4;
     }
-    if (my_tiles > 0) prefetch(0);
   }
-  // The batch codes: loads go out now and fly during the zero fill.
+  // The batch codes are the first thing on the critical path of tile 0: two dependent cold misses (index -> code row).
+  // Their loads go out BEFORE any bulk traffic (148 CTAs x 3 stages of D tiles plus the gradient rows of the first
+  // tiles would queue ~15 MB -- and the page walks of 100 MB of first-touched arrays -- ahead of them: measured 4 us
+  // on the first MMA) and fly during the zero fill.
   // worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
   float vv[2][16];
 #pragma unroll
@@ -825,20 +835,28 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     const int nz = (2 * (dbuf + gbuf)) >> 3;
     for (int e = tid; e < nz; e += NTHREADS_GRAD) z[e] = make_uint4(0u, 0u, 0u, 0u);
   }
-  fence_proxy_async();  // the zero fill (generic proxy) is ordered before the tensor core's (async proxy) reads
+  // zero fill (generic proxy) ordered before the tensor core's (async proxy) reads.  The fence is a MEMBAR.ALL.CTA: it
+  // also waits for the code loads above, which is what the bulk traffic below is held back for.
+  fence_proxy_async();
   __syncthreads();
   STAMP(1);
+  if (warp < NW && my_tiles > 0) prefetch(0);  // gradient rows of tile 0: land while the codes go to tensor memory
+  // (the setmaxnreg instructions open the role branches below)
 
   if (warp == WARP_LOAD_G) {
+    reg_dealloc<24>();
     // ===== loader: the remaining D tiles, each as soon as its stage has been recycled (by the workers' dictionary split
     // and, in the fused step, by the AdamW pass of the epilogue warps).  Plain dD output: the epilogue warps write
     // the dD tile into the stage and it leaves here as one TMA bulk store (full-line writes whatever the row pitch);
     // the stage is reused when the copy engine has read it. =====
     const bool leader = elect_one();
     const bool dD_out = a.want_dD && !fused;
-    for (int it = 1; it < my_tiles + NS; ++it) {
+    if (a.nraw > 0 && leader)
+      for (int it = 0; it < NS && it < my_tiles; ++it) load_raw(it);
+    __syncwarp();
+    for (int it = NS; it < my_tiles + NS; ++it) {
       const int jt = it - NS;  // the tile whose stage is recycled now
-      if (jt >= 0) {
+      {
         const int sj = jt % NS;
         if (dD_out) {
           mbar_wait(epi_done + sj, (jt / NS) & 1);
@@ -864,6 +882,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     __syncwarp();
   } else if (warp == WARP_MMA_G) {
     // ===== issuer =====
+    reg_dealloc<24>();
     const uint32_t idesc_dD = make_idesc_bf16(128, TP, false, true);
     const uint32_t idesc_dv = make_idesc_bf16(128, a.Kp, false, true);
     const uint32_t gb = smem_u32(Gi), db = smem_u32(Di);
@@ -925,7 +944,9 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     }
   } else if (warp >= WARP_EPI + NE) {
     // (warps 24, 25: idle filler so that the issuer and the loader land on schedulers 2 and 3)
+    reg_dealloc<24>();
   } else if (warp >= WARP_EPI) {
+    reg_alloc<96>();
     // ===== epilogue warps (8, two per scheduler).  Phase A: the warps whose TMEM quadrant holds atoms (quadrant q,
     // pixel half h: atoms [32q, 32q+32) of pixels [h TP/2, (h+1) TP/2)) read the dD^T accumulator (lane = atom,
     // column = pixel), release it to the tensor core, multiply by 1/std and write it flat -- [pixel][atom], like the
@@ -975,7 +996,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           if (!fused && a.nraw == 0 && j >= NS) mbar_wait(full_raw + sj, ((j / NS) - 1) & 1);
           const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TP + half * HALF);
 #pragma unroll
-          for (int c0 = 0; c0 < HALF; c0 += 8) {  // eight columns at a time: low register pressure
+          for (int c0 = 0; c0 < HALF; c0 += 8) {  // eight columns at a time: spills are far dearer than the extra waits
             float r[8];
             tmem_ld8_nowait(tcol + (uint32_t)c0, r);
             tmem_ld_wait();
@@ -1001,6 +1022,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           const int n4 = (rows * K) >> 2;
           const size_t base = (size_t)p0 * K;
 #ifndef ADIL_EXP_NO_EPI
+#ifndef ADIL_V_LOADFIRST
 #pragma unroll
           for (int u = 0; u < NPF; ++u) {
             const int e4 = etid + u * (NE * 32);
@@ -1019,6 +1041,41 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
               *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sp[u];
             }
           }
+#else
+          {  // NPF items per thread in flight: all shared-memory loads, then the arithmetic, then the stores
+            float4 Dv[NPF], gd[NPF];
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+              const int e4 = etid + u * (NE * 32);
+              if (e4 < n4) {
+                Dv[u] = *reinterpret_cast<const float4*>(stage + 4 * e4);
+                gd[u] = *reinterpret_cast<const float4*>(gtile + 4 * e4);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+              const int e4 = etid + u * (NE * 32);
+              if (e4 < n4) {
+                adamw_update_fast(Dv[u].x, Mp[u].x, Sp[u].x, gd[u].x, a.hp);
+                adamw_update_fast(Dv[u].y, Mp[u].y, Sp[u].y, gd[u].y, a.hp);
+                adamw_update_fast(Dv[u].z, Mp[u].z, Sp[u].z, gd[u].z, a.hp);
+                adamw_update_fast(Dv[u].w, Mp[u].w, Sp[u].w, gd[u].w, a.hp);
+                if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
+                  Dv[u].x = clamp1(Dv[u].x); Dv[u].y = clamp1(Dv[u].y); Dv[u].z = clamp1(Dv[u].z); Dv[u].w = clamp1(Dv[u].w);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+              const int e4 = etid + u * (NE * 32);
+              if (e4 < n4) {
+                *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv[u];
+                *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mp[u];
+                *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sp[u];
+              }
+            }
+          }
+#endif
           for (int e4 = etid + NPF * (NE * 32); e4 < n4; e4 += NE * 32) {  // (large K: beyond the prefetched part)
             float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
             float4 Mv = ld_global4(a.m + base + 4 * (size_t)e4);
@@ -1460,7 +1517,7 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
             ch[0] - ch[10], ch[1] - ch[10], ch[2] - ch[10], ch[3] - ch[10], ch[4] - ch[10], ch[5] - ch[10], ch[6] - ch[10], ch[9] - ch[10], ch[7] - ch[10], ch[8] - ch[10]);
   }
 #endif
-#ifdef ADIL_TIMING
+#ifdef ADIL_CHAIN
   {
     long long st8[8];
     cudaMemcpyFromSymbol(st8, g_stamp, sizeof(st8));
