@@ -82,9 +82,9 @@ constexpr int WARP_EPI = NW;
 constexpr int WARP_MMA_G = NW + NE + 2;   // backward: issuer warp (26)
 constexpr int WARP_LOAD_G = NW + NE + 3;  // backward: loader warp (27)
 constexpr int NTHREADS_GRAD = (NW + NE + 4) * 32;  // 896 threads -> at most 72 registers each
-constexpr int NIO = 4;              // synthesis: warps 17..20 move the image rows (cp.async in, coalesced stores out)
+constexpr int NIO = 8;              // synthesis: warps 17..24 move the image rows (cp.async in, coalesced stores out)
 constexpr int NTIO = NIO * 32;
-constexpr int NTHREADS_SYNTH = NT + 32 + NTIO;  // 672 threads -> at most 96 registers each
+constexpr int NTHREADS_SYNTH = NT + 32 + NTIO;  // 800 threads -> at most 80 registers each
 constexpr int NS = 3;               // stages of the raw dictionary tiles
 constexpr int NSX = 3;              // stages of the image-row tiles (synthesis)
 constexpr int SMEM_LIMIT = 227 * 1024;
