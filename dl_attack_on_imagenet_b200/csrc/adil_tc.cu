@@ -85,6 +85,9 @@ constexpr int NTHREADS_GRAD = (NW + NE + 4) * 32;  // 896 threads -> at most 72 
 constexpr int NIO = 8;              // synthesis: warps 17..24 move the image rows (cp.async in, coalesced stores out)
 constexpr int NTIO = NIO * 32;
 constexpr int NTHREADS_SYNTH = NT + 32 + NTIO;  // 800 threads -> at most 80 registers each
+#ifndef ADIL_SYNTH_EARLY_X
+#define ADIL_SYNTH_EARLY_X 0         // image-row stages requested before the zero fill (measured: 0 best -- early bulk traffic delays the code loads)
+#endif
 constexpr int NS = 3;               // stages of the raw dictionary tiles
 constexpr int NSX = 3;              // stages of the image-row tiles (synthesis)
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -393,6 +396,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool need_x = (a.x != nullptr) && (a.out != nullptr);
   const int xstage = B * XP;
+  const bool ragged = (P % TP) != 0;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
@@ -402,6 +406,15 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     mbar_init(staged, NW);
     mbar_init(staged + 1, NW);
     fence_mbar_init();
+    // The dictionary tiles depend on nothing: without a ragged last tile (whose stale stage rows must be zeroed first)
+    // the first NS of them are requested right here, ahead of the index -> code-row chain of the prologue.
+    if (!ragged) {
+      for (int it = 0; it < NS && it < my_tiles; ++it) {
+        const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+        mbar_expect_tx(full_raw + it, (uint32_t)(TP * K * 4));
+        bulk_g2s(raw + it * a.raw_floats, a.D2 + (size_t)p0 * K, (uint32_t)(TP * K * 4), full_raw + it);
+      }
+    }
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
   for (int b = tid; b < B; b += NTHREADS_SYNTH) {
@@ -426,14 +439,31 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
     }
   }
-  // zero the dictionary images (contraction padding k in [K, Kp8) must be zero) and the raw stages (a partial last
-  // tile leaves stale rows behind, which must stay finite)
-  {
-    float4* z = reinterpret_cast<float4*>(raw);
-    const int nz = (NS * a.raw_floats + 4 * a.dimg) >> 2;
-    for (int e = tid; e < nz; e += NTHREADS_SYNTH) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // I/O warps: the image rows of the first tiles are requested as soon as the row offsets are known (the row stages
+  // are never zero-filled), next to the code loads.
+  const int iot = tid - WARP_LOAD * 32;
+  auto load_x = [&](int j) {
+    if (need_x && j < my_tiles) {
+      const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+      float* dst = xs + (j % NSX) * xstage;
+      for (int e = iot; e < B * Q4; e += NTIO) {
+        const int b = e / Q4, col = (e - b * Q4) * 4;
+        if (p0 + col < P) cp_async16(dst + b * XP + col, a.x + xoff_s[b] + p0 + col);
+      }
+    }
+    cp_async_arrive_noinc(full_x + (j % NSX));  // rows landed (or, without x, simply: stage free)
+  };
+  if (warp >= WARP_LOAD) {
+    for (int j = 0; j < ADIL_SYNTH_EARLY_X; ++j) load_x(j);
+  } else {
+    // zero the dictionary images (contraction padding k in [K, Kp8) must be zero) and, with a ragged last tile, the
+    // raw stages (stale rows must stay finite).  The proxy fence is a MEMBAR.ALL.CTA -- it waits for the loads in
+    // flight -- so the I/O warps stay out of this.
+    float4* z = reinterpret_cast<float4*>(ragged ? raw : Dimg);
+    const int nz = ((ragged ? NS * a.raw_floats : 0) + 4 * a.dimg) >> 2;
+    for (int e = tid; e < nz; e += WARP_LOAD * 32) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the async-proxy accesses
   }
-  fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes into the same stages
   __syncthreads();
   // From here the roles run free: the issuer and the I/O warps start fetching at once, the workers write the codes to
   // tensor memory (the issuer cannot start before every worker has handed over tile 0).
@@ -443,20 +473,8 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     // TMEM.  Per tile j: wait until the workers have staged the finished tile, store it with coalesced 128-bit
     // streaming stores, and refill the stage with the rows of tile j+NSX by cp.async (each thread overwrites exactly
     // the elements it has just read). =====
-    const int iot = tid - WARP_LOAD * 32;
     float* dstg = a.out != nullptr ? a.out : a.delta;
-    auto load_x = [&](int j) {
-      if (need_x && j < my_tiles) {
-        const int p0 = (blockIdx.x + j * gridDim.x) * TP;
-        float* dst = xs + (j % NSX) * xstage;
-        for (int e = iot; e < B * Q4; e += NTIO) {
-          const int b = e / Q4, col = (e - b * Q4) * 4;
-          if (p0 + col < P) cp_async16(dst + b * XP + col, a.x + xoff_s[b] + p0 + col);
-        }
-      }
-      cp_async_arrive_noinc(full_x + (j % NSX));  // rows landed (or, without x, simply: stage free)
-    };
-    for (int j = 0; j < NSX; ++j) load_x(j);
+    for (int j = ADIL_SYNTH_EARLY_X; j < NSX; ++j) load_x(j);
     for (int j = 0; j < my_tiles; ++j) {
       const int p0 = (blockIdx.x + j * gridDim.x) * TP;
       const int sx = j % NSX;
@@ -486,7 +504,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       mbar_expect_tx(full_raw + it % NS, bytes);
       bulk_g2s(raw + (it % NS) * a.raw_floats, a.D2 + (size_t)p0 * K, bytes, full_raw + it % NS);
     };
-    if (leader)
+    if (leader && ragged)
       for (int it = 0; it < NS && it < my_tiles; ++it) load_D(it);
     for (int it = 0; it < my_tiles; ++it) {
       // Workers staged tile `it`.  An mbarrier per image buffer, not a named barrier: with double-buffered images a
