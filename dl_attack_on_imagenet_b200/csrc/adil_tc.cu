@@ -858,7 +858,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   fence_proxy_async();
   __syncthreads();
   STAMP(1);
-  if (warp < NW && my_tiles > 0) prefetch(0);  // gradient rows of tile 0: land while the codes go to tensor memory
   // (the setmaxnreg instructions open the role branches below)
 
   if (warp == WARP_LOAD_G) {
@@ -1158,7 +1157,11 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         }
       }
       STAMP(7);
+      if (my_tiles > 0) prefetch(0);  // gradient rows of tile 0 (requested only now: next to the 32 code registers the
+                                      // compiler would spill the load targets, i.e. wait for the loads, first)
       tmem_st_wait();
+    } else if (my_tiles > 0) {
+      prefetch(0);
     }
     STAMP(2);
     for (int it = 0; it < my_tiles; ++it) {
