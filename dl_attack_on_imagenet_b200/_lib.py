@@ -40,6 +40,8 @@ SIGNATURES = {
     "adil_project_atoms_scratch_bytes": (_SZ, [_I]),
     "adil_project_atoms": (_I, [_P, _I, _I, _I, _P, _P]),
     "adil_adamw_clamp": (_I, [_P, _P, _P, _P, _LL, _HP, _F, _P]),
+    "adil_image_errors_scratch_bytes": (_SZ, [_I]),
+    "adil_image_errors": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
 }
 
 _lib = None

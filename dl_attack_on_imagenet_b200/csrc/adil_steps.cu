@@ -384,3 +384,94 @@ extern "C" int adil_project_atoms(float* D2, int P, int K, int atoms_mode, void*
   atom_scale_kernel<<<elem_grid(n), 256, 0, st>>>(D2, n, K, scale);
   return check_cuda(cudaGetLastError(), "atom_scale_kernel launch");
 }
+
+// ------------------------------------------------------------------------------------------------------
+// evaluation metrics (performance.py:249-266): per-image sum of squared error, clean energy and l_inf error in one
+// streaming pass.  grid = (kErrSegs, n): CTA (seg, i) reduces one contiguous eighth of image i (128-bit streaming
+// loads, per-thread accumulation, shuffle tree, one partial triple); a second tiny kernel adds the kErrSegs partials
+// of each image in a fixed order.  HBM-bound: 8 n P bytes.
+// ------------------------------------------------------------------------------------------------------
+namespace adil {
+namespace {
+constexpr int kErrSegs = 8;
+constexpr int kErrThreads = 512;
+
+__global__ void __launch_bounds__(kErrThreads) image_errors_partial_kernel(const float* __restrict__ adv,
+                                                                           const float* __restrict__ clean, int P,
+                                                                           float* __restrict__ partial) {
+  const int seg = blockIdx.x, img = blockIdx.y;
+  const int n4 = P >> 2;
+  const int per = (n4 + kErrSegs - 1) / kErrSegs;
+  const int lo = seg * per, hi = min(n4, lo + per);
+  const float* a = adv + (size_t)img * P;
+  const float* c = clean + (size_t)img * P;
+  float e2 = 0.0f, r2 = 0.0f, mx = 0.0f;
+#pragma unroll 4
+  for (int i = lo + (int)threadIdx.x; i < hi; i += kErrThreads) {
+    const float4 x = ld_stream4(a + 4 * (size_t)i);
+    const float4 y = ld_stream4(c + 4 * (size_t)i);
+    const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+    e2 = fmaf(d0, d0, e2); e2 = fmaf(d1, d1, e2); e2 = fmaf(d2, d2, e2); e2 = fmaf(d3, d3, e2);
+    r2 = fmaf(y.x, y.x, r2); r2 = fmaf(y.y, y.y, r2); r2 = fmaf(y.z, y.z, r2); r2 = fmaf(y.w, y.w, r2);
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))));
+  }
+  __shared__ float sh[3][kErrThreads / 32];
+  e2 = warp_sum(e2);
+  r2 = warp_sum(r2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = e2; sh[1][warp] = r2; sh[2][warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    float t0 = lane < kErrThreads / 32 ? sh[0][lane] : 0.0f;
+    float t1 = lane < kErrThreads / 32 ? sh[1][lane] : 0.0f;
+    float t2 = lane < kErrThreads / 32 ? sh[2][lane] : 0.0f;
+    t0 = warp_sum(t0);
+    t1 = warp_sum(t1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t2 = fmaxf(t2, __shfl_xor_sync(0xffffffffu, t2, o));
+    if (lane == 0) {
+      float* out = partial + ((size_t)img * kErrSegs + seg) * 3;
+      out[0] = t0; out[1] = t1; out[2] = t2;
+    }
+  }
+}
+
+__global__ void image_errors_final_kernel(const float* __restrict__ partial, int n, float* err2, float* ref2, float* linf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float e = 0.0f, r = 0.0f, m = 0.0f;
+#pragma unroll
+  for (int s = 0; s < kErrSegs; ++s) {
+    const float* p = partial + ((size_t)i * kErrSegs + s) * 3;
+    e += p[0]; r += p[1]; m = fmaxf(m, p[2]);
+  }
+  if (err2) err2[i] = e;
+  if (ref2) ref2[i] = r;
+  if (linf) linf[i] = m;
+}
+}  // namespace
+}  // namespace adil
+
+extern "C" size_t adil_image_errors_scratch_bytes(int n) {
+  return n > 0 ? (size_t)n * adil::kErrSegs * 3 * sizeof(float) : 0;
+}
+
+extern "C" int adil_image_errors(float* err2, float* ref2, float* linf, const float* adv, const float* clean, int n,
+                                 int P, void* scratch, size_t scratch_bytes, void* stream) {
+  using namespace adil;
+  if (!adv || !clean) return set_error(-1, "adil_image_errors: null pointer");
+  if (n < 0 || P <= 0 || P % 4 != 0) return set_error(-1, "adil_image_errors: bad shape n=%d P=%d (P %% 4 == 0)", n, P);
+  if ((((uintptr_t)adv | (uintptr_t)clean) & 15) != 0) return set_error(-1, "adil_image_errors: adv/clean must be 16-byte aligned");
+  if (n == 0) return 0;
+  if (n > 65535) return set_error(-1, "adil_image_errors: n=%d exceeds 65535 images per call", n);
+  if (!scratch || scratch_bytes < adil_image_errors_scratch_bytes(n))
+    return set_error(-2, "adil_image_errors: scratch too small (%zu < %zu bytes)", scratch_bytes, adil_image_errors_scratch_bytes(n));
+  cudaStream_t st = (cudaStream_t)stream;
+  image_errors_partial_kernel<<<dim3(kErrSegs, n), kErrThreads, 0, st>>>(adv, clean, P, (float*)scratch);
+  int rc = check_cuda(cudaGetLastError(), "image_errors_partial_kernel launch");
+  if (rc) return rc;
+  image_errors_final_kernel<<<(n + 127) / 128, 128, 0, st>>>((const float*)scratch, n, err2, ref2, linf);
+  return check_cuda(cudaGetLastError(), "image_errors_final_kernel launch");
+}

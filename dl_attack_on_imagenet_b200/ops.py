@@ -231,6 +231,25 @@ def adamw_clamp(p, m, s, g, hp, bound=0.0):
     _lib.check(rc, "adil_adamw_clamp")
 
 
+def image_errors(adv, clean):
+    """Per-image sum_p (adv-clean)^2, sum_p clean^2 and max_p |adv-clean| in one pass (the reductions of
+    performance.py:249-266 and adil.py:503-505).  adv, clean: [n, ...] CUDA fp32; returns three [n] tensors."""
+    a, c = _f32(adv.detach().contiguous(), "adv"), _f32(clean.detach().contiguous(), "clean")
+    if a.shape != c.shape:
+        raise ValueError("image_errors: adv %s and clean %s differ in shape" % (tuple(a.shape), tuple(c.shape)))
+    n = a.shape[0]
+    P = a.numel() // max(n, 1)
+    out = torch.empty(3, n, device=a.device, dtype=torch.float32)
+    if n == 0:
+        return out[0], out[1], out[2]
+    nbytes = _lib.lib().adil_image_errors_scratch_bytes(n)
+    scratch = _get_scratch(a.device, nbytes, "image_errors")
+    rc = _lib.lib().adil_image_errors(_ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(a), _ptr(c), n, P,
+                                      _ptr(scratch), nbytes, _stream(a.device))
+    _lib.check(rc, "adil_image_errors")
+    return out[0], out[1], out[2]
+
+
 class SynthFunction(torch.autograd.Function):
     """autograd bridge: forward = adil_synth, backward = adil_grad.  Lets user code differentiate through the
     fused synthesis like through adil.py:24-27 (the drivers in adil.py call the kernels directly instead)."""

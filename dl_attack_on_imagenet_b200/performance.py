@@ -1,0 +1,127 @@
+"""Evaluation of crafted images: device-side mirror of the reference's performance.py for the ADiL path (SURVEY
+section 8(f) row 3: what main.py / performance.py call per evaluated batch, and the transfer sweep of BASELINE
+configs[4]).  Same names, argument meaning and return types as the reference; the per-image error reductions run in
+one fused CUDA pass (adil_image_errors), the classifier passes stay in PyTorch / cuDNN.  No CPU fallback."""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def compute_fooling_rate(model, adversary, clean, reduction='sum'):
+    """Number ('sum') or fraction ('mean') of images whose predicted label changes (performance.py:238-246)."""
+    with torch.no_grad():
+        label_clean = model.eval()(clean).argmax(dim=1)
+        label_adversary = model.eval()(adversary).argmax(dim=1)
+    label_different = (label_clean != label_adversary)
+    if reduction == 'sum':
+        return label_different.float().sum().item()
+    elif reduction == 'mean':
+        return label_different.float().mean().item()
+
+
+def _errors(adversary, clean):
+    if not adversary.is_cuda:
+        raise RuntimeError("performance metrics run on the CUDA device of the attack; there is no CPU fallback")
+    return ops.image_errors(adversary.float(), clean.float())
+
+
+def compute_rmse(adversary, clean, reduction='sum'):
+    """Relative squared error ||adv - clean||^2 / ||clean||^2 per image, summed or averaged (performance.py:249-257)."""
+    upper, lower, _ = _errors(adversary, clean)
+    ratio = upper / lower
+    if reduction == 'sum':
+        return torch.sum(ratio).item()
+    elif reduction == 'mean':
+        return torch.mean(ratio).item()
+
+
+def compute_mse(adversary, clean, reduction='sum'):
+    """Squared error ||adv - clean||^2 per image, summed or averaged (performance.py:260-266)."""
+    upper, _, _ = _errors(adversary, clean)
+    if reduction == 'sum':
+        return torch.sum(upper).item()
+    elif reduction == 'mean':
+        return torch.mean(upper).item()
+
+
+def batch_metrics(model, adversary, clean):
+    """fooling count, sum of relative errors and sum of squared errors of one batch as DEVICE scalars: the three
+    reference metrics with one error pass and no host synchronisation (used by the loops below)."""
+    with torch.no_grad():
+        fooled = (model(clean).argmax(dim=1) != model(adversary).argmax(dim=1)).sum()
+    upper, lower, _ = _errors(adversary, clean)
+    return fooled, (upper / lower).sum(), upper.sum()
+
+
+def performance(attack, model, data, device=None):
+    """performance.py:154-177: attack every correctly classified image of `data`, report fooling rate, rmse, mse."""
+    device = attack.device
+    model = model.eval()
+    num_samples = torch.zeros((), dtype=torch.long, device=device)
+    acc = torch.zeros(3, dtype=torch.float64, device=device)
+    for x, y in data:
+        x, y = x.to(device=device), y.to(device=device)
+        with torch.no_grad():
+            ind = model(x).argmax(dim=-1) == y
+        x, y = x[ind], y[ind]
+        num_samples += ind.sum()
+        if x.shape[0] == 0:
+            continue
+        adversary = attack(x, y)
+        if isinstance(adversary, tuple):  # forward_unsupervised returns (adv_best, dv_norm_inf), adil.py:506
+            adversary = adversary[0]
+        f, r, m = batch_metrics(model, adversary, x)
+        acc += torch.stack([f.double(), r.double(), m.double()])
+    n = num_samples.item()
+    vals = (acc / max(n, 1)).tolist()
+    return {"fooling_rate": vals[0], "rmse": vals[1], "mse": vals[2]}
+
+
+def empty_transfer_performance(model_transfer):
+    """performance.py:198-202."""
+    return {name: {'fooling_rate': np.nan, 'rmse': np.nan, 'mse': np.nan} for name in model_transfer.keys()}
+
+
+def get_transfer_performance_aux(attack, model_transfer, data, device=None):
+    """performance.py:205-232: craft the adversarial images once per batch, evaluate them on every model.  Sharded
+    evaluation: when torch.distributed is initialised each rank passes its own shard of `data` and the counters are
+    summed (images are independent; no other exchange)."""
+    device = attack.device
+    names = list(model_transfer.keys())
+    acc = torch.zeros(len(names), 3, dtype=torch.float64, device=device)
+    count = torch.zeros((), dtype=torch.float64, device=device)
+    for x, y in data:
+        x, y = x.to(device=device), y.to(device=device)
+        adversary = attack(x, y)
+        if isinstance(adversary, tuple):
+            adversary = adversary[0]
+        upper, lower, _ = _errors(adversary, x)
+        r, m = (upper / lower).sum().double(), upper.sum().double()
+        count += x.shape[0]
+        for i, name in enumerate(names):
+            model = model_transfer[name].to(device=device).eval()
+            with torch.no_grad():
+                f = (model(x).argmax(dim=1) != model(adversary).argmax(dim=1)).sum().double()
+            acc[i] += torch.stack([f, r, m])
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(acc)
+            dist.all_reduce(count)
+    except ImportError:
+        pass
+    vals = (acc / count.clamp(min=1)).tolist()
+    return {name: {'fooling_rate': vals[i][0], 'rmse': vals[i][1], 'mse': vals[i][2]} for i, name in enumerate(names)}
+
+
+def get_transfer_performance(atks, models, data, device=None):
+    """performance.py:183-195."""
+    perf_transfer = dict()
+    for name in atks.keys():
+        if len(atks[name]) > 0:
+            perf_tmp = get_transfer_performance_aux(atks[name][0], models, data=data, device=device)
+        else:
+            perf_tmp = empty_transfer_performance(models)
+        perf_transfer.update({name: perf_tmp})
+    return perf_transfer

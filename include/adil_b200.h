@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ADIL_VERSION 100
+#define ADIL_VERSION 101
 
 #define ADIL_MAX_CHANNELS 8
 #define ADIL_MAX_ATOMS 256
@@ -130,6 +130,16 @@ int adil_project_atoms(float* D2, int P, int K, int atoms_mode, void* scratch, v
  * (adil.py:531,554-555).  bound <= 0: no clamp. */
 int adil_adamw_clamp(float* p, float* m, float* s, const float* grad, long long n, const adil_adamw_t* hp,
                      float bound, void* stream);
+
+/* Per-image error reductions of a batch of adversarial images against the clean ones: the sums behind
+ * compute_rmse / compute_mse (performance.py:249-266) and the l_inf norm printed by forward_unsupervised
+ * (adil.py:503-505), in ONE pass over both arrays:
+ *   err2[i] = sum_p (adv[i,p] - clean[i,p])^2      ref2[i] = sum_p clean[i,p]^2      linf[i] = max_p |adv - clean|
+ * adv, clean: [n, P] (P % 4 == 0, 16-byte aligned); err2 / ref2 / linf: [n] each, any of them may be NULL.
+ * Fixed summation order (no atomics): bit-reproducible.  scratch: adil_image_errors_scratch_bytes(n) bytes. */
+size_t adil_image_errors_scratch_bytes(int n);
+int adil_image_errors(float* err2, float* ref2, float* linf, const float* adv, const float* clean, int n, int P,
+                      void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,10 +42,11 @@ def test_binding_covers_header_exactly():
 def test_host_only_entry_points(library):
     from dl_attack_on_imagenet_b200 import _lib
     lib = _lib.lib()
-    assert lib.adil_version() == 100
+    assert lib.adil_version() >= 101
     assert lib.adil_grad_scratch_bytes(100, 50) >= 148 * 100 * 50 * 4
     assert lib.adil_grad_scratch_bytes(0, 50) == 0
     assert lib.adil_project_atoms_scratch_bytes(64) > 0
+    assert lib.adil_image_errors_scratch_bytes(100) >= 100 * 3 * 4 and lib.adil_image_errors_scratch_bytes(0) == 0
     assert lib.adil_set_impl(7) != 0 and b"bad impl" in lib.adil_last_error()
     assert lib.adil_set_impl(0) == 0
 
@@ -61,6 +62,10 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc < 0 and b"ADIL_MAX_ATOMS" in lib.adil_last_error()
     rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, None, 0, None)
     assert rc < 0
+    rc = lib.adil_image_errors(one, one, one, one, one, 4, 10, one, 1 << 20, None)
+    assert rc < 0 and b"P % 4" in lib.adil_last_error()
+    rc = lib.adil_image_errors(one, one, one, one, one, 4, 12, one, 8, None)
+    assert rc == -2 and b"scratch" in lib.adil_last_error()
 
 
 def test_no_cpu_fallback():

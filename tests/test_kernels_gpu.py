@@ -294,3 +294,60 @@ def test_full_size_adjointness_and_linearity(ops, K, impl):
         assert (out - ref_out).abs().max() <= 1e-6
     finally:
         ops.set_impl(ops.IMPL_AUTO)
+
+
+# ---- evaluation metrics (performance.py:238-266) --------------------------------------------
+@pytest.mark.parametrize("n,shape", [(1, (3, 8, 8)), (7, (3, 32, 32)), (100, (3, 224, 224))])
+def test_image_errors_match_float64_formulas(ops, n, shape):
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    clean = torch.rand(n, *shape, device="cuda", generator=gen)
+    adv = (clean + (8 / 255) * (2 * torch.rand(n, *shape, device="cuda", generator=gen) - 1)).clamp(0, 1)
+    e2, r2, li = ops.image_errors(adv, clean)
+    d = (adv.double() - clean.double()).flatten(1)
+    # fp32 accumulation in a fixed tree over <= 150 528 terms: relative error well below 1e-5
+    assert (e2.double() - (d ** 2).sum(1)).abs().max() <= 1e-5 * (d ** 2).sum(1).max()
+    assert (r2.double() - (clean.double() ** 2).flatten(1).sum(1)).abs().max() <= 1e-5 * (clean.double() ** 2).flatten(1).sum(1).max()
+    assert torch.equal(li, (adv - clean).abs().flatten(1).amax(1))  # max of exact fp32 differences: bit-exact
+    e2b, r2b, lib_ = ops.image_errors(adv, clean)
+    assert torch.equal(e2, e2b) and torch.equal(r2, r2b) and torch.equal(li, lib_)  # run-to-run bit equality
+
+
+def test_performance_module_matches_reference_formulas(ops):
+    """compute_rmse / compute_mse / compute_fooling_rate / performance / transfer sweep against the reference's
+    PyTorch expressions (performance.py:154-266) on the same device."""
+    from dl_attack_on_imagenet_b200 import performance as perf
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 16 * 16, 10)).cuda().eval()
+    other = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 16 * 16, 10)).cuda().eval()
+    clean = torch.rand(24, 3, 16, 16, device="cuda")
+    adv = (clean + 0.1 * torch.randn_like(clean)).clamp(0, 1)
+    up = ((adv - clean) ** 2).sum(dim=[1, 2, 3])
+    lo = (clean ** 2).sum(dim=[1, 2, 3])
+    for red, f in (("sum", torch.sum), ("mean", torch.mean)):
+        assert abs(perf.compute_rmse(adv, clean, red) - f(up / lo).item()) <= 1e-5 * f(up / lo).item()
+        assert abs(perf.compute_mse(adv, clean, red) - f(up).item()) <= 1e-5 * f(up).item()
+    fooled = (model(clean).argmax(1) != model(adv).argmax(1)).float()
+    assert perf.compute_fooling_rate(model, adv, clean) == fooled.sum().item()
+    assert perf.compute_fooling_rate(model, adv, clean, "mean") == fooled.mean().item()
+
+    class Shift(object):  # a stand-in attack with the Attack calling convention
+        device = torch.device("cuda")
+
+        def __call__(self, x, y):
+            return (x + 0.05).clamp(0, 1)
+
+    labels = model(clean).argmax(1)
+    labels[::5] = (labels[::5] + 1) % 10  # some misclassified images: skipped by performance()
+    data = [(clean[:12].cpu(), labels[:12].cpu()), (clean[12:].cpu(), labels[12:].cpu())]
+    res = perf.performance(Shift(), model, data)
+    keep = model(clean).argmax(1) == labels
+    xk = clean[keep]
+    ak = (xk + 0.05).clamp(0, 1)
+    assert abs(res["fooling_rate"] - (model(xk).argmax(1) != model(ak).argmax(1)).float().mean().item()) < 1e-6
+    assert abs(res["mse"] - ((ak - xk) ** 2).sum(dim=[1, 2, 3]).mean().item()) <= 1e-5 * res["mse"]
+    tr = perf.get_transfer_performance({"adil": [Shift()], "none": []}, {"a": model, "b": other}, data)
+    assert set(tr) == {"adil", "none"} and set(tr["adil"]) == {"a", "b"}
+    a_all = (clean + 0.05).clamp(0, 1)
+    assert abs(tr["adil"]["b"]["fooling_rate"] - (other(clean).argmax(1) != other(a_all).argmax(1)).float().mean().item()) < 1e-6
+    assert abs(tr["adil"]["a"]["rmse"] - (((a_all - clean) ** 2).sum(dim=[1, 2, 3]) / lo).mean().item()) <= 1e-5
+    assert tr["none"]["a"]["mse"] != tr["none"]["a"]["mse"]  # NaN, like empty_transfer_performance
