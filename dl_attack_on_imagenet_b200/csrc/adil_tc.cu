@@ -1013,16 +1013,21 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           if (!fused && a.nraw == 0 && j >= NS) mbar_wait(full_raw + sj, ((j / NS) - 1) & 1);
           const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TP + half * HALF);
 #pragma unroll
-          for (int c0 = 0; c0 < HALF; c0 += 8) {  // eight columns at a time: spills are far dearer than the extra waits
-            float r[8];
-            tmem_ld8_nowait(tcol + (uint32_t)c0, r);
+          for (int c0 = 0; c0 < HALF; c0 += 16) {  // sixteen columns per wait (all of them at once would spill: far dearer)
+            constexpr int NC = (HALF % 16 == 0) ? 16 : 8;  // (HALF is 8, 16, 24 or 32)
+            const int nc = (HALF - c0 >= 16) ? 16 : 8;
+            float r[16];
+            tmem_ld8_nowait(tcol + (uint32_t)c0, &r[0]);
+            if (NC == 16 || nc == 16) tmem_ld8_nowait(tcol + (uint32_t)(c0 + 8), &r[8]);
             tmem_ld_wait();
             if (k_ok) {
               float* col = gtile + (half * HALF + c0) * K + k;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float sc = a.cc.use ? ((half * HALF + c0 + i) >= tc.bnd ? tc.rstd1 : tc.rstd0) : 1.0f;
-                col[i * K] = __fmul_rn(r[i], sc);  // (rows past a ragged end are written too: never stored)
+              for (int i = 0; i < 16; ++i) {
+                if (i < nc) {
+                  const float sc = a.cc.use ? ((half * HALF + c0 + i) >= tc.bnd ? tc.rstd1 : tc.rstd0) : 1.0f;
+                  col[i * K] = __fmul_rn(r[i], sc);  // (rows past a ragged end are written too: never stored)
+                }
               }
             }
           }
