@@ -66,9 +66,12 @@ __device__ __forceinline__ long long gtime2() { long long t; asm volatile("mov.u
 #define CHAIN(i, tile) do { if (blockIdx.x == 5 && (tile) == 6 && (threadIdx.x & 31) == 0) g_chain[i] = gtime2(); } while (0)
 __device__ long long g_stamp[8];
 #define STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_stamp[i] = gtime2(); } while (0)
+__device__ long long g_sstamp[16];
+#define SSTAMP(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_sstamp[i] = gtime2(); } while (0)
 #else
 #define CHAIN(i, tile)
 #define STAMP(i)
+#define SSTAMP(i)
 #endif
 
 constexpr int NW = 16;              // worker warps
@@ -397,6 +400,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   const bool need_x = (a.x != nullptr) && (a.out != nullptr);
   const int xstage = B * XP;
   const bool ragged = (P % TP) != 0;
+  if (tid == 0) SSTAMP(0);
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
@@ -424,6 +428,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 0) SSTAMP(1);
   const uint32_t tmem_base = *tmem_slot;
   // The batch codes are the first thing on the critical path of tile 0: their loads go out BEFORE any bulk prefetch of
   // dictionary tiles and image rows (which would queue megabytes ahead of them) and fly during the zero fill.
@@ -465,6 +470,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the async-proxy accesses
   }
   __syncthreads();
+  if (tid == 0) SSTAMP(2);
   // From here the roles run free: the issuer and the I/O warps start fetching at once, the workers write the codes to
   // tensor memory (the issuer cannot start before every worker has handed over tile 0).
 
@@ -480,13 +486,17 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       const int sx = j % NSX;
       const float* xt = xs + sx * xstage;
       mbar_wait(out_ready + sx, (j / NSX) & 1);
+      if (warp == WARP_LOAD && j == 0) SSTAMP(7);
+      if (warp == WARP_LOAD && j == my_tiles - 1) SSTAMP(9);
 #pragma unroll 4
       for (int e = iot; e < B * Q4; e += NTIO) {
         const int b = e / Q4, col = (e - b * Q4) * 4;
         if (p0 + col < P) st_stream4(dstg + (size_t)b * P + p0 + col, *reinterpret_cast<const float4*>(xt + b * XP + col));
       }
+      if (warp == WARP_LOAD && j == 0) SSTAMP(8);
       load_x(j + NSX);
     }
+    if (warp == WARP_LOAD) SSTAMP(10);
   } else if (warp == WARP_MMA) {
     // ===== issuer: 3 x ksteps MMAs per tile into the accumulator buffer (it & 1) =====
     const uint32_t idesc = make_idesc_tf32(128, TP, false, false);
@@ -512,6 +522,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       // bar.arrive of the same warp would complete the named barrier early.
       mbar_wait(staged + (it & 1), (it >> 1) & 1);
       tc_fence_after();
+      if (it == 0) SSTAMP(4);
       if (leader) {
         if (it + NS < my_tiles) load_D(it + NS);
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * TP);
@@ -561,6 +572,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       }
       tmem_st_wait();
     }
+    if (warp == 0) SSTAMP(3);
 
     auto epilogue = [&](int j) {
       const int tile = blockIdx.x + j * gridDim.x;
@@ -570,8 +582,10 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       mbar_wait(mma_done + (j & 1), (j >> 1) & 1);  // accumulator of tile j complete
       tc_fence_after();
       TIM(9);
+      if (warp == 0 && j == 0) SSTAMP(5);
       mbar_wait(full_x + sx, (j / NSX) & 1);        // rows landed / the I/O warps are done with this stage
       TIM(3);
+      if (warp == 0 && j == 0) SSTAMP(6);
       // phase 1: thread <-> image row b; 16 accumulator columns per warp
       if (cg < NCG) {
         const int b = quad * 32 + lane;
@@ -701,6 +715,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (tid == 0) SSTAMP(11);
 }
 
 // =========================================================================================================
@@ -1461,6 +1476,16 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     if (rc) return rc;
     rc = check_cuda(cudaGetLastError(), "synth_kernel launch");
     if (rc) return rc;
+#ifdef ADIL_CHAIN
+    {
+      cudaDeviceSynchronize();
+      long long h[16];
+      cudaMemcpyFromSymbol(h, g_sstamp, sizeof(h));
+      fprintf(stderr, "synth CTA0 stamps (ns from entry): sync1=%lld sync2=%lld codes_in_tmem=%lld staged0=%lld mma0_done=%lld x0_landed=%lld out0_ready=%lld "
+              "out0_stored=%lld last_out_ready=%lld last_stored=%lld exit=%lld\n", h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0],
+              h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0], h[11] - h[0]);
+    }
+#endif
 #ifdef ADIL_TIMING
     {
       cudaDeviceSynchronize();
