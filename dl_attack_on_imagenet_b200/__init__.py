@@ -7,7 +7,7 @@ first use and its absence is an error (no CPU fallback).
 from . import ops  # noqa: F401
 from .adil import ADIL, AdilState, Attack_dict_model, split_normalize  # noqa: F401
 from .build import build_library  # noqa: F401
-from .data import IndexedTensorDataset, Normalize, build_classifier, synthetic_images  # noqa: F401
+from .data import HostBatchPrefetcher, IndexedTensorDataset, Normalize, build_classifier, synthetic_images  # noqa: F401
 
 __all__ = ["ADIL", "AdilState", "Attack_dict_model", "split_normalize", "ops", "build_library",
-           "IndexedTensorDataset", "Normalize", "build_classifier", "synthetic_images"]
+           "HostBatchPrefetcher", "IndexedTensorDataset", "Normalize", "build_classifier", "synthetic_images"]

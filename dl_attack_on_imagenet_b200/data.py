@@ -62,3 +62,74 @@ def synthetic_images(n, seed, size=224, channels=3):
     x = torch.rand(n, channels, size, size, generator=g)
     y = torch.randint(0, 1000, (n,), generator=g)
     return x, y
+
+
+class HostBatchPrefetcher(object):
+    """Host -> device staging of minibatches for `ADIL.fit_batch` when the image set lives in host memory (the
+    reference's DataLoader path, adil.py:130,168): the rows of batch i+1 are gathered into pinned memory and copied
+    on a side stream while the GPU computes batch i.  Every batch is still copied from pinned host memory; the copy
+    just no longer serialises with the kernels.
+
+        pf = HostBatchPrefetcher(x_host, device)
+        pf.submit(idx0)
+        for i in range(steps):
+            x_dev = pf.get()                      # current stream waits for the copy of batch i
+            loss, fooled = attack.fit_batch(idx[i], x_dev)
+            pf.release()                          # batch i consumed (its device buffer may be refilled later)
+            if i + 1 < steps: pf.submit(idx[i + 1])
+    """
+
+    def __init__(self, x_host, device, depth=2):
+        self.x_host = x_host
+        self.device = torch.device(device)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._pinned, self._dev = [None] * depth, [None] * depth
+        self._copied = [torch.cuda.Event() for _ in range(depth)]     # H2D of slot k finished
+        self._consumed = [None] * depth                               # compute that read slot k was enqueued
+        self._head = 0   # next slot to fill
+        self._tail = 0   # next slot to hand out
+        self._inflight = 0
+
+    def submit(self, index):
+        """Gather x_host[index] into pinned memory and start its copy to the device (returns at once)."""
+        if self._inflight >= self.depth:
+            raise RuntimeError("HostBatchPrefetcher: all %d slots are in flight; call get()/release() first" % self.depth)
+        k = self._head
+        index = torch.as_tensor(index, dtype=torch.long)
+        shape = (index.numel(),) + tuple(self.x_host.shape[1:])
+        if self._pinned[k] is None or tuple(self._pinned[k].shape) != shape:
+            self._pinned[k] = torch.empty(shape, dtype=self.x_host.dtype, pin_memory=True)
+            self._dev[k] = torch.empty(shape, dtype=self.x_host.dtype, device=self.device)
+        else:
+            self._copied[k].synchronize()          # the previous copy out of this pinned buffer has finished
+        torch.index_select(self.x_host, 0, index, out=self._pinned[k])
+        with torch.cuda.stream(self.copy_stream):
+            if self._consumed[k] is not None:
+                self.copy_stream.wait_event(self._consumed[k])    # the kernels that read this device buffer are done
+            self._dev[k].copy_(self._pinned[k], non_blocking=True)
+            self._copied[k].record(self.copy_stream)
+        self._head = (k + 1) % self.depth
+        self._inflight += 1
+
+    def get(self):
+        """Device tensor of the oldest submitted batch; the current stream waits for its copy."""
+        if self._inflight == 0:
+            raise RuntimeError("HostBatchPrefetcher: nothing submitted")
+        k = self._tail
+        torch.cuda.current_stream(self.device).wait_event(self._copied[k])
+        return self._dev[k]
+
+    def release(self):
+        """Mark the batch returned by the last get() as consumed by the work enqueued so far."""
+        k = self._tail
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._consumed[k] = ev
+        self._tail = (k + 1) % self.depth
+        self._inflight -= 1
+
+    @property
+    def bytes_per_batch(self):
+        b = self._pinned[(self._head - 1) % self.depth]
+        return 0 if b is None else b.numel() * b.element_size()

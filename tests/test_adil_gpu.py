@@ -269,3 +269,26 @@ def test_fooling_rate_on_imagenet_classifier(monkeypatch):
         adv = model(x.cuda() + dv).argmax(-1)
     rate = (clean != adv).float().mean().item()
     assert 0.0 <= rate <= 1.0
+
+
+def test_host_batch_prefetcher_delivers_the_gathered_rows_in_order():
+    """Double-buffered pinned gather + side-stream H2D: every batch arrives intact while later batches are staged."""
+    from dl_attack_on_imagenet_b200 import HostBatchPrefetcher
+    g = torch.Generator().manual_seed(3)
+    x_host = torch.rand(64, 3, 16, 16, generator=g)
+    batches = [torch.randperm(64, generator=g)[:10] for _ in range(7)]
+    pf = HostBatchPrefetcher(x_host, torch.device("cuda"))
+    pf.submit(batches[0])
+    seen = []
+    for i in range(len(batches)):
+        xb = pf.get()
+        seen.append((xb * 2).sum(dim=(1, 2, 3)))      # some work on the current stream that reads the buffer
+        snapshot = xb.clone()
+        pf.release()
+        if i + 1 < len(batches):
+            pf.submit(batches[i + 1])
+        assert torch.equal(snapshot.cpu(), x_host[batches[i]])
+    for i, s in enumerate(seen):
+        assert torch.allclose(s.cpu(), (x_host[batches[i]] * 2).sum(dim=(1, 2, 3)), rtol=1e-5)
+    with pytest.raises(RuntimeError):
+        pf.get()
