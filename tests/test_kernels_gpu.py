@@ -41,8 +41,9 @@ def make_problem(B, hw, K, N=None, seed=0, dense_v=False):
     return D2, v, x, idx, gr
 
 
+# (the last two give every persistent CTA several tiles -- stage recycling, buffer parity -- and a ragged last tile)
 SHAPES = [(4, 64, 6), (32, 1024, 10), (100, 784, 50), (33, 400, 64), (7, 256, 200), (100, 196, 100), (1, 64, 1),
-          (130, 100, 37)]
+          (130, 100, 37), (100, 15796, 50), (37, 5300, 33)]
 
 
 @pytest.mark.parametrize("B,hw,K", SHAPES)
@@ -97,7 +98,8 @@ def test_grad_matches_oracle(ops, B, hw, K, impl):
         ops.set_impl(ops.IMPL_AUTO)
 
 
-@pytest.mark.parametrize("B,hw,K", [(4, 64, 6), (100, 784, 50), (33, 400, 64), (16, 256, 200), (24, 100, 37)])
+@pytest.mark.parametrize("B,hw,K", [(4, 64, 6), (100, 784, 50), (33, 400, 64), (16, 256, 200), (24, 100, 37),
+                                    (100, 15796, 50), (64, 15796, 24), (37, 5300, 33)])
 @pytest.mark.parametrize("impl", ["fma", "auto"])
 def test_fused_grad_dict_step(ops, B, hw, K, impl):
     """Fused kernel == unfused grad followed by the oracle's AdamW + clamp on the SAME dD (teacher-forced), for a
