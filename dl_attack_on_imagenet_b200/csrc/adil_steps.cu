@@ -180,22 +180,53 @@ __global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
       x[i] = k < K ? a.v[base + k] : 0.0f;
     }
     if (a.do_adamw) {
+      // every global load of the row goes out before anything is consumed: the moments, and (B <= 128) this lane's
+      // four batch indices -- the scan below would otherwise be a chain of dependent round trips
+      float mv[EPL], sv[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int k = lane + 32 * i;
+        mv[i] = k < K ? a.m[base + k] : 0.0f;
+        sv[i] = k < K ? a.s[base + k] : 0.0f;
+      }
       float g[EPL];
 #pragma unroll
       for (int i = 0; i < EPL; ++i) g[i] = 0.0f;
       if (a.dvb != nullptr) {
         // gather the batch slots that map to this row (ascending slot order; duplicates accumulate)
-        for (int b0 = 0; b0 < a.B; b0 += 32) {
-          const int b = b0 + lane;
-          const bool hit = b < a.B && (a.vidx ? a.vidx[b] : (int64_t)b) == (int64_t)row;
-          unsigned mask = __ballot_sync(0xffffffffu, hit);
-          while (mask) {
-            const int bb = b0 + __ffs(mask) - 1;
-            mask &= mask - 1;
+        if (a.B <= 128) {
+          bool hit[4];
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-              const int k = lane + 32 * i;
-              if (k < K) g[i] += a.dvb[(size_t)bb * K + k];
+          for (int j = 0; j < 4; ++j) {
+            const int b = 32 * j + lane;
+            hit[j] = b < a.B && (a.vidx ? a.vidx[b] : (int64_t)b) == (int64_t)row;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            unsigned mask = __ballot_sync(0xffffffffu, hit[j]);
+            while (mask) {
+              const int bb = 32 * j + __ffs(mask) - 1;
+              mask &= mask - 1;
+#pragma unroll
+              for (int i = 0; i < EPL; ++i) {
+                const int k = lane + 32 * i;
+                if (k < K) g[i] += a.dvb[(size_t)bb * K + k];
+              }
+            }
+          }
+        } else {
+          for (int b0 = 0; b0 < a.B; b0 += 32) {
+            const int b = b0 + lane;
+            const bool hit = b < a.B && (a.vidx ? a.vidx[b] : (int64_t)b) == (int64_t)row;
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+              const int bb = b0 + __ffs(mask) - 1;
+              mask &= mask - 1;
+#pragma unroll
+              for (int i = 0; i < EPL; ++i) {
+                const int k = lane + 32 * i;
+                if (k < K) g[i] += a.dvb[(size_t)bb * K + k];
+              }
             }
           }
         }
@@ -204,10 +235,9 @@ __global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
       for (int i = 0; i < EPL; ++i) {
         const int k = lane + 32 * i;
         if (k < K) {
-          float mv = a.m[base + k], sv = a.s[base + k];
-          adamw_update(x[i], mv, sv, g[i], a.hp);
-          a.m[base + k] = mv;
-          a.s[base + k] = sv;
+          adamw_update(x[i], mv[i], sv[i], g[i], a.hp);
+          a.m[base + k] = mv[i];
+          a.s[base + k] = sv[i];
         }
       }
     }
