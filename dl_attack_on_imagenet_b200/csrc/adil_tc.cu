@@ -10,15 +10,23 @@
 //               (0,1)(0,0).  bf16 because the gradient tile is contracted over images for dD and over pixels for dv:
 //               one shared-memory image of a 16-bit operand can be read in both majors, a TF32 operand cannot.
 //
-// Roles (one CTA per SM, 18 warps):
-//   warps 0..15  workers: operand split (fp32 -> hi/lo or bf16x3 images in the UMMA canonical no-swizzle layout),
-//                epilogues (TMEM -> registers -> shared-memory staging -> coalesced 128-bit global stores), AdamW
-//   warp 16      MMA issuer: one lane issues tcgen05.mma and commits to an mbarrier
-//   warp 17      loader: 1-D TMA bulk copies (cp.async.bulk + mbarrier expect_tx) of the contiguous D / m / s tiles
-//                and cp.async (LDGSTS) of the image rows, running up to three tiles ahead of the workers
+// Roles (one persistent CTA per SM; hand-offs between roles are mbarriers):
+//   synthesis (800 threads)
+//     warps 0..15   workers: dictionary tile split (fp32 -> hi/lo images, UMMA canonical no-swizzle layout) and the
+//                   epilogue (TMEM -> registers -> +x, clamps, Normalize -> shared-memory staging)
+//     warp 16       MMA issuer (one elected lane issues tcgen05.mma and commits to an mbarrier) + dictionary-tile TMA
+//     warps 17..24  I/O: every global access of the image rows (cp.async in, coalesced 128-bit streaming stores out)
+//   backward (896 threads)
+//     warps 0..15   workers: operand staging only (gradient rows -> three bf16 images, TMA-landed dictionary rows ->
+//                   three bf16 images of D / std)
+//     warps 16..23  epilogue: dD^T accumulator -> flat [pixel][atom] tile in shared memory -> AdamW + clamp with the
+//                   moments prefetched from global memory into registers -> coalesced stores (or, plain dD output,
+//                   into the stage that the loader writes out with one TMA bulk store)
+//     warp 26 / 27  MMA issuer / loader (1-D TMA bulk copies of the contiguous D tiles, bulk stores of dD tiles);
+//                   warps 24, 25 only place them on schedulers 2 and 3
 // Tiles of TP pixels are assigned round-robin (tile = blockIdx.x + i * gridDim.x).  Per tile the workers stage the
-// operands of tile i, hand them to the issuer, and run the epilogue of tile i-1 while the MMAs of tile i execute;
-// accumulators are double-buffered in TMEM.
+// operands of tile i while the MMAs of tile i-1 run and the epilogue of tile i-2 finishes; operand images and
+// accumulators are double-buffered.
 //
 // Shared-memory operand images (no swizzle): 128-byte core matrices of 8 "rows" x 16 bytes,
 //     off(r, c) = (c / E) * S + (r / 8) * 128 + (r % 8) * 16 + (c % E) * sizeof(elem)      E = 16 / sizeof(elem)
@@ -37,14 +45,13 @@ int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, 
 namespace {
 
 // Phase timing (debug builds only, -DADIL_TIMING): thread 0 of every CTA accumulates clock64 deltas per pipeline phase;
-// the launchers print the per-CTA-tile averages to stderr.  Never compiled into the product library.
+// the launchers print the per-CTA-tile averages to stderr.  Never compiled into the product library.  Synthesis
+// kernel only: the counter arrays cost ~30 registers, and the backward kernel (capped at 72) spills under them and slows
+// down several-fold -- it carries the cheap -DADIL_CHAIN stamps below instead.
 #ifdef ADIL_TIMING
 __device__ long long g_tim[16];
 #define TIM_DECL long long tim_last = clock64(); long long tim_acc[12] = {0}
 #define TIM(i) do { if (tid == 0) { const long long t_ = clock64(); tim_acc[i] += t_ - tim_last; tim_last = t_; } } while (0)
-#define ETIM_DECL long long etim_last = clock64(); long long etim_acc[4] = {0}
-#define ETIM(i) do { if (tid == WARP_EPI * 32) { const long long t_ = clock64(); etim_acc[i] += t_ - etim_last; etim_last = t_; } } while (0)
-#define ETIM_FLUSH() do { if (tid == WARP_EPI * 32) { for (int i_ = 0; i_ < 4; ++i_) atomicAdd((unsigned long long*)&g_tim[4 + i_], (unsigned long long)etim_acc[i_]); } } while (0)
 #define TIM_FLUSH(n) do { if (tid == 0) { for (int i_ = 0; i_ < 12; ++i_) atomicAdd((unsigned long long*)&g_tim[i_], (unsigned long long)tim_acc[i_]); atomicAdd((unsigned long long*)&g_tim[12], (unsigned long long)(n)); } } while (0)
 __device__ long long g_stamp[8];
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -54,9 +61,6 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #define TIM_DECL
 #define TIM(i)
 #define TIM_FLUSH(n)
-#define ETIM_DECL
-#define ETIM(i)
-#define ETIM_FLUSH()
 #endif
 // Hand-off chain of one tile (debug builds only, -DADIL_CHAIN; cheap enough not to disturb the schedule): global-timer
 // stamps of CTA 5, tile 6, written by lane 0 of whichever warp passes the probe.
@@ -257,15 +261,6 @@ __device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&r)[8]
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
-  uint32_t u[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* r) {
   uint32_t u[8];
@@ -994,7 +989,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       const int etid = tid - WARP_EPI * 32;
       TileChan tc;
       tile_chan_init(tc);
-      ETIM_DECL;
       // AdamW moments: straight from global memory into registers, one tile ahead (they never need shared memory)
       float4 Mp[NPF], Sp[NPF];
       auto prefetch_ms = [&](int j) {
@@ -1021,7 +1015,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           if (a.cc.use) tile_chan_update(tc, a.cc, p0);
           mbar_wait(mma_done + buf, (j >> 1) & 1);  // MMAs of tile j retired: its dD accumulator is complete
           tc_fence_after();
-          ETIM(0);
           if (warp == WARP_EPI) CHAIN(3, j);
           // (plain dD output with dv: the stage held the D rows of the dictionary split, which every worker finished
           // before the MMAs of this tile were issued; without dv it is a staging buffer handed back by the loader)
@@ -1049,17 +1042,14 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + buf);  // the accumulator has been read: the tensor core may reuse it
-          ETIM(1);
           if (warp == WARP_EPI) CHAIN(4, j);
         }
         if (fused) {
           bar_sync(3, NE * 32);  // gradient tile complete (and every warp is done with the tile two steps back)
-          ETIM(2);
           mbar_wait(full_raw + sj, (j / NS) & 1);  // D rows landed
           const int n4 = (rows * K) >> 2;
           const size_t base = (size_t)p0 * K;
 #ifndef ADIL_EXP_NO_EPI
-#ifndef ADIL_V_LOADFIRST
 #pragma unroll
           for (int u = 0; u < NPF; ++u) {
             const int e4 = etid + u * (NE * 32);
@@ -1078,41 +1068,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
               *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sp[u];
             }
           }
-#else
-          {  // NPF items per thread in flight: all shared-memory loads, then the arithmetic, then the stores
-            float4 Dv[NPF], gd[NPF];
-#pragma unroll
-            for (int u = 0; u < NPF; ++u) {
-              const int e4 = etid + u * (NE * 32);
-              if (e4 < n4) {
-                Dv[u] = *reinterpret_cast<const float4*>(stage + 4 * e4);
-                gd[u] = *reinterpret_cast<const float4*>(gtile + 4 * e4);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < NPF; ++u) {
-              const int e4 = etid + u * (NE * 32);
-              if (e4 < n4) {
-                adamw_update_fast(Dv[u].x, Mp[u].x, Sp[u].x, gd[u].x, a.hp);
-                adamw_update_fast(Dv[u].y, Mp[u].y, Sp[u].y, gd[u].y, a.hp);
-                adamw_update_fast(Dv[u].z, Mp[u].z, Sp[u].z, gd[u].z, a.hp);
-                adamw_update_fast(Dv[u].w, Mp[u].w, Sp[u].w, gd[u].w, a.hp);
-                if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
-                  Dv[u].x = clamp1(Dv[u].x); Dv[u].y = clamp1(Dv[u].y); Dv[u].z = clamp1(Dv[u].z); Dv[u].w = clamp1(Dv[u].w);
-                }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < NPF; ++u) {
-              const int e4 = etid + u * (NE * 32);
-              if (e4 < n4) {
-                *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv[u];
-                *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mp[u];
-                *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sp[u];
-              }
-            }
-          }
-#endif
           for (int e4 = etid + NPF * (NE * 32); e4 < n4; e4 += NE * 32) {  // (large K: beyond the prefetched part)
             float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
             float4 Mv = ld_global4(a.m + base + 4 * (size_t)e4);
@@ -1138,10 +1093,8 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           __syncwarp();
           if (lane == 0) mbar_arrive(epi_done + sj);
         }
-        ETIM(3);
         if (warp == WARP_EPI) CHAIN(5, j);
       }
-      ETIM_FLUSH();
     }
   } else {
     // ===== workers: stage the operand images of tile `it` while the MMAs of tile it-1 run =====
@@ -1151,7 +1104,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
 
     TileChan tc;
     tile_chan_init(tc);
-    TIM_DECL;
     STAMP(3);
     if (a.want_dD) {
       // batch codes (three bf16 terms) -> tensor memory, once per CTA: a column holds the image pair (2c, 2c+1)
@@ -1194,7 +1146,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         mbar_wait(mma_done + buf, ((it - 2) >> 1) & 1);  // MMAs(it-2) retired: this image buffer is free again
         tc_fence_after();
       }
-      TIM(0);
       // gradient tile: registers -> three bf16 images
 #pragma unroll
       for (int j = 0; j < GJ; ++j) {
@@ -1210,13 +1161,11 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         }
       }
       if (it + 1 < my_tiles) prefetch(it + 1);      // the registers are free again: next tile's rows fly from here on
-      TIM(1);
       if (a.want_dv) {
         // dictionary tile (pre-update values): TMA-landed raw rows -> three bf16 images of D / std.  Rows past the end
         // of the array (ragged last tile) were never written: they are staged as zeros.
         if (warp == 0) { CHAIN(7, it - NS); CHAIN(10, it); }
         mbar_wait(full_raw + s, (it / NS) & 1);
-        TIM(2);
         if (warp == 0) CHAIN(8, it - NS);
         const float* rt = raw + s * a.raw_floats;
         const int nvalid = min(TP, P - p0) * kv;
@@ -1301,7 +1250,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         mbar_arrive(staged + buf);                  // hand the tile to the issuer warp, keep going
         if (a.want_dv) mbar_arrive(empty_raw + s);  // this warp is done with the raw dictionary rows
       }
-      TIM(3);
       if (warp == 0) CHAIN(9, it);
     }
     STAMP(4);
@@ -1337,7 +1285,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         }
       }
     }
-    TIM_FLUSH(my_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -1546,19 +1493,6 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
     default: rc = launch_grad_tp<16>(a, pl.smem, grid, st); break;
   }
   if (rc) return rc;
-#ifdef ADIL_TIMING
-  {
-    cudaDeviceSynchronize();
-    long long h[16];
-    cudaMemcpyFromSymbol(h, g_tim, sizeof(h));
-    long long z[16] = {0};
-    cudaMemcpyToSymbol(g_tim, z, sizeof(z));
-    const char* nm[10] = {"wait_mma", "g_split+prefetch", "wait_raw", "D_split+arrive", "E:wait_mma", "E:tmem_ld", "E:wait_raw", "E:adamw+store", "-", "-"};
-    fprintf(stderr, "grad TP=%d tiles=%lld cycles/tile:", pl.TP, h[12]);
-    long long tot = 0;
-    for (int i = 0; i < 10; ++i) { fprintf(stderr, " %s=%.0f", nm[i], (double)h[i] / (double)h[12]); tot += h[i]; }
-    fprintf(stderr, " | total=%.0f\n", (double)tot / (double)h[12]);
-#endif
 #ifdef ADIL_CHAIN
   {
     cudaDeviceSynchronize();
