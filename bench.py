@@ -252,18 +252,20 @@ def run_ours(args):
     def step_resident(i, record=False):
         """Device-resident step: images already in HBM, gathered inside the synthesis kernel."""
         idx = idx_dev[i % n_batches]
+        idx_h = idx_cpu[i % n_batches]     # the DataLoader's CPU index tensor (adil.py:168): the synthesis / backward
+                                           # kernels take it as kernel parameters, like ADIL._fit_step does
         with torch.no_grad():
             labels = model(x_dev[idx].view(-1, *shape)).argmax(-1)               # adil.py:172
-        xin, _ = timed("synth", lambda: ops.synth(st.D2, st.v, idx, x=x_dev, x_index=idx, mean=mean, std=std,
+        xin, _ = timed("synth", lambda: ops.synth(st.D2, st.v, idx_h, x=x_dev, x_index=idx_h, mean=mean, std=std,
                                                   flags=flags), record)
         loss, g, out = atk._classifier_grad(xin.view(-1, *shape), labels, 'sum')
         g2 = g.view(B, P_IMG)
         if world == 1:
             st.tD += 1
-            dvb = timed("grad", lambda: ops.grad_dict_step(st.D2, st.mD, st.sD, g2, st.v, idx,
+            dvb = timed("grad", lambda: ops.grad_dict_step(st.D2, st.mD, st.sD, g2, st.v, idx_h,
                                                            ops.adamw_params(st.tD, 0.01), std, ops.ATOMS_CLAMP1), record)
         else:
-            _, dvb = timed("grad", lambda: ops.grad(g2, st.D2, st.v, idx, std, dD2=dD2), record)
+            _, dvb = timed("grad", lambda: ops.grad(g2, st.D2, st.v, idx_h, std, dD2=dD2), record)
             dist.all_reduce(dD2, op=dist.ReduceOp.SUM)                           # the one data-path collective
             st.tD += 1
             timed("dict", lambda: ops.dict_step(st.D2, st.mD, st.sD, dD2, ops.adamw_params(st.tD, 0.01),

@@ -266,10 +266,14 @@ class ADIL(Attack):
         xb = x_src[x_index] if x_index is not None else x_src
         return self._clean_labels(xb.view(-1, *shape))
 
-    def _fit_step(self, st, x_src, x_index, v_index, labels, shape, update, lr_d, lr_v):
-        """One minibatch of adil.py:168-188 (update='both'), :268-284 ('v') or :295-311 ('d')."""
+    def _fit_step(self, st, x_src, x_index, v_index, labels, shape, update, lr_d, lr_v, index_cpu=None):
+        """One minibatch of adil.py:168-188 (update='both'), :268-284 ('v') or :295-311 ('d').  `index_cpu`: the same
+        indices as `v_index` as the CPU tensor the DataLoader produced (adil.py:168); when given, the synthesis and
+        backward kernels take them as kernel parameters (no cold miss on the index array)."""
         flags = ops.SYNTH_NORMALIZE if self._mean is not None else 0
-        xin, _ = ops.synth(st.D2, st.v, v_index, x=x_src, x_index=x_index, mean=self._mean, std=self._std, flags=flags,
+        kv_index = index_cpu if index_cpu is not None else v_index
+        kx_index = (index_cpu if index_cpu is not None else x_index) if x_index is not None else None
+        xin, _ = ops.synth(st.D2, st.v, kv_index, x=x_src, x_index=kx_index, mean=self._mean, std=self._std, flags=flags,
                            n_channels=shape[0])
         loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
         g = g.view(g.shape[0], -1)
@@ -277,14 +281,14 @@ class ADIL(Attack):
         dvb = None
         if update == 'both':
             st.tD += 1
-            dvb = ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, v_index, ops.adamw_params(st.tD, lr_d), self._std,
+            dvb = ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, kv_index, ops.adamw_params(st.tD, lr_d), self._std,
                                      ops.ATOMS_CLAMP1)
         elif update == 'd':
             st.tD += 1
-            ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, v_index, ops.adamw_params(st.tD, lr_d), self._std,
+            ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, kv_index, ops.adamw_params(st.tD, lr_d), self._std,
                                ops.ATOMS_CLAMP1, want_dv=False)
         else:
-            _, dvb = ops.grad(g, st.D2, st.v, v_index, self._std, want_dD=False)
+            _, dvb = ops.grad(g, st.D2, st.v, kv_index, self._std, want_dD=False)
         if update in ('both', 'v'):
             st.tv += 1
             ops.code_step(st.v, st.mv, st.sv, dvb, v_index, ops.adamw_params(st.tv, lr_v), ops.ROWS_L1BALL, self.eps)
@@ -299,11 +303,12 @@ class ADIL(Attack):
             raise RuntimeError("fit_batch: call begin_fit(n_img, image_shape) or fit() first")
         x = x.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
         shape = tuple(x.shape[1:])
-        v_index = torch.as_tensor(index, dtype=torch.long).to(self.device, non_blocking=True)
+        index = torch.as_tensor(index, dtype=torch.long)
+        v_index = index.to(self.device, non_blocking=True)
         if labels is None:
             labels = self._clean_labels(x)                                 # adil.py:172
         return self._fit_step(st, x.view(x.shape[0], -1), None, v_index, labels, shape, 'both', self.step_size,
-                              self.step_size)
+                              self.step_size, index_cpu=index if not index.is_cuda else None)
 
     def begin_fit(self, n_img, image_shape, warm_start=False):
         """Allocate and initialise D, v and the AdamW state for `n_img` images (adil.py:138-154)."""
@@ -342,7 +347,7 @@ class ADIL(Attack):
                 v_index = x_index if x_index is not None else index.to(self.device, non_blocking=True)
                 labels = self._labels_for(v_index, index, x_src, x_index, shape)
                 loss, fooled = self._fit_step(st, x_src, x_index, v_index, labels, shape, 'both', self.step_size,
-                                              self.step_size)
+                                              self.step_size, index_cpu=index if not index.is_cuda else None)
                 loss_full += loss
                 fooling_sample += fooled
             loss_all.append(loss_full.item() / n_img)
@@ -378,7 +383,8 @@ class ADIL(Attack):
                         v_index = x_index if x_index is not None else index.to(self.device, non_blocking=True)
                         labels = self._labels_for(v_index, index, x_src, x_index, shape)
                         loss, fooled = self._fit_step(st, x_src, x_index, v_index, labels, shape, phase,
-                                                      2 * self.step_size, self.step_size)
+                                                      2 * self.step_size, self.step_size,
+                                                      index_cpu=index if not index.is_cuda else None)
                         loss_full = loss_full + loss if phase == 'v' else loss  # adil.py:313: last d-batch only
                         fooling_sample += fooled
                     epoch += 1

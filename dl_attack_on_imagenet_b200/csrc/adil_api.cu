@@ -39,6 +39,16 @@ int sm_count() {
   return cached[dev];
 }
 
+bool is_host_pointer(const void* p) {
+  if (p == nullptr) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();  // (pre-11.0 behaviour for unregistered host memory)
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered || at.type == cudaMemoryTypeHost;
+}
+
 AdamwDev make_adamw(const adil_adamw_t* hp) {
   AdamwDev d;
   const double t = (double)hp->step;
@@ -146,6 +156,9 @@ extern "C" int adil_synth(float* out, float* delta_out, const float* x, const in
   if (use_tc(tc_synth_ok(B, P, K, norm ? hw : P), B, P, K, &rc, "adil_synth"))
     return launch_synth_tc(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
   if (rc) return rc;
+  if (is_host_pointer(x_index) || is_host_pointer(v_index))
+    return set_error(-4, "adil_synth: host index arrays travel as kernel parameters of the tcgen05 path; shape B=%d P=%d K=%d "
+                     "(or ADIL_IMPL_FMA) needs device index arrays", B, P, K);
   return launch_synth_fma(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
 }
 
@@ -176,6 +189,9 @@ int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, fl
     return launch_grad_tc(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
                           scratch_bytes, st);
   if (rc) return rc;
+  if (is_host_pointer(v_index))
+    return set_error(-4, "%s: a host index array travels as kernel parameters of the tcgen05 path; shape B=%d P=%d K=%d (or "
+                     "ADIL_IMPL_FMA) needs a device index array", fn, B, P, K);
   return launch_grad_fma(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
                          scratch_bytes, st);
 }

@@ -121,6 +121,7 @@ __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int sm_count();
+bool is_host_pointer(const void* p);  // true for pageable / pinned host memory (index arrays may live on the host)
 AdamwDev make_adamw(const adil_adamw_t* hp);
 ChannelConsts make_consts(int C, int hw, const float* mean_host, const float* std_host, bool use);
 

@@ -355,6 +355,8 @@ struct SynthArgs {
   const float* D2;
   const float* v;
   const int64_t* vidx;
+  int hx_on, hv_on;      // the batch indices travel in the kernel parameters (host index arrays, B <= 128): no
+  int hx[128], hv[128];  // dependent cold miss on an index array at the top of the kernel
   int B, P, K;
   int Kp8;               // contraction length: round_up(K, 8)
   int Sd;                // byte stride between 4-atom groups of a dictionary image
@@ -417,8 +419,8 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
   for (int b = tid; b < B; b += NTHREADS_SYNTH) {
-    xoff_s[b] = (a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
-    vrow_s[b] = a.vidx ? (long long)a.vidx[b] : (long long)b;
+    xoff_s[b] = (a.hx_on ? (long long)a.hx[b] : a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
+    vrow_s[b] = a.hv_on ? (long long)a.hv[b] : a.vidx ? (long long)a.vidx[b] : (long long)b;
   }
   tc_fence_before();
   __syncthreads();
@@ -738,6 +740,8 @@ struct GradArgs {
   const float* D2;
   const float* v;
   const int64_t* vidx;
+  int hv_on;          // the batch indices travel in the kernel parameters (host index array)
+  int hv[128];
   int B, P, K;
   int Bp;             // contraction length of dD: round_up(B, 16)
   int Kp;             // N of the dv MMA: round_up(K, 16)
@@ -792,7 +796,8 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
   for (int b = tid; b < 128; b += NTHREADS_GRAD)  // element offset of the code row of image b (rows >= B: row of image B-1)
-    vrow_s[b] = (a.vidx ? (long long)a.vidx[min(b, B - 1)] : (long long)min(b, B - 1)) * (long long)K;
+    vrow_s[b] = (a.hv_on ? (long long)a.hv[min(b, B - 1)] : a.vidx ? (long long)a.vidx[min(b, B - 1)] : (long long)min(b, B - 1)) *
+                (long long)K;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1391,6 +1396,7 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
                     int flags, cudaStream_t st) {
   const bool norm = (flags & ADIL_SYNTH_NORMALIZE) != 0;
   const int hw = norm ? cc.hw : P;
+  const bool x_index_on_host = x_index && is_host_pointer(x_index), v_index_on_host = v_index && is_host_pointer(v_index);
   // images beyond 128 go through further launches (M = 128 image lanes per pass)
   for (int b0 = 0; b0 < B; b0 += 128) {
     const int nb = B - b0 < 128 ? B - b0 : 128;
@@ -1401,9 +1407,20 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     a.delta = delta_out ? delta_out + (size_t)b0 * P : nullptr;
     a.x = x ? (x_index ? x : x + (size_t)b0 * P) : nullptr;
     a.xidx = x_index ? x_index + b0 : nullptr;
+    a.hx_on = 0; a.hv_on = 0;
+    if (x_index && x_index_on_host) {
+      for (int i = 0; i < nb; ++i) a.hx[i] = (int)x_index[b0 + i];
+      a.hx_on = 1;
+    }
+    if (v_index && v_index_on_host) {
+      for (int i = 0; i < nb; ++i) a.hv[i] = (int)v_index[b0 + i];
+      a.hv_on = 1;
+    }
     a.D2 = D2;
     a.v = v_index ? v : v + (size_t)b0 * K;
     a.vidx = v_index ? v_index + b0 : nullptr;
+    if (a.hx_on) a.xidx = nullptr;
+    if (a.hv_on) a.vidx = nullptr;
     a.B = nb; a.P = P; a.K = K; a.Kp8 = pl.Kp8; a.Sd = pl.Sd; a.dimg = pl.dimg;
     a.raw_floats = pl.raw_floats; a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.tmem_cols = pl.tmem_cols;
     a.eps = eps; a.flags = flags; a.cc = cc;
@@ -1471,6 +1488,12 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
   if (!pl.ok) return set_error(-4, "adil_grad: shape B=%d P=%d K=%d does not qualify for the tcgen05 path", B, P, K);
   GradArgs a;
   a.dD2 = dD2; a.D2w = D2_rw; a.m = m; a.s = s; a.partial = scratch; a.g = g; a.D2 = D2; a.v = v; a.vidx = v_index;
+  a.hv_on = 0;
+  if (v_index && is_host_pointer(v_index)) {
+    for (int i = 0; i < B; ++i) a.hv[i] = (int)v_index[i];
+    a.hv_on = 1;
+    a.vidx = nullptr;
+  }
   a.B = B; a.P = P; a.K = K; a.Bp = pl.Bp; a.Kp = pl.Kp; a.Sg = pl.Sg; a.Sd = pl.Sd;
   a.dimg = pl.dimg; a.gimg = pl.gimg; a.raw_floats = pl.raw_floats; a.nraw = pl.nraw;
   a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.tmem_cols = pl.tmem_cols;

@@ -44,6 +44,24 @@ def _idx(t, name, device):
     return t.contiguous()
 
 
+def _idx_any(t, name, device, P, K, bit):
+    """Index array for the kernels that take host OR device indices (synth: bit 1, grad*: bit 2).  A CPU index tensor
+    of at most 128 entries stays on the host when the tcgen05 path applies -- the indices then travel as kernel
+    parameters (no H2D copy, no cold miss in the kernel) -- anything else goes to the device."""
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(list(t) if not hasattr(t, '__array__') else t, dtype=torch.long)
+    if t.dtype != torch.long:
+        t = t.long()
+    if (not t.is_cuda) and 0 < t.numel() <= 128 and get_impl() != IMPL_FMA and (
+            _lib.lib().adil_tc_supported(int(t.numel()), int(P), int(K)) & bit):
+        return t.contiguous()
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -100,8 +118,8 @@ def synth(D2, v, v_index=None, x=None, x_index=None, mean=None, std=None, eps=0.
     v = _f32(v, "v")
     dev = D2.device
     P, K = D2.shape
-    v_index = _idx(v_index, "v_index", dev)
-    x_index = _idx(x_index, "x_index", dev)
+    v_index = _idx_any(v_index, "v_index", dev, P, K, 1)
+    x_index = _idx_any(x_index, "x_index", dev, P, K, 1)
     B = v_index.numel() if v_index is not None else v.shape[0]
     if x is not None:
         x = _f32(x, "x")
@@ -135,7 +153,7 @@ def grad(g, D2, v, v_index=None, std=None, want_dD=True, want_dv=True, dD2=None,
     v = _f32(v, "v")
     dev = D2.device
     P, K = D2.shape
-    v_index = _idx(v_index, "v_index", dev)
+    v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
     B = v_index.numel() if v_index is not None else v.shape[0]
     if g.numel() != B * P:
         raise ValueError("g has %d elements, expected B*P = %d" % (g.numel(), B * P))
@@ -161,7 +179,7 @@ def grad_dict_step(D2, m, s, g, v, v_index, hp, std=None, atoms_mode=ATOMS_CLAMP
     v = _f32(v, "v")
     dev = D2.device
     P, K = D2.shape
-    v_index = _idx(v_index, "v_index", dev)
+    v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
     B = v_index.numel() if v_index is not None else v.shape[0]
     if g.numel() != B * P:
         raise ValueError("g has %d elements, expected B*P = %d" % (g.numel(), B * P))

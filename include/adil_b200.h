@@ -14,6 +14,11 @@
  *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
  *  - return value: 0 = ok; >0 = cudaError_t; <0 = argument / capability error.  adil_last_error() returns
  *    a thread-local description of the last non-zero return.
+ *  - the int64 index arrays of adil_synth / adil_grad / adil_grad_dict_step (x_index, v_index) may ALSO be HOST
+ *    pointers (pageable or pinned; the reference's DataLoader hands out CPU index tensors, adil.py:168): the
+ *    indices are then read at call time and travel as kernel parameters, which removes the dependent cold
+ *    miss on the index array at the top of the kernel (~1.4 us).  Needs the tcgen05 path (B <= 128 per pass,
+ *    K <= 128, adil_tc_supported); otherwise -4 is returned and the caller passes device arrays.
  *  - P = C*hw pixels per image (hw = H*W), must be a multiple of 4.  K = atoms (1..256).  D2 is the
  *    dictionary viewed as [P, K] row-major (atoms innermost, adil.py:148 creates [C,H,W,K]).
  */
@@ -27,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ADIL_VERSION 101
+#define ADIL_VERSION 102
 
 #define ADIL_MAX_CHANNELS 8
 #define ADIL_MAX_ATOMS 256

@@ -11,6 +11,7 @@ ap.add_argument("--N", type=int, default=1024)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--impls", default="fma,auto")
 ap.add_argument("--only", default="")
+ap.add_argument("--device-index", action="store_true", help="pass the batch indices as a device array (default: CPU tensor -> kernel parameters)")
 args = ap.parse_args()
 P = 3 * 224 * 224
 B, K, N = args.B, args.K, args.N
@@ -22,6 +23,8 @@ v = torch.rand(N, K, device=dev) * 1e-3
 x = torch.rand(B, P, device=dev)
 g = torch.randn(B, P, device=dev) * 1e-3
 idx = torch.randperm(N, device=dev)[:B]
+if not args.device_index:
+    idx = idx.cpu()
 out = torch.empty(B, P, device=dev)
 dD = torch.empty(P, K, device=dev)
 dvb = torch.empty(B, K, device=dev)
@@ -55,6 +58,7 @@ for impl in args.impls.split(","):
         print(f"{impl:5s} {name:15s} median {med*1e3:8.1f} us  best {best*1e3:8.1f} us  {nbytes/med/1e6:7.0f} GB/s  {100*nbytes/med/1e6/PEAK:5.1f}% of measured HBM peak", flush=True)
 ops.set_impl(ops.IMPL_AUTO)
 vv = torch.rand(N, K, device=dev) * 1e-2; mv = torch.zeros_like(vv); sv = torch.zeros_like(vv)
-med, best = timeit(lambda: ops.code_step(vv, mv, sv, dvb, idx, ops.adamw_params(3, 0.01), ops.ROWS_L1BALL, 8 / 255), args.iters)
+idx_d = idx.to(dev)
+med, best = timeit(lambda: ops.code_step(vv, mv, sv, dvb, idx_d, ops.adamw_params(3, 0.01), ops.ROWS_L1BALL, 8 / 255), args.iters)
 print(f"code_step N={N} K={K}: median {med*1e3:.1f} us best {best*1e3:.1f} us")
 print(json.dumps(res))

@@ -353,3 +353,46 @@ def test_performance_module_matches_reference_formulas(ops):
     assert abs(tr["adil"]["b"]["fooling_rate"] - (other(clean).argmax(1) != other(a_all).argmax(1)).float().mean().item()) < 1e-6
     assert abs(tr["adil"]["a"]["rmse"] - (((a_all - clean) ** 2).sum(dim=[1, 2, 3]) / lo).mean().item()) <= 1e-5
     assert tr["none"]["a"]["mse"] != tr["none"]["a"]["mse"]  # NaN, like empty_transfer_performance
+
+
+# ---- host index arrays as kernel parameters ---------------------------------------------------------------------
+@pytest.mark.parametrize("B,hw,K", [(100, 784, 50), (33, 400, 64), (1, 64, 1), (37, 5300, 33)])
+def test_host_index_arrays_give_identical_results(ops, B, hw, K):
+    """CPU index tensors (adil.py:168) travel as kernel parameters of the tcgen05 kernels: same bits as device indices."""
+    D2, v, x, idx, g = make_problem(B, hw, K, seed=5)
+    assert not idx.is_cuda
+    Dd, vd, xd, gd, idx_d = dev(D2), dev(v), dev(x), dev(g), dev(idx)
+    out_h, _ = ops.synth(Dd, vd, idx, x=xd, x_index=idx, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE)
+    out_d, _ = ops.synth(Dd, vd, idx_d, x=xd, x_index=idx_d, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE)
+    assert torch.equal(out_h, out_d)
+    dD_h, dv_h = ops.grad(gd, Dd, vd, idx, STD)
+    dD_d, dv_d = ops.grad(gd, Dd, vd, idx_d, STD)
+    assert torch.equal(dD_h, dD_d) and torch.equal(dv_h, dv_d)
+    hp = ops.adamw_params(2, 0.01)
+    Da, ma, sa = Dd.clone(), torch.zeros_like(Dd), torch.zeros_like(Dd)
+    Db, mb, sb = Dd.clone(), torch.zeros_like(Dd), torch.zeros_like(Dd)
+    dva = ops.grad_dict_step(Da, ma, sa, gd, vd, idx, hp, STD)
+    dvb = ops.grad_dict_step(Db, mb, sb, gd, vd, idx_d, hp, STD)
+    assert torch.equal(Da, Db) and torch.equal(ma, mb) and torch.equal(sa, sb) and torch.equal(dva, dvb)
+
+
+def test_host_index_arrays_need_the_tensor_core_path(ops):
+    """Outside the tcgen05 limits (B > 128 for the backward kernels) the binding moves CPU indices to the device itself;
+    the C ABI refuses host arrays on the FMA path instead of dereferencing them on the GPU."""
+    import ctypes
+    from dl_attack_on_imagenet_b200 import _lib
+    D2, v, x, idx, g = make_problem(130, 100, 37, seed=6)
+    dD, dv = ops.grad(dev(g), dev(D2), dev(v), idx, STD)          # CPU index, B = 130: staged to the device by ops
+    dD2, dv2 = ops.grad(dev(g), dev(D2), dev(v), dev(idx), STD)
+    assert torch.equal(dD, dD2) and torch.equal(dv, dv2)
+    ops.set_impl(ops.IMPL_FMA)
+    try:
+        gd, Dd, vd = dev(g[:8]), dev(D2), dev(v)
+        host_idx = idx[:8].contiguous()
+        out = torch.empty(8, 37, device="cuda")
+        rc = _lib.lib().adil_grad(None, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(gd.data_ptr()),
+                                  ctypes.c_void_p(Dd.data_ptr()), ctypes.c_void_p(vd.data_ptr()),
+                                  ctypes.c_void_p(host_idx.data_ptr()), 8, 300, 37, 1, 300, None, None, 0, None)
+        assert rc == -4 and b"host index" in _lib.lib().adil_last_error()
+    finally:
+        ops.set_impl(ops.IMPL_AUTO)
