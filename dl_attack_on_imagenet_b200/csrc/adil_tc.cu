@@ -1039,8 +1039,27 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           // before the MMAs of this tile were issued; without dv it is a staging buffer handed back by the loader)
           if (!fused && a.nraw == 0 && j >= NS) mbar_wait(full_raw + sj, ((j / NS) - 1) & 1);
           const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TP + half * HALF);
+          if constexpr (!FUSED) {
+            // plain dD output: no prefetched moments in registers, so the whole share of the accumulator is read with
+            // one wait and the tensor core gets it back before the shared-memory writes (57 -> 54 us)
+            float r[HALF];
 #pragma unroll
-          for (int c0 = 0; c0 < HALF; c0 += 16) {  // sixteen columns per wait (all of them at once would spill: far dearer)
+            for (int c0 = 0; c0 < HALF; c0 += 8) tmem_ld8_nowait(tcol + (uint32_t)c0, &r[c0]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);  // the accumulator is in registers: the tensor core may reuse it
+            if (k_ok) {
+              float* col = gtile + (half * HALF) * K + k;
+#pragma unroll
+              for (int i = 0; i < HALF; ++i) {
+                const float sc = (a.cc.use && !G_SCALED) ? ((half * HALF + i) >= tc.bnd ? tc.rstd1 : tc.rstd0) : 1.0f;
+                col[i * K] = __fmul_rn(r[i], sc);
+              }
+            }
+          } else {
+#pragma unroll
+          for (int c0 = 0; c0 < HALF; c0 += 16) {  // sixteen columns per wait (all at once spills next to the moments: dearer)
             constexpr int NC = (HALF % 16 == 0) ? 16 : 8;  // (HALF is 8, 16, 24 or 32)
             const int nc = (HALF - c0 >= 16) ? 16 : 8;
             float r[16];
@@ -1061,6 +1080,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + buf);  // the accumulator has been read: the tensor core may reuse it
+          }
           if (warp == WARP_EPI) CHAIN(4, j);
         }
         if (fused) {
