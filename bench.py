@@ -207,7 +207,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # (keeps NCCL's version banner off stdout: ONE JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs go to stderr: ONE JSON line on stdout
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
