@@ -207,8 +207,18 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs go to stderr: ONE JSON line on stdout
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator comes up: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     torch.backends.cudnn.benchmark = not args.no_cudnn_autotune
