@@ -2,22 +2,25 @@
 section 8(f) row 3: what main.py / performance.py call per evaluated batch, and the transfer sweep of BASELINE
 configs[4]).  Same names, argument meaning and return types as the reference; the per-image error reductions run in
 one fused CUDA pass (adil_image_errors), the classifier passes stay in PyTorch / cuDNN.  No CPU fallback."""
-import numpy as np
 import torch
 
 from . import ops
 
 
+def _reduce(values, reduction):
+    if reduction == 'sum':
+        return values.sum().item()
+    if reduction == 'mean':
+        return values.mean().item()
+    return None  # (the reference returns None for any other reduction as well)
+
+
 def compute_fooling_rate(model, adversary, clean, reduction='sum'):
     """Number ('sum') or fraction ('mean') of images whose predicted label changes (performance.py:238-246)."""
+    net = model.eval()
     with torch.no_grad():
-        label_clean = model.eval()(clean).argmax(dim=1)
-        label_adversary = model.eval()(adversary).argmax(dim=1)
-    label_different = (label_clean != label_adversary)
-    if reduction == 'sum':
-        return label_different.float().sum().item()
-    elif reduction == 'mean':
-        return label_different.float().mean().item()
+        changed = net(clean).argmax(dim=1).ne(net(adversary).argmax(dim=1))
+    return _reduce(changed.float(), reduction)
 
 
 def _errors(adversary, clean):
@@ -28,21 +31,14 @@ def _errors(adversary, clean):
 
 def compute_rmse(adversary, clean, reduction='sum'):
     """Relative squared error ||adv - clean||^2 / ||clean||^2 per image, summed or averaged (performance.py:249-257)."""
-    upper, lower, _ = _errors(adversary, clean)
-    ratio = upper / lower
-    if reduction == 'sum':
-        return torch.sum(ratio).item()
-    elif reduction == 'mean':
-        return torch.mean(ratio).item()
+    err2, ref2, _ = _errors(adversary, clean)
+    return _reduce(err2 / ref2, reduction)
 
 
 def compute_mse(adversary, clean, reduction='sum'):
     """Squared error ||adv - clean||^2 per image, summed or averaged (performance.py:260-266)."""
-    upper, _, _ = _errors(adversary, clean)
-    if reduction == 'sum':
-        return torch.sum(upper).item()
-    elif reduction == 'mean':
-        return torch.mean(upper).item()
+    err2, _, _ = _errors(adversary, clean)
+    return _reduce(err2, reduction)
 
 
 def batch_metrics(model, adversary, clean):
@@ -79,8 +75,9 @@ def performance(attack, model, data, device=None):
 
 
 def empty_transfer_performance(model_transfer):
-    """performance.py:198-202."""
-    return {name: {'fooling_rate': np.nan, 'rmse': np.nan, 'mse': np.nan} for name in model_transfer.keys()}
+    """NaN entries for an attack family without a trained attack (performance.py:198-202)."""
+    nan = float('nan')
+    return {name: dict(fooling_rate=nan, rmse=nan, mse=nan) for name in model_transfer}
 
 
 def get_transfer_performance_aux(attack, model_transfer, data, device=None):
@@ -116,12 +113,7 @@ def get_transfer_performance_aux(attack, model_transfer, data, device=None):
 
 
 def get_transfer_performance(atks, models, data, device=None):
-    """performance.py:183-195."""
-    perf_transfer = dict()
-    for name in atks.keys():
-        if len(atks[name]) > 0:
-            perf_tmp = get_transfer_performance_aux(atks[name][0], models, data=data, device=device)
-        else:
-            perf_tmp = empty_transfer_performance(models)
-        perf_transfer.update({name: perf_tmp})
-    return perf_transfer
+    """Transfer performance of the first attack of every family on every model (performance.py:183-195)."""
+    return {family: (get_transfer_performance_aux(members[0], models, data=data, device=device) if len(members) > 0
+                     else empty_transfer_performance(models))
+            for family, members in atks.items()}
