@@ -435,13 +435,14 @@ class ADIL(Attack):
         for iteration in range(int(self.steps)):
             stats = torch.zeros(2, device=self.device, dtype=torch.float64)
             for per_rank in dsh.epoch_schedule(n_img, world, batch_size, iteration, seed=dsh.schedule_seed(self)):
-                idx_local = (per_rank[rank] - lo).to(self.device)
+                idx_host = per_rank[rank] - lo                       # CPU indices: kernel parameters of synth / grad
+                idx_local = idx_host.to(self.device)
                 if idx_local.numel() > 0:
-                    xin, _ = ops.synth(st.D2, st.v, idx_local, x=x_local, x_index=idx_local, mean=self._mean,
+                    xin, _ = ops.synth(st.D2, st.v, idx_host, x=x_local, x_index=idx_host, mean=self._mean,
                                        std=self._std, flags=flags, n_channels=nc)
                     labels = labels_local[idx_local]
                     loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
-                    _, dvb = ops.grad(g.view(g.shape[0], -1), st.D2, st.v, idx_local, self._std, dD2=dD2)
+                    _, dvb = ops.grad(g.view(g.shape[0], -1), st.D2, st.v, idx_host, self._std, dD2=dD2)
                     stats[0] += loss.double()
                     stats[1] += (out.argmax(-1) != labels).sum().double()
                 else:

@@ -292,3 +292,43 @@ def test_host_batch_prefetcher_delivers_the_gathered_rows_in_order():
         assert torch.allclose(s.cpu(), (x_host[batches[i]] * 2).sum(dim=(1, 2, 3)), rtol=1e-5)
     with pytest.raises(RuntimeError):
         pf.get()
+
+
+def test_distributed_fit_with_one_rank_matches_the_fused_single_gpu_fit(monkeypatch):
+    """learn_dictionary_distributed (plain contractions -> NCCL SUM all-reduce -> stand-alone dictionary step) on a
+    one-rank NCCL group follows the same trajectory as learn_dictionary_a (fused step) driven with the same minibatch
+    schedule: the first epochs agree to rounding."""
+    import torch.distributed as dist
+    from dl_attack_on_imagenet_b200 import distributed as dsh
+    if not dist.is_available():
+        pytest.skip("torch.distributed not available")
+    torch.manual_seed(1234)
+    st0 = O.init_state(C, H, W, N, K, EPS, 'linf')
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        a = make_attack(monkeypatch, st0, 1234, steps=2, model_name='dist', is_distributed=True)
+        assert a.state is not None and os.path.exists(a.model_file)
+        d_file, v_file, loss_dist, fool_dist, _ = torch.load(a.model_file, weights_only=False)
+        assert tuple(d_file.shape) == (C, H, W, K) and tuple(v_file.shape) == (N, K)
+        from dl_attack_on_imagenet_b200 import ADIL
+        monkeypatch.setattr(ADIL, "run_validation", False)
+        b = make_attack(monkeypatch, st0, 1234, steps=0, model_name='fused')        # steps=0: constructed, no epochs
+        b._batch_schedule = lambda epoch: dsh.union_schedule(N, 1, B, epoch, seed=dsh.schedule_seed(b))
+        b.steps = 2
+        xtr, ytr, _, _ = tiny_data()
+        from dl_attack_on_imagenet_b200 import IndexedTensorDataset
+        b.learn_dictionary_a(IndexedTensorDataset(xtr, ytr), None)
+        _, _, loss_fused, fool_fused, _ = torch.load(b.model_file, weights_only=False)
+        assert len(loss_dist) == len(loss_fused) == 2
+        assert abs(loss_dist[0] - loss_fused[0]) <= 1e-4 * abs(loss_fused[0]) + 1e-6
+        assert fool_dist[0] == fool_fused[0]
+        assert (a.state.D - b.state.D).abs().max() <= 2 * 0.01 * 2 * ((N + B - 1) // B)   # never further than the steps taken
+        assert torch.isfinite(a.state.D).all() and torch.isfinite(a.state.v).all()
+    finally:
+        if created:
+            dist.destroy_process_group()
