@@ -396,3 +396,49 @@ def test_host_index_arrays_need_the_tensor_core_path(ops):
         assert rc == -4 and b"host index" in _lib.lib().adil_last_error()
     finally:
         ops.set_impl(ops.IMPL_AUTO)
+
+
+# ---- randomized shape sweep: tcgen05 path against the CUDA-core path (both ours; the latter is oracle-checked above) ----
+def _random_shapes(n, seed):
+    import random
+    rnd = random.Random(seed)
+    shapes = []
+    while len(shapes) < n:
+        B = rnd.choice([1, 2, 7, 16, 31, 32, 33, 64, 100, 127, 128])
+        K = rnd.choice([1, 2, 3, 8, 10, 24, 31, 50, 64, 65, 96, 100, 127, 128])
+        hw = 4 * rnd.randint(4, 1500)
+        shapes.append((B, hw, K))
+    return shapes
+
+
+@pytest.mark.parametrize("B,hw,K", _random_shapes(24, seed=11))
+def test_random_shapes_tensor_core_path_matches_fma_path(ops, B, hw, K):
+    """Every tile size (64/48/32/16), ragged ends, odd K, single images: the tcgen05 kernels agree with the FMA kernels
+    to the split-precision bound on synth, both contractions and the fused dictionary step."""
+    if not ops.tc_supported(B, 3 * hw, K):
+        pytest.skip("shape outside the tcgen05 limits")
+    D2, v, x, idx, g = make_problem(B, hw, K, seed=B * 1000 + K)
+    Dd, vd, xd, gd, idx_d = dev(D2), dev(v), dev(x), dev(g), dev(idx)
+    hp = ops.adamw_params(3, 0.01)
+    res = {}
+    for impl in (ops.IMPL_FMA, ops.IMPL_AUTO):
+        ops.set_impl(impl)
+        try:
+            out, _ = ops.synth(Dd, vd, idx_d, x=xd, x_index=idx_d, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE)
+            dD, dv = ops.grad(gd, Dd, vd, idx_d, STD)
+            Df, mf, sf = Dd.clone(), torch.zeros_like(Dd), torch.zeros_like(Dd)
+            dvf = ops.grad_dict_step(Df, mf, sf, gd, vd, idx_d, hp, STD)
+            res[impl] = (out, dD, dv, Df, mf, sf, dvf)
+        finally:
+            ops.set_impl(ops.IMPL_AUTO)
+    a, b = res[ops.IMPL_FMA], res[ops.IMPL_AUTO]
+    assert (a[0] - b[0]).abs().max() <= 2e-6
+    assert (a[1] - b[1]).abs().max() <= 1e-5 * a[1].abs().max() + 1e-12
+    assert (a[2] - b[2]).abs().max() <= 1e-5 * a[2].abs().max() + 1e-12
+    assert (a[4] - b[4]).abs().max() <= 1e-5 * a[4].abs().max() + 1e-12            # m is linear in dD
+    assert (a[6] - b[6]).abs().max() <= 1e-5 * a[6].abs().max() + 1e-12
+    # D after one AdamW step (zero moments): the update is ~lr * g / (|g| / c + 1e-8), i.e. sign-like and, for entries
+    # with |g| near the 1e-8 floor, proportional to g -- there an ABSOLUTE gradient error of 1e-5 * max|dD| is amplified
+    # by lr / 1e-8.  Compare where the gradient is not negligible.
+    big = a[1].abs() > 1e-3 * a[1].abs().max()
+    assert ((a[3] - b[3]).abs() * big).max() <= 1e-5
