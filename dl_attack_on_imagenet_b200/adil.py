@@ -513,7 +513,7 @@ class ADIL(Attack):
                                    delta_out=delta)
                 adv = adv.view_as(images)
                 fooling = self.model(adv).argmax(dim=1) != pre_labels
-                mse = ((images - adv) ** 2).sum(dim=[1, 2, 3])
+                mse, _, _ = ops.image_errors(adv, images)                   # adil.py:491, one fused pass
                 first = ~flag & fooling                                    # adil.py:492-496
                 same = ~first & ((flag & fooling) | (~flag & ~fooling)) & (mse < best)   # adil.py:497-501
                 best = torch.where(same, mse, best)
