@@ -417,7 +417,9 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       }
     }
   }
+  if (tid == 0) SSTAMP(13);
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (tid == 0) SSTAMP(12);
   for (int b = tid; b < B; b += NTHREADS_SYNTH) {
     xoff_s[b] = (a.hx_on ? (long long)a.hx[b] : a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
     vrow_s[b] = a.hv_on ? (long long)a.hv[b] : a.vidx ? (long long)a.vidx[b] : (long long)b;
@@ -1527,8 +1529,8 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
       long long h[16];
       cudaMemcpyFromSymbol(h, g_sstamp, sizeof(h));
       fprintf(stderr, "synth CTA0 stamps (ns from entry): sync1=%lld sync2=%lld codes_in_tmem=%lld staged0=%lld mma0_done=%lld x0_landed=%lld out0_ready=%lld "
-              "out0_stored=%lld last_out_ready=%lld last_stored=%lld exit=%lld\n", h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0],
-              h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0], h[11] - h[0]);
+              "out0_stored=%lld last_out_ready=%lld last_stored=%lld exit=%lld | init+tma=%lld tmem_alloc=%lld\n", h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0],
+              h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0], h[11] - h[0], h[13] - h[0], h[12] - h[0]);
     }
 #endif
 #ifdef ADIL_TIMING
