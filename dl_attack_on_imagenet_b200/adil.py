@@ -100,6 +100,7 @@ class ADIL(Attack):
     resident_data = True        # keep tensor-backed datasets in HBM and gather rows inside the synthesis kernel
     run_validation = True       # per-epoch validation coder (adil.py:198-205)
     fuse_normalize = True       # fold a leading Normalize module into the kernels
+    allow_pickle = False        # dictionary files are loaded with weights_only=True (tensors / lists / floats only)
     verbose = True
     dict_dir = 'trained_dicts/'
 
@@ -218,7 +219,7 @@ class ADIL(Attack):
         if warm_start:
             path = "dict_model_ImageNet_version_constrained/"
             fname = f"ImageNet_{self.model_name}_num_atom_{self.n_atoms}_nepoch_{self.steps}_AdamW_{200}.bin"
-            d, _, _, _ = torch.load(os.path.join(path, fname), weights_only=False)
+            d, _, _, _ = torch.load(os.path.join(path, fname), weights_only=not self.allow_pickle)
             d = d.to(dev).float().contiguous()
         elif self.norm == 'l2':
             d = self.projection_d(torch.randn(nc, nx, ny, self.n_atoms, device=dev))
@@ -278,17 +279,17 @@ class ADIL(Attack):
         loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
         g = g.view(g.shape[0], -1)
         fooled = (out.argmax(dim=-1) != labels).sum()
-        dvb = None
+        dvb = None   # (code gradient: left as per-CTA partial slabs that the code step adds up itself)
         if update == 'both':
             st.tD += 1
             dvb = ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, kv_index, ops.adamw_params(st.tD, lr_d), self._std,
-                                     ops.ATOMS_CLAMP1)
+                                     ops.ATOMS_CLAMP1, keep_partials=True)
         elif update == 'd':
             st.tD += 1
             ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, kv_index, ops.adamw_params(st.tD, lr_d), self._std,
                                ops.ATOMS_CLAMP1, want_dv=False)
         else:
-            _, dvb = ops.grad(g, st.D2, st.v, kv_index, self._std, want_dD=False)
+            _, dvb = ops.grad(g, st.D2, st.v, kv_index, self._std, want_dD=False, keep_partials=True)
         if update in ('both', 'v'):
             st.tv += 1
             ops.code_step(st.v, st.mv, st.sv, dvb, v_index, ops.adamw_params(st.tv, lr_v), ops.ROWS_L1BALL, self.eps)
@@ -477,7 +478,7 @@ class ADIL(Attack):
         if self.dictionary is None:
             if not os.path.exists(self.model_file):
                 raise RuntimeError("no learned dictionary: %s does not exist and fit() was not called" % self.model_file)
-            rlts = torch.load(self.model_file, weights_only=False)      # adil.py:444-445
+            rlts = torch.load(self.model_file, weights_only=not self.allow_pickle)      # adil.py:444-445
             self.dictionary = rlts[0].to(self.device).float().contiguous()
         return self.dictionary
 

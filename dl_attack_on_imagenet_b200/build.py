@@ -14,8 +14,10 @@ LIB_PATH = os.environ.get("ADIL_B200_LIB") or os.path.join(PKG_DIR, "libadil_b20
 SOURCES = ["adil_api.cu", "adil_fma.cu", "adil_steps.cu", "adil_tc.cu"]
 HEADERS = [os.path.join(CSRC, "adil_common.cuh"), os.path.join(ROOT, "include", "adil_b200.h")]
 
+# -cudart shared: the library binds to the CUDA runtime the process already has (PyTorch's) instead of carrying a
+# private static copy of it -- one runtime instance per process, and a smaller .so
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared"]
+              "-shared", "-cudart", "shared"]
 
 
 def _nvcc():

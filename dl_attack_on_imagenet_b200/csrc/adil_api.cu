@@ -170,8 +170,8 @@ extern "C" size_t adil_grad_scratch_bytes(int B, int K) {
 namespace {
 int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g,
                 const float* D2, const float* v, const int64_t* v_index, int B, int P, int K, int C, int hw,
-                const float* std_host, const adil_adamw_t* hp, int atoms_mode, void* scratch, size_t scratch_bytes,
-                void* stream) {
+                const float* std_host, const adil_adamw_t* hp, int atoms_mode, int flags, int* nslabs_out,
+                void* scratch, size_t scratch_bytes, void* stream) {
   const bool scale = std_host != nullptr;
   int rc = check_shape(fn, B, P, K, C, hw, scale);
   if (rc) return rc;
@@ -179,39 +179,57 @@ int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, fl
   if (!aligned16(g) || !aligned16(D2) || !aligned16(dD2) || !aligned16(m) || !aligned16(s))
     return set_error(-1, "%s: g/D2/dD2/m/s must be 16-byte aligned", fn);
   if (B == 0) return set_error(-1, "%s: empty batch", fn);
+  if (flags & ~(ADIL_GRAD_ACCUMULATE_DD | ADIL_GRAD_KEEP_PARTIALS)) return set_error(-1, "%s: unknown flags 0x%x", fn, flags);
+  GradOpts opt;
+  opt.accumulate = (flags & ADIL_GRAD_ACCUMULATE_DD) ? 1 : 0;
+  opt.keep_partials = (flags & ADIL_GRAD_KEEP_PARTIALS) ? 1 : 0;
+  opt.nslabs_out = nslabs_out;
+  if (opt.keep_partials && !nslabs_out) return set_error(-1, "%s: ADIL_GRAD_KEEP_PARTIALS needs nslabs_out", fn);
+  if (opt.accumulate && (D2_rw != nullptr || dD2 == nullptr))
+    return set_error(-1, "%s: ADIL_GRAD_ACCUMULATE_DD applies to the plain dD2 output only", fn);
+  const bool want_dv = dvb != nullptr || opt.keep_partials;
   ChannelConsts cc = make_consts(C, hw, nullptr, std_host, scale);
   AdamwDev dev;
   memset(&dev, 0, sizeof(dev));
   if (hp) dev = make_adamw(hp);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(tc_grad_ok(B, P, K, scale ? hw : P, dD2 != nullptr || D2_rw != nullptr, dvb != nullptr, D2_rw != nullptr), B, P,
+  if (use_tc(tc_grad_ok(B, P, K, scale ? hw : P, dD2 != nullptr || D2_rw != nullptr, want_dv, D2_rw != nullptr), B, P,
              K, &rc, fn))
     return launch_grad_tc(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
-                          scratch_bytes, st);
+                          scratch_bytes, opt, st);
   if (rc) return rc;
   if (is_host_pointer(v_index))
     return set_error(-4, "%s: a host index array travels as kernel parameters of the tcgen05 path; shape B=%d P=%d K=%d (or "
                      "ADIL_IMPL_FMA) needs a device index array", fn, B, P, K);
   return launch_grad_fma(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
-                         scratch_bytes, st);
+                         scratch_bytes, opt, st);
 }
 }  // namespace
 
 extern "C" int adil_grad(float* dD2, float* dvb, const float* g, const float* D2, const float* v,
-                         const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host,
-                         void* scratch, size_t scratch_bytes, void* stream) {
-  if (!dD2 && !dvb) return set_error(-1, "adil_grad: nothing to compute (dD2 and dvb both NULL)");
+                         const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host, int flags,
+                         int* nslabs_out, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!dD2 && !dvb && !(flags & ADIL_GRAD_KEEP_PARTIALS))
+    return set_error(-1, "adil_grad: nothing to compute (dD2 and dvb both NULL)");
   return grad_common("adil_grad", dD2, nullptr, nullptr, nullptr, dvb, g, D2, v, v_index, B, P, K, C, hw, std_host,
-                     nullptr, ADIL_ATOMS_NONE, scratch, scratch_bytes, stream);
+                     nullptr, ADIL_ATOMS_NONE, flags, nslabs_out, scratch, scratch_bytes, stream);
+}
+
+extern "C" int adil_grad_max_batch(int P, int K, int hw, int fused) {
+  if (P <= 0 || K < 1 || K > ADIL_MAX_ATOMS) return 0;
+  if (hw <= 0) hw = P;
+  if (g_impl != ADIL_IMPL_FMA && tc_grad_ok(128, P, K, hw, true, true, fused != 0)) return 128;
+  if (g_impl == ADIL_IMPL_TC) return 0;
+  return grad_fma_max_batch(K, true, true);
 }
 
 extern "C" int adil_grad_dict_step(float* D2, float* m, float* s, float* dvb, const float* g, const float* v,
                                    const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host,
-                                   const adil_adamw_t* hp, int atoms_mode, void* scratch, size_t scratch_bytes,
-                                   void* stream) {
+                                   const adil_adamw_t* hp, int atoms_mode, int flags, int* nslabs_out, void* scratch,
+                                   size_t scratch_bytes, void* stream) {
   if (!D2 || !m || !s || !hp) return set_error(-1, "adil_grad_dict_step: null pointer");
   if (atoms_mode != ADIL_ATOMS_NONE && atoms_mode != ADIL_ATOMS_CLAMP1)
     return set_error(-1, "adil_grad_dict_step: atoms_mode %d cannot be fused (use adil_project_atoms)", atoms_mode);
   return grad_common("adil_grad_dict_step", nullptr, D2, m, s, dvb, g, D2, v, v_index, B, P, K, C, hw, std_host, hp,
-                     atoms_mode, scratch, scratch_bytes, stream);
+                     atoms_mode, flags, nslabs_out, scratch, scratch_bytes, stream);
 }

@@ -125,13 +125,22 @@ bool is_host_pointer(const void* p);  // true for pageable / pinned host memory 
 AdamwDev make_adamw(const adil_adamw_t* hp);
 ChannelConsts make_consts(int C, int hw, const float* mean_host, const float* std_host, bool use);
 
+// options of the backward entry points (adil_grad / adil_grad_dict_step flags)
+struct GradOpts {
+  int accumulate;     // ADIL_GRAD_ACCUMULATE_DD: dD2 += instead of dD2 =
+  int keep_partials;  // ADIL_GRAD_KEEP_PARTIALS: leave the per-CTA code-gradient slabs in scratch (no reduction launch)
+  int* nslabs_out;    // host: number of slabs written (keep_partials)
+};
+
 // FMA-path launchers (adil_fma.cu)
 int launch_synth_fma(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
                      const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
                      int flags, cudaStream_t st);
 int launch_grad_fma(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
-                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, cudaStream_t st);
+                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, const GradOpts& opt,
+                    cudaStream_t st);
+int grad_fma_max_batch(int K, bool want_dD, bool want_dv);
 
 // tcgen05-path launchers (adil_tc.cu)
 bool tc_synth_ok(int B, int P, int K, int hw);
@@ -141,7 +150,8 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
                     int flags, cudaStream_t st);
 int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
-                   const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, cudaStream_t st);
+                   const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, const GradOpts& opt,
+                   cudaStream_t st);
 
 // number of partial [B,K] slabs the grad kernels may write into scratch
 constexpr int kMaxGradCtas = 592;  // 148 SMs x 4

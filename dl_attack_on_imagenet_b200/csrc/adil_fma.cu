@@ -197,6 +197,7 @@ struct GradArgs {
   const int64_t* vidx;
   int B, P, K, Kp;
   int want_dD, want_dv, atoms_mode;
+  int accumulate;  // unfused output: dD2 += instead of dD2 =
   ChannelConsts cc;
   AdamwDev hp;
 };
@@ -218,11 +219,21 @@ __device__ __forceinline__ void dict_epilogue(const GradArgs& a, const float (&a
       const size_t idx = rowoff + k;
       if (a.D2w == nullptr) {
         if (VK == 4) {
-          *reinterpret_cast<float4*>(a.dD2 + idx) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+          float4 o = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+          if (a.accumulate) {
+            const float4 t = *reinterpret_cast<const float4*>(a.dD2 + idx);
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+          }
+          *reinterpret_cast<float4*>(a.dD2 + idx) = o;
         } else if (VK == 2) {
-          *reinterpret_cast<float2*>(a.dD2 + idx) = make_float2(acc[j][c0], acc[j][c0 + 1]);
+          float2 o = make_float2(acc[j][c0], acc[j][c0 + 1]);
+          if (a.accumulate) {
+            const float2 t = *reinterpret_cast<const float2*>(a.dD2 + idx);
+            o.x += t.x; o.y += t.y;
+          }
+          *reinterpret_cast<float2*>(a.dD2 + idx) = o;
         } else {
-          a.dD2[idx] = acc[j][c0];
+          a.dD2[idx] = a.accumulate ? a.dD2[idx] + acc[j][c0] : acc[j][c0];
         }
       } else {
         float dv[VK], mv[VK], sv[VK];
@@ -519,13 +530,15 @@ int launch_synth_fma(float* out, float* delta_out, const float* x, const int64_t
 
 int launch_grad_fma(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
-                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, cudaStream_t st) {
+                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, const GradOpts& opt,
+                    cudaStream_t st) {
   GradArgs a;
   a.dD2 = dD2; a.D2w = D2_rw; a.m = m; a.s = s; a.partial = scratch;
   a.g = g; a.D2 = D2; a.v = v; a.vidx = v_index;
   a.B = B; a.P = P; a.K = K; a.Kp = round_up(K, 4);
   a.want_dD = (dD2 != nullptr || D2_rw != nullptr) ? 1 : 0;
-  a.want_dv = (dvb != nullptr) ? 1 : 0;
+  a.want_dv = (dvb != nullptr || opt.keep_partials) ? 1 : 0;
+  a.accumulate = (opt.accumulate && D2_rw == nullptr) ? 1 : 0;
   a.atoms_mode = atoms_mode;
   a.cc = cc;
   if (hp) a.hp = *hp;
@@ -563,8 +576,25 @@ int launch_grad_fma(float* dD2, float* D2_rw, float* m, float* s, float* dvb, co
     default: rc = launch_grad_tp<16>(a, smem, grid, st); break;
   }
   if (rc) return rc;
-  if (a.want_dv) return launch_reduce_partials(dvb, scratch, B * K, grid, st);
+  if (a.want_dv) {
+    if (opt.keep_partials) {
+      if (opt.nslabs_out) *opt.nslabs_out = grid;
+      return 0;
+    }
+    return launch_reduce_partials(dvb, scratch, B * K, grid, st);
+  }
   return 0;
+}
+
+// Largest batch one call of the FMA backward kernel can take at this atom count (smallest tile, 227 KB of shared memory).
+int grad_fma_max_batch(int K, bool want_dD, bool want_dv) {
+  const int Kp = round_up(K, 4);
+  int lo = 0, hi = 1 << 16;
+  while (lo < hi) {  // grad_smem_bytes is increasing in B
+    const int mid = (lo + hi + 1) / 2;
+    if (grad_smem_bytes(16, mid, Kp, want_dD, want_dv) <= (size_t)227 * 1024) lo = mid; else hi = mid - 1;
+  }
+  return lo;
 }
 
 }  // namespace adil

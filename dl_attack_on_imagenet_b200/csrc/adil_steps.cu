@@ -159,41 +159,149 @@ struct CodeArgs {
   float* m;
   float* s;
   const float* dvb;
+  const float* partial;  // [nslabs][B][K] per-CTA slabs of the backward kernel (dvb == nullptr): reduced here
   const int64_t* vidx;
   int B, N, K;
+  int nslabs;
   int do_adamw, mode;
+  int pdl;               // launched with programmatic stream serialisation: wait before touching the slabs
   float radius;
   AdamwDev hp;
 };
 
+constexpr int kCodeWarps = 8;
+
+// AdamW + projection of one row held by one warp (EPL elements per lane), gradient g given.
+template <int EPL>
+__device__ __forceinline__ void code_row_update(const CodeArgs& a, int row, int lane, float (&x)[EPL], float (&mv)[EPL],
+                                                float (&sv)[EPL], const float (&g)[EPL], float* sorted) {
+  const int K = a.K;
+  const size_t base = (size_t)row * K;
+  if (a.do_adamw) {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) {
+        adamw_update(x[i], mv[i], sv[i], g[i], a.hp);
+        a.m[base + k] = mv[i];
+        a.s[base + k] = sv[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < EPL; ++i)
+    if (lane + 32 * i >= K) x[i] = 0.0f;
+  // padding lanes hold 0 and indices >= K, so the index tie-break keeps them behind every real element
+  project_row<EPL>(x, K, lane, a.mode, a.radius, sorted);
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int k = lane + 32 * i;
+    if (k < K) a.v[base + k] = x[i];
+  }
+}
+
+// Grid: [slot CTAs: one per batch slot, only with `partial`] + [row CTAs: 8 rows each, one warp per row].
+//   row CTA   : AdamW (zero gradient, or the dvb rows gathered by index) + projection of its rows.  With `partial`
+//               the rows of the batch are skipped here.
+//   slot CTA b: owns row vidx[b] (if b is the first slot naming that row): its 8 warps add the per-CTA slabs of the
+//               backward kernel for every slot that maps to the row -- warp w takes slabs w, w+8, ..., all loads in
+//               flight at once; the eight partial sums are combined in warp order, so the summation tree depends only
+//               on nslabs (bit-reproducible) -- and warp 0 applies AdamW + projection.  This replaces a separate
+//               reduction launch between the backward kernel and the code step.
 template <int EPL>
 __global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
-  __shared__ float sorted_all[8][32 * EPL];
+  __shared__ float sorted_all[kCodeWarps][32 * EPL];
+  __shared__ float red[kCodeWarps][32 * EPL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = a.K;
-  for (int row = blockIdx.x * 8 + warp; row < a.N; row += gridDim.x * 8) {
-    float x[EPL];
+  const int nslot = a.partial != nullptr ? a.B : 0;
+  if ((int)blockIdx.x < nslot) {
+    // ---------------- slot CTA ----------------
+    const int b = blockIdx.x;
+    const int64_t row64 = a.vidx ? a.vidx[b] : (int64_t)b;
+    // an earlier slot with the same row owns it (duplicates accumulate there, like index_put_(accumulate=True))
+    bool dup = false;
+    for (int b0 = 0; b0 < b; b0 += 32) {
+      const int j = b0 + lane;
+      const bool hit = j < b && (a.vidx ? a.vidx[j] : (int64_t)j) == row64;
+      if (__any_sync(0xffffffffu, hit)) { dup = true; break; }
+    }
+    if (dup || row64 < 0 || row64 >= (int64_t)a.N) return;
+    const int row = (int)row64;
+    const size_t base = (size_t)row * K;
+    float x[EPL], mv[EPL], sv[EPL], g[EPL];
+    if (warp == 0) {
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int k = lane + 32 * i;
+        x[i] = k < K ? a.v[base + k] : 0.0f;
+        mv[i] = k < K ? a.m[base + k] : 0.0f;
+        sv[i] = k < K ? a.s[base + k] : 0.0f;
+        g[i] = 0.0f;
+      }
+    }
+    if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");  // the slabs of the backward kernel are complete
+    const size_t slab = (size_t)a.B * K;
+    for (int b0 = b; b0 < a.B; b0 += 32) {  // every slot j >= b with the same row, in ascending order
+      const int j = b0 + lane;
+      const bool hit = j < a.B && (j == b || (a.vidx ? a.vidx[j] : (int64_t)j) == row64);
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const int bb = b0 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        float acc[EPL];
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) acc[i] = 0.0f;
+        const float* src = a.partial + (size_t)bb * K;
+#pragma unroll 4
+        for (int c = warp; c < a.nslabs; c += kCodeWarps) {
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) {
+            const int k = lane + 32 * i;
+            if (k < K) acc[i] += __ldcg(src + (size_t)c * slab + k);
+          }
+        }
+        __syncthreads();  // (previous slot's partial sums consumed)
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) red[warp][lane + 32 * i] = acc[i];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) {
+            float t = red[0][lane + 32 * i];
+#pragma unroll
+            for (int w = 1; w < kCodeWarps; ++w) t += red[w][lane + 32 * i];
+            g[i] += t;
+          }
+        }
+      }
+    }
+    if (warp == 0) code_row_update<EPL>(a, row, lane, x, mv, sv, g, sorted_all[0]);
+    return;
+  }
+  // ---------------- row CTAs ----------------
+  const int nrow_ctas = gridDim.x - nslot;
+  for (int row = ((int)blockIdx.x - nslot) * kCodeWarps + warp; row < a.N; row += nrow_ctas * kCodeWarps) {
+    float x[EPL], mv[EPL], sv[EPL], g[EPL];
     const size_t base = (size_t)row * K;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
       const int k = lane + 32 * i;
       x[i] = k < K ? a.v[base + k] : 0.0f;
+      mv[i] = 0.0f; sv[i] = 0.0f; g[i] = 0.0f;
     }
+    bool skip = false;
     if (a.do_adamw) {
       // every global load of the row goes out before anything is consumed: the moments, and (B <= 128) this lane's
       // four batch indices -- the scan below would otherwise be a chain of dependent round trips
-      float mv[EPL], sv[EPL];
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
         const int k = lane + 32 * i;
         mv[i] = k < K ? a.m[base + k] : 0.0f;
         sv[i] = k < K ? a.s[base + k] : 0.0f;
       }
-      float g[EPL];
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) g[i] = 0.0f;
-      if (a.dvb != nullptr) {
-        // gather the batch slots that map to this row (ascending slot order; duplicates accumulate)
+      if (a.dvb != nullptr || a.partial != nullptr) {
+        // the batch slots that map to this row (ascending slot order; duplicates accumulate)
         if (a.B <= 128) {
           bool hit[4];
 #pragma unroll
@@ -204,7 +312,8 @@ __global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             unsigned mask = __ballot_sync(0xffffffffu, hit[j]);
-            while (mask) {
+            if (mask && a.dvb == nullptr) skip = true;  // a slot CTA owns this row
+            while (mask && a.dvb != nullptr) {
               const int bb = 32 * j + __ffs(mask) - 1;
               mask &= mask - 1;
 #pragma unroll
@@ -219,6 +328,7 @@ __global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
             const int b = b0 + lane;
             const bool hit = b < a.B && (a.vidx ? a.vidx[b] : (int64_t)b) == (int64_t)row;
             unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (mask && a.dvb == nullptr) { skip = true; break; }
             while (mask) {
               const int bb = b0 + __ffs(mask) - 1;
               mask &= mask - 1;
@@ -231,33 +341,9 @@ __global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
           }
         }
       }
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) {
-        const int k = lane + 32 * i;
-        if (k < K) {
-          adamw_update(x[i], mv[i], sv[i], g[i], a.hp);
-          a.m[base + k] = mv[i];
-          a.s[base + k] = sv[i];
-        }
-      }
     }
-#pragma unroll
-    for (int i = 0; i < EPL; ++i)
-      if (lane + 32 * i >= K) x[i] = 0.0f;
-    // padding lanes hold 0 and indices >= K, so the index tie-break keeps them behind every real element
-    {
-      float xs[EPL];
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) xs[i] = x[i];
-      project_row<EPL>(xs, K, lane, a.mode, a.radius, sorted_all[warp]);
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) x[i] = xs[i];
-    }
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < K) a.v[base + k] = x[i];
-    }
+    if (skip) continue;
+    code_row_update<EPL>(a, row, lane, x, mv, sv, g, sorted_all[warp]);
   }
 }
 
@@ -322,9 +408,10 @@ int elem_grid(long long work_items) {
 int launch_code(const CodeArgs& a, cudaStream_t st) {
   if (a.K < 1 || a.K > ADIL_MAX_ATOMS) return set_error(-1, "adil_code_step: K=%d out of range [1,%d]", a.K, ADIL_MAX_ATOMS);
   if (a.N <= 0) return 0;
-  int grid = (a.N + 7) / 8;
+  int grid = (a.N + kCodeWarps - 1) / kCodeWarps;
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
+  if (a.partial != nullptr) grid += a.B;  // slot CTAs first
   if (a.K <= 32) code_step_kernel<1><<<grid, 256, 0, st>>>(a);
   else if (a.K <= 64) code_step_kernel<2><<<grid, 256, 0, st>>>(a);
   else if (a.K <= 128) code_step_kernel<4><<<grid, 256, 0, st>>>(a);
@@ -362,12 +449,16 @@ extern "C" int adil_adamw_clamp(float* p, float* m, float* s, const float* grad,
 }
 
 extern "C" int adil_code_step(float* v, float* m, float* s, const float* dvb, const int64_t* v_index, int B, int N,
-                              int K, const adil_adamw_t* hp, int rows_mode, float radius, void* stream) {
+                              int K, const adil_adamw_t* hp, int rows_mode, float radius, const float* partial,
+                              int nslabs, void* stream) {
   if (!v || !m || !s || !hp) return set_error(-1, "adil_code_step: null pointer");
   if (rows_mode < ADIL_ROWS_NONE || rows_mode > ADIL_ROWS_SOFTSHRINK)
     return set_error(-1, "adil_code_step: bad rows_mode %d", rows_mode);
+  if (partial != nullptr && (dvb != nullptr || nslabs < 1 || B < 1))
+    return set_error(-1, "adil_code_step: partial slabs exclude dvb and need nslabs >= 1, B >= 1");
   CodeArgs a;
-  a.v = v; a.m = m; a.s = s; a.dvb = dvb; a.vidx = v_index; a.B = dvb ? B : 0; a.N = N; a.K = K;
+  a.v = v; a.m = m; a.s = s; a.dvb = dvb; a.partial = partial; a.vidx = v_index;
+  a.B = (dvb || partial) ? B : 0; a.N = N; a.K = K; a.nslabs = partial ? nslabs : 0; a.pdl = 0;
   a.do_adamw = 1; a.mode = rows_mode; a.radius = radius; a.hp = make_adamw(hp);
   return launch_code(a, (cudaStream_t)stream);
 }
@@ -377,17 +468,110 @@ extern "C" int adil_project_rows(float* v, int N, int K, int rows_mode, float ra
   if (rows_mode < ADIL_ROWS_NONE || rows_mode > ADIL_ROWS_SOFTSHRINK)
     return set_error(-1, "adil_project_rows: bad rows_mode %d", rows_mode);
   CodeArgs a;
-  a.v = v; a.m = nullptr; a.s = nullptr; a.dvb = nullptr; a.vidx = nullptr; a.B = 0; a.N = N; a.K = K;
+  a.v = v; a.m = nullptr; a.s = nullptr; a.dvb = nullptr; a.partial = nullptr; a.vidx = nullptr; a.B = 0; a.N = N; a.K = K;
+  a.nslabs = 0; a.pdl = 0;
   a.do_adamw = 0; a.mode = rows_mode; a.radius = radius; a.hp = AdamwDev();
   return launch_code(a, (cudaStream_t)stream);
 }
 
-extern "C" size_t adil_project_atoms_scratch_bytes(int K) {
-  if (K < 1) return 0;
-  return ((size_t)kNormCtas * K + K) * sizeof(float);
+namespace adil {
+namespace {
+// ---------------------------------------------------------------------------------------------
+// per-atom l1-ball projection (utils.py:55-56): project_onto_l1_ball(d[:, :, :, k], 1) views atom k as [C, H*W], i.e.
+// every (channel, atom) column of hw pixels is projected onto the unit l1 ball on its own (utils.py:21-41).  The
+// reference sorts each column; here the threshold theta of a column (the root of sum_p max(|x_p| - theta, 0) = 1) is
+// bracketed by kL1Iters bisection passes over the dictionary -- all C*K columns at once, the columns of a pixel row
+// are contiguous -- and then evaluated with the reference's closed form theta = (sum of the active set - 1) / |active
+// set| (utils.py:37-38).  Columns strictly inside the ball are left untouched (utils.py:33).  Deterministic: per-chunk
+// partial sums combined in a fixed order.  Init-time only (adil.py:635-638 with an 'l1ball' constraint set).
+// ---------------------------------------------------------------------------------------------
+constexpr int kL1Chunks = 32;
+constexpr int kL1Iters = 30;
+
+// mode 0: (sum |x|, max |x|); mode 1: (sum max(|x| - thr, 0), -); mode 2: (sum over |x| > thr, count over |x| > thr)
+__global__ void __launch_bounds__(256) atom_l1_pass_kernel(const float* __restrict__ D2, int hw, int K, int mode,
+                                                           const float* __restrict__ thr /*[C][K]*/,
+                                                           float* __restrict__ pa, float* __restrict__ pb /*[chunk][C][K]*/) {
+  __shared__ float sa[256], sb[256];
+  const int chunk = blockIdx.x, c = blockIdx.y, C = gridDim.y;
+  const int per = 256 / K;  // pixel rows handled per CTA pass (K <= 256)
+  const int k = threadIdx.x % K, r0 = threadIdx.x / K;
+  const int rows_per_chunk = (hw + kL1Chunks - 1) / kL1Chunks;
+  const int lo = chunk * rows_per_chunk, hi = min(hw, lo + rows_per_chunk);
+  const float t = (mode != 0) ? thr[c * K + k] : 0.0f;
+  float a = 0.0f, b = 0.0f;
+  if (r0 < per) {
+    const float* base = D2 + (size_t)c * hw * K + k;
+    for (int r = lo + r0; r < hi; r += per) {
+      const float x = fabsf(base[(size_t)r * K]);
+      if (mode == 0) { a += x; b = fmaxf(b, x); }
+      else if (mode == 1) { a += fmaxf(x - t, 0.0f); }
+      else if (x > t) { a += x; b += 1.0f; }
+    }
+  }
+  sa[threadIdx.x] = (r0 < per) ? a : 0.0f;
+  sb[threadIdx.x] = (r0 < per) ? b : 0.0f;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float ta = 0.0f, tb = 0.0f;
+    for (int j = 0; j < per; ++j) {
+      ta += sa[j * K + threadIdx.x];
+      tb = (mode == 0) ? fmaxf(tb, sb[j * K + threadIdx.x]) : tb + sb[j * K + threadIdx.x];
+    }
+    pa[((size_t)chunk * C + c) * K + threadIdx.x] = ta;
+    pb[((size_t)chunk * C + c) * K + threadIdx.x] = tb;
+  }
 }
 
-extern "C" int adil_project_atoms(float* D2, int P, int K, int atoms_mode, void* scratch, void* stream) {
+// state per column: lo, hi, thr (the threshold the next pass uses), theta (final; 0 = column untouched)
+__global__ void atom_l1_update_kernel(const float* __restrict__ pa, const float* __restrict__ pb, int CK, int mode,
+                                      int last, float* __restrict__ lo, float* __restrict__ hi, float* __restrict__ thr,
+                                      float* __restrict__ theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= CK) return;
+  float a = 0.0f, b = 0.0f;
+  for (int ch = 0; ch < kL1Chunks; ++ch) {
+    a += pa[(size_t)ch * CK + i];
+    b = (mode == 0) ? fmaxf(b, pb[(size_t)ch * CK + i]) : b + pb[(size_t)ch * CK + i];
+  }
+  if (mode == 0) {
+    const bool inside = a < 1.0f;  // utils.py:33 (strict)
+    lo[i] = 0.0f;
+    hi[i] = inside ? 0.0f : b;     // inside: the bracket collapses to theta = 0 (the column is left as it is)
+    thr[i] = 0.5f * hi[i];
+  } else if (mode == 1) {
+    if (a > 1.0f) lo[i] = thr[i]; else hi[i] = thr[i];
+    thr[i] = last ? lo[i] : 0.5f * (lo[i] + hi[i]);
+  } else {
+    theta[i] = (hi[i] > 0.0f && b > 0.0f) ? fmaxf((a - 1.0f) / b, 0.0f) : 0.0f;  // utils.py:38
+  }
+}
+
+__global__ void __launch_bounds__(256) atom_l1_apply_kernel(float* __restrict__ D2, long long n, int hw, int K,
+                                                            const float* __restrict__ theta) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int k = (int)(i % K);
+    const int c = (int)((i / K) / hw);
+    const float t = theta[c * K + k];
+    if (t > 0.0f) {
+      const float x = D2[i];
+      const float pr = fmaxf(fabsf(x) - t, 0.0f);  // utils.py:39-40
+      D2[i] = x > 0.0f ? pr : (x < 0.0f ? -pr : 0.0f);
+    }
+  }
+}
+}  // namespace
+}  // namespace adil
+
+extern "C" size_t adil_project_atoms_scratch_bytes(int K) {
+  if (K < 1) return 0;
+  const size_t l2 = ((size_t)kNormCtas * K + K) * sizeof(float);
+  const size_t l1 = ((size_t)2 * kL1Chunks + 4) * kMaxC * K * sizeof(float);
+  return l2 > l1 ? l2 : l1;
+}
+
+extern "C" int adil_project_atoms(float* D2, int P, int K, int C, int atoms_mode, void* scratch, void* stream) {
   if (!D2) return set_error(-1, "adil_project_atoms: null pointer");
   if (K < 1 || K > ADIL_MAX_ATOMS) return set_error(-1, "adil_project_atoms: K=%d out of range", K);
   cudaStream_t st = (cudaStream_t)stream;
@@ -396,6 +580,27 @@ extern "C" int adil_project_atoms(float* D2, int P, int K, int atoms_mode, void*
   if (atoms_mode == ADIL_ATOMS_CLAMP1) {
     clamp1_kernel<<<elem_grid(n), 256, 0, st>>>(D2, n);
     return check_cuda(cudaGetLastError(), "clamp1_kernel launch");
+  }
+  if (atoms_mode == ADIL_ATOMS_L1BALL) {
+    if (C < 1 || C > kMaxC || P % C != 0) return set_error(-1, "adil_project_atoms: l1ball needs 1 <= C <= %d dividing P=%d (C=%d)", kMaxC, P, C);
+    if (!scratch) return set_error(-1, "adil_project_atoms: scratch required for the l1ball mode");
+    const int hw = P / C, CK = C * K;
+    float* pa = (float*)scratch;
+    float* pb = pa + (size_t)kL1Chunks * CK;
+    float* lo = pb + (size_t)kL1Chunks * CK;
+    float *hi = lo + CK, *thr = hi + CK, *theta = thr + CK;
+    const dim3 grid(kL1Chunks, C);
+    const int ug = (CK + 127) / 128;
+    atom_l1_pass_kernel<<<grid, 256, 0, st>>>(D2, hw, K, 0, nullptr, pa, pb);
+    atom_l1_update_kernel<<<ug, 128, 0, st>>>(pa, pb, CK, 0, 0, lo, hi, thr, theta);
+    for (int it = 0; it < kL1Iters; ++it) {
+      atom_l1_pass_kernel<<<grid, 256, 0, st>>>(D2, hw, K, 1, thr, pa, pb);
+      atom_l1_update_kernel<<<ug, 128, 0, st>>>(pa, pb, CK, 1, it == kL1Iters - 1 ? 1 : 0, lo, hi, thr, theta);
+    }
+    atom_l1_pass_kernel<<<grid, 256, 0, st>>>(D2, hw, K, 2, thr, pa, pb);
+    atom_l1_update_kernel<<<ug, 128, 0, st>>>(pa, pb, CK, 2, 0, lo, hi, thr, theta);
+    atom_l1_apply_kernel<<<elem_grid(n), 256, 0, st>>>(D2, n, hw, K, theta);
+    return check_cuda(cudaGetLastError(), "atom_l1 kernels launch");
   }
   if (atoms_mode != ADIL_ATOMS_L2BALL && atoms_mode != ADIL_ATOMS_L2SPHERE)
     return set_error(-1, "adil_project_atoms: unsupported atoms_mode %d", atoms_mode);

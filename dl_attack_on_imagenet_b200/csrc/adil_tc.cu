@@ -92,9 +92,6 @@ constexpr int NTHREADS_GRAD = (NW + NE + 4) * 32;  // 896 threads -> at most 72 
 constexpr int NIO = 8;              // synthesis: warps 17..24 move the image rows (cp.async in, coalesced stores out)
 constexpr int NTIO = NIO * 32;
 constexpr int NTHREADS_SYNTH = NT + 32 + NTIO;  // 800 threads -> at most 80 registers each
-#ifndef ADIL_SYNTH_EARLY_X
-#define ADIL_SYNTH_EARLY_X 0         // image-row stages requested before the zero fill (measured: 0 best -- early bulk traffic delays the code loads)
-#endif
 constexpr int NS = 3;               // stages of the raw dictionary tiles
 constexpr int NSX = 3;              // stages of the image-row tiles (synthesis)
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -160,6 +157,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // shared -> global bulk copy (TMA store): full-line writes whatever the row pitch of the tile
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+// shared -> global bulk reduction (TMA): global[i] += shared[i] (fp32); chunks of a batch accumulate in stream order
+__device__ __forceinline__ void bulk_red_add_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -367,6 +370,7 @@ struct SynthArgs {
   uint32_t tmem_cols;
   float eps;
   int flags;
+  int early_x;           // image-row stages requested before the zero fill (0..NSX)
   ChannelConsts cc;
 };
 
@@ -385,7 +389,6 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   uint64_t* staged = mma_done + 2;                             // [2] dictionary images of buffer 0 / 1 written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
   long long* xoff_s = reinterpret_cast<long long*>(smem_raw + 256);  // [128]
-  long long* vrow_s = xoff_s + 128;                                   // [128] row of v of each image
   float* raw = reinterpret_cast<float*>(smem_raw + HDR_BYTES);       // [NS][raw_floats]
   float* Dimg = raw + NS * a.raw_floats;                             // [2 buffers][hi, lo][dimg]
   float* xs = Dimg + 4 * a.dimg;                                     // [NSX][B][XP]
@@ -398,6 +401,23 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   const int xstage = B * XP;
   const bool ragged = (P % TP) != 0;
   if (tid == 0) SSTAMP(0);
+  // The batch codes are the first thing on the critical path of tile 0: their loads go out at kernel entry, ahead of
+  // the set-up barrier and of any bulk prefetch (which would queue megabytes ahead of them), and fly during the zero
+  // fill.  With host indices (kernel parameters) or identity rows this is one cold miss, with a device index array two.
+  // worker thread <-> image b = 32*quad + lane (its TMEM lane); the warps of a quadrant share the 8-atom chunks.
+  float vv[4][8];
+  if (warp < NW) {
+    const int b = (warp & 3) * 32 + lane;
+    const int bi = min(b, B - 1);
+    const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
+    const float* vrow = a.v + row * K;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      const int k0 = 8 * ((warp >> 2) + 4 * ci);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+    }
+  }
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
@@ -422,27 +442,12 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   if (tid == 0) SSTAMP(12);
   for (int b = tid; b < B; b += NTHREADS_SYNTH) {
     xoff_s[b] = (a.hx_on ? (long long)a.hx[b] : a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
-    vrow_s[b] = a.hv_on ? (long long)a.hv[b] : a.vidx ? (long long)a.vidx[b] : (long long)b;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (tid == 0) SSTAMP(1);
   const uint32_t tmem_base = *tmem_slot;
-  // The batch codes are the first thing on the critical path of tile 0: their loads go out BEFORE any bulk prefetch of
-  // dictionary tiles and image rows (which would queue megabytes ahead of them) and fly during the zero fill.
-  // worker thread <-> image b = 32*quad + lane (its TMEM lane); the warps of a quadrant share the 8-atom chunks.
-  float vv[4][8];
-  if (warp < NW) {
-    const int b = (warp & 3) * 32 + lane;
-    const float* vrow = a.v + vrow_s[min(b, B - 1)] * K;
-#pragma unroll
-    for (int ci = 0; ci < 4; ++ci) {
-      const int k0 = 8 * ((warp >> 2) + 4 * ci);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
-    }
-  }
   // I/O warps: the image rows of the first tiles are requested as soon as the row offsets are known (the row stages
   // are never zero-filled), next to the code loads.
   const int iot = tid - WARP_LOAD * 32;
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     cp_async_arrive_noinc(full_x + (j % NSX));  // rows landed (or, without x, simply: stage free)
   };
   if (warp >= WARP_LOAD) {
-    for (int j = 0; j < ADIL_SYNTH_EARLY_X; ++j) load_x(j);
+    for (int j = 0; j < a.early_x; ++j) load_x(j);
   } else {
     // zero the dictionary images (contraction padding k in [K, Kp8) must be zero) and, with a ragged last tile, the
     // raw stages (stale rows must stay finite).  The proxy fence is a MEMBAR.ALL.CTA -- it waits for the loads in
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     // streaming stores, and refill the stage with the rows of tile j+NSX by cp.async (each thread overwrites exactly
     // the elements it has just read). =====
     float* dstg = a.out != nullptr ? a.out : a.delta;
-    for (int j = ADIL_SYNTH_EARLY_X; j < NSX; ++j) load_x(j);
+    for (int j = a.early_x; j < NSX; ++j) load_x(j);
     for (int j = 0; j < my_tiles; ++j) {
       const int p0 = (blockIdx.x + j * gridDim.x) * TP;
       const int sx = j % NSX;
@@ -756,6 +761,8 @@ struct GradArgs {
   unsigned gdiv;      // ceil(2^32 / ceil(K / 8)): 8-atom groups of the G_SCALED dictionary split
   uint32_t tmem_cols;
   int want_dD, want_dv, atoms_mode;
+  int accumulate;     // plain dD output: dD2 += tile (TMA reduce-add store) instead of dD2 = tile
+  int early;          // host indices: code loads at kernel entry, bulk loads right after the set-up barrier
   ChannelConsts cc;
   AdamwDev hp;
 };
@@ -776,7 +783,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   uint64_t* acc_empty = staged + 2;                            // [2] dD accumulator 0 / 1 read out (epilogue warps -> issuer)
   uint64_t* epi_done = acc_empty + 2;                          // [NS] output tile written into the stage (epilogue warps -> loader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + NS);
-  long long* vrow_s = reinterpret_cast<long long*>(smem_raw + 256 + 1024);  // [128] row of v of each image
   typedef unsigned short bf16_t;
   const int dbuf = 3 * a.dimg, gbuf = 3 * a.gimg + 1024;          // bf16 elements per buffer (gradient: + 2 KB pad)
   bf16_t* Di = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);   // [2 buffers][3 terms] dictionary images
@@ -803,7 +809,34 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   const int tile_elems = TP * K;
   const uint32_t ne_tmem = 2u * (uint32_t)((K + 31) / 32);  // epilogue warps whose TMEM quadrant holds atoms
   STAMP(0);
-
+  // The batch codes are the first thing on the critical path of tile 0: their loads are issued here, ahead of the
+  // set-up barrier.  With host indices (kernel parameters) or identity rows this is ONE cold miss, and the roles start
+  // their bulk traffic right after that barrier (`early`); with a device index array it is a chain of two dependent
+  // misses, and the bulk traffic -- 148 CTAs x 3 stages of D tiles plus the gradient rows of the first tiles would
+  // queue ~15 MB ahead of the second hop: measured 4 us on the first MMA -- is held back until the codes are in.
+  // worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
+  const bool early = (a.hv_on != 0 || a.vidx == nullptr) && a.early != 0;
+  float vv[2][16];
+  if (warp < NW && a.want_dD && (warp & 3) * 32 < K) {  // (a quadrant whose 32 atoms are all padding keeps zeros)
+    const int m = (warp & 3) * 32 + lane;
+    const float* vcol = a.v + min(m, K - 1);
+    const float keep = m < K ? 1.0f : 0.0f;
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      const int b0 = 16 * ((warp >> 2) + 4 * ci);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int bi = min(b0 + i, B - 1);
+        const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
+        vv[ci][i] = __ldg(vcol + row * K) * ((b0 + i < B) ? keep : 0.0f);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) vv[ci][i] = 0.0f;
+  }
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, (a.want_dv ? NW : 0) + (fused ? NE : 0) + ((a.want_dv || fused) ? 0 : 1));
                                    mbar_init(epi_done + i, ne_tmem); }
@@ -811,9 +844,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  for (int b = tid; b < 128; b += NTHREADS_GRAD)  // element offset of the code row of image b (rows >= B: row of image B-1)
-    vrow_s[b] = (a.hv_on ? (long long)a.hv[min(b, B - 1)] : a.vidx ? (long long)a.vidx[min(b, B - 1)] : (long long)min(b, B - 1)) *
-                (long long)K;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -857,37 +887,26 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       gdst[j] = (q >> 1) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (q & 1) * 4;
     }
   }
-  // The batch codes are the first thing on the critical path of tile 0: two dependent cold misses (index -> code row).
-  // Their loads go out BEFORE any bulk traffic (148 CTAs x 3 stages of D tiles plus the gradient rows of the first
-  // tiles would queue ~15 MB -- and the page walks of 100 MB of first-touched arrays -- ahead of them: measured 4 us
-  // on the first MMA) and fly during the zero fill.
-  // worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
-  float vv[2][16];
-#pragma unroll
-  for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) vv[ci][i] = 0.0f;
-  if (warp < NW && a.want_dD && (warp & 3) * 32 < K) {  // (a quadrant whose 32 atoms are all padding keeps zeros)
-    const int m = (warp & 3) * 32 + lane;
-    const float* vcol = a.v + min(m, K - 1);
-    const float keep = m < K ? 1.0f : 0.0f;
-#pragma unroll
-    for (int ci = 0; ci < 2; ++ci) {
-      const int b0 = 16 * ((warp >> 2) + 4 * ci);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) vv[ci][i] = __ldg(vcol + vrow_s[b0 + i]) * ((b0 + i < B) ? keep : 0.0f);
+  if (early) {
+    // only the workers zero the operand images and meet at a named barrier: the loader, the epilogue warps and the
+    // issuer go straight to their roles (the issuer's first MMA follows the workers' first hand-off)
+    if (warp < NW) {
+      uint4* z = reinterpret_cast<uint4*>(Di);
+      const int nz = (2 * (dbuf + gbuf)) >> 3;
+      for (int e = tid; e < nz; e += NT) z[e] = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async();
+      bar_sync(2, NT);
     }
-  }
-  {
+  } else {
     // zero the operand images once: contraction padding must be zero, over-read regions finite
     uint4* z = reinterpret_cast<uint4*>(Di);
     const int nz = (2 * (dbuf + gbuf)) >> 3;
     for (int e = tid; e < nz; e += NTHREADS_GRAD) z[e] = make_uint4(0u, 0u, 0u, 0u);
+    // zero fill (generic proxy) ordered before the tensor core's (async proxy) reads.  The fence is a MEMBAR.ALL.CTA: it
+    // also waits for the code loads above, which is what the bulk traffic below is held back for.
+    fence_proxy_async();
+    __syncthreads();
   }
-  // zero fill (generic proxy) ordered before the tensor core's (async proxy) reads.  The fence is a MEMBAR.ALL.CTA: it
-  // also waits for the code loads above, which is what the bulk traffic below is held back for.
-  fence_proxy_async();
-  __syncthreads();
   STAMP(1);
   // (the setmaxnreg instructions open the role branches below)
 
@@ -910,7 +929,8 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           mbar_wait(epi_done + sj, (jt / NS) & 1);
           if (leader) {
             const int p0 = (blockIdx.x + jt * gridDim.x) * TP;
-            bulk_s2g(a.dD2 + (size_t)p0 * K, raw + sj * a.raw_floats, (uint32_t)(min(TP, P - p0) * K * 4));
+            if (a.accumulate) bulk_red_add_s2g(a.dD2 + (size_t)p0 * K, raw + sj * a.raw_floats, (uint32_t)(min(TP, P - p0) * K * 4));
+            else bulk_s2g(a.dD2 + (size_t)p0 * K, raw + sj * a.raw_floats, (uint32_t)(min(TP, P - p0) * K * 4));
             bulk_commit();
             if (it < my_tiles) {  // the stage is about to be refilled
               bulk_wait_read0();
@@ -1508,6 +1528,9 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     a.raw_floats = pl.raw_floats; a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.tmem_cols = pl.tmem_cols;
     a.eps = eps; a.flags = flags; a.cc = cc;
     a.cc.use = norm ? 1 : 0;
+    static const int early_x_knob = getenv("ADIL_SYNTH_EARLY_X") ? atoi(getenv("ADIL_SYNTH_EARLY_X")) : 0;    // tuning knobs
+    a.early_x = early_x_knob < 0 ? 0 : (early_x_knob > NSX ? NSX : early_x_knob);
+    if (x_index && !a.hx_on) a.early_x = 0;  // device x indices: the row offsets are a dependent load
     const int ntiles = (P + pl.TP - 1) / pl.TP;
     int grid = sm_count();
     if (grid > ntiles) grid = ntiles;
@@ -1567,8 +1590,10 @@ int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
 
 int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
-                   const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, cudaStream_t st) {
-  const bool want_dD = dD2 != nullptr || D2_rw != nullptr, want_dv = dvb != nullptr, fused = D2_rw != nullptr;
+                   const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, const GradOpts& opt,
+                   cudaStream_t st) {
+  const bool want_dD = dD2 != nullptr || D2_rw != nullptr, want_dv = dvb != nullptr || opt.keep_partials != 0,
+             fused = D2_rw != nullptr;
   if (!want_dD && !want_dv) return 0;
   const int hw = cc.use ? cc.hw : P;
   const GradPlan pl = plan_grad(B, P, K, hw, want_dD, want_dv, fused);
@@ -1585,6 +1610,9 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
   a.dimg = pl.dimg; a.gimg = pl.gimg; a.raw_floats = pl.raw_floats; a.nraw = pl.nraw;
   a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.gdiv = div_magic((K + 7) / 8); a.tmem_cols = pl.tmem_cols;
   a.want_dD = want_dD ? 1 : 0; a.want_dv = want_dv ? 1 : 0; a.atoms_mode = atoms_mode; a.cc = cc;
+  a.accumulate = (opt.accumulate && !fused) ? 1 : 0;
+  static const int early_knob = getenv("ADIL_GRAD_EARLY") ? atoi(getenv("ADIL_GRAD_EARLY")) : 1;  // tuning knob
+  a.early = early_knob;
   if (hp) a.hp = *hp;
   const int ntiles = (P + pl.TP - 1) / pl.TP;
   int grid = sm_count();
@@ -1620,7 +1648,13 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
             st8[1] - st8[0], st8[3] - st8[0], st8[7] - st8[0], st8[2] - st8[0], st8[4] - st8[0], st8[5] - st8[0], st8[6] - st8[0]);
   }
 #endif
-  if (want_dv) return launch_reduce_partials(dvb, scratch, B * K, grid, st);
+  if (want_dv) {
+    if (opt.keep_partials) {
+      if (opt.nslabs_out) *opt.nslabs_out = grid;
+      return 0;
+    }
+    return launch_reduce_partials(dvb, scratch, B * K, grid, st);
+  }
   return 0;
 }
 

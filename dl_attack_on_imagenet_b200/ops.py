@@ -14,7 +14,8 @@ from ._lib import AdamwParams
 # flags / modes (include/adil_b200.h)
 SYNTH_NORMALIZE, SYNTH_CLAMP_DELTA, SYNTH_CLAMP01 = 1, 2, 4
 ROWS_NONE, ROWS_L1BALL, ROWS_L2BALL, ROWS_SOFTSHRINK = 0, 1, 2, 3
-ATOMS_NONE, ATOMS_CLAMP1, ATOMS_L2BALL, ATOMS_L2SPHERE = 0, 1, 2, 3
+ATOMS_NONE, ATOMS_CLAMP1, ATOMS_L2BALL, ATOMS_L2SPHERE, ATOMS_L1BALL = 0, 1, 2, 3, 4
+GRAD_ACCUMULATE_DD, GRAD_KEEP_PARTIALS = 1, 2
 IMPL_AUTO, IMPL_FMA, IMPL_TC = 0, 1, 2
 
 _scratch = {}
@@ -78,12 +79,28 @@ def _host3(vals, C):
 
 
 def _get_scratch(device, nbytes, tag):
-    key = (device.index, tag)
+    """Scratch buffer per (device, stream, purpose): two streams calling the same kernel concurrently never share
+    one (the partial code-gradient slabs of a backward call live here until the code step has consumed them)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
         _scratch[key] = buf
     return buf
+
+
+class CodePartials(object):
+    """Per-CTA partial code gradients [nslabs, B, K] a backward call left in its scratch buffer
+    (`keep_partials=True`); `code_step` adds them up itself.  Valid until the next backward call on the same
+    stream."""
+
+    def __init__(self, buf, nslabs, B, K):
+        self.buf, self.nslabs, self.B, self.K = buf, int(nslabs), int(B), int(K)
+
+    def reduce(self):
+        """[B, K] code gradient (fixed summation order) -- for callers that want dvb after all."""
+        n = self.nslabs * self.B * self.K
+        return self.buf[:4 * n].view(torch.float32).view(self.nslabs, self.B, self.K).sum(dim=0)
 
 
 def adamw_params(step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2):
@@ -146,32 +163,92 @@ def _grad_scratch(dev, B, K):
     return _get_scratch(dev, nbytes, "grad"), nbytes
 
 
-def grad(g, D2, v, v_index=None, std=None, want_dD=True, want_dv=True, dD2=None, dvb=None):
-    """Backward contractions (adil.py:185): returns (dD2 [P,K] or None, dvb [B,K] or None)."""
+def grad_max_batch(P, K, hw=None, fused=False):
+    """Largest minibatch one backward kernel call takes for this shape (larger ones are chunked by the wrappers)."""
+    return int(_lib.lib().adil_grad_max_batch(int(P), int(K), int(hw if hw else P), 1 if fused else 0))
+
+
+def _host_index_retry(call, v_index, dev):
+    """Run `call(index)`; a host index array refused by the C side (-4: the shape does not run on the tcgen05 path
+    after all) is moved to the device and the call repeated once."""
+    rc = call(v_index)
+    if rc == -4 and v_index is not None and not v_index.is_cuda:
+        rc = call(v_index.to(dev))
+    return rc
+
+
+def _grad_call(dD2, dvb, g, D2, v, v_index, B, P, K, std, flags, dev):
+    """One adil_grad call (B within the per-call limit).  Returns nslabs (KEEP_PARTIALS) or 0."""
+    C = len(std) if std is not None else 1
+    scratch, nbytes = _grad_scratch(dev, B, K)
+    nslabs = ctypes.c_int(0)
+    v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
+    rc = _host_index_retry(
+        lambda ix: _lib.lib().adil_grad(_ptr(dD2), _ptr(dvb), _ptr(g), _ptr(D2), _ptr(v), _ptr(ix), B, P, K, C, P // C,
+                                        _host3(std, C), int(flags), ctypes.byref(nslabs), _ptr(scratch), nbytes,
+                                        _stream(dev)), v_index, dev)
+    _lib.check(rc, "adil_grad")
+    return scratch, nslabs.value
+
+
+def grad(g, D2, v, v_index=None, std=None, want_dD=True, want_dv=True, dD2=None, dvb=None, accumulate=False,
+         keep_partials=False):
+    """Backward contractions (adil.py:185): returns (dD2 [P,K] or None, dvb [B,K] or None).
+
+    accumulate: dD2 += instead of dD2 = .  keep_partials: the second result is a `CodePartials` handle for
+    `code_step` instead of the reduced dvb (one launch fewer).  Minibatches beyond the per-call limit of the kernels
+    (128 images on the tcgen05 path) are processed in chunks that accumulate into dD2."""
     g = _f32(g, "g")
     D2 = _f32(D2, "D2")
     v = _f32(v, "v")
     dev = D2.device
     P, K = D2.shape
-    v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
+    if v_index is not None and not torch.is_tensor(v_index):
+        v_index = torch.as_tensor(list(v_index) if not hasattr(v_index, '__array__') else v_index, dtype=torch.long)
     B = v_index.numel() if v_index is not None else v.shape[0]
     if g.numel() != B * P:
         raise ValueError("g has %d elements, expected B*P = %d" % (g.numel(), B * P))
+    if accumulate and (dD2 is None or not want_dD):
+        raise ValueError("grad: accumulate needs an existing dD2")
     if want_dD and dD2 is None:
         dD2 = torch.empty((P, K), dtype=torch.float32, device=dev)
+    if want_dD:
+        _f32(dD2, "dD2")
+    C = len(std) if std is not None else 1
+    bmax = grad_max_batch(P, K, P // C, False)
+    if bmax < 1:
+        raise RuntimeError("grad: shape P=%d K=%d is not supported by the selected kernel family" % (P, K))
+    g2 = g.view(B, P)
+    if B <= bmax:
+        if want_dv and not keep_partials and dvb is None:
+            dvb = torch.empty((B, K), dtype=torch.float32, device=dev)
+        flags = (GRAD_ACCUMULATE_DD if accumulate else 0) | (GRAD_KEEP_PARTIALS if (want_dv and keep_partials) else 0)
+        scratch, nslabs = _grad_call(dD2 if want_dD else None, dvb if (want_dv and not keep_partials) else None, g2,
+                                     D2, v, v_index, B, P, K, std, flags, dev)
+        second = None
+        if want_dv:
+            second = CodePartials(scratch, nslabs, B, K) if keep_partials else dvb
+        return (dD2 if want_dD else None), second
+    # ---- chunked: B beyond one pass --------------------------------------------------------------------------
     if want_dv and dvb is None:
         dvb = torch.empty((B, K), dtype=torch.float32, device=dev)
-    C = len(std) if std is not None else 1
-    scratch, nbytes = _grad_scratch(dev, B, K)
-    rc = _lib.lib().adil_grad(_ptr(dD2) if want_dD else None, _ptr(dvb) if want_dv else None, _ptr(g), _ptr(D2),
-                              _ptr(v), _ptr(v_index), B, P, K, C, P // C, _host3(std, C), _ptr(scratch), nbytes,
-                              _stream(dev))
-    _lib.check(rc, "adil_grad")
+    for i, b0 in enumerate(range(0, B, bmax)):
+        b1 = min(B, b0 + bmax)
+        if v_index is not None:
+            vi, ix = v, v_index[b0:b1]
+        else:
+            vi, ix = v[b0:b1], None
+        flags = GRAD_ACCUMULATE_DD if (want_dD and (accumulate or i > 0)) else 0
+        _grad_call(dD2 if want_dD else None, dvb[b0:b1] if want_dv else None, g2[b0:b1], D2, vi, ix, b1 - b0, P, K, std,
+                   flags, dev)
     return (dD2 if want_dD else None), (dvb if want_dv else None)
 
 
-def grad_dict_step(D2, m, s, g, v, v_index, hp, std=None, atoms_mode=ATOMS_CLAMP1, want_dv=True, dvb=None):
-    """Single-GPU fused backward + dictionary AdamW + clamp (adil.py:185-188 for D).  Returns dvb [B,K] or None."""
+def grad_dict_step(D2, m, s, g, v, v_index, hp, std=None, atoms_mode=ATOMS_CLAMP1, want_dv=True, dvb=None,
+                   keep_partials=False):
+    """Single-GPU fused backward + dictionary AdamW + clamp (adil.py:185-188 for D).  Returns dvb [B,K] (or a
+    `CodePartials` handle with keep_partials) or None.  Minibatches beyond the per-call limit run as chunked plain
+    contractions that accumulate dD, followed by the stand-alone dictionary step."""
     D2 = _f32(D2, "D2")
     m = _f32(m, "m")
     s = _f32(s, "s")
@@ -179,19 +256,36 @@ def grad_dict_step(D2, m, s, g, v, v_index, hp, std=None, atoms_mode=ATOMS_CLAMP
     v = _f32(v, "v")
     dev = D2.device
     P, K = D2.shape
-    v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
+    if v_index is not None and not torch.is_tensor(v_index):
+        v_index = torch.as_tensor(list(v_index) if not hasattr(v_index, '__array__') else v_index, dtype=torch.long)
     B = v_index.numel() if v_index is not None else v.shape[0]
     if g.numel() != B * P:
         raise ValueError("g has %d elements, expected B*P = %d" % (g.numel(), B * P))
-    if want_dv and dvb is None:
-        dvb = torch.empty((B, K), dtype=torch.float32, device=dev)
     C = len(std) if std is not None else 1
+    bmax = grad_max_batch(P, K, P // C, True)
+    if bmax < 1:
+        raise RuntimeError("grad_dict_step: shape P=%d K=%d is not supported by the selected kernel family" % (P, K))
+    if B > bmax:
+        dD2 = _get_scratch(dev, 4 * P * K, "dD")[:4 * P * K].view(torch.float32).view(P, K)
+        _, dvb = grad(g, D2, v, v_index, std, want_dD=True, want_dv=want_dv, dD2=dD2, dvb=dvb)
+        dict_step(D2, m, s, dD2, hp, atoms_mode)
+        return dvb if want_dv else None
+    if want_dv and not keep_partials and dvb is None:
+        dvb = torch.empty((B, K), dtype=torch.float32, device=dev)
+    flags = GRAD_KEEP_PARTIALS if (want_dv and keep_partials) else 0
     scratch, nbytes = _grad_scratch(dev, B, K)
-    rc = _lib.lib().adil_grad_dict_step(_ptr(D2), _ptr(m), _ptr(s), _ptr(dvb) if want_dv else None, _ptr(g), _ptr(v),
-                                        _ptr(v_index), B, P, K, C, P // C, _host3(std, C), ctypes.byref(hp),
-                                        int(atoms_mode), _ptr(scratch), nbytes, _stream(dev))
+    nslabs = ctypes.c_int(0)
+    v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
+    rc = _host_index_retry(
+        lambda ix: _lib.lib().adil_grad_dict_step(_ptr(D2), _ptr(m), _ptr(s),
+                                                  _ptr(dvb) if (want_dv and not keep_partials) else None, _ptr(g),
+                                                  _ptr(v), _ptr(ix), B, P, K, C, P // C, _host3(std, C),
+                                                  ctypes.byref(hp), int(atoms_mode), flags, ctypes.byref(nslabs),
+                                                  _ptr(scratch), nbytes, _stream(dev)), v_index, dev)
     _lib.check(rc, "adil_grad_dict_step")
-    return dvb if want_dv else None
+    if not want_dv:
+        return None
+    return CodePartials(scratch, nslabs.value, B, K) if keep_partials else dvb
 
 
 def dict_step(D2, m, s, dD2, hp, atoms_mode=ATOMS_CLAMP1):
@@ -206,16 +300,23 @@ def dict_step(D2, m, s, dD2, hp, atoms_mode=ATOMS_CLAMP1):
 
 
 def code_step(v, m, s, dvb, v_index, hp, rows_mode=ROWS_L1BALL, radius=0.0):
-    """AdamW on every row of v (zero gradient outside the batch) + row projection (adil.py:186-187)."""
+    """AdamW on every row of v (zero gradient outside the batch) + row projection (adil.py:186-187).  `dvb`: [B,K]
+    code gradient, a `CodePartials` handle of a backward call (reduced here), or None (zero gradient)."""
     v, m, s = _f32(v, "v"), _f32(m, "m"), _f32(s, "s")
-    dvb = _f32(dvb, "dvb", allow_none=True)
     N, K = v.shape
     v_index = _idx(v_index, "v_index", v.device)
-    B = 0 if dvb is None else dvb.shape[0]
-    if dvb is not None and v_index is not None and v_index.numel() != B:
-        raise ValueError("code_step: v_index has %d entries, dvb %d rows" % (v_index.numel(), B))
+    partial, nslabs = None, 0
+    if isinstance(dvb, CodePartials):
+        if dvb.K != K:
+            raise ValueError("code_step: partials have K=%d, v has K=%d" % (dvb.K, K))
+        partial, nslabs, B, dvb = dvb.buf, dvb.nslabs, dvb.B, None
+    else:
+        dvb = _f32(dvb, "dvb", allow_none=True)
+        B = 0 if dvb is None else dvb.shape[0]
+    if (dvb is not None or partial is not None) and v_index is not None and v_index.numel() != B:
+        raise ValueError("code_step: v_index has %d entries, the gradient %d rows" % (v_index.numel(), B))
     rc = _lib.lib().adil_code_step(_ptr(v), _ptr(m), _ptr(s), _ptr(dvb), _ptr(v_index), B, N, K, ctypes.byref(hp),
-                                   int(rows_mode), float(radius), _stream(v.device))
+                                   int(rows_mode), float(radius), _ptr(partial), int(nslabs), _stream(v.device))
     _lib.check(rc, "adil_code_step")
 
 
@@ -229,13 +330,15 @@ def project_rows(v, rows_mode, radius):
 
 
 def project_atoms(D, atoms_mode):
-    """In-place per-atom projection of D[..., K] (adil.py:635-642, utils.py:44-57)."""
+    """In-place per-atom projection of D[..., K] (adil.py:635-642, utils.py:44-57).  The l1ball mode follows
+    utils.py:23,56: atom k is viewed as [D.shape[0], -1] and every row is projected onto the unit l1 ball."""
     D = _f32(D, "D")
     K = D.shape[-1]
     P = D.numel() // K
+    C = D.shape[0] if (D.dim() >= 3 and atoms_mode == ATOMS_L1BALL) else 1
     nbytes = _lib.lib().adil_project_atoms_scratch_bytes(K)
     scratch = _get_scratch(D.device, nbytes, "atoms")
-    rc = _lib.lib().adil_project_atoms(_ptr(D), P, K, int(atoms_mode), _ptr(scratch), _stream(D.device))
+    rc = _lib.lib().adil_project_atoms(_ptr(D), P, K, int(C), int(atoms_mode), _ptr(scratch), _stream(D.device))
     _lib.check(rc, "adil_project_atoms")
     return D
 
@@ -287,7 +390,13 @@ class SynthFunction(torch.autograd.Function):
         D, v, v_index = ctx.saved_tensors
         K = D.shape[-1]
         B = v_index.numel()
-        dD2, dvb = grad(gout.contiguous().reshape(B, -1), D.reshape(-1, K), v, v_index, ctx.std)
-        gv = torch.zeros_like(v)
-        gv.index_add_(0, v_index, dvb)
-        return dD2.reshape(D.shape), gv, None, None, None, None, None
+        need_D, need_v = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_D or need_v):
+            return None, None, None, None, None, None, None
+        dD2, dvb = grad(gout.contiguous().reshape(B, -1), D.reshape(-1, K), v, v_index, ctx.std, want_dD=need_D,
+                        want_dv=need_v)
+        gv = None
+        if need_v:
+            gv = torch.zeros_like(v)
+            gv.index_add_(0, v_index, dvb)
+        return (dD2.reshape(D.shape) if need_D else None), gv, None, None, None, None, None

@@ -19,10 +19,9 @@ def project_onto_l1_ball(x, eps):
 
 
 def constraint_dict(d, constr_set='l2ball'):
-    """Per-atom projection of d[C,H,W,K] (utils.py:44-57): 'l2sphere' or 'l2ball'.  In place, like the reference."""
-    mode = {'l2sphere': ops.ATOMS_L2SPHERE, 'l2ball': ops.ATOMS_L2BALL}.get(constr_set)
-    if mode is None:
-        raise NotImplementedError("constraint_dict(%r): only l2sphere / l2ball are used on the ADiL path" % constr_set)
+    """Per-atom projection of d[C,H,W,K] (utils.py:44-57): 'l2sphere', 'l2ball', anything else = the l1 ball of
+    radius 1 applied to every channel row of every atom (utils.py:55-56).  In place, like the reference."""
+    mode = {'l2sphere': ops.ATOMS_L2SPHERE, 'l2ball': ops.ATOMS_L2BALL}.get(constr_set, ops.ATOMS_L1BALL)
     if not d.is_contiguous():
         raise ValueError("constraint_dict needs a contiguous dictionary")
     ops.project_atoms(d, mode)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ADIL_VERSION 102
+#define ADIL_VERSION 200
 
 #define ADIL_MAX_CHANNELS 8
 #define ADIL_MAX_ATOMS 256
@@ -53,6 +53,15 @@ extern "C" {
 #define ADIL_ATOMS_CLAMP1   1 /* adil.py:33-35,642  clamp(D, -1, 1)                    */
 #define ADIL_ATOMS_L2BALL   2 /* utils.py:52-54     d_k / max(||d_k||_2, 1)            */
 #define ADIL_ATOMS_L2SPHERE 3 /* utils.py:49-51     d_k / ||d_k||_2                    */
+#define ADIL_ATOMS_L1BALL   4 /* utils.py:55-56     project_onto_l1_ball(d[:,:,:,k], 1): every (channel, atom)
+                               *                    column of H*W pixels onto the unit l1 ball (adil_project_atoms only) */
+
+/* adil_grad / adil_grad_dict_step flags */
+#define ADIL_GRAD_ACCUMULATE_DD 1 /* adil_grad: dD2 += g^T v instead of dD2 = (minibatches larger than one pass:
+                                   * chunks of the batch accumulate in stream order) */
+#define ADIL_GRAD_KEEP_PARTIALS 2 /* leave the per-CTA partial code gradients [nslabs][B][K] in `scratch` instead of
+                                   * reducing them into dvb (dvb may be NULL): adil_code_step adds them up itself,
+                                   * which saves the reduction launch between the two kernels */
 
 /* kernel implementation selector for adil_synth / adil_grad* (adil_set_impl) */
 #define ADIL_IMPL_AUTO 0 /* tcgen05 when the shape qualifies, else FMA */
@@ -99,17 +108,25 @@ size_t adil_grad_scratch_bytes(int B, int K);
 /* Backward contractions (replaces the autograd backward of adil.py:25-26 + Normalize: adil.py:185,281,308,606):
  *     gx = g / std[c]      (std_host == NULL: gx = g)
  *     dD2[p,k] = sum_b gx[b,p] * v[v_index[b],k]          (skipped when dD2 == NULL)
- *     dvb[b,k] = sum_p gx[b,p] * D2[p,k]                  (skipped when dvb == NULL)
- * g: [B,P] gradient w.r.t. the classifier input.  dvb: [B,K] in batch order (the caller scatters by v_index). */
+ *     dvb[b,k] = sum_p gx[b,p] * D2[p,k]                  (skipped when dvb == NULL and KEEP_PARTIALS is not set)
+ * g: [B,P] gradient w.r.t. the classifier input.  dvb: [B,K] in batch order (the caller scatters by v_index).
+ * flags: ADIL_GRAD_*.  nslabs_out (host int, may be NULL): number of partial slabs left in scratch (KEEP_PARTIALS).
+ * B is limited per call (adil_grad_max_batch); larger minibatches are passed in chunks with ACCUMULATE_DD. */
 int adil_grad(float* dD2, float* dvb, const float* g, const float* D2, const float* v, const int64_t* v_index, int B,
-              int P, int K, int C, int hw, const float* std_host, void* scratch, size_t scratch_bytes, void* stream);
+              int P, int K, int C, int hw, const float* std_host, int flags, int* nslabs_out, void* scratch,
+              size_t scratch_bytes, void* stream);
+
+/* Largest B one adil_grad / adil_grad_dict_step call accepts for this shape with the current kernel family
+ * (tcgen05 path: 128 images per pass; FMA path: bounded by shared memory). */
+int adil_grad_max_batch(int P, int K, int hw, int fused);
 
 /* Single-GPU fusion of adil_grad with the dictionary AdamW step and projection (adil.py:185-188 for D):
  * dD2 never touches HBM; D2, m, s are updated in place.  atoms_mode: ADIL_ATOMS_NONE or ADIL_ATOMS_CLAMP1.
- * dvb is computed against the PRE-update D2, like autograd does. */
+ * dvb is computed against the PRE-update D2, like autograd does.  flags: ADIL_GRAD_KEEP_PARTIALS. */
 int adil_grad_dict_step(float* D2, float* m, float* s, float* dvb, const float* g, const float* v,
                         const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host,
-                        const adil_adamw_t* hp, int atoms_mode, void* scratch, size_t scratch_bytes, void* stream);
+                        const adil_adamw_t* hp, int atoms_mode, int flags, int* nslabs_out, void* scratch,
+                        size_t scratch_bytes, void* stream);
 
 /* Dictionary AdamW step + elementwise projection on n contiguous elements (a [P_begin,P_end) x K slice):
  * replaces optimise.step() on d + update_d (adil.py:186,188 ; 310-311).  Used after the dD all-reduce on
@@ -119,17 +136,21 @@ int adil_dict_step(float* D2, float* m, float* s, const float* dD2, long long n,
 
 /* Code AdamW step over ALL N rows (dense gradient, zero outside the batch -- adil.py:154,186) fused with the
  * scatter of dvb by v_index (duplicates accumulate, like index_put_(accumulate=True)) and the row projection
- * (adil.py:187 update_v).  v, m, s: [N,K]; dvb: [B,K] (NULL: zero gradient). */
+ * (adil.py:187 update_v).  v, m, s: [N,K]; dvb: [B,K] (NULL: zero gradient).
+ * partial / nslabs: instead of dvb, the per-CTA slabs [nslabs][B][K] a backward call left in its scratch
+ * (ADIL_GRAD_KEEP_PARTIALS): the gradient of batch slot b is the sum over the slabs, added up in a fixed order. */
 int adil_code_step(float* v, float* m, float* s, const float* dvb, const int64_t* v_index, int B, int N, int K,
-                   const adil_adamw_t* hp, int rows_mode, float radius, void* stream);
+                   const adil_adamw_t* hp, int rows_mode, float radius, const float* partial, int nslabs,
+                   void* stream);
 
 /* Row projection only (adil.py:625-633 projection_v ; utils.py:21-41 ; utils.py:159-161).  In place. */
 int adil_project_rows(float* v, int N, int K, int rows_mode, float radius, void* stream);
 
-/* Per-atom projection of D2 [P,K] (adil.py:635-642 projection_d ; utils.py:44-57 constraint_dict).
+/* Per-atom projection of D2 [P,K] (adil.py:635-642 projection_d ; utils.py:44-57 constraint_dict).  C = number of
+ * channels (P = C*hw; only the l1ball mode uses it: utils.py:23 views an atom as [C, H*W] rows).
  * scratch: device buffer of adil_project_atoms_scratch_bytes(K) bytes (unused for CLAMP1). */
 size_t adil_project_atoms_scratch_bytes(int K);
-int adil_project_atoms(float* D2, int P, int K, int atoms_mode, void* scratch, void* stream);
+int adil_project_atoms(float* D2, int P, int K, int C, int atoms_mode, void* scratch, void* stream);
 
 /* Elementwise AdamW + clamp(+-bound) on n elements: the z update of forward_supervised_DDrague
  * (adil.py:531,554-555).  bound <= 0: no clamp. */

@@ -42,7 +42,8 @@ def test_binding_covers_header_exactly():
 def test_host_only_entry_points(library):
     from dl_attack_on_imagenet_b200 import _lib
     lib = _lib.lib()
-    assert lib.adil_version() >= 101
+    assert lib.adil_version() >= 200
+    assert lib.adil_grad_max_batch(150528, 50, 50176, 1) == 128 and lib.adil_grad_max_batch(150528, 300, 50176, 0) == 0
     assert lib.adil_grad_scratch_bytes(100, 50) >= 148 * 100 * 50 * 4
     assert lib.adil_grad_scratch_bytes(0, 50) == 0
     assert lib.adil_project_atoms_scratch_bytes(64) > 0
@@ -60,8 +61,17 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc < 0 and b"multiple of 4" in lib.adil_last_error()
     rc = lib.adil_synth(one, None, None, None, one, one, None, 4, 12, 300, 1, 12, None, None, 0.0, 0, None)
     assert rc < 0 and b"ADIL_MAX_ATOMS" in lib.adil_last_error()
-    rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, None, 0, None)
-    assert rc < 0
+    rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, 0, None, None, 0, None)
+    assert rc < 0 and b"nothing to compute" in lib.adil_last_error()
+    rc = lib.adil_grad(one, None, one, one, one, None, 4, 12, 3, 1, 12, None, 64, None, None, 0, None)
+    assert rc < 0 and b"unknown flags" in lib.adil_last_error()
+    rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, 2, None, None, 0, None)
+    assert rc < 0 and b"nslabs_out" in lib.adil_last_error()
+    rc = lib.adil_code_step(one, one, one, one, None, 4, 8, 3, ctypes.byref(_lib.AdamwParams(0.01, 0.9, 0.999, 1e-8, 0.01, 1)),
+                            1, 0.1, one, 3, None)
+    assert rc < 0 and b"partial slabs exclude dvb" in lib.adil_last_error()
+    rc = lib.adil_project_atoms(one, 12, 3, 5, 4, one, None)
+    assert rc < 0 and b"l1ball" in lib.adil_last_error()
     rc = lib.adil_image_errors(one, one, one, one, one, 4, 10, one, 1 << 20, None)
     assert rc < 0 and b"P % 4" in lib.adil_last_error()
     rc = lib.adil_image_errors(one, one, one, one, one, 4, 12, one, 8, None)

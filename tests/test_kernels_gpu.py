@@ -392,7 +392,7 @@ def test_host_index_arrays_need_the_tensor_core_path(ops):
         out = torch.empty(8, 37, device="cuda")
         rc = _lib.lib().adil_grad(None, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(gd.data_ptr()),
                                   ctypes.c_void_p(Dd.data_ptr()), ctypes.c_void_p(vd.data_ptr()),
-                                  ctypes.c_void_p(host_idx.data_ptr()), 8, 300, 37, 1, 300, None, None, 0, None)
+                                  ctypes.c_void_p(host_idx.data_ptr()), 8, 300, 37, 1, 300, None, 0, None, None, 0, None)
         assert rc == -4 and b"host index" in _lib.lib().adil_last_error()
     finally:
         ops.set_impl(ops.IMPL_AUTO)
