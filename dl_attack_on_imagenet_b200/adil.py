@@ -46,15 +46,31 @@ class _IndexOnly(torch.utils.data.Dataset):
 
 
 class AdilState(object):
-    """Learnables and AdamW state, all resident in HBM.  D: [C,H,W,K] (atoms innermost), v: [N,K]."""
+    """Learnables and AdamW state, all resident in HBM.  D: [C,H,W,K] (atoms innermost), v: [N,K].
 
-    def __init__(self, D, v):
-        self.D = D.contiguous()
+    With `shard` (a distributed.ShardedDictStep) the dictionary lives in a buffer padded to equal pixel slices per
+    rank, its AdamW moments exist only for this rank's slice (mD, sD are those slices), and a second padded buffer
+    holds this rank's dictionary gradient for the reduce-scatter."""
+
+    def __init__(self, D, v, shard=None):
         self.K = D.shape[-1]
-        self.D2 = self.D.view(-1, self.K)
+        self.shard = shard
+        if shard is None:
+            self.D = D.contiguous()
+            self.D2 = self.D.view(-1, self.K)
+            self.mD = torch.zeros_like(self.D2)
+            self.sD = torch.zeros_like(self.D2)
+            self.D_full = self.dD_full = self.dD2 = None
+        else:
+            P = D.numel() // self.K
+            self.D_full = shard.alloc()
+            self.D_full[:P].copy_(D.reshape(P, self.K))
+            self.D2 = self.D_full[:P]
+            self.D = self.D2.view(D.shape)
+            self.dD_full = shard.alloc()
+            self.dD2 = self.dD_full[:P]
+            self.mD, self.sD = shard.m, shard.s
         self.v = v.contiguous()
-        self.mD = torch.zeros_like(self.D2)
-        self.sD = torch.zeros_like(self.D2)
         self.mv = torch.zeros_like(self.v)
         self.sv = torch.zeros_like(self.v)
         self.tD = 0
@@ -270,17 +286,40 @@ class ADIL(Attack):
     def _fit_step(self, st, x_src, x_index, v_index, labels, shape, update, lr_d, lr_v, index_cpu=None):
         """One minibatch of adil.py:168-188 (update='both'), :268-284 ('v') or :295-311 ('d').  `index_cpu`: the same
         indices as `v_index` as the CPU tensor the DataLoader produced (adil.py:168); when given, the synthesis and
-        backward kernels take them as kernel parameters (no cold miss on the index array)."""
+        backward kernels take them as kernel parameters (no cold miss on the index array).
+
+        Image-sharded state (`st.shard`): the dictionary gradient of this rank's images goes through reduce-scatter ->
+        AdamW + clamp on this rank's pixel slice -> all-gather on a side stream while the (purely local) code step
+        runs; an empty local batch (v_index of length 0) still takes part in the collectives."""
         flags = ops.SYNTH_NORMALIZE if self._mean is not None else 0
         kv_index = index_cpu if index_cpu is not None else v_index
         kx_index = (index_cpu if index_cpu is not None else x_index) if x_index is not None else None
+        shard = st.shard
+        if shard is not None:
+            shard.wait()                                   # the dictionary of the previous step is complete
+        nb = kv_index.numel() if kv_index is not None else x_src.shape[0]
+        if nb == 0:
+            if shard is None or update == 'v':
+                return torch.zeros((), device=self.device), torch.zeros((), dtype=torch.long, device=self.device)
+            st.dD2.zero_()
+            st.tD += 1
+            shard.step(st.D_full, st.dD_full, ops.adamw_params(st.tD, lr_d), ops.ATOMS_CLAMP1)
+            if update == 'both':
+                st.tv += 1
+                ops.code_step(st.v, st.mv, st.sv, None, None, ops.adamw_params(st.tv, lr_v), ops.ROWS_L1BALL, self.eps)
+            return torch.zeros((), device=self.device), torch.zeros((), dtype=torch.long, device=self.device)
         xin, _ = ops.synth(st.D2, st.v, kv_index, x=x_src, x_index=kx_index, mean=self._mean, std=self._std, flags=flags,
                            n_channels=shape[0])
         loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
         g = g.view(g.shape[0], -1)
         fooled = (out.argmax(dim=-1) != labels).sum()
         dvb = None   # (code gradient: left as per-CTA partial slabs that the code step adds up itself)
-        if update == 'both':
+        if update in ('both', 'd') and shard is not None:
+            _, dvb = ops.grad(g, st.D2, st.v, kv_index, self._std, want_dv=(update == 'both'), dD2=st.dD2,
+                              keep_partials=True)
+            st.tD += 1
+            shard.step(st.D_full, st.dD_full, ops.adamw_params(st.tD, lr_d), ops.ATOMS_CLAMP1)
+        elif update == 'both':
             st.tD += 1
             dvb = ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, kv_index, ops.adamw_params(st.tD, lr_d), self._std,
                                      ops.ATOMS_CLAMP1, keep_partials=True)
@@ -298,7 +337,9 @@ class ADIL(Attack):
     def fit_batch(self, index, x, labels=None):
         """One joint ('gd') learning step on one minibatch -- the body of the loop at adil.py:168-188 -- on the
         state created by `begin_fit`.  `index`: int64 rows of v (host or device); `x`: [B,C,H,W] images (host,
-        e.g. pinned, or device).  Returns (loss, fooled_count) as device scalars."""
+        e.g. pinned, or device).  Returns (loss, fooled_count) as device scalars.  After
+        `begin_fit(..., distributed=True)` every rank calls this with its own images (rows of its local v) and the
+        dictionary update is the sharded reduce-scatter / AdamW / all-gather step."""
         st = self.state
         if st is None:
             raise RuntimeError("fit_batch: call begin_fit(n_img, image_shape) or fit() first")
@@ -311,10 +352,43 @@ class ADIL(Attack):
         return self._fit_step(st, x.view(x.shape[0], -1), None, v_index, labels, shape, 'both', self.step_size,
                               self.step_size, index_cpu=index if not index.is_cuda else None)
 
-    def begin_fit(self, n_img, image_shape, warm_start=False):
-        """Allocate and initialise D, v and the AdamW state for `n_img` images (adil.py:138-154)."""
+    def fit_batch_resident(self, index, labels=None):
+        """`fit_batch` on images registered with `set_resident_images`: only the batch indices cross PCIe, the rows are
+        gathered inside the synthesis kernel, and the clean-prediction labels are computed once per image and cached
+        (the product defaults `resident_data` / `cache_clean_labels`)."""
+        st = self.state
+        if st is None or getattr(self, '_resident_x', None) is None:
+            raise RuntimeError("fit_batch_resident: call begin_fit(...) and set_resident_images(...) first")
+        index = torch.as_tensor(index, dtype=torch.long)
+        v_index = index.to(self.device, non_blocking=True)
+        shape = self._resident_shape
+        if labels is None:
+            labels = self._labels_for(v_index, index, self._resident_x, v_index, shape)
+        return self._fit_step(st, self._resident_x, v_index, v_index, labels, shape, 'both', self.step_size,
+                              self.step_size, index_cpu=index if not index.is_cuda else None)
+
+    def set_resident_images(self, images):
+        """Keep `images` [N,C,H,W] (host or device) in HBM for `fit_batch_resident`; row i belongs to row i of v."""
+        images = images.to(self.device, dtype=torch.float32).contiguous()
+        self._resident_shape = tuple(images.shape[1:])
+        self._resident_x = images.view(images.shape[0], -1)
+        self._label_cache = None
+
+    def begin_fit(self, n_img, image_shape, warm_start=False, distributed=False):
+        """Allocate and initialise D, v and the AdamW state for `n_img` images (adil.py:138-154).  distributed: one
+        process per GPU in an initialised torch.distributed group; `n_img` counts THIS rank's images (their code rows
+        stay local), the dictionary is rank 0's draw, and its optimizer state is sharded over the ranks."""
         nc, nx, ny = image_shape
-        self.state = self._init_state(n_img, nc, nx, ny, warm_start)
+        if not distributed:
+            self.state = self._init_state(n_img, nc, nx, ny, warm_start)
+            return self.state
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("begin_fit(distributed=True) needs an initialised torch.distributed process group")
+        st0 = self._init_state(n_img, nc, nx, ny, warm_start)
+        dist.broadcast(st0.D, 0)
+        shard = dsh.ShardedDictStep(nc * nx * ny, self.n_atoms, self.device)
+        self.state = AdilState(st0.D, st0.v, shard=shard)
         return self.state
 
     def _validate(self, val, batch_size, D):
@@ -404,8 +478,10 @@ class ADIL(Attack):
 
         The reference's DDP variant (adil.py:334-430) is non-functional; this implements its intent: each rank
         owns a contiguous shard of the images and of their code rows (v never crosses the wire), D is
-        replicated, and the per-step dictionary gradient is SUM-all-reduced (the reference loss is
-        CrossEntropy(reduction='sum'), so R ranks x B images == one GPU with batch R*B)."""
+        replicated, and the per-step dictionary gradient is SUMmed over the ranks (the reference loss is
+        CrossEntropy(reduction='sum'), so R ranks x B images == one GPU with batch R*B) by a reduce-scatter; every
+        rank applies AdamW + clamp to its pixel slice of D (optimizer state sharded R-fold) and the slices are
+        all-gathered (distributed.ShardedDictStep) -- on a side stream, under the local code step."""
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("learn_dictionary_distributed needs an initialised torch.distributed process group")
@@ -424,37 +500,23 @@ class ADIL(Attack):
         v_full = st_full.v if rank == 0 else torch.empty(n_img, self.n_atoms, device=self.device)
         dist.broadcast(D, 0)
         dist.broadcast(v_full, 0)
-        st = AdilState(D, v_full[lo:hi].clone())
+        st = AdilState(D, v_full[lo:hi].clone(), shard=dsh.ShardedDictStep(P, self.n_atoms, self.device))
         self.state = st
-        del v_full, st_full
+        del v_full, st_full, D
         with torch.no_grad():
             labels_local = torch.cat([self.model(x_local[i:i + 256].view(-1, *shape)).argmax(-1)
                                       for i in range(0, hi - lo, 256)]) if hi > lo else torch.empty(0, dtype=torch.long)
-        dD2 = torch.empty_like(st.D2)
-        flags = ops.SYNTH_NORMALIZE if self._mean is not None else 0
         loss_all, fooling_rate_all = [], []
         for iteration in range(int(self.steps)):
             stats = torch.zeros(2, device=self.device, dtype=torch.float64)
             for per_rank in dsh.epoch_schedule(n_img, world, batch_size, iteration, seed=dsh.schedule_seed(self)):
                 idx_host = per_rank[rank] - lo                       # CPU indices: kernel parameters of synth / grad
                 idx_local = idx_host.to(self.device)
-                if idx_local.numel() > 0:
-                    xin, _ = ops.synth(st.D2, st.v, idx_host, x=x_local, x_index=idx_host, mean=self._mean,
-                                       std=self._std, flags=flags, n_channels=nc)
-                    labels = labels_local[idx_local]
-                    loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
-                    _, dvb = ops.grad(g.view(g.shape[0], -1), st.D2, st.v, idx_host, self._std, dD2=dD2)
-                    stats[0] += loss.double()
-                    stats[1] += (out.argmax(-1) != labels).sum().double()
-                else:
-                    dD2.zero_()
-                    dvb, idx_local = None, None
-                dist.all_reduce(dD2, op=dist.ReduceOp.SUM)
-                st.tD += 1
-                ops.dict_step(st.D2, st.mD, st.sD, dD2, ops.adamw_params(st.tD, self.step_size), ops.ATOMS_CLAMP1)
-                st.tv += 1
-                ops.code_step(st.v, st.mv, st.sv, dvb, idx_local, ops.adamw_params(st.tv, self.step_size),
-                              ops.ROWS_L1BALL, self.eps)
+                labels = labels_local[idx_local] if idx_local.numel() > 0 else None
+                loss, fooled = self._fit_step(st, x_local, idx_local, idx_local, labels, shape, 'both', self.step_size,
+                                              self.step_size, index_cpu=idx_host)
+                stats[0] += loss.double()
+                stats[1] += fooled.double()
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)
             loss_all.append(stats[0].item() / n_img)
             fooling_rate_all.append(stats[1].item() / n_img)
@@ -462,10 +524,12 @@ class ADIL(Attack):
                 print(loss_all[-1], fooling_rate_all[-1])
             if iteration > 1 and abs(loss_all[iteration] - loss_all[iteration - 1]) < 1e-6:
                 break
+        st.shard.wait()
         v_all = dsh.gather_rows(st.v, n_img, world, rank)
         if rank == 0:
-            full = AdilState(st.D, v_all)
-            self._save(full, loss_all, fooling_rate_all, torch.zeros(()))
+            torch.cuda.synchronize(self.device)
+            import types
+            self._save(types.SimpleNamespace(D=st.D, v=v_all), loss_all, fooling_rate_all, torch.zeros(()))
         dist.barrier()
         return st
 

@@ -269,7 +269,8 @@ def init_state(nc, nx, ny, n_img, n_atoms, eps, norm='linf', v_zero=False, devic
 
 
 def learn_dictionary_a(model, dataset, eps, steps, n_atoms, batch_size, step_size=0.01, norm='linf', loss='ce',
-                       kappa=50, targeted=False, state=None, val=None, fused_normalize=False):
+                       kappa=50, targeted=False, state=None, val=None, fused_normalize=False, val_coder=True,
+                       on_step=None):
     """Joint ('gd') fit.  Returns (state, loss_all, fooling_rate_all, val_fooling_rate).
 
     `val` (optional dataset of (x, y)) reproduces the per-epoch validation coder of adil.py:198-205, including
@@ -277,7 +278,11 @@ def learn_dictionary_a(model, dataset, eps, steps, n_atoms, batch_size, step_siz
 
     `dataset[i]` -> (x, y) with `.indexed` False, (i, x, y) with True (imagenet_loading.py:8-18).
     With `fused_normalize` the leading Normalize module is peeled off `model` and applied by `synth` / `grad`
-    (what the CUDA path does); otherwise the model is called on x+delta exactly like adil.py:26."""
+    (what the CUDA path does); otherwise the model is called on x+delta exactly like adil.py:26.
+
+    `val_coder=False` iterates the validation loader (same CPU-RNG draws) but skips the 100-iteration coder, like the
+    stubbed reference runs of oracle/make_golden_imagenet.py.  `on_step(st, index, x, xin, g, loss, phase)` is called
+    with phase 'before' (state untouched, classifier gradient known) and 'after' (state stepped) on every minibatch."""
     dataset.indexed = False
     n_img = len(dataset)
     x0, _ = next(iter(dataset))
@@ -300,7 +305,11 @@ def learn_dictionary_a(model, dataset, eps, steps, n_atoms, batch_size, step_siz
             xin, _ = synth(x.reshape(len(index), P), st.D2, st.v, index, mean, std, eps, flags)
             lval, g, out = classifier_grad(net, xin.reshape(x.shape), label, loss, kappa, targeted, 'sum')
             fooled += int((out.argmax(dim=-1) != label).sum())
+            if on_step is not None:
+                on_step(st, index, x, xin, g, lval, 'before')
             joint_step_(st, g.reshape(len(index), P), index, step_size, eps, std)
+            if on_step is not None:
+                on_step(st, index, x, xin, g, lval, 'after')
             loss_full = loss_full + lval
         loss_all.append(float(loss_full) / n_img)
         fool_all.append(fooled / n_img)
@@ -308,8 +317,9 @@ def learn_dictionary_a(model, dataset, eps, steps, n_atoms, batch_size, step_siz
         if val_loader is not None:
             val_fool = 0
             for xv, _ in val_loader:
-                val_fool = val_fool + coder_adamw(model, xv, st.D(), eps, norm, loss, kappa, targeted, mode='train',
-                                                  fused_normalize=fused_normalize)
+                if val_coder:
+                    val_fool = val_fool + coder_adamw(model, xv, st.D(), eps, norm, loss, kappa, targeted,
+                                                      mode='train', fused_normalize=fused_normalize)
             val_fool = val_fool / len(val)
         if it > 1 and abs(loss_all[it] - loss_all[it - 1]) < 1e-6:     # adil.py:207
             break

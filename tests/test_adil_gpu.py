@@ -248,29 +248,6 @@ def test_attack_dict_model_autograd_bridge():
     assert adm.d.data.abs().max() <= 1
 
 
-def test_fooling_rate_on_imagenet_classifier(monkeypatch):
-    """Config-1-like smoke at real image size: random-init ResNet-18, 16 images, 10 atoms, l_inf 8/255 -- loss goes
-    down, perturbation respects the budget, fooling rate equals the PyTorch-op evaluation of the same D, v."""
-    from dl_attack_on_imagenet_b200 import ADIL, IndexedTensorDataset, build_classifier, synthetic_images
-    monkeypatch.setattr(ADIL, "verbose", False)
-    monkeypatch.setattr(ADIL, "run_validation", False)
-    model = build_classifier('resnet18', seed=0, device='cuda')
-    x, y = synthetic_images(16, seed=1)
-    torch.manual_seed(1234)
-    atk = ADIL(model, eps=EPS, steps=4, n_atoms=10, batch_size=8, data_train=IndexedTensorDataset(x, y),
-               model_name='t_resnet18', loss='ce', method='gd')
-    D, v, loss_all, fool_all, _ = torch.load(atk.model_file, weights_only=False)
-    assert loss_all[-1] < loss_all[0]
-    assert D.abs().max() <= 1 and (v.abs().sum(1) <= EPS * (1 + 1e-5)).all()
-    dv = torch.tensordot(v, D, dims=([1], [3]))
-    assert dv.abs().max() <= EPS * (1 + 1e-5)
-    with torch.no_grad():
-        clean = model(x.cuda()).argmax(-1)
-        adv = model(x.cuda() + dv).argmax(-1)
-    rate = (clean != adv).float().mean().item()
-    assert 0.0 <= rate <= 1.0
-
-
 def test_host_batch_prefetcher_delivers_the_gathered_rows_in_order():
     """Double-buffered pinned gather + side-stream H2D: every batch arrives intact while later batches are staged."""
     from dl_attack_on_imagenet_b200 import HostBatchPrefetcher

@@ -83,6 +83,13 @@ def _problem():
     return D, v, x
 
 
+def _oracle_slice_step(D_slice, m, s, dD_slice, hp, atoms_mode):
+    """AdamW + clamp on a pixel slice (what ops.dict_step does on the GPU) -- test infrastructure."""
+    O.adamw_step_(D_slice, dD_slice, m, s, hp.step, hp.lr)
+    if atoms_mode == ops.ATOMS_CLAMP1:
+        D_slice.clamp_(-1, 1)
+
+
 def _sharded_worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -94,6 +101,11 @@ def _sharded_worker(rank, world, port, out_dir):
     P = C * H * W
     lo, hi = dsh.shard_bounds(N, world, rank)
     st = O.State(D, v[lo:hi])                      # each rank owns its images' code rows only
+    # the product's sharded dictionary step (reduce-scatter -> slice AdamW -> all-gather), oracle arithmetic on CPU
+    shard = dsh.ShardedDictStep(P, K, 'cpu', step_fn=_oracle_slice_step)
+    D_full, dD_full = shard.alloc(), shard.alloc()
+    D_full[:P].copy_(st.D2)
+    st.D2 = D_full[:P]
     for epoch in range(2):
         for step in dsh.epoch_schedule(N, world, B, epoch, seed=5):
             idx = step[rank]
@@ -105,19 +117,22 @@ def _sharded_worker(rank, world, port, out_dir):
                 dD2, dvb = O.grad(g.reshape(len(idx), P), st.D2, st.v[idx - lo], std)
             else:
                 dD2, dvb = torch.zeros_like(st.D2), torch.zeros(0, K)
-            dsh.allreduce_sum_(dD2)                # the one data-path collective
-            O.dict_step_(st, dD2, 0.01)
+            dD_full.zero_()
+            dD_full[:P].copy_(dD2)
+            st.tD += 1
+            shard.step(D_full, dD_full, ops.adamw_params(st.tD, 0.01), ops.ATOMS_CLAMP1)   # the data-path collectives
+            shard.wait()
             O.code_step_(st, dvb, idx - lo, 0.01, EPS)
     v_all = dsh.gather_rows(st.v, N, world, rank)
     if rank == 0:
-        torch.save({"D2": st.D2, "v": v_all}, os.path.join(out_dir, "sharded.pt"))
+        torch.save({"D2": st.D2.clone(), "v": v_all, "m_rows": shard.m.shape[0]}, os.path.join(out_dir, "sharded.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_matches_single_process(tmp_path):
-    world = 2
-    port = 29500 + (os.getpid() % 2000)
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_gloo_ranks_match_single_process(tmp_path, world):
+    port = 29500 + (os.getpid() % 2000) + 37 * world
     mp.spawn(_sharded_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     got = torch.load(os.path.join(str(tmp_path), "sharded.pt"))
     # single process, union batches
@@ -136,3 +151,42 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
             O.joint_step_(st, g.reshape(len(idx), P), idx, 0.01, EPS, std)
     assert (got["D2"] - st.D2).abs().max() < 2e-6
     assert (got["v"] - st.v).abs().max() < 2e-6
+    assert got["m_rows"] == (C * H * W + world - 1) // world       # optimizer state sharded R-fold
+
+
+def _padded_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, K = 100, 7                                   # 100 rows over 3 ranks: slices of 34 rows, 2 rows of padding
+    shard = dsh.ShardedDictStep(P, K, 'cpu', step_fn=_oracle_slice_step)
+    g = torch.Generator().manual_seed(3)
+    D0 = -1 + 2 * torch.rand(P, K, generator=g)
+    grads = [torch.randn(world, P, K, generator=g) * 1e-3 for _ in range(3)]
+    D_full, dD_full = shard.alloc(), shard.alloc()
+    D_full[:P].copy_(D0)
+    for t, gr in enumerate(grads):
+        dD_full[:P].copy_(gr[rank])
+        shard.step(D_full, dD_full, ops.adamw_params(t + 1, 0.01), ops.ATOMS_CLAMP1)
+        shard.wait()
+    if rank == 1:
+        torch.save({"D": D_full.clone(), "rows": (shard.rows, shard.rows_total)}, os.path.join(out_dir, "padded.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_dict_step_with_padded_slices(tmp_path):
+    world = 3
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_padded_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "padded.pt"))
+    assert got["rows"] == (34, 102)
+    P, K = 100, 7
+    g = torch.Generator().manual_seed(3)
+    D = -1 + 2 * torch.rand(P, K, generator=g)
+    grads = [torch.randn(world, P, K, generator=g) * 1e-3 for _ in range(3)]
+    m, s = torch.zeros_like(D), torch.zeros_like(D)
+    for t, gr in enumerate(grads):
+        O.adamw_step_(D, gr.sum(0), m, s, t + 1, 0.01)
+        D.clamp_(-1, 1)
+    assert (got["D"][:P] - D).abs().max() < 2e-6 and (got["D"][P:] == 0).all()

@@ -442,3 +442,163 @@ def test_random_shapes_tensor_core_path_matches_fma_path(ops, B, hw, K):
     # by lr / 1e-8.  Compare where the gradient is not negligible.
     big = a[1].abs() > 1e-3 * a[1].abs().max()
     assert ((a[3] - b[3]).abs() * big).max() <= 1e-5
+
+
+# ---- round 2: per-atom l1 ball, code gradient reduced inside the code step, batch chunking, full-size fused step ------
+def test_project_atoms_l1ball(ops, golden):
+    """constraint_dict(d, 'l1ball') (utils.py:55-56): every (channel, atom) column onto the unit l1 ball.  The kernel
+    brackets the threshold by bisection instead of sorting; compared with the reference's own output and the oracle."""
+    got = ops.project_atoms(dev(torch.from_numpy(golden["atoms_rand_in"])), ops.ATOMS_L1BALL).cpu()
+    assert (got - torch.from_numpy(golden["atoms_rand_l1ball"])).abs().max() <= 2e-6
+    gen = torch.Generator().manual_seed(12)
+    for shape, scale in (((3, 16, 16, 50), 0.05), ((3, 24, 24, 100), 0.01), ((1, 8, 8, 200), 1.0), ((3, 12, 12, 7), 1e-4)):
+        D = torch.randn(*shape, generator=gen) * scale
+        D[..., 0] *= 1e-3                      # a column strictly inside the ball stays bit-identical
+        D[0, :, :, 1] = 0
+        ref = O.project_atoms(D, O.ATOMS_L1BALL)
+        got = ops.project_atoms(dev(D), ops.ATOMS_L1BALL).cpu()
+        assert (got - ref).abs().max() <= 2e-6, shape
+        assert torch.equal(got[..., 0], D[..., 0])
+        l1 = got.abs().flatten(1, 2).sum(1)    # [C, K]
+        assert (l1 <= 1 + 1e-4).all()
+    from dl_attack_on_imagenet_b200 import utils as U
+    D = torch.randn(3, 10, 10, 9, generator=gen)
+    assert (U.constraint_dict(dev(D), 'l1ball').cpu() - O.project_atoms(D, O.ATOMS_L1BALL)).abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("B,hw,K,N", [(100, 784, 50, 300), (33, 400, 64, 40), (7, 256, 200, 12), (128, 196, 100, 128),
+                                      (16, 64, 10, 2000)])
+@pytest.mark.parametrize("impl", ["fma", "auto"])
+def test_code_step_adds_up_the_partial_slabs_itself(ops, B, hw, K, N, impl):
+    """KEEP_PARTIALS: the backward kernel leaves its per-CTA slabs, adil_code_step reduces them (slot CTAs) -- same
+    result as the reduced dvb path to rounding, rows outside the batch bit-identical, run-to-run bit-reproducible."""
+    ops.set_impl(ops.IMPL_FMA if impl == "fma" else ops.IMPL_AUTO)
+    try:
+        D2, v, _, idx, g = make_problem(B, hw, K, N=N, seed=13)
+        hp = ops.adamw_params(2, 0.01)
+        gen = torch.Generator().manual_seed(14)
+        m0, s0 = torch.randn(N, K, generator=gen) * 1e-3, torch.rand(N, K, generator=gen) * 1e-6
+        res = []
+        for keep in (False, True, True):
+            Dd, md, sd = dev(D2), dev(torch.zeros_like(D2)), dev(torch.zeros_like(D2))
+            vd, mv, sv = dev(v), dev(m0), dev(s0)
+            dvb = ops.grad_dict_step(Dd, md, sd, dev(g), vd, idx, hp, STD, keep_partials=keep)
+            assert isinstance(dvb, ops.CodePartials) == keep
+            if keep:
+                red = dvb.reduce()
+            ops.code_step(vd, mv, sv, dvb, dev(idx), hp, ops.ROWS_L1BALL, EPS)
+            res.append((vd, mv, sv, Dd, red if keep else dvb))
+        a, b, c = res
+        assert torch.equal(a[3], b[3])                                       # the dictionary step does not depend on it
+        assert (a[4] - b[4]).abs().max() <= 2e-6 * a[4].abs().max() + 1e-12   # the same sum in another order
+        assert (a[1] - b[1]).abs().max() <= 2e-6 * a[1].abs().max() + 1e-12   # m is linear in the gradient
+        assert (a[0] - b[0]).abs().max() <= 2e-6
+        out = torch.ones(N, dtype=torch.bool)
+        out[idx] = False
+        assert torch.equal(a[0][out.cuda()], b[0][out.cuda()])
+        assert torch.equal(b[0], c[0]) and torch.equal(b[1], c[1]) and torch.equal(b[2], c[2])
+        # against the oracle, teacher-forced with the reduced gradient
+        st = O.State(torch.zeros(1, 1, 4, K), v)
+        st.mv, st.sv, st.tv = m0.clone(), s0.clone(), 1
+        O.code_step_(st, b[4].cpu(), idx, 0.01, EPS)
+        assert (b[0].cpu() - st.v).abs().max() <= 2e-7
+        # duplicate rows in the batch accumulate (index_put_(accumulate=True)); code-only update keeps partials too
+        idx2 = idx.clone()
+        if B >= 3:
+            idx2[2] = idx2[0]
+        vd, mv, sv = dev(v), dev(m0), dev(s0)
+        _, part = ops.grad(dev(g), dev(D2), vd, idx2, STD, want_dD=False, keep_partials=True)
+        red = part.reduce().cpu()
+        ops.code_step(vd, mv, sv, part, dev(idx2), hp, ops.ROWS_L1BALL, EPS)
+        st = O.State(torch.zeros(1, 1, 4, K), v)
+        st.mv, st.sv, st.tv = m0.clone(), s0.clone(), 1
+        O.code_step_(st, red, idx2, 0.01, EPS)
+        assert (vd.cpu() - st.v).abs().max() <= 2e-7
+    finally:
+        ops.set_impl(ops.IMPL_AUTO)
+
+
+@pytest.mark.parametrize("B,hw,K", [(300, 400, 100), (129, 196, 50), (260, 64, 200), (515, 100, 10)])
+def test_minibatches_beyond_one_pass_are_chunked(ops, B, hw, K):
+    """B > 128 (tcgen05) / beyond the FMA kernel's shared memory: the wrappers split the batch, dD accumulates across
+    the chunks (TMA reduce-add store / read-modify-write), the fused step falls back to chunks + adil_dict_step."""
+    D2, v, x, idx, g = make_problem(B, hw, K, seed=15)
+    assert B > ops.grad_max_batch(3 * hw, K, hw, True) or K > 128
+    vb = v[idx]
+    ref_dD, ref_dv = O.grad(g.double(), D2.double(), vb.double(), STD)
+    for index in (idx, dev(idx)):                                   # CPU index tensor (sliced per chunk) and device index
+        dD, dvb = ops.grad(dev(g), dev(D2), dev(v), index, STD)
+        assert (dD.cpu().double() - ref_dD).abs().max() <= 1e-5 * ref_dD.abs().max()
+        assert (dvb.cpu().double() - ref_dv).abs().max() <= 1e-5 * ref_dv.abs().max()
+    dD_b, dvb_b = ops.grad(dev(g), dev(D2), dev(v), dev(idx), STD)
+    assert torch.equal(dD_b, dD) and torch.equal(dvb_b, dvb)        # chunks accumulate in stream order: reproducible
+    # identity rows (v_index None): v itself holds the batch codes
+    dD_n, dv_n = ops.grad(dev(g), dev(D2), dev(vb), None, STD)
+    assert (dD_n - dD).abs().max() <= 1e-6 * dD.abs().max() and (dv_n - dvb).abs().max() <= 1e-6 * dvb.abs().max()
+    # accumulate flag on its own: 2 x dD
+    acc = dD.clone()
+    ops.grad(dev(g), dev(D2), dev(v), dev(idx), STD, want_dv=False, dD2=acc, accumulate=True)
+    assert (acc - 2 * dD).abs().max() <= 1e-6 * dD.abs().max()
+    # fused step on the big batch == oracle AdamW on the chunk-accumulated dD
+    hp = ops.adamw_params(1, 0.01)
+    Dd, md, sd = dev(D2), dev(torch.zeros_like(D2)), dev(torch.zeros_like(D2))
+    dv_f = ops.grad_dict_step(Dd, md, sd, dev(g), dev(v), idx, hp, STD, keep_partials=True)
+    assert torch.is_tensor(dv_f) and torch.equal(dv_f, dvb)
+    p, m, s = D2.clone(), torch.zeros_like(D2), torch.zeros_like(D2)
+    O.adamw_step_(p, dD.cpu(), m, s, 1, 0.01)
+    assert (Dd.cpu() - p.clamp(-1, 1)).abs().max() <= 1e-6
+    # synthesis beyond 128 images
+    ref, _ = O.synth(x, D2, v, idx, MEAN, STD, EPS, O.F_NORMALIZE, x_index=idx)
+    out, _ = ops.synth(dev(D2), dev(v), idx, x=dev(x), x_index=idx, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE)
+    assert (out.cpu() - ref).abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("K,steps", [(50, (1,)), (64, (1,)), (100, (1, 7)), (128, (1,))])
+def test_fused_step_at_the_benchmarked_size(ops, K, steps):
+    """grad_kernel<64, fused> at P = 150 528, B = 100 -- the instance bench.py times -- against float64 torch on the
+    device: dD (through m, which is linear in it), dv, and D / m / s after AdamW + clamp; fresh (t=1) and warm (t=7)."""
+    B, P, N = 100, 3 * 224 * 224, 1024
+    gen = torch.Generator(device="cuda").manual_seed(100 + K)
+    D0 = (-1 + 2 * torch.rand(P, K, device="cuda", generator=gen)) * 1.1      # some entries beyond the clamp
+    v = torch.rand(N, K, device="cuda", generator=gen) * (EPS / K)
+    idx = torch.randperm(N, device="cuda", generator=gen)[:B].cpu()          # host indices: the benchmarked path
+    g = torch.randn(B, P, device="cuda", generator=gen) * 1e-3
+    std_t = torch.tensor(STD, device="cuda", dtype=torch.float64).repeat_interleave(224 * 224)
+    gx = g.double() / std_t
+    ref_dD = gx.t() @ v[idx.cuda()].double()
+    ref_dv = gx @ D0.double()
+    assert ops.tc_supported(B, P, K)
+    for t in steps:
+        warm = t > 1
+        m0 = torch.randn(P, K, device="cuda", generator=gen) * 1e-4 if warm else torch.zeros(P, K, device="cuda")
+        s0 = torch.rand(P, K, device="cuda", generator=gen) * 1e-8 if warm else torch.zeros(P, K, device="cuda")
+        D2, m, s = D0.clone(), m0.clone(), s0.clone()
+        hp = ops.adamw_params(t, 0.01)
+        part = ops.grad_dict_step(D2, m, s, g, v, idx, hp, STD, ops.ATOMS_CLAMP1, keep_partials=True)
+        dvb = part.reduce()
+        assert (dvb.double() - ref_dv).abs().max() <= 1e-5 * ref_dv.abs().max()
+        # m = m0 + 0.1 (dD - m0): recovers the kernel's dD to fp32 rounding of m
+        dD_kernel = (m.double() - 0.9 * m0.double()) / 0.1
+        assert (dD_kernel - ref_dD).abs().max() <= 1e-5 * ref_dD.abs().max() + 1e-6 * m0.abs().max().item() * 10
+        # the oracle's AdamW (same op order as torch.optim) on the float64 gradient rounded to fp32, on the device
+        p, mr, sr = D0.clone(), m0.clone(), s0.clone()
+        O.adamw_step_(p, ref_dD.float(), mr, sr, t, 0.01)
+        p.clamp_(-1, 1)
+        assert (m - mr).abs().max() <= 1e-5 * mr.abs().max()
+        assert (s - sr).abs().max() <= 2e-5 * sr.abs().max()
+        # AdamW's step is ~ lr * m / (sqrt(s) + 1e-8): entries whose gradient is within rounding of 0 are
+        # ill-conditioned (SURVEY section 7 #0); everywhere else D agrees to the north-star bound
+        big = ref_dD.abs() > 1e-3 * ref_dD.abs().max()
+        assert ((D2 - p).abs() * big).max() <= 1e-5
+        assert ((D2 - p).abs() > 1e-5).float().mean() <= 1e-3
+        assert D2.abs().max() <= 1.0
+        # teacher-forced on the kernel's own gradient the whole dictionary agrees (also the ill-conditioned entries)
+        dD_plain, _ = ops.grad(g, D0, v, idx, STD, want_dv=False)
+        p2, m2, s2 = D0.clone(), m0.clone(), s0.clone()
+        O.adamw_step_(p2, dD_plain, m2, s2, t, 0.01)
+        assert (D2 - p2.clamp(-1, 1)).abs().max() <= 1e-6
+    # run-to-run bit equality of the benchmarked instance
+    D2b, mb, sb = D0.clone(), m0.clone(), s0.clone()
+    part_b = ops.grad_dict_step(D2b, mb, sb, g, v, idx, ops.adamw_params(steps[-1], 0.01), STD, ops.ATOMS_CLAMP1,
+                                keep_partials=True)
+    assert torch.equal(D2b, D2) and torch.equal(mb, m) and torch.equal(part_b.reduce(), dvb)
