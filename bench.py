@@ -3,14 +3,18 @@
 GB/s vs peak).
 
     python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA kernels behind the C ABI)
-    python bench.py --impl reference --steps K --warmup W    # reference arm: the oracle port of the reference's
-                                                             # own PyTorch-CPU path on the box's host cores
-    torchrun --nproc-per-node N bench.py --gpus N ...        # image-sharded weak scaling, dD all-reduce over NCCL
+    python bench.py --impl reference --steps K --warmup W    # reference arm: the reference's own PyTorch-CPU step
+                                                             # (oracle port doing the reference's work) on the host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...        # image-sharded weak scaling: reduce-scatter of dD ->
+                                                             # AdamW on this rank's pixel slice -> all-gather of D
+    python bench.py --config {1..5} ...                      # BASELINE.json configs[0..4] presets
 
-A "step" is one minibatch of the joint dictionary/code update (adil.py:168-188): clean forward for the labels,
-perturbation synthesis, classifier forward + backward, fused backward contractions + AdamW(D) + clamp, code AdamW
-+ l1 projection.  Workload at N=1: BASELINE.json configs[1] -- random-init ResNet-50, 1024 synthetic 3x224x224
-images, 50 atoms, batch 100, l_inf eps=8/255, fp32.  Prints ONE JSON line on rank 0.
+A "step" is one minibatch of the joint dictionary/code update (adil.py:168-188) with the reference's work: clean
+forward for the labels, perturbation synthesis, classifier forward + backward, backward contractions + AdamW(D) +
+clamp, code AdamW + l1 projection.  Default workload (N=1): BASELINE.json configs[1] -- random-init ResNet-50, 1024
+synthetic 3x224x224 images, 50 atoms, batch 100, l_inf eps=8/255, fp32.  Both arms go through the same public API a
+user calls (ADIL.begin_fit / fit_batch / fit_batch_resident); kernel times come from ops.kernel_timer().  Prints ONE
+JSON line on rank 0.
 """
 import argparse
 import json
@@ -28,6 +32,15 @@ import torch  # noqa: E402
 P_IMG = 3 * 224 * 224
 EPS = 8.0 / 255.0
 
+# BASELINE.json configs[0..4]: (model, total images, atoms, batch per GPU, norm, GPUs the config is quoted on)
+PRESETS = {
+    1: ("resnet18", 32, 10, 32, "linf", 1),
+    2: ("resnet50", 1024, 50, 100, "linf", 1),
+    3: ("densenet121", 8192, 100, 100, "linf", 8),
+    4: ("vgg16", 4096, 64, 100, "l2", 8),
+    5: ("resnet50", 16384, 200, 100, "linf", 8),   # fit side of the transfer sweep (scripts/run_configs.py evaluates it)
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -35,18 +48,40 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="resnet50")
-    ap.add_argument("--atoms", type=int, default=50)
-    ap.add_argument("--images", type=int, default=1024, help="images per GPU (weak scaling)")
-    ap.add_argument("--batch", type=int, default=100, help="minibatch per GPU")
-    ap.add_argument("--ref-batch", type=int, default=32, help="images per step of the CPU reference sample")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(PRESETS), help="BASELINE.json configs[config-1]")
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--atoms", type=int, default=None)
+    ap.add_argument("--images", type=int, default=None, help="images per GPU (weak scaling)")
+    ap.add_argument("--batch", type=int, default=None, help="minibatch per GPU")
+    ap.add_argument("--norm", default=None, choices=["linf", "l2"])
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in the cuDNN classifier (default: strict fp32)")
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "fma", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cudnn-autotune", action="store_true",
                     help="cudnn.benchmark off (profiling runs: fewer trial kernels in the launch list)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    model, total, atoms, batch, norm, quoted_gpus = PRESETS[args.config]
+    args.model = args.model or model
+    args.atoms = args.atoms or atoms
+    args.batch = args.batch or batch
+    args.norm = args.norm or norm
+    if args.images is None:   # weak scaling: the per-GPU share of the config at the GPU count it is quoted on
+        args.images = max(total // quoted_gpus, args.batch)
+    return args
+
+
+def make_config(args, world):
+    """The workload description both arms print (same keys, same values: what is measured, not how)."""
+    return {
+        "workload": "BASELINE configs[%d]: ADiL joint dictionary/code update ('gd', adil.py:168-188) on random-init %s, "
+                    "%d synthetic 3x224x224 images per GPU, %d atoms, minibatch %d per GPU, %s eps=8/255, AdamW lr 0.01, "
+                    "CE loss; per step: clean forward (labels), synthesis, classifier forward+backward, dictionary and "
+                    "code updates" % (args.config - 1, args.model, args.images, args.atoms, args.batch,
+                                      "l_inf" if args.norm == "linf" else "l2-init / l_inf"),
+        "baseline_config": args.config - 1, "model": args.model, "images_per_gpu": args.images, "atoms": args.atoms,
+        "batch_per_gpu": args.batch, "norm": args.norm, "n_gpus": world,
+    }
 
 
 def measured_traffic(kernel):
@@ -130,32 +165,44 @@ def make_images(n, seed, pin):
     return x
 
 
+def batch_schedule(n_img, batch, seed):
+    perm = torch.randperm(n_img, generator=torch.Generator().manual_seed(seed))
+    n_batches = max(n_img // batch, 1)
+    return [perm[i * batch:(i + 1) * batch].contiguous() for i in range(n_batches)]
+
+
 # ----------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference's PyTorch-CPU path on the host cores
+# reference arm / cpu_baseline: the reference's own CPU step (oracle port, doing the reference's work) on the host cores
 # ----------------------------------------------------------------------------------------------------------
-def cpu_reference(model_name, K, batch, steps, warmup, budget_s=None):
-    """Times `steps` minibatch steps (adil.py:168-188 restated in oracle/adil_oracle.py) on the CPU.  Each step is a
-    bounded sample of the workload: `batch` images instead of 100.  Returns (images/s, ms/step, cores, sample)."""
+def cpu_reference(args, steps, warmup, budget_s=None):
+    """Times minibatch steps of adil.py:168-188 on the CPU with ALL the work the reference does per step: the clean
+    forward builds an autograd graph (adil.py:172 has no no_grad), the classifier's weights require grad so that
+    loss.backward() also computes -- and accumulates, the reference never zeroes them -- weight gradients
+    (adil.py:175,185), AdamW steps every row of v and every entry of D, update_v / update_d project.  The arithmetic is
+    the oracle's restatement (bit-exact against the unmodified reference, tests/test_oracle_golden.py and
+    test_oracle_imagenet.py); the reference's Python sources cannot travel to the GPU box.  Same model, atoms, images
+    and batch as our arm.  Returns (images/s, ms/step, cores, sample description, steps timed)."""
     from dl_attack_on_imagenet_b200.data import build_classifier
     from oracle import adil_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = build_classifier(model_name, seed=0, device="cpu")
-    net, mean, std = O.split_normalize(model)
-    n_img = max(4 * batch, 64)
-    x = make_images(n_img, 1, pin=False)
+    B, K, N = args.batch, args.atoms, args.images
+    model = build_classifier(args.model, seed=0, device="cpu")   # parameters keep requires_grad=True like the reference's
+    x = make_images(N, 1, pin=False)
     torch.manual_seed(1234)
-    st = O.init_state(3, 224, 224, n_img, K, EPS)
-    perm = torch.randperm(n_img)
+    st = O.init_state(3, 224, 224, N, K, EPS, args.norm)
+    sched = batch_schedule(N, B, 7)
 
     def one_step(i):
-        idx = perm[(i * batch) % (n_img - batch + 1):][:batch]
+        idx = sched[i % len(sched)]
         xb = x[idx]
-        with torch.no_grad():
-            labels = model(xb).argmax(-1)
-        xin, _ = O.synth(xb.reshape(batch, P_IMG), st.D2, st.v, idx, mean, std, EPS, O.F_NORMALIZE)
-        _, g, _ = O.classifier_grad(net, xin.reshape(batch, 3, 224, 224), labels, 'ce', 50, False, 'sum')
-        O.joint_step_(st, g.reshape(batch, P_IMG), idx, 0.01, EPS, std)
+        labels = model(xb).argmax(dim=-1)                         # adil.py:172 (graph built, unused)
+        vb = st.v[idx]
+        xadv = (xb + (vb @ st.D2.t()).reshape(xb.shape)).requires_grad_(True)      # adil.py:25-26
+        out = model(xadv)                                         # Normalize is layer 0 of the model (demo:55-59)
+        loss = -torch.nn.functional.cross_entropy(out, labels, reduction='sum')   # adil.py:136,180
+        loss.backward()                                           # adil.py:185: input AND weight gradients
+        O.joint_step_(st, xadv.grad.reshape(len(idx), P_IMG), idx, 0.01, EPS, None)   # adil.py:186-188
 
     t_w = time.perf_counter()
     for i in range(warmup):
@@ -167,22 +214,22 @@ def cpu_reference(model_name, K, batch, steps, warmup, budget_s=None):
     for i in range(steps):
         one_step(warmup + i)
     dt = time.perf_counter() - t0
-    sample = ("%d steps x %d images (of the 100-image minibatch), %s, K=%d, N=%d resident images, oracle port of "
-              "adil.py:168-188 on torch-CPU" % (steps, batch, model_name, K, n_img))
-    return batch * steps / dt, 1e3 * dt / steps, cores, sample, steps
+    sample = ("%d steps x %d images (the full minibatch), %s, K=%d, N=%d images, %d warm-up steps; per step: clean forward "
+              "with graph, x+D.v, forward, backward incl. weight gradients, AdamW on D and all rows of v, l1 projection, "
+              "clamp -- oracle port of adil.py:168-188 on torch-CPU" % (steps, B, args.model, K, N, warmup))
+    return B * steps / dt, 1e3 * dt / steps, cores, sample, steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, cores, sample, steps = cpu_reference(args.model, args.atoms, args.ref_batch, args.steps, args.warmup)
+    value, ms, cores, sample, steps = cpu_reference(args, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "ADiL attack images/sec", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ADiL joint dictionary/code update, random-init %s, %d atoms, l_inf eps=8/255, fp32; "
-                               "CPU sample of %d images per step" % (args.model, args.atoms, args.ref_batch)},
+        "config": make_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -193,10 +240,15 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
+def stats(ms):
+    s = sorted(ms)
+    return {"min": s[0], "median": s[len(s) // 2], "max": s[-1], "mean": sum(s) / len(s)}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from dl_attack_on_imagenet_b200 import ADIL, ops
-    from dl_attack_on_imagenet_b200.data import build_classifier
+    from dl_attack_on_imagenet_b200.data import HostBatchPrefetcher, build_classifier
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,88 +282,30 @@ def run_ours(args):
     for p in model.parameters():
         p.requires_grad_(False)
     x_host = make_images(N, 1 + rank, pin=True)           # this rank's image shard, pinned host memory
-    x_dev = x_host.to(dev).view(N, P_IMG)                 # resident copy for the device-timed run
     ADIL.verbose = False
-    atk = ADIL(model, eps=EPS, n_atoms=K, batch_size=B, model_name="bench_%d" % rank, step_size=0.01, loss='ce',
-               method='gd')
+    atk = ADIL(model, eps=EPS, n_atoms=K, batch_size=B, norm=args.norm, model_name="bench_%d" % rank, step_size=0.01,
+               loss='ce', method='gd')
     torch.manual_seed(1234)
-    st = atk.begin_fit(N, shape)
-    if world > 1:                                         # replicated dictionary: rank 0's draw
-        dist.broadcast(st.D, 0)
-    g_perm = torch.Generator().manual_seed(7 + rank)
-    perm = torch.randperm(N, generator=g_perm)
-    n_batches = max(N // B, 1)
-    idx_cpu = [perm[(i % n_batches) * B:(i % n_batches) * B + B].contiguous() for i in range(n_batches)]
-    idx_dev = [t.to(dev) for t in idx_cpu]
-    dD2 = torch.empty_like(st.D2) if world > 1 else None
-    flags = ops.SYNTH_NORMALIZE
-    mean, std = atk._mean, atk._std
+    st = atk.begin_fit(N, shape, distributed=(world > 1))  # world > 1: rank 0's dictionary, sharded optimizer state
+    atk.set_resident_images(x_host)                        # resident copy of the shard for the device-timed region
+    sched = batch_schedule(N, B, 7 + rank)                 # CPU index tensors, like the reference's DataLoader yields
     hbm_peak, peak_src = measured_peaks()
 
-    ev = {k: [] for k in ("synth", "grad", "code", "dict")}
+    def step_resident(i):
+        """Device-resident step through the public API: images in HBM (gathered inside the synthesis kernel), the
+        reference's per-step work (clean forward for the labels included)."""
+        return atk.fit_batch_resident(sched[i % len(sched)])
 
-    def timed(name, fn, record):
-        if not record:
-            return fn()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = fn()
-        b.record()
-        ev[name].append((a, b))
-        return out
-
-    def step_resident(i, record=False):
-        """Device-resident step: images already in HBM, gathered inside the synthesis kernel."""
-        idx = idx_dev[i % n_batches]
-        idx_h = idx_cpu[i % n_batches]     # the DataLoader's CPU index tensor (adil.py:168): the synthesis / backward
-                                           # kernels take it as kernel parameters, like ADIL._fit_step does
-        with torch.no_grad():
-            labels = model(x_dev[idx].view(-1, *shape)).argmax(-1)               # adil.py:172
-        xin, _ = timed("synth", lambda: ops.synth(st.D2, st.v, idx_h, x=x_dev, x_index=idx_h, mean=mean, std=std,
-                                                  flags=flags), record)
-        loss, g, out = atk._classifier_grad(xin.view(-1, *shape), labels, 'sum')
-        g2 = g.view(B, P_IMG)
-        if world == 1:
-            st.tD += 1
-            dvb = timed("grad", lambda: ops.grad_dict_step(st.D2, st.mD, st.sD, g2, st.v, idx_h,
-                                                           ops.adamw_params(st.tD, 0.01), std, ops.ATOMS_CLAMP1), record)
-        else:
-            _, dvb = timed("grad", lambda: ops.grad(g2, st.D2, st.v, idx_h, std, dD2=dD2), record)
-            dist.all_reduce(dD2, op=dist.ReduceOp.SUM)                           # the one data-path collective
-            st.tD += 1
-            timed("dict", lambda: ops.dict_step(st.D2, st.mD, st.sD, dD2, ops.adamw_params(st.tD, 0.01),
-                                                ops.ATOMS_CLAMP1), record)
-        st.tv += 1
-        timed("code", lambda: ops.code_step(st.v, st.mv, st.sv, dvb, idx, ops.adamw_params(st.tv, 0.01),
-                                            ops.ROWS_L1BALL, EPS), record)
-        return loss
-
-    from dl_attack_on_imagenet_b200.data import HostBatchPrefetcher
     prefetch = HostBatchPrefetcher(x_host, dev)    # public staging helper: pinned gather + H2D on a side stream
 
     def step_e2e(i, last):
-        """End-to-end step through the public API: host gather into pinned memory + H2D (HostBatchPrefetcher: the
-        copy of batch i+1 overlaps the kernels of batch i), ADIL.fit_batch (multi-GPU: the same kernels +
-        all-reduce), D2H of loss and fooled count."""
-        idx = idx_cpu[i % n_batches]
+        """End-to-end step through the public API: host gather into pinned memory + H2D (HostBatchPrefetcher: the copy
+        of batch i+1 overlaps the kernels of batch i), ADIL.fit_batch, D2H of loss and fooled count."""
         xb = prefetch.get()
-        if world == 1:
-            loss, fooled = atk.fit_batch(idx, xb)
-        else:
-            idd = idx.to(dev, non_blocking=True)
-            labels = atk._clean_labels(xb)
-            xin, _ = ops.synth(st.D2, st.v, idd, x=xb.view(B, P_IMG), mean=mean, std=std, flags=flags)
-            loss, g, out = atk._classifier_grad(xin.view(-1, *shape), labels, 'sum')
-            fooled = (out.argmax(-1) != labels).sum()
-            _, dvb = ops.grad(g.view(B, P_IMG), st.D2, st.v, idd, std, dD2=dD2)
-            dist.all_reduce(dD2, op=dist.ReduceOp.SUM)
-            st.tD += 1
-            ops.dict_step(st.D2, st.mD, st.sD, dD2, ops.adamw_params(st.tD, 0.01), ops.ATOMS_CLAMP1)
-            st.tv += 1
-            ops.code_step(st.v, st.mv, st.sv, dvb, idd, ops.adamw_params(st.tv, 0.01), ops.ROWS_L1BALL, EPS)
+        loss, fooled = atk.fit_batch(sched[i % len(sched)], xb)
         prefetch.release()
         if not last:
-            prefetch.submit(idx_cpu[(i + 1) % n_batches])   # gathered and copied while the GPU runs step i
+            prefetch.submit(sched[(i + 1) % len(sched)])   # gathered and copied while the GPU runs step i
         return loss.item(), fooled.item()
 
     def barrier():
@@ -326,35 +320,53 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    def gather_ranks(values):
+        """[world, len(values)] on every rank."""
+        t = torch.tensor(values, device=dev, dtype=torch.float64)
+        if world == 1:
+            return t.unsqueeze(0).cpu()
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return torch.stack(out).cpu()
+
     # ---- device-resident timed region -------------------------------------------------------------------
+    atk.cache_clean_labels = False                 # reference work: the clean forward runs every step (adil.py:172)
     for i in range(args.warmup):
         step_resident(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step_resident(args.warmup + i, record=True)
-    e1.record()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ops.kernel_timer() as kt:
+        marks[0].record()
+        for i in range(args.steps):
+            step_resident(args.warmup + i)
+            marks[i + 1].record()
     barrier()
     clocks = sampler.finish()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = max_over_ranks(marks[0].elapsed_time(marks[-1]))
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
-    launches_per_step = 4 if world == 1 else 5     # synth, grad(+reduce_partials), [dict], code
-    kt = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v)) if v else None for k, v in ev.items()}
+    ksum = kt.summary()
+    launches = kt.launches
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+    all_steps = gather_ranks(per_step)             # [world, steps]
+    all_clocks = gather_ranks([float(clocks["sm_mhz"] or 0)])
+    per_rank = {"step_ms": [stats(r.tolist()) for r in all_steps], "sm_mhz_median": [c[0] for c in all_clocks.tolist()],
+                "slowest_rank_per_step": all_steps.argmax(dim=0).tolist() if world > 1 else None}
 
-    # ---- end-to-end region (host buffers, copies inside) ---------------------------------------------------
-    e2e = None
+    # ---- end-to-end regions --------------------------------------------------------------------------------
+    e2e, e2e_variants = None, {}
     if not args.no_e2e:
-        prefetch.submit(idx_cpu[0])
+        # (1) headline: host buffers, H2D of every batch + D2H of loss / fooled count inside the timed region
+        prefetch.submit(sched[0])
         for i in range(args.warmup):
             step_e2e(i, last=(i == args.warmup - 1))
         barrier()
         t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        prefetch.submit(idx_cpu[args.warmup % n_batches])   # exactly `steps` H2D copies inside the timed region
+        prefetch.submit(sched[args.warmup % len(sched)])   # exactly `steps` H2D copies inside the timed region
         for i in range(args.steps):
             step_e2e(args.warmup + i, last=(i == args.steps - 1))
         e1.record()
@@ -362,39 +374,65 @@ def run_ours(args):
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
         e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                "h2d_bytes_per_step": B * P_IMG * 4 + B * 8, "d2h_bytes_per_step": 4 + 8,
-               "ms_per_step": ms_e2e / args.steps}
+               "ms_per_step": ms_e2e / args.steps,
+               "what": "reference-faithful work through ADIL.fit_batch: host images (pinned) -> H2D every step, clean "
+                       "forward every step, loss + fooled count read back every step"}
+        e2e_variants["reference_faithful_host_images"] = e2e["value"]
+        # (2) product default: resident shard, clean labels cached per image; only indices cross PCIe
+        atk.cache_clean_labels = True
+        atk._label_cache = None
+        for i in range(args.warmup):                       # (the first call labels the whole shard once)
+            step_resident(i)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(args.steps):
+            loss, fooled = step_resident(args.warmup + i)
+            loss.item(), fooled.item()
+        e1.record()
+        barrier()
+        ms_prod = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+        e2e_variants["product_default_resident_cached_labels"] = world * B * args.steps / (ms_prod * 1e-3)
+        e2e_variants["note"] = ("headline e2e = reference_faithful_host_images; the product default (ADIL.fit: images "
+                                "resident in HBM, clean labels cached -- results identical) is reported beside it")
+        atk.cache_clean_labels = False
 
     # ---- roofline of the dominant ADiL kernel -----------------------------------------------------------------
-    if world == 1:
-        alg_bytes = 4.0 * P_IMG * (B + 6 * K) + 8.0 * B * K
-        kname = "grad_dict_step (dD=g^T v, dv=g D, AdamW(D), clamp fused; adil_grad_dict_step)"
-    else:
-        alg_bytes = 4.0 * P_IMG * (B + 2 * K) + 8.0 * B * K
-        kname = "grad (dD=g^T v, dv=g D; adil_grad) before the NCCL all-reduce"
-    synth_bytes = 4.0 * P_IMG * (2 * B + K) + 4.0 * B * K
-    roofline = None
     kernels = {}
-    if kt["grad"]:
-        ach = alg_bytes / (kt["grad"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak,
-                    "traffic": measured_traffic("adil_grad_dict_step" if world == 1 else "adil_grad"),
-                    "alg_bytes": alg_bytes, "kernel_ms": kt["grad"], "peak_source": peak_src}
-        kernels["grad"] = {"ms": kt["grad"], "GBps": ach, "frac": ach / hbm_peak}
-    if kt["synth"]:
-        ach = synth_bytes / (kt["synth"] * 1e-3) / 1e9
-        kernels["synth"] = {"ms": kt["synth"], "GBps": ach, "frac": ach / hbm_peak, "alg_bytes": synth_bytes}
-    if kt["code"]:
-        kernels["code_step"] = {"ms": kt["code"], "alg_bytes": 28.0 * N * K}
-    if kt["dict"]:
-        ach = 28.0 * P_IMG * K / (kt["dict"] * 1e-3) / 1e9
-        kernels["dict_step"] = {"ms": kt["dict"], "GBps": ach, "frac": ach / hbm_peak}
 
-    # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample ------------------------------
+    def add(name, key, nbytes):
+        if key in ksum:
+            ms = ksum[key]["ms_mean"]
+            ach = nbytes / (ms * 1e-3) / 1e9
+            kernels[name] = {"ms": ms, "GBps": ach, "frac": ach / hbm_peak, "alg_bytes": nbytes, "calls": ksum[key]["calls"]}
+    add("synth", "adil_synth", 4.0 * P_IMG * (2 * B + K) + 4.0 * B * K)
+    add("grad_dict_step", "adil_grad_dict_step", 4.0 * P_IMG * (B + 6 * K) + 8.0 * B * K)
+    add("grad", "adil_grad", 4.0 * P_IMG * (B + 2 * K) + 8.0 * B * K)
+    add("dict_step_slice", "adil_dict_step", 28.0 * P_IMG * K / world)
+    add("code_step", "adil_code_step", 28.0 * N * K)
+    if world == 1:
+        dom, kname, tname = "grad_dict_step", "grad_dict_step (dD=g^T v, dv=g D, AdamW(D), clamp fused; adil_grad_dict_step)", "adil_grad_dict_step"
+    else:
+        dom, kname, tname = "grad", "grad (dD=g^T v, dv=g D; adil_grad) before the reduce-scatter", "adil_grad"
+    roofline = None
+    if dom in kernels:
+        k = kernels[dom]
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": k["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": k["frac"], "traffic": measured_traffic(tname), "alg_bytes": k["alg_bytes"],
+                    "kernel_ms": k["ms"], "peak_source": peak_src}
+    if world > 1 and all(n in kernels for n in ("synth", "grad", "dict_step_slice")):
+        # the whole multi-GPU ADiL step against its algorithmic bytes 4P(3B+10K)
+        ms = kernels["synth"]["ms"] + kernels["grad"]["ms"] + kernels["dict_step_slice"]["ms"]
+        nbytes = 4.0 * P_IMG * (3 * B + 10 * K)
+        kernels["adil_step_multi_gpu"] = {"ms": ms, "alg_bytes": nbytes, "GBps": nbytes / (ms * 1e-3) / 1e9,
+                                          "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                                          "note": "synth + grad + AdamW on this rank's slice (the full 28PK bytes counted)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's CPU step on the host cores, bounded sample -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v_cpu, _, cores, sample, _ = cpu_reference(args.model, K, args.ref_batch, 4, 1, budget_s=20.0)
+            v_cpu, _, cores, sample, _ = cpu_reference(args, 4, 1, budget_s=20.0)
             cpu = {"value": v_cpu, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
         except Exception as exc:  # keep the GPU numbers even if the host run fails
             cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % exc}
@@ -404,18 +442,18 @@ def run_ours(args):
             "metric": "ADiL attack images/sec", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "BASELINE configs[1]: ADiL joint dictionary/code update ('gd', adil.py:168-188) on "
-                            "random-init %s, %d synthetic 3x224x224 images per GPU, %d atoms, minibatch %d per GPU, "
-                            "l_inf eps=8/255, AdamW lr 0.01, CE loss" % (args.model, N, K, B),
+            "config": make_config(args, world),
+            "impl_notes": {
                 "classifier_math": "cuDNN TF32 allowed" if args.tf32 else "strict fp32 (TF32 off)",
                 "adil_kernels": "tcgen05 split precision (3xTF32 synthesis, bf16x3 backward), fp32 accumulate; FMA "
-                                "fallback for shapes outside B<=128, K<=128 (impl=%s)" % args.kernel_impl,
+                                "fallback outside K<=128 (impl=%s); batches beyond 128 images are chunked" % args.kernel_impl,
                 "l2": "inputs larger than L2: each step touches >150 MB of ADiL state + GBs of activations",
-                "parallelism": "image-sharded x%d, dD SUM all-reduce (NCCL)" % world if world > 1 else "single GPU",
+                "parallelism": ("image-sharded x%d: dD reduce-scatter (NCCL) -> AdamW on this rank's pixel slice -> D "
+                                "all-gather, on a side stream under the local code step" % world) if world > 1 else "single GPU",
+                "api": "ADIL.begin_fit / fit_batch_resident (value) / fit_batch (e2e); kernel times from ops.kernel_timer()",
             },
-            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "kernels": kernels,
+            "e2e": e2e, "e2e_variants": e2e_variants, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels, "per_rank": per_rank,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

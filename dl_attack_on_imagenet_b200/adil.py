@@ -77,6 +77,64 @@ class AdilState(object):
         self.tv = 0
 
 
+class _ClassifierGraph(object):
+    """CUDA-graph capture of the frozen classifier's share of one step -- forward, attack loss, input-gradient
+    backward, fooled count (adil.py:176-185 without the ADiL kernels) -- for one batch shape: the several hundred cuDNN /
+    elementwise launches of a step become one graph launch.  The synthesis kernel writes straight into the static
+    input `xin2`; `g`, `out`, `loss`, `fooled` are static outputs, valid until the next replay."""
+
+    def __init__(self, attack, nb, shape, reduction):
+        dev = attack.device
+        self.xin = torch.zeros(nb, *shape, device=dev, requires_grad=True)
+        self.xin2 = self.xin.detach().view(nb, -1)
+        self.labels = torch.zeros(nb, dtype=torch.long, device=dev)
+
+        def body():
+            out = attack._net(self.xin)
+            loss = attack._attack_loss(out, self.labels, reduction)
+            (g,) = torch.autograd.grad(loss, self.xin)
+            return out, loss, g.contiguous(), (out.argmax(dim=-1) != self.labels).sum()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up off the capture (cuDNN autotuning, lazy init)
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out, self.loss, self.g, self.fooled = body()
+
+    def replay(self, labels):
+        self.labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return self.loss.detach(), self.g, self.out.detach()
+
+
+class _LabelGraph(object):
+    """CUDA-graph capture of the clean-prediction forward `model(x).argmax(-1)` (adil.py:172) for one batch shape."""
+
+    def __init__(self, attack, nb, shape):
+        dev = attack.device
+        self.x = torch.zeros(nb, *shape, device=dev)
+
+        def body():
+            with torch.no_grad():
+                return attack.model(self.x).argmax(dim=-1)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.labels = body()
+
+    def replay(self):
+        self.graph.replay()
+        return self.labels
+
+
 class Attack_dict_model(nn.Module):
     """Mirror of adil.py:16-35 (learnables d, v; forward = synthesis + classifier; projections)."""
 
@@ -117,6 +175,7 @@ class ADIL(Attack):
     run_validation = True       # per-epoch validation coder (adil.py:198-205)
     fuse_normalize = True       # fold a leading Normalize module into the kernels
     allow_pickle = False        # dictionary files are loaded with weights_only=True (tensors / lists / floats only)
+    use_cuda_graphs = True      # replay the classifier's forward/backward of a step as one CUDA graph per batch shape
     verbose = True
     dict_dir = 'trained_dicts/'
 
@@ -147,6 +206,9 @@ class ADIL(Attack):
         self.state = None
         self._net, self._mean, self._std = split_normalize(self.model) if self.fuse_normalize else (self.model, None, None)
         self._batch_schedule = None  # optional: callable(epoch) -> list of CPU index tensors (tests / sharding)
+        self._graphs = {}            # (kind, batch, shape, ...) -> captured CUDA graph of the classifier part
+        self._resident_x = None
+        self._label_cache = None
         if not os.path.exists(self.model_file) and data_train is not None:
             self.fit(data_train, data_val, warm_start=warm_start, is_distributed=is_distributed)
 
@@ -170,7 +232,7 @@ class ADIL(Attack):
     # ------------------------------------------------------------------------------------------------
     def f_loss(self, outputs, labels):
         """CW-style logit margin (adil.py:103-112): the label slot is zeroed, not masked to -inf."""
-        onehot = torch.nn.functional.one_hot(labels, outputs.shape[1]).to(outputs.dtype)
+        onehot = (torch.arange(outputs.shape[1], device=outputs.device) == labels.unsqueeze(1)).to(outputs.dtype)
         other = ((1 - onehot) * outputs).max(dim=1).values
         true = (onehot * outputs).sum(dim=1)
         margin = (other - true) if self._targeted else (true - other)
@@ -184,9 +246,39 @@ class ADIL(Attack):
             return self.f_loss(outputs, labels).sum()
         raise ValueError("loss must be 'ce' or 'logits'")
 
+    def _graph(self, kind, nb, shape, reduction=None):
+        """The captured classifier graph for this batch shape (None: graphs off, or capture failed once -- eager)."""
+        if not self.use_cuda_graphs or self._graphs.get('disabled'):
+            return None
+        key = (kind, nb, tuple(shape), reduction, self.loss, bool(self.targeted))
+        gr = self._graphs.get(key)
+        if gr is None:
+            if len(self._graphs) >= 6:                     # odd batch sizes come and go: keep the cache small
+                self._graphs.pop(next(iter(self._graphs)))
+            try:
+                gr = _ClassifierGraph(self, nb, shape, reduction) if kind == 'grad' else _LabelGraph(self, nb, shape)
+            except Exception as exc:                       # e.g. a classifier with host-synchronising ops
+                torch.cuda.synchronize(self.device)
+                self._graphs = {'disabled': repr(exc)}
+                if self.verbose:
+                    print("ADIL: CUDA-graph capture of the classifier failed (%r); running it eagerly" % (exc,))
+                return None
+            self._graphs[key] = gr
+        return gr
+
+    def _xin_buffer(self, nb, shape, reduction):
+        """Static classifier-input buffer [nb, P] of the captured graph for this batch shape -- the synthesis kernel
+        writes into it directly -- or None when the classifier runs eagerly."""
+        gr = self._graph('grad', nb, shape, reduction)
+        return gr.xin2 if gr is not None else None
+
     def _classifier_grad(self, xin, labels, reduction):
         """Loss, d loss / d xin and logits through the frozen classifier (PyTorch / cuDNN).  Only the input
-        gradient is requested, so no weight gradients are computed (the reference accumulates them unused)."""
+        gradient is requested, so no weight gradients are computed (the reference accumulates them unused).  When
+        `xin` is the static buffer handed out by `_xin_buffer`, the captured CUDA graph is replayed instead."""
+        gr = self._graphs.get(('grad', xin.shape[0], tuple(xin.shape[1:]), reduction, self.loss, bool(self.targeted)))
+        if gr is not None and xin.data_ptr() == gr.xin.data_ptr():
+            return gr.replay(labels)
         xin.requires_grad_(True)
         out = self._net(xin)
         loss = self._attack_loss(out, labels, reduction)
@@ -194,6 +286,10 @@ class ADIL(Attack):
         return loss.detach(), g.contiguous(), out.detach()
 
     def _clean_labels(self, x):
+        gr = self._graph('labels', x.shape[0], x.shape[1:]) if x.is_cuda else None
+        if gr is not None:
+            gr.x.copy_(x)
+            return gr.replay().clone()
         with torch.no_grad():
             return self.model(x).argmax(dim=-1)
 
@@ -309,7 +405,7 @@ class ADIL(Attack):
                 ops.code_step(st.v, st.mv, st.sv, None, None, ops.adamw_params(st.tv, lr_v), ops.ROWS_L1BALL, self.eps)
             return torch.zeros((), device=self.device), torch.zeros((), dtype=torch.long, device=self.device)
         xin, _ = ops.synth(st.D2, st.v, kv_index, x=x_src, x_index=kx_index, mean=self._mean, std=self._std, flags=flags,
-                           n_channels=shape[0])
+                           n_channels=shape[0], out=self._xin_buffer(nb, shape, 'sum'))
         loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
         g = g.view(g.shape[0], -1)
         fooled = (out.argmax(dim=-1) != labels).sum()
@@ -634,13 +730,23 @@ class ADIL(Attack):
         flags = ops.SYNTH_NORMALIZE if self._mean is not None else 0
         labels = self._clean_labels(images)
         idx = torch.arange(n, device=self.device)
+        # The reference leaves the loop at the first iteration whose update moved v by less than 1e-6 (adil.py:611-614,
+        # a host read per iteration).  Here the test stays on the device: once it has fired, later iterations leave v
+        # untouched, and the host looks at the flag every tenth iteration only -- same result, no per-iteration sync.
+        stopped = torch.zeros((), dtype=torch.bool, device=self.device)
+        v_old = torch.empty_like(v)
+        xin_buf = self._xin_buffer(n, shape, 'mean')
         for it in range(1, 101):
-            xin, _ = ops.synth(D2, v, None, x=x2, mean=self._mean, std=self._std, flags=flags, n_channels=shape[0])
+            xin, _ = ops.synth(D2, v, None, x=x2, mean=self._mean, std=self._std, flags=flags, n_channels=shape[0],
+                               out=xin_buf)
             _, g, _ = self._classifier_grad(xin.view(n, *shape), labels, 'mean')
-            _, dvb = ops.grad(g.view(n, -1), D2, v, None, self._std, want_dD=False)
-            v_old = v.clone()
+            _, dvb = ops.grad(g.view(n, -1), D2, v, None, self._std, want_dD=False, keep_partials=True)
+            v_old.copy_(v)
             ops.code_step(v, mv, sv, dvb, idx, ops.adamw_params(it, 1e-2), ops.ROWS_L1BALL, self.eps)
-            if (v - v_old).abs().max() < 1e-6:
+            newly = (v - v_old).abs().max() < 1e-6
+            v.copy_(torch.where(stopped, v_old, v))
+            stopped |= newly
+            if it % 10 == 0 and bool(stopped):
                 break
         vproj = self.projection_v(v)                                       # adil.py:617
         if model == 'train':

@@ -574,6 +574,31 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
           tmem_st8(lane_base + (uint32_t)(a.Kp8 + 8 * c), lo);
         }
       }
+      if (nchunks > 16) {
+        // more than 128 atoms (up to 224: the codes take 2 Kp8 of the 512 TMEM columns): the chunks beyond the 16 that
+        // were loaded at kernel entry follow in a second round -- one more cold miss, at large K only
+        const int b = quad * 32 + lane;
+        const int bi = min(b, B - 1);
+        const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
+        const float* vrow = a.v + row * K;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int k0 = 8 * (16 + cg + 4 * ci);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+        }
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = 16 + cg + 4 * ci;
+          if (c < nchunks) {  // warp-uniform
+            float hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_tf32(vv[ci][i], hi[i], lo[i]);
+            tmem_st8(lane_base + (uint32_t)(8 * c), hi);
+            tmem_st8(lane_base + (uint32_t)(a.Kp8 + 8 * c), lo);
+          }
+        }
+      }
       tmem_st_wait();
     }
     if (warp == 0) SSTAMP(3);
@@ -1422,7 +1447,7 @@ struct SynthPlan {
 SynthPlan plan_synth(int B, int P, int K, int hw) {
   SynthPlan pl{};
   pl.ok = false;
-  if (B < 1 || B > 128 || K < 1 || K > 128 || P % 4 != 0 || hw % 4 != 0) return pl;
+  if (B < 1 || B > 128 || K < 1 || K > 224 || P % 4 != 0 || hw % 4 != 0) return pl;  // (codes: 2 Kp8 <= 448 TMEM columns)
   const int tps[4] = {64, 48, 32, 16};
   for (int i = 0; i < 4; ++i) {
     const int TP = tps[i];

@@ -95,7 +95,7 @@ class ShardedDictStep(object):
 
     `D2` and `dD2` must be the first P rows of buffers with `rows_total` rows (see `alloc`), so that every rank's slice
     has the same size.  `step_fn(D_slice, m, s, dD_slice, hp, atoms_mode)` defaults to the CUDA kernel
-    (ops.dict_step); the gloo/CPU test injects the oracle there.  The collectives run on `stream` (a side stream: the
+    (ops.dict_step); the gloo/CPU test injects a host implementation there.  The collectives run on `stream` (a side stream: the
     local code step proceeds concurrently); `wait()` makes the current stream wait for the gathered dictionary."""
 
     def __init__(self, P, K, device, group=None, step_fn=None, side_stream=True):

@@ -21,6 +21,63 @@ IMPL_AUTO, IMPL_FMA, IMPL_TC = 0, 1, 2
 _scratch = {}
 
 
+class KernelTimer(object):
+    """Opt-in device timing of the library's launches (the reference has only a wall-clock bracket around whole
+    attacks, performance.py:136-144).  Inside `with ops.kernel_timer() as kt:` every wrapper below brackets its C-ABI
+    call with CUDA events on the launching stream; `kt.summary()` (after a synchronize) gives calls and mean / total
+    milliseconds per entry point.  Outside the context the wrappers record nothing."""
+
+    def __init__(self):
+        self.events = {}
+        self.launches = 0
+
+    def __enter__(self):
+        global _timer
+        self._prev, _timer = _timer, self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = self._prev
+        return False
+
+    def summary(self):
+        out = {}
+        for name, pairs in self.events.items():
+            ms = [a.elapsed_time(b) for a, b in pairs]
+            out[name] = {"calls": len(ms), "ms_mean": sum(ms) / len(ms), "ms_total": sum(ms),
+                         "ms_min": min(ms), "ms_max": max(ms)}
+        return out
+
+
+_timer = None
+
+
+def kernel_timer():
+    return KernelTimer()
+
+
+class _Timed(object):
+    __slots__ = ("name", "device", "start", "n")
+
+    def __init__(self, name, device, launches=1):
+        self.name, self.device, self.n = name, device, launches
+
+    def __enter__(self):
+        if _timer is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if _timer is not None and exc[0] is None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record(torch.cuda.current_stream(self.device))
+            _timer.events.setdefault(self.name, []).append((self.start, end))
+            _timer.launches += self.n
+        return False
+
+
 def _f32(t, name, allow_none=False):
     if t is None:
         if allow_none:
@@ -152,8 +209,9 @@ def synth(D2, v, v_index=None, x=None, x_index=None, mean=None, std=None, eps=0.
     C = n_channels if n_channels is not None else (len(mean) if mean is not None else 1)
     hw = P // C
     mean_h, std_h = _host3(mean, C), _host3(std, C)
-    rc = _lib.lib().adil_synth(_ptr(out), _ptr(delta_out), _ptr(x), _ptr(x_index), _ptr(D2), _ptr(v), _ptr(v_index),
-                               B, P, K, C, hw, mean_h, std_h, float(eps), int(flags), _stream(dev))
+    with _Timed("adil_synth", dev, (B + 127) // 128):
+        rc = _lib.lib().adil_synth(_ptr(out), _ptr(delta_out), _ptr(x), _ptr(x_index), _ptr(D2), _ptr(v),
+                                   _ptr(v_index), B, P, K, C, hw, mean_h, std_h, float(eps), int(flags), _stream(dev))
     _lib.check(rc, "adil_synth")
     return out, delta_out
 
@@ -183,10 +241,11 @@ def _grad_call(dD2, dvb, g, D2, v, v_index, B, P, K, std, flags, dev):
     scratch, nbytes = _grad_scratch(dev, B, K)
     nslabs = ctypes.c_int(0)
     v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
-    rc = _host_index_retry(
-        lambda ix: _lib.lib().adil_grad(_ptr(dD2), _ptr(dvb), _ptr(g), _ptr(D2), _ptr(v), _ptr(ix), B, P, K, C, P // C,
-                                        _host3(std, C), int(flags), ctypes.byref(nslabs), _ptr(scratch), nbytes,
-                                        _stream(dev)), v_index, dev)
+    with _Timed("adil_grad", dev, 1 if (flags & GRAD_KEEP_PARTIALS or dvb is None) else 2):
+        rc = _host_index_retry(
+            lambda ix: _lib.lib().adil_grad(_ptr(dD2), _ptr(dvb), _ptr(g), _ptr(D2), _ptr(v), _ptr(ix), B, P, K, C,
+                                            P // C, _host3(std, C), int(flags), ctypes.byref(nslabs), _ptr(scratch),
+                                            nbytes, _stream(dev)), v_index, dev)
     _lib.check(rc, "adil_grad")
     return scratch, nslabs.value
 
@@ -276,12 +335,13 @@ def grad_dict_step(D2, m, s, g, v, v_index, hp, std=None, atoms_mode=ATOMS_CLAMP
     scratch, nbytes = _grad_scratch(dev, B, K)
     nslabs = ctypes.c_int(0)
     v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
-    rc = _host_index_retry(
-        lambda ix: _lib.lib().adil_grad_dict_step(_ptr(D2), _ptr(m), _ptr(s),
-                                                  _ptr(dvb) if (want_dv and not keep_partials) else None, _ptr(g),
-                                                  _ptr(v), _ptr(ix), B, P, K, C, P // C, _host3(std, C),
-                                                  ctypes.byref(hp), int(atoms_mode), flags, ctypes.byref(nslabs),
-                                                  _ptr(scratch), nbytes, _stream(dev)), v_index, dev)
+    with _Timed("adil_grad_dict_step", dev, 2 if (want_dv and not keep_partials) else 1):
+        rc = _host_index_retry(
+            lambda ix: _lib.lib().adil_grad_dict_step(_ptr(D2), _ptr(m), _ptr(s),
+                                                      _ptr(dvb) if (want_dv and not keep_partials) else None, _ptr(g),
+                                                      _ptr(v), _ptr(ix), B, P, K, C, P // C, _host3(std, C),
+                                                      ctypes.byref(hp), int(atoms_mode), flags, ctypes.byref(nslabs),
+                                                      _ptr(scratch), nbytes, _stream(dev)), v_index, dev)
     _lib.check(rc, "adil_grad_dict_step")
     if not want_dv:
         return None
@@ -294,8 +354,9 @@ def dict_step(D2, m, s, dD2, hp, atoms_mode=ATOMS_CLAMP1):
     n = D2.numel()
     if not (m.numel() == n and s.numel() == n and dD2.numel() == n):
         raise ValueError("dict_step: size mismatch")
-    rc = _lib.lib().adil_dict_step(_ptr(D2), _ptr(m), _ptr(s), _ptr(dD2), n, ctypes.byref(hp), int(atoms_mode),
-                                   _stream(D2.device))
+    with _Timed("adil_dict_step", D2.device):
+        rc = _lib.lib().adil_dict_step(_ptr(D2), _ptr(m), _ptr(s), _ptr(dD2), n, ctypes.byref(hp), int(atoms_mode),
+                                       _stream(D2.device))
     _lib.check(rc, "adil_dict_step")
 
 
@@ -315,8 +376,9 @@ def code_step(v, m, s, dvb, v_index, hp, rows_mode=ROWS_L1BALL, radius=0.0):
         B = 0 if dvb is None else dvb.shape[0]
     if (dvb is not None or partial is not None) and v_index is not None and v_index.numel() != B:
         raise ValueError("code_step: v_index has %d entries, the gradient %d rows" % (v_index.numel(), B))
-    rc = _lib.lib().adil_code_step(_ptr(v), _ptr(m), _ptr(s), _ptr(dvb), _ptr(v_index), B, N, K, ctypes.byref(hp),
-                                   int(rows_mode), float(radius), _ptr(partial), int(nslabs), _stream(v.device))
+    with _Timed("adil_code_step", v.device):
+        rc = _lib.lib().adil_code_step(_ptr(v), _ptr(m), _ptr(s), _ptr(dvb), _ptr(v_index), B, N, K, ctypes.byref(hp),
+                                       int(rows_mode), float(radius), _ptr(partial), int(nslabs), _stream(v.device))
     _lib.check(rc, "adil_code_step")
 
 

@@ -49,6 +49,8 @@ for impl in args.impls.split(","):
         "synth": (lambda: ops.synth(D2, v, idx, x=x, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE, out=out), 4.0 * P * (2 * B + K) + 4.0 * B * K),
         "grad": (lambda: ops.grad(g, D2, v, idx, STD, dD2=dD, dvb=dvb), 4.0 * P * (B + 2 * K) + 8.0 * B * K),
         "grad_dict_step": (lambda: ops.grad_dict_step(D2, m, s, g, v, idx, ops.adamw_params(3, 0.01), STD, dvb=dvb), 4.0 * P * (B + 6 * K) + 8.0 * B * K),
+        "grad_dict_step_partials": (lambda: ops.grad_dict_step(D2, m, s, g, v, idx, ops.adamw_params(3, 0.01), STD, keep_partials=True), 4.0 * P * (B + 6 * K) + 8.0 * B * K),
+        "grad_partials": (lambda: ops.grad(g, D2, v, idx, STD, dD2=dD, keep_partials=True), 4.0 * P * (B + 2 * K) + 8.0 * B * K),
         "dict_step": (lambda: ops.dict_step(D2, m, s, dD, ops.adamw_params(3, 0.01)), 28.0 * P * K),
     }
     for name, (fn, nbytes) in cases.items():
@@ -61,4 +63,21 @@ vv = torch.rand(N, K, device=dev) * 1e-2; mv = torch.zeros_like(vv); sv = torch.
 idx_d = idx.to(dev)
 med, best = timeit(lambda: ops.code_step(vv, mv, sv, dvb, idx_d, ops.adamw_params(3, 0.01), ops.ROWS_L1BALL, 8 / 255), args.iters)
 print(f"code_step N={N} K={K}: median {med*1e3:.1f} us best {best*1e3:.1f} us")
+res["code_step"] = {"ms_median": med, "ms_best": best}
+part = ops.grad_dict_step(D2, m, s, g, v, idx, ops.adamw_params(3, 0.01), STD, keep_partials=True)
+med, best = timeit(lambda: ops.code_step(vv, mv, sv, part, idx_d, ops.adamw_params(3, 0.01), ops.ROWS_L1BALL, 8 / 255), args.iters)
+print(f"code_step (reduces {part.nslabs} partial slabs itself) N={N} K={K}: median {med*1e3:.1f} us best {best*1e3:.1f} us")
+res["code_step_partials"] = {"ms_median": med, "ms_best": best}
+def pair():
+    p_ = ops.grad_dict_step(D2, m, s, g, v, idx, ops.adamw_params(3, 0.01), STD, keep_partials=True)
+    ops.code_step(vv, mv, sv, p_, idx_d, ops.adamw_params(3, 0.01), ops.ROWS_L1BALL, 8 / 255)
+med, best = timeit(pair, args.iters)
+print(f"grad_dict_step + code_step (2 launches): median {med*1e3:.1f} us best {best*1e3:.1f} us")
+res["grad_dict_step+code_step"] = {"ms_median": med, "ms_best": best}
+def pair_old():
+    ops.grad_dict_step(D2, m, s, g, v, idx, ops.adamw_params(3, 0.01), STD, dvb=dvb)
+    ops.code_step(vv, mv, sv, dvb, idx_d, ops.adamw_params(3, 0.01), ops.ROWS_L1BALL, 8 / 255)
+med, best = timeit(pair_old, args.iters)
+print(f"grad_dict_step + reduce + code_step (3 launches): median {med*1e3:.1f} us best {best*1e3:.1f} us")
+res["grad_dict_step+reduce+code_step"] = {"ms_median": med, "ms_best": best}
 print(json.dumps(res))

@@ -309,3 +309,46 @@ def test_distributed_fit_with_one_rank_matches_the_fused_single_gpu_fit(monkeypa
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_cuda_graph_replay_of_the_classifier_is_bit_identical_to_eager(monkeypatch):
+    """ADIL.use_cuda_graphs: the classifier's forward / loss / input-gradient backward of a step (and the clean-label
+    forward) replayed as captured CUDA graphs, the ADiL kernels launched around them -- same bits as the eager path for
+    the fit ('gd' and 'alter', ragged last batch included) and for the 100-iteration validation coder."""
+    from dl_attack_on_imagenet_b200 import ADIL
+    torch.manual_seed(77)
+    st0 = O.init_state(C, H, W, N, K, EPS, 'linf')
+    res = {}
+    for graphs in (False, True):
+        monkeypatch.setattr(ADIL, "use_cuda_graphs", graphs)
+        monkeypatch.setattr(ADIL, "cache_clean_labels", False)      # the clean forward runs (and replays) every step
+        for method, kw in (("gd", {}), ("alter", {"steps_in": 1})):
+            atk = make_attack(monkeypatch, st0, 78, steps=2, method=method, model_name="g%d_%s" % (graphs, method), **kw)
+            D, v, loss_all, fool_all, vf = torch.load(atk.model_file, weights_only=True)
+            res[(graphs, method)] = (D, v, loss_all, fool_all, float(vf))
+            if graphs:
+                assert any(k[0] == 'grad' for k in atk._graphs) and any(k[0] == 'labels' for k in atk._graphs)
+            else:
+                assert not atk._graphs
+        _, _, xva, yva = tiny_data()
+        res[(graphs, "coder")] = atk.forward_supervised_AdamW(xva, yva, res[(graphs, "gd")][0].cuda(), 'eval')
+    for key in ("gd", "alter"):
+        a, b = res[(False, key)], res[(True, key)]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3] and a[4] == b[4]
+    assert torch.equal(res[(False, "coder")], res[(True, "coder")])
+
+
+def test_validation_coder_stops_where_the_reference_stops(monkeypatch):
+    """The device-side convergence flag freezes v at the iteration where adil.py:611-614 breaks: a dictionary of zeros
+    gives a zero gradient, the first AdamW step moves nothing, the reference stops after one iteration."""
+    from dl_attack_on_imagenet_b200 import ADIL
+    monkeypatch.setattr(ADIL, "verbose", False)
+    model = O.tiny_classifier(seed=0).cuda()
+    os.makedirs("trained_dicts", exist_ok=True)
+    torch.save([torch.zeros(C, H, W, K), torch.zeros(N, K), [], [], 0.0], "trained_dicts/ImageNet_t_stop.bin")
+    atk = ADIL(model, eps=EPS, n_atoms=K, model_name='t_stop')
+    _, _, xva, yva = tiny_data()
+    adv = atk.forward_supervised_AdamW(xva, yva, torch.zeros(C, H, W, K).cuda(), 'eval')
+    assert torch.equal(adv.cpu(), xva.clamp(0, 1))
+    ref = O.coder_adamw(O.tiny_classifier(seed=0), xva, torch.zeros(C, H, W, K), EPS, mode='eval')
+    assert torch.equal(adv.cpu(), ref)
