@@ -209,7 +209,7 @@ __device__ __forceinline__ void code_row_update(const CodeArgs& a, int row, int 
 //               on nslabs (bit-reproducible) -- and warp 0 applies AdamW + projection.  This replaces a separate
 //               reduction launch between the backward kernel and the code step.
 template <int EPL>
-__global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
+__global__ void __launch_bounds__(256, 2) code_step_kernel(const CodeArgs a) {
   __shared__ float sorted_all[kCodeWarps][32 * EPL];
   __shared__ float red[kCodeWarps][32 * EPL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -253,13 +253,23 @@ __global__ void __launch_bounds__(256) code_step_kernel(const CodeArgs a) {
 #pragma unroll
         for (int i = 0; i < EPL; ++i) acc[i] = 0.0f;
         const float* src = a.partial + (size_t)bb * K;
-#pragma unroll 4
-        for (int c = warp; c < a.nslabs; c += kCodeWarps) {
+        // U slabs per warp in flight at once (148 slabs / 8 warps = 19 per warp on the tcgen05 path: one or two round trips)
+        constexpr int U = EPL == 1 ? 20 : (EPL == 2 ? 10 : (EPL == 4 ? 5 : 3));
+        for (int c0 = warp; c0 < a.nslabs; c0 += kCodeWarps * U) {
+          float t[U][EPL];
 #pragma unroll
-          for (int i = 0; i < EPL; ++i) {
-            const int k = lane + 32 * i;
-            if (k < K) acc[i] += __ldcg(src + (size_t)c * slab + k);
+          for (int u = 0; u < U; ++u) {
+            const int c = c0 + u * kCodeWarps;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+              const int k = lane + 32 * i;
+              t[u][i] = (c < a.nslabs && k < K) ? __ldcg(src + (size_t)c * slab + k) : 0.0f;
+            }
           }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) acc[i] += t[u][i];
         }
         __syncthreads();  // (previous slot's partial sums consumed)
 #pragma unroll

@@ -808,6 +808,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   uint64_t* acc_empty = staged + 2;                            // [2] dD accumulator 0 / 1 read out (epilogue warps -> issuer)
   uint64_t* epi_done = acc_empty + 2;                          // [NS] output tile written into the stage (epilogue warps -> loader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + NS);
+  long long* vrow_s = reinterpret_cast<long long*>(smem_raw + 256 + 1024);  // [128] row of v of each image
   typedef unsigned short bf16_t;
   const int dbuf = 3 * a.dimg, gbuf = 3 * a.gimg + 1024;          // bf16 elements per buffer (gradient: + 2 KB pad)
   bf16_t* Di = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);   // [2 buffers][3 terms] dictionary images
@@ -834,34 +835,12 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   const int tile_elems = TP * K;
   const uint32_t ne_tmem = 2u * (uint32_t)((K + 31) / 32);  // epilogue warps whose TMEM quadrant holds atoms
   STAMP(0);
-  // The batch codes are the first thing on the critical path of tile 0: their loads are issued here, ahead of the
-  // set-up barrier.  With host indices (kernel parameters) or identity rows this is ONE cold miss, and the roles start
-  // their bulk traffic right after that barrier (`early`); with a device index array it is a chain of two dependent
-  // misses, and the bulk traffic -- 148 CTAs x 3 stages of D tiles plus the gradient rows of the first tiles would
-  // queue ~15 MB ahead of the second hop: measured 4 us on the first MMA -- is held back until the codes are in.
-  // worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
+  // `early`: with host indices (kernel parameters) or identity rows the code rows of the batch are ONE cold miss away,
+  // and the roles start their bulk traffic right after the set-up barrier, next to the code loads.  With a device index
+  // array the codes are a chain of two dependent misses, and the bulk traffic -- 148 CTAs x 3 stages of D tiles plus the
+  // gradient rows of the first tiles would queue ~15 MB ahead of the second hop: measured 4 us on the first MMA -- is
+  // held back until the codes are in.
   const bool early = (a.hv_on != 0 || a.vidx == nullptr) && a.early != 0;
-  float vv[2][16];
-  if (warp < NW && a.want_dD && (warp & 3) * 32 < K) {  // (a quadrant whose 32 atoms are all padding keeps zeros)
-    const int m = (warp & 3) * 32 + lane;
-    const float* vcol = a.v + min(m, K - 1);
-    const float keep = m < K ? 1.0f : 0.0f;
-#pragma unroll
-    for (int ci = 0; ci < 2; ++ci) {
-      const int b0 = 16 * ((warp >> 2) + 4 * ci);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int bi = min(b0 + i, B - 1);
-        const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
-        vv[ci][i] = __ldg(vcol + row * K) * ((b0 + i < B) ? keep : 0.0f);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-      for (int i = 0; i < 16; ++i) vv[ci][i] = 0.0f;
-  }
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, (a.want_dv ? NW : 0) + (fused ? NE : 0) + ((a.want_dv || fused) ? 0 : 1));
                                    mbar_init(epi_done + i, ne_tmem); }
@@ -869,6 +848,9 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
+  for (int b = tid; b < 128; b += NTHREADS_GRAD)  // element offset of the code row of image b (rows >= B: row of image B-1)
+    vrow_s[b] = (a.hv_on ? (long long)a.hv[min(b, B - 1)] : a.vidx ? (long long)a.vidx[min(b, B - 1)] : (long long)min(b, B - 1)) *
+                (long long)K;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -910,6 +892,25 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       gsrc[j] = (b < B) ? 4 * q : -1;
       grow[j] = a.g + (size_t)min(b, B - 1) * P + 4 * q;
       gdst[j] = (q >> 1) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (q & 1) * 4;
+    }
+  }
+  // The batch codes are the first thing on the critical path of tile 0: their loads go out first (one straight-line
+  // block: a per-element choice of the index source turns into 32 branchy, serialised misses -- measured +8 us) and fly
+  // during the zero fill.  worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
+  float vv[2][16];
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) vv[ci][i] = 0.0f;
+  if (warp < NW && a.want_dD && (warp & 3) * 32 < K) {  // (a quadrant whose 32 atoms are all padding keeps zeros)
+    const int m = (warp & 3) * 32 + lane;
+    const float* vcol = a.v + min(m, K - 1);
+    const float keep = m < K ? 1.0f : 0.0f;
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      const int b0 = 16 * ((warp >> 2) + 4 * ci);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) vv[ci][i] = __ldg(vcol + vrow_s[b0 + i]) * ((b0 + i < B) ? keep : 0.0f);
     }
   }
   if (early) {

@@ -7,6 +7,8 @@ torchvision classifiers, CPU, same seeds as SURVEY.md section 8(d):
                 resnet18 / vgg11 / densenet121
 
     python oracle/make_golden_imagenet.py [case ...]        # build container only; ~1 h of CPU for all cases
+    python oracle/make_golden_imagenet.py fr_vgg11+floor    # the reference's own sensitivity floor of a case: the same
+                                                            # run with an ulp-level change of the Normalize layer
 
 Stored per case (all small): per-epoch loss and training fooling rate (adil.py:194-195), checksums of the initial
 state (so that a test can prove it regenerated the same D0 / v0), the final codes v, and the final dictionary /
@@ -52,7 +54,47 @@ def checksum(t):
     return np.asarray([t.sum().item(), t.abs().sum().item()], dtype=np.float64)
 
 
+class NormalizeUlp(torch.nn.Module):
+    """Normalize with the same mean / std, evaluated as input * (1/std) - mean * (1/std) instead of (input - mean) / std:
+    an ulp-level change of the classifier input.  Running the UNMODIFIED reference on a model that starts with this
+    layer measures the reference's own sensitivity floor (SURVEY.md section 7 #0) for a case."""
+
+    def __init__(self, base):
+        super().__init__()
+        self.register_buffer('mean', base.mean.clone())
+        self.register_buffer('std', base.std.clone())
+
+    def forward(self, x):
+        r = (1.0 / self.std).reshape(1, -1, 1, 1)
+        return x * r - self.mean.reshape(1, -1, 1, 1) * r
+
+
+def run_floor(ref, name, out):
+    """`<case>_loss_ulp`, `<case>_fool_ulp`: the reference's trajectory when only the Normalize layer's rounding changes."""
+    arch, n_img, K, B, steps = CASES[name]
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_classifier(arch, seed=0)
+    model = torch.nn.Sequential(NormalizeUlp(model[0]), model[1]).eval()
+    x, y = synthetic_images(n_img, seed=1)
+    xv, yv = synthetic_images(1, seed=2)
+    tr, va = IndexedTensorDataset(x, y), IndexedTensorDataset(xv, yv)
+    ref.ADIL.forward_supervised_AdamW = lambda self, images, labels, d, model='train': torch.zeros((), dtype=torch.long)
+    t0 = time.time()
+    torch.manual_seed(1234)
+    atk = ref.ADIL(model, eps=EPS, steps=steps, norm='linf', n_atoms=K, batch_size=B, data_train=tr, data_val=va,
+                   model_name=name + "_ulp", step_size=0.01, loss='ce', method='gd')
+    D, v, loss_all, fool_all, _ = torch.load(atk.model_file, weights_only=False)
+    out[name + "_loss_ulp"] = np.asarray(loss_all, dtype=np.float64)
+    out[name + "_fool_ulp"] = np.asarray(fool_all, dtype=np.float64)
+    pix = pixel_subset()
+    out[name + "_Dv_sub_ulp"] = (v @ D.reshape(P, K)[pix].t()).numpy()
+    print("%s (ulp-perturbed Normalize): %d epochs in %.0f s, fooling %s" % (
+        name, len(loss_all), time.time() - t0, np.round(np.asarray(fool_all), 4).tolist()), flush=True)
+
+
 def run_case(ref, name, out):
+    if name.endswith("+floor"):
+        return run_floor(ref, name[:-len("+floor")], out)
     arch, n_img, K, B, steps = CASES[name]
     torch.set_num_threads(os.cpu_count() or 1)
     model = build_classifier(arch, seed=0)                       # manual_seed(0) + torchvision init, Sequential(Normalize, net)
