@@ -33,11 +33,13 @@ SIGNATURES = {
     "adil_tc_supported": (_I, [_I, _I, _I]),
     "adil_synth": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float_p, c_float_p, _F, _I, _P]),
     "adil_grad_scratch_bytes": (_SZ, [_I, _I]),
-    "adil_grad": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float_p, _I, _IP, _P, _SZ, _P]),
+    "adil_grad": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float_p, _P, _F, _I, _IP, _P, _SZ, _P]),
     "adil_grad_max_batch": (_I, [_I, _I, _I, _I]),
     "adil_grad_dict_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float_p, _HP, _I, _I, _IP, _P, _SZ,
                                  _P]),
     "adil_dict_step": (_I, [_P, _P, _P, _P, _LL, _HP, _I, _P]),
+    "adil_dict_step_atoms": (_I, [_P, _P, _P, _P, _I, _I, _HP, _F, _I, _P, _P]),
+    "adil_code_prox_step": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _F, _P]),
     "adil_code_step": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _HP, _I, _F, _P, _I, _P]),
     "adil_project_rows": (_I, [_P, _I, _I, _I, _F, _P]),
     "adil_project_atoms_scratch_bytes": (_SZ, [_I]),

@@ -171,7 +171,7 @@ namespace {
 int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g,
                 const float* D2, const float* v, const int64_t* v_index, int B, int P, int K, int C, int hw,
                 const float* std_host, const adil_adamw_t* hp, int atoms_mode, int flags, int* nslabs_out,
-                void* scratch, size_t scratch_bytes, void* stream) {
+                void* scratch, size_t scratch_bytes, void* stream, const float* delta = nullptr, float l2_coef = 0.0f) {
   const bool scale = std_host != nullptr;
   int rc = check_shape(fn, B, P, K, C, hw, scale);
   if (rc) return rc;
@@ -184,6 +184,10 @@ int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, fl
   opt.accumulate = (flags & ADIL_GRAD_ACCUMULATE_DD) ? 1 : 0;
   opt.keep_partials = (flags & ADIL_GRAD_KEEP_PARTIALS) ? 1 : 0;
   opt.nslabs_out = nslabs_out;
+  const bool penalised = delta != nullptr && l2_coef != 0.0f;
+  opt.delta = penalised ? delta : nullptr;
+  opt.l2_coef = penalised ? l2_coef : 0.0f;
+  if (penalised && !aligned16(delta)) return set_error(-1, "%s: delta must be 16-byte aligned", fn);
   if (opt.keep_partials && !nslabs_out) return set_error(-1, "%s: ADIL_GRAD_KEEP_PARTIALS needs nslabs_out", fn);
   if (opt.accumulate && (D2_rw != nullptr || dD2 == nullptr))
     return set_error(-1, "%s: ADIL_GRAD_ACCUMULATE_DD applies to the plain dD2 output only", fn);
@@ -193,7 +197,8 @@ int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, fl
   memset(&dev, 0, sizeof(dev));
   if (hp) dev = make_adamw(hp);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(tc_grad_ok(B, P, K, scale ? hw : P, dD2 != nullptr || D2_rw != nullptr, want_dv, D2_rw != nullptr), B, P,
+  if (!penalised &&  // (the l2-penalised contractions run on the CUDA-core kernels)
+      use_tc(tc_grad_ok(B, P, K, scale ? hw : P, dD2 != nullptr || D2_rw != nullptr, want_dv, D2_rw != nullptr), B, P,
              K, &rc, fn))
     return launch_grad_tc(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, cc, &dev, atoms_mode, (float*)scratch,
                           scratch_bytes, opt, st);
@@ -207,17 +212,19 @@ int grad_common(const char* fn, float* dD2, float* D2_rw, float* m, float* s, fl
 }  // namespace
 
 extern "C" int adil_grad(float* dD2, float* dvb, const float* g, const float* D2, const float* v,
-                         const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host, int flags,
-                         int* nslabs_out, void* scratch, size_t scratch_bytes, void* stream) {
+                         const int64_t* v_index, int B, int P, int K, int C, int hw, const float* std_host,
+                         const float* delta, float l2_coef, int flags, int* nslabs_out, void* scratch,
+                         size_t scratch_bytes, void* stream) {
   if (!dD2 && !dvb && !(flags & ADIL_GRAD_KEEP_PARTIALS))
     return set_error(-1, "adil_grad: nothing to compute (dD2 and dvb both NULL)");
   return grad_common("adil_grad", dD2, nullptr, nullptr, nullptr, dvb, g, D2, v, v_index, B, P, K, C, hw, std_host,
-                     nullptr, ADIL_ATOMS_NONE, flags, nslabs_out, scratch, scratch_bytes, stream);
+                     nullptr, ADIL_ATOMS_NONE, flags, nslabs_out, scratch, scratch_bytes, stream, delta, l2_coef);
 }
 
 extern "C" int adil_grad_max_batch(int P, int K, int hw, int fused) {
   if (P <= 0 || K < 1 || K > ADIL_MAX_ATOMS) return 0;
   if (hw <= 0) hw = P;
+  if (fused < 0) return grad_fma_max_batch(K, true, true);  // the CUDA-core kernels' limit (l2-penalised contractions)
   if (g_impl != ADIL_IMPL_FMA && tc_grad_ok(128, P, K, hw, true, true, fused != 0)) return 128;
   if (g_impl == ADIL_IMPL_TC) return 0;
   return grad_fma_max_batch(K, true, true);

@@ -127,9 +127,11 @@ ChannelConsts make_consts(int C, int hw, const float* mean_host, const float* st
 
 // options of the backward entry points (adil_grad / adil_grad_dict_step flags)
 struct GradOpts {
-  int accumulate;     // ADIL_GRAD_ACCUMULATE_DD: dD2 += instead of dD2 =
-  int keep_partials;  // ADIL_GRAD_KEEP_PARTIALS: leave the per-CTA code-gradient slabs in scratch (no reduction launch)
-  int* nslabs_out;    // host: number of slabs written (keep_partials)
+  int accumulate;      // ADIL_GRAD_ACCUMULATE_DD: dD2 += instead of dD2 =
+  int keep_partials;   // ADIL_GRAD_KEEP_PARTIALS: leave the per-CTA code-gradient slabs in scratch (no reduction launch)
+  int* nslabs_out;     // host: number of slabs written (keep_partials)
+  const float* delta;  // l2 penalty: gx += l2_coef * delta (FMA path only)
+  float l2_coef;
 };
 
 // FMA-path launchers (adil_fma.cu)

@@ -198,6 +198,8 @@ struct GradArgs {
   int B, P, K, Kp;
   int want_dD, want_dv, atoms_mode;
   int accumulate;  // unfused output: dD2 += instead of dD2 =
+  const float* delta;  // l2 penalty (adil_regularized.py:112-114): gx += l2_coef * delta
+  float l2_coef;
   ChannelConsts cc;
   AdamwDev hp;
 };
@@ -319,6 +321,13 @@ __global__ void __launch_bounds__(kThreads) grad_fma_kernel(const GradArgs a) {
           val.y = __fdiv_rn(val.y, a.cc.stdv[(p + 1) / a.cc.hw]);
           val.z = __fdiv_rn(val.z, a.cc.stdv[(p + 2) / a.cc.hw]);
           val.w = __fdiv_rn(val.w, a.cc.stdv[(p + 3) / a.cc.hw]);
+        }
+        if (a.delta != nullptr) {  // gradient of 0.5 * l2_coef * ||D v||^2 w.r.t. the perturbation
+          const float4 dl = ld_stream4(a.delta + (size_t)b * P + p);
+          val.x = fmaf(a.l2_coef, dl.x, val.x);
+          val.y = fmaf(a.l2_coef, dl.y, val.y);
+          val.z = fmaf(a.l2_coef, dl.z, val.z);
+          val.w = fmaf(a.l2_coef, dl.w, val.w);
         }
       }
       *reinterpret_cast<float4*>(gs + b * TPS + 4 * q) = val;
@@ -539,6 +548,8 @@ int launch_grad_fma(float* dD2, float* D2_rw, float* m, float* s, float* dvb, co
   a.want_dD = (dD2 != nullptr || D2_rw != nullptr) ? 1 : 0;
   a.want_dv = (dvb != nullptr || opt.keep_partials) ? 1 : 0;
   a.accumulate = (opt.accumulate && D2_rw == nullptr) ? 1 : 0;
+  a.delta = opt.delta;
+  a.l2_coef = opt.l2_coef;
   a.atoms_mode = atoms_mode;
   a.cc = cc;
   if (hp) a.hp = *hp;

@@ -3,6 +3,8 @@
 //   code_step   : scatter + AdamW on all rows of v + row projection (adil.py:186-187 ; utils.py:21-41)
 //   project_rows / project_atoms : initial / final projections (adil.py:625-642 ; utils.py:44-57)
 //   adamw_clamp : z update of forward_supervised_DDrague (adil.py:554-555)
+#include <cstring>
+
 #include "adil_common.cuh"
 
 namespace adil {
@@ -384,6 +386,77 @@ __global__ void __launch_bounds__(256) atom_sumsq_kernel(const float* __restrict
   }
 }
 
+// dictionary update fused with the column sums of squares of the UPDATED dictionary (first pass of a per-atom l2
+// projection): same thread layout as atom_sumsq_kernel (coalesced along atoms), fixed summation order
+template <bool ADAMW>
+__global__ void __launch_bounds__(256) dict_update_sumsq_kernel(float* __restrict__ D2, float* __restrict__ m,
+                                                                float* __restrict__ s, const float* __restrict__ dD2,
+                                                                int P, int K, AdamwDev hp, float step,
+                                                                float* __restrict__ partial /*[grid][K] or null*/) {
+  extern __shared__ float sh[];  // [256]
+  const int per = 256 / K;
+  const int k = threadIdx.x % K, r0 = threadIdx.x / K;
+  float acc = 0.0f;
+  if (r0 < per) {
+    for (long long r = (long long)blockIdx.x * per + r0; r < P; r += (long long)gridDim.x * per) {
+      const size_t i = (size_t)r * K + k;
+      float d = D2[i];
+      const float g = dD2[i];
+      if (ADAMW) {
+        float mv = m[i], sv = s[i];
+        adamw_update_fast(d, mv, sv, g, hp);
+        m[i] = mv;
+        s[i] = sv;
+      } else {
+        d = __fmaf_rn(-step, g, d);
+      }
+      D2[i] = d;
+      acc = fmaf(d, d, acc);
+    }
+  }
+  if (partial == nullptr) return;
+  sh[threadIdx.x] = (r0 < per) ? acc : 0.0f;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float t = 0.0f;
+    for (int j = 0; j < per; ++j) t += sh[j * K + threadIdx.x];
+    partial[(size_t)blockIdx.x * K + threadIdx.x] = t;
+  }
+}
+
+// proximal gradient step on the code rows of one minibatch: one warp per batch slot
+template <int EPL>
+__global__ void __launch_bounds__(256) code_prox_kernel(float* __restrict__ v, const float* __restrict__ dvb,
+                                                        const int64_t* __restrict__ vidx, int B, int N, int K, float step,
+                                                        int mode, float radius) {
+  __shared__ float sorted_all[8][32 * EPL];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
+    const int64_t row = vidx ? vidx[b] : (int64_t)b;
+    if (row < 0 || row >= (int64_t)N) continue;
+    // a row named again by a later slot takes that slot's update (v[ind] = ... with repeated indices: last write wins)
+    bool later = false;
+    for (int b0 = b + 1; b0 < B; b0 += 32) {
+      const int j = b0 + lane;
+      if (__any_sync(0xffffffffu, j < B && (vidx ? vidx[j] : (int64_t)j) == row)) { later = true; break; }
+    }
+    if (later) continue;
+    float x[EPL];
+    const size_t base = (size_t)row * K;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int k = lane + 32 * i;
+      x[i] = k < K ? __fmaf_rn(-step, dvb[(size_t)b * K + k], v[base + k]) : 0.0f;
+    }
+    project_row<EPL>(x, K, lane, mode, radius, sorted_all[warp]);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) v[base + k] = x[i];
+    }
+  }
+}
+
 __global__ void atom_scale_finalize_kernel(const float* __restrict__ partial, int nslabs, int K, int mode,
                                            float* __restrict__ scale /*[K]: divisor*/) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -446,6 +519,61 @@ extern "C" int adil_dict_step(float* D2, float* m, float* s, const float* dD2, l
   adamw_elem_kernel<true><<<elem_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(
       D2, m, s, dD2, n, make_adamw(hp), atoms_mode == ADIL_ATOMS_CLAMP1 ? 1.0f : 0.0f);
   return check_cuda(cudaGetLastError(), "adamw_elem_kernel launch");
+}
+
+extern "C" int adil_dict_step_atoms(float* D2, float* m, float* s, const float* dD2, int P, int K, const adil_adamw_t* hp,
+                                    float step, int atoms_mode, void* scratch, void* stream) {
+  if (!D2 || !dD2 || (hp && (!m || !s))) return set_error(-1, "adil_dict_step_atoms: null pointer");
+  if (K < 1 || K > ADIL_MAX_ATOMS || P < 1) return set_error(-1, "adil_dict_step_atoms: bad shape P=%d K=%d", P, K);
+  if (atoms_mode < ADIL_ATOMS_NONE || atoms_mode > ADIL_ATOMS_L2SPHERE)
+    return set_error(-1, "adil_dict_step_atoms: unsupported atoms_mode %d", atoms_mode);
+  const bool l2 = atoms_mode == ADIL_ATOMS_L2BALL || atoms_mode == ADIL_ATOMS_L2SPHERE;
+  if (l2 && !scratch) return set_error(-1, "adil_dict_step_atoms: scratch required for l2 modes");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = l2 ? (float*)scratch : nullptr;
+  const int per = 256 / K;
+  int grid = (P + per - 1) / per;
+  if (grid > kNormCtas) grid = kNormCtas;
+  AdamwDev dev;
+  memset(&dev, 0, sizeof(dev));
+  if (hp) {
+    dev = make_adamw(hp);
+    dict_update_sumsq_kernel<true><<<grid, 256, 256 * sizeof(float), st>>>(D2, m, s, dD2, P, K, dev, 0.0f, partial);
+  } else {
+    dict_update_sumsq_kernel<false><<<grid, 256, 256 * sizeof(float), st>>>(D2, nullptr, nullptr, dD2, P, K, dev, step, partial);
+  }
+  int rc = check_cuda(cudaGetLastError(), "dict_update_sumsq_kernel launch");
+  if (rc) return rc;
+  const long long n = (long long)P * K;
+  if (atoms_mode == ADIL_ATOMS_CLAMP1) {
+    clamp1_kernel<<<elem_grid(n), 256, 0, st>>>(D2, n);
+    return check_cuda(cudaGetLastError(), "clamp1_kernel launch");
+  }
+  if (!l2) return 0;
+  float* scale = partial + (size_t)kNormCtas * K;
+  atom_scale_finalize_kernel<<<(K + 127) / 128, 128, 0, st>>>(partial, grid, K, atoms_mode, scale);
+  rc = check_cuda(cudaGetLastError(), "atom_scale_finalize_kernel launch");
+  if (rc) return rc;
+  atom_scale_kernel<<<elem_grid(n), 256, 0, st>>>(D2, n, K, scale);
+  return check_cuda(cudaGetLastError(), "atom_scale_kernel launch");
+}
+
+extern "C" int adil_code_prox_step(float* v, const float* dvb, const int64_t* v_index, int B, int N, int K, float step,
+                                   int rows_mode, float radius, void* stream) {
+  if (!v || !dvb) return set_error(-1, "adil_code_prox_step: null pointer");
+  if (K < 1 || K > ADIL_MAX_ATOMS) return set_error(-1, "adil_code_prox_step: K=%d out of range [1,%d]", K, ADIL_MAX_ATOMS);
+  if (rows_mode < ADIL_ROWS_NONE || rows_mode > ADIL_ROWS_SOFTSHRINK)
+    return set_error(-1, "adil_code_prox_step: bad rows_mode %d", rows_mode);
+  if (B <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (B + 7) / 8;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (K <= 32) code_prox_kernel<1><<<grid, 256, 0, st>>>(v, dvb, v_index, B, N, K, step, rows_mode, radius);
+  else if (K <= 64) code_prox_kernel<2><<<grid, 256, 0, st>>>(v, dvb, v_index, B, N, K, step, rows_mode, radius);
+  else if (K <= 128) code_prox_kernel<4><<<grid, 256, 0, st>>>(v, dvb, v_index, B, N, K, step, rows_mode, radius);
+  else code_prox_kernel<8><<<grid, 256, 0, st>>>(v, dvb, v_index, B, N, K, step, rows_mode, radius);
+  return check_cuda(cudaGetLastError(), "code_prox_kernel launch");
 }
 
 extern "C" int adil_adamw_clamp(float* p, float* m, float* s, const float* grad, long long n, const adil_adamw_t* hp,

@@ -235,7 +235,7 @@ def _host_index_retry(call, v_index, dev):
     return rc
 
 
-def _grad_call(dD2, dvb, g, D2, v, v_index, B, P, K, std, flags, dev):
+def _grad_call(dD2, dvb, g, D2, v, v_index, B, P, K, std, flags, dev, delta=None, l2_coef=0.0):
     """One adil_grad call (B within the per-call limit).  Returns nslabs (KEEP_PARTIALS) or 0."""
     C = len(std) if std is not None else 1
     scratch, nbytes = _grad_scratch(dev, B, K)
@@ -244,15 +244,18 @@ def _grad_call(dD2, dvb, g, D2, v, v_index, B, P, K, std, flags, dev):
     with _Timed("adil_grad", dev, 1 if (flags & GRAD_KEEP_PARTIALS or dvb is None) else 2):
         rc = _host_index_retry(
             lambda ix: _lib.lib().adil_grad(_ptr(dD2), _ptr(dvb), _ptr(g), _ptr(D2), _ptr(v), _ptr(ix), B, P, K, C,
-                                            P // C, _host3(std, C), int(flags), ctypes.byref(nslabs), _ptr(scratch),
-                                            nbytes, _stream(dev)), v_index, dev)
+                                            P // C, _host3(std, C), _ptr(delta), float(l2_coef), int(flags),
+                                            ctypes.byref(nslabs), _ptr(scratch), nbytes, _stream(dev)), v_index, dev)
     _lib.check(rc, "adil_grad")
     return scratch, nslabs.value
 
 
 def grad(g, D2, v, v_index=None, std=None, want_dD=True, want_dv=True, dD2=None, dvb=None, accumulate=False,
-         keep_partials=False):
+         keep_partials=False, delta=None, l2_coef=0.0):
     """Backward contractions (adil.py:185): returns (dD2 [P,K] or None, dvb [B,K] or None).
+
+    delta, l2_coef: l2 penalty 0.5 * l2_coef * ||D v||^2 of the regularised variants (adil_regularized.py:112-114):
+    `delta` [B,P] is the synthesised perturbation (synth's delta_out); the contractions then run on gx + l2_coef * delta.
 
     accumulate: dD2 += instead of dD2 = .  keep_partials: the second result is a `CodePartials` handle for
     `code_step` instead of the reduced dvb (one launch fewer).  Minibatches beyond the per-call limit of the kernels
@@ -274,7 +277,16 @@ def grad(g, D2, v, v_index=None, std=None, want_dD=True, want_dv=True, dD2=None,
     if want_dD:
         _f32(dD2, "dD2")
     C = len(std) if std is not None else 1
-    bmax = grad_max_batch(P, K, P // C, False)
+    penalised = delta is not None and l2_coef != 0.0
+    if penalised:
+        delta = _f32(delta, "delta")
+        if delta.numel() != B * P:
+            raise ValueError("delta has %d elements, expected B*P = %d" % (delta.numel(), B * P))
+        delta = delta.view(B, P)
+        bmax = min(grad_max_batch(P, K, P // C, False), int(_lib.lib().adil_grad_max_batch(int(P), int(K), int(P // C), -1)))
+    else:
+        delta = None
+        bmax = grad_max_batch(P, K, P // C, False)
     if bmax < 1:
         raise RuntimeError("grad: shape P=%d K=%d is not supported by the selected kernel family" % (P, K))
     g2 = g.view(B, P)
@@ -283,7 +295,7 @@ def grad(g, D2, v, v_index=None, std=None, want_dD=True, want_dv=True, dD2=None,
             dvb = torch.empty((B, K), dtype=torch.float32, device=dev)
         flags = (GRAD_ACCUMULATE_DD if accumulate else 0) | (GRAD_KEEP_PARTIALS if (want_dv and keep_partials) else 0)
         scratch, nslabs = _grad_call(dD2 if want_dD else None, dvb if (want_dv and not keep_partials) else None, g2,
-                                     D2, v, v_index, B, P, K, std, flags, dev)
+                                     D2, v, v_index, B, P, K, std, flags, dev, delta, l2_coef)
         second = None
         if want_dv:
             second = CodePartials(scratch, nslabs, B, K) if keep_partials else dvb
@@ -299,7 +311,7 @@ def grad(g, D2, v, v_index=None, std=None, want_dD=True, want_dv=True, dD2=None,
             vi, ix = v[b0:b1], None
         flags = GRAD_ACCUMULATE_DD if (want_dD and (accumulate or i > 0)) else 0
         _grad_call(dD2 if want_dD else None, dvb[b0:b1] if want_dv else None, g2[b0:b1], D2, vi, ix, b1 - b0, P, K, std,
-                   flags, dev)
+                   flags, dev, delta[b0:b1] if penalised else None, l2_coef)
     return (dD2 if want_dD else None), (dvb if want_dv else None)
 
 
@@ -358,6 +370,41 @@ def dict_step(D2, m, s, dD2, hp, atoms_mode=ATOMS_CLAMP1):
         rc = _lib.lib().adil_dict_step(_ptr(D2), _ptr(m), _ptr(s), _ptr(dD2), n, ctypes.byref(hp), int(atoms_mode),
                                        _stream(D2.device))
     _lib.check(rc, "adil_dict_step")
+
+
+def dict_step_atoms(D2, dD2, atoms_mode, hp=None, m=None, s=None, step=0.0):
+    """Dictionary step with any per-atom projection (adil_regularized.py:27-28,141-146,283-285): AdamW (hp, m, s) or,
+    with hp None, the plain gradient step D2 -= step * dD2; then NONE / CLAMP1 / L2BALL / L2SPHERE over the atoms."""
+    D2, dD2 = _f32(D2, "D2"), _f32(dD2, "dD2")
+    K = D2.shape[-1]
+    P = D2.numel() // K
+    if dD2.numel() != D2.numel():
+        raise ValueError("dict_step_atoms: size mismatch")
+    if hp is not None:
+        m, s = _f32(m, "m"), _f32(s, "s")
+    nbytes = _lib.lib().adil_project_atoms_scratch_bytes(K)
+    scratch = _get_scratch(D2.device, nbytes, "atoms")
+    with _Timed("adil_dict_step_atoms", D2.device, 3):
+        rc = _lib.lib().adil_dict_step_atoms(_ptr(D2), _ptr(m) if hp is not None else None,
+                                             _ptr(s) if hp is not None else None, _ptr(dD2), P, K,
+                                             ctypes.byref(hp) if hp is not None else None, float(step), int(atoms_mode),
+                                             _ptr(scratch), _stream(D2.device))
+    _lib.check(rc, "adil_dict_step_atoms")
+    return D2
+
+
+def code_prox_step(v, dvb, v_index, step, rows_mode=ROWS_SOFTSHRINK, radius=0.0):
+    """v[v_index] = prox(v[v_index] - step * dvb) on the rows of one minibatch (adil_regularized.py:304,414-416)."""
+    v, dvb = _f32(v, "v"), _f32(dvb, "dvb")
+    N, K = v.shape
+    v_index = _idx(v_index, "v_index", v.device)
+    B = dvb.shape[0]
+    if v_index is not None and v_index.numel() != B:
+        raise ValueError("code_prox_step: v_index has %d entries, dvb %d rows" % (v_index.numel(), B))
+    rc = _lib.lib().adil_code_prox_step(_ptr(v), _ptr(dvb), _ptr(v_index), B, N, K, float(step), int(rows_mode),
+                                        float(radius), _stream(v.device))
+    _lib.check(rc, "adil_code_prox_step")
+    return v
 
 
 def code_step(v, m, s, dvb, v_index, hp, rows_mode=ROWS_L1BALL, radius=0.0):

@@ -44,6 +44,14 @@ def get_prox_l1(param):
     return _SoftShrink(param)
 
 
+def get_target(img, label, targeted, classifier):
+    """Second most probable class of the clean image (targeted) or the given label (utils.py:164-174)."""
+    with torch.no_grad():
+        if targeted:
+            return classifier(img).sort().indices[:, -2]
+        return label
+
+
 class QuickAttackDataset(torch.utils.data.Dataset):
     """utils.py:177-186."""
 

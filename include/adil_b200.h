@@ -111,13 +111,16 @@ size_t adil_grad_scratch_bytes(int B, int K);
  *     dvb[b,k] = sum_p gx[b,p] * D2[p,k]                  (skipped when dvb == NULL and KEEP_PARTIALS is not set)
  * g: [B,P] gradient w.r.t. the classifier input.  dvb: [B,K] in batch order (the caller scatters by v_index).
  * flags: ADIL_GRAD_*.  nslabs_out (host int, may be NULL): number of partial slabs left in scratch (KEEP_PARTIALS).
- * B is limited per call (adil_grad_max_batch); larger minibatches are passed in chunks with ACCUMULATE_DD. */
+ * B is limited per call (adil_grad_max_batch); larger minibatches are passed in chunks with ACCUMULATE_DD.
+ * delta / l2_coef: the l2 penalty 0.5 * l2_coef * ||D v||^2 of the regularised variants (adil_regularized.py:112-114,
+ * 273-274): with delta = the synthesised perturbation [B,P] (adil_synth's delta_out) the contractions run on
+ * gx + l2_coef * delta.  delta == NULL or l2_coef == 0: no penalty.  (The penalised form runs on the CUDA-core kernels.) */
 int adil_grad(float* dD2, float* dvb, const float* g, const float* D2, const float* v, const int64_t* v_index, int B,
-              int P, int K, int C, int hw, const float* std_host, int flags, int* nslabs_out, void* scratch,
-              size_t scratch_bytes, void* stream);
+              int P, int K, int C, int hw, const float* std_host, const float* delta, float l2_coef, int flags,
+              int* nslabs_out, void* scratch, size_t scratch_bytes, void* stream);
 
 /* Largest B one adil_grad / adil_grad_dict_step call accepts for this shape with the current kernel family
- * (tcgen05 path: 128 images per pass; FMA path: bounded by shared memory). */
+ * (tcgen05 path: 128 images per pass; FMA path: bounded by shared memory; fused < 0: the FMA path's limit). */
 int adil_grad_max_batch(int P, int K, int hw, int fused);
 
 /* Single-GPU fusion of adil_grad with the dictionary AdamW step and projection (adil.py:185-188 for D):
@@ -133,6 +136,21 @@ int adil_grad_dict_step(float* D2, float* m, float* s, float* dvb, const float* 
  * multi-GPU runs.  atoms_mode: ADIL_ATOMS_NONE or ADIL_ATOMS_CLAMP1. */
 int adil_dict_step(float* D2, float* m, float* s, const float* dD2, long long n, const adil_adamw_t* hp,
                    int atoms_mode, void* stream);
+
+/* Dictionary step with any per-atom projection (the regularised variants: adil_regularized.py:23-28,141-146,283-285,
+ * 467-469 -- `d = d - step * grad_d ; d = constraint_dict(d)`):
+ *     hp != NULL: AdamW update with these hyper-parameters;  hp == NULL: plain gradient step D2 -= step * dD2
+ *     then atoms_mode: NONE, CLAMP1, L2BALL, L2SPHERE (column norms over all P rows: two passes, fixed summation order)
+ * D2, dD2 (and m, s with AdamW): [P,K].  scratch: adil_project_atoms_scratch_bytes(K) bytes. */
+int adil_dict_step_atoms(float* D2, float* m, float* s, const float* dD2, int P, int K, const adil_adamw_t* hp, float step,
+                         int atoms_mode, void* scratch, void* stream);
+
+/* Proximal gradient step on the code rows of ONE minibatch (adil_regularized.py:304, 414-416, 570-573):
+ *     v[v_index[b], :] = prox(v[v_index[b], :] - step * dvb[b, :])
+ * rows_mode / radius as adil_project_rows (SOFTSHRINK with radius = step * lambda is the l1 prox).  Rows outside the
+ * batch are untouched; a row named twice takes the update of its last slot. */
+int adil_code_prox_step(float* v, const float* dvb, const int64_t* v_index, int B, int N, int K, float step,
+                        int rows_mode, float radius, void* stream);
 
 /* Code AdamW step over ALL N rows (dense gradient, zero outside the batch -- adil.py:154,186) fused with the
  * scatter of dvb by v_index (duplicates accumulate, like index_put_(accumulate=True)) and the row projection

@@ -525,3 +525,79 @@ def tiny_classifier(seed=0, n_classes=10, width=8):
         for p in net.parameters():
             p.copy_(torch.randn(p.shape, generator=g) * (0.5 if p.dim() > 1 else 0.1))
     return torch.nn.Sequential(Normalize(), net).eval()
+
+
+# ------------------------------------------------------------------------------------------------
+# regularised variant (attacks/attacks_classes/adil_regularized.py): SADiL, the stochastic forward-backward scheme
+# ------------------------------------------------------------------------------------------------
+def get_target(model, x, y, targeted):
+    """utils.py:164-174: second most probable class of the clean image (targeted) or the given label."""
+    with torch.no_grad():
+        if targeted:
+            return model(x).sort().indices[:, -2]
+        return y
+
+
+def penalised_grad(model, x, D2, vb, target, coeff, l2_fool):
+    """Gradients of coeff * CE_sum(model(x + D vb), target) + 0.5 * l2_fool * ||D vb||^2 w.r.t. D2 and vb
+    (adil_regularized.py:273-279,291-297): gx = d CE / d(x + dv) + l2_fool * dv ; dD2 = gx^T vb ; dvb = gx D2."""
+    n, P = x.shape[0], D2.shape[0]
+    dv = vb @ D2.t()
+    xin = (x.reshape(n, P) + dv).reshape(x.shape).detach().requires_grad_(True)
+    loss = coeff * torch.nn.functional.cross_entropy(model(xin), target, reduction='sum')
+    (g,) = torch.autograd.grad(loss, xin)
+    gx = g.reshape(n, P) + l2_fool * dv
+    return gx.t() @ vb, gx @ D2, float(loss) + 0.5 * l2_fool * float((dv ** 2).sum())
+
+
+def sadil_loss(model, loader, slices, D2, v, coeff, l2_fool, lambda_coding, targeted):
+    """loss_all of adil_regularized.py:245-254 (loss-only pass over the whole set)."""
+    total = 0.0
+    with torch.no_grad():
+        for i, (x, y) in enumerate(loader):
+            n = x.shape[0]
+            dv = v[slices[i]] @ D2.t()
+            out = model((x.reshape(n, -1) + dv).reshape(x.shape))
+            total += (coeff * torch.nn.functional.cross_entropy(out, get_target(model, x, y, targeted), reduction='sum')
+                      + 0.5 * l2_fool * torch.sum(dv ** 2)).item()
+    return total + (lambda_coding * torch.sum(torch.abs(v))).item()
+
+
+def sadil(model, dataset, targeted=True, nepochs=10, batchsize=1, lambda_coding=1., l2_fool=1., stepsize=1., n_atom=5,
+          dict_set='l2ball', D0=None):
+    """SADiL, adil_regularized.py:200-312: per minibatch a gradient step on D followed by the per-atom projection
+    (constraint_dict), then -- with the new D -- a proximal gradient step (soft threshold stepsize * lambda) on the
+    code rows of the batch.  Returns (D [C,H,W,K], v [N,K], loss list)."""
+    nimg = len(dataset)
+    x0, _ = next(iter(dataset))
+    nc, nx, ny = x0.shape
+    P = nc * nx * ny
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False)
+    coeff = 1. if targeted else -1.
+    slices = [list(range(i, min(i + batchsize, nimg))) for i in range(0, nimg, batchsize)]   # utils.py:153-156
+    mode = {'l2ball': ATOMS_L2BALL, 'l2sphere': ATOMS_L2SPHERE}.get(dict_set, ATOMS_L1BALL)
+    D = project_atoms(torch.randn(3, nx, ny, n_atom), mode) if D0 is None else D0.clone()
+    D2 = D.reshape(P, n_atom).clone()
+    v = torch.zeros(nimg, n_atom)
+    # Reference behaviour (adil_regularized.py:287-304): `v` becomes a leaf that requires grad at the first V-step and
+    # its `.grad` is never zeroed, so every later backward -- the D-step's (v takes part in D v) and the V-step's --
+    # ACCUMULATES into it; the V-step then uses the accumulated rows `grad_v[ind]`.
+    gv_acc = torch.zeros(nimg, n_atom)
+    v_has_grad = False
+    loss = [sadil_loss(model, loader, slices, D2, v, coeff, l2_fool, lambda_coding, targeted)]
+    for _ in range(int(nepochs)):
+        for i, (x, y) in enumerate(loader):
+            ind = slices[i]
+            target = get_target(model, x, y, targeted)
+            dD2, dvb, _ = penalised_grad(model, x, D2, v[ind], target, coeff, l2_fool)        # D-step
+            if v_has_grad:
+                gv_acc[ind] += dvb
+            D2 = project_atoms((D2 - stepsize * dD2).reshape(nc, nx, ny, n_atom), mode).reshape(P, n_atom)
+            _, dvb, _ = penalised_grad(model, x, D2, v[ind], target, coeff, l2_fool)          # V-step, new D
+            v_has_grad = True
+            gv_acc[ind] += dvb
+            v[ind] = softshrink(v[ind] - stepsize * gv_acc[ind], stepsize * lambda_coding)
+        loss.append(sadil_loss(model, loader, slices, D2, v, coeff, l2_fool, lambda_coding, targeted))
+        if abs(loss[-1] - loss[-2]) < 1e-6:
+            break
+    return D2.reshape(nc, nx, ny, n_atom), v, loss

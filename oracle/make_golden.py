@@ -39,6 +39,19 @@ def tiny_data():
     return xtr, ytr, xva, yva
 
 
+class QuickDataset(torch.utils.data.Dataset):
+    """(x, y) pairs, like the reference's QuickAttackDataset (utils.py:177-186)."""
+
+    def __init__(self, images, labels):
+        self.images, self.labels = images, labels
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, item):
+        return self.images[item], self.labels[item]
+
+
 def main():
     torch.set_num_threads(1)
     ref = ref_shim.load_reference()
@@ -179,6 +192,26 @@ def main():
         out["sample_sphere_l2"] = atk_a.sample_sphere(5).numpy()
     finally:
         os.chdir(cwd)
+
+    # ---- regularised variant: SADiL through the reference's own function (adil_regularized.py:200-312) ---------------
+    import importlib
+    reg = importlib.import_module("attacks.attacks_classes.adil_regularized")
+    tmp2 = tempfile.mkdtemp()
+    for tag, kw in (("sadil_untargeted", dict(targeted=False, batchsize=4, lambdaCoding=0.01, l2_fool=0.5, stepsize=0.05,
+                                               n_atom=K, dict_set='l2ball')),
+                    ("sadil_targeted", dict(targeted=True, batchsize=3, lambdaCoding=0.02, l2_fool=2.0, stepsize=0.02,
+                                            n_atom=5, dict_set='l2sphere'))):
+        torch.manual_seed(4321)
+        state = torch.get_rng_state()
+        D0 = ru.constraint_dict(torch.randn(3, H, W, kw["n_atom"]), constr_set=kw["dict_set"])   # the draw sadil makes
+        torch.set_rng_state(state)
+        Dr, vr, _ = reg.sadil(QuickDataset(xtr, ytr), model, nepochs=3, device=torch.device("cpu"),
+                              model_file=os.path.join(tmp2, tag + ".bin"), **kw)
+        _, loss_r = torch.load(os.path.join(tmp2, tag + ".bin"), weights_only=False)
+        out[tag + "_D0"] = D0.numpy()
+        out[tag + "_D"] = Dr.detach().numpy()
+        out[tag + "_v"] = vr.detach().numpy()
+        out[tag + "_loss"] = np.asarray(loss_r, dtype=np.float64)
 
     out["meta_torch_version"] = np.asarray(torch.__version__)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

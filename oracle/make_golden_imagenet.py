@@ -41,7 +41,7 @@ CASES = {
     "cfg1": ("resnet18", 32, 10, 32, 20),
     "fr_resnet18": ("resnet18", 200, 10, 100, 26),
     "fr_vgg11": ("vgg11", 200, 10, 100, 8),
-    "fr_densenet121": ("densenet121", 200, 10, 100, 12),
+    "fr_densenet121": ("densenet121", 200, 10, 100, 10),
 }
 
 

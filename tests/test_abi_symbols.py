@@ -61,12 +61,16 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc < 0 and b"multiple of 4" in lib.adil_last_error()
     rc = lib.adil_synth(one, None, None, None, one, one, None, 4, 12, 300, 1, 12, None, None, 0.0, 0, None)
     assert rc < 0 and b"ADIL_MAX_ATOMS" in lib.adil_last_error()
-    rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, 0, None, None, 0, None)
+    rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, None, 0.0, 0, None, None, 0, None)
     assert rc < 0 and b"nothing to compute" in lib.adil_last_error()
-    rc = lib.adil_grad(one, None, one, one, one, None, 4, 12, 3, 1, 12, None, 64, None, None, 0, None)
+    rc = lib.adil_grad(one, None, one, one, one, None, 4, 12, 3, 1, 12, None, None, 0.0, 64, None, None, 0, None)
     assert rc < 0 and b"unknown flags" in lib.adil_last_error()
-    rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, 2, None, None, 0, None)
+    rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, None, 0.0, 2, None, None, 0, None)
     assert rc < 0 and b"nslabs_out" in lib.adil_last_error()
+    rc = lib.adil_dict_step_atoms(one, None, None, one, 12, 3, None, 0.1, 4, None, None)
+    assert rc < 0 and b"unsupported atoms_mode" in lib.adil_last_error()
+    rc = lib.adil_code_prox_step(one, one, None, 4, 8, 3, 0.1, 9, 0.1, None)
+    assert rc < 0 and b"bad rows_mode" in lib.adil_last_error()
     rc = lib.adil_code_step(one, one, one, one, None, 4, 8, 3, ctypes.byref(_lib.AdamwParams(0.01, 0.9, 0.999, 1e-8, 0.01, 1)),
                             1, 0.1, one, 3, None)
     assert rc < 0 and b"partial slabs exclude dvb" in lib.adil_last_error()

@@ -352,3 +352,28 @@ def test_validation_coder_stops_where_the_reference_stops(monkeypatch):
     assert torch.equal(adv.cpu(), xva.clamp(0, 1))
     ref = O.coder_adamw(O.tiny_classifier(seed=0), xva, torch.zeros(C, H, W, K), EPS, mode='eval')
     assert torch.equal(adv.cpu(), ref)
+
+
+# ---- regularised variant: SADiL on the kernels -----------------------------------------------
+@pytest.mark.parametrize("tag,kw", [
+    ("sadil_untargeted", dict(targeted=False, batchsize=4, lambdaCoding=0.01, l2_fool=0.5, stepsize=0.05, n_atom=6,
+                              dict_set='l2ball')),
+    ("sadil_targeted", dict(targeted=True, batchsize=3, lambdaCoding=0.02, l2_fool=2.0, stepsize=0.02, n_atom=5,
+                            dict_set='l2sphere'))])
+def test_sadil_on_the_kernels_matches_the_reference(golden, tag, kw):
+    """dl_attack_on_imagenet_b200.adil_regularized.sadil -- l2-penalised backward contractions, gradient step +
+    per-atom l2 projection of D, soft-threshold proximal step on the batch codes, loss-only passes -- against the
+    output of the reference's own sadil() on the same data, initial dictionary and hyper-parameters."""
+    from dl_attack_on_imagenet_b200.adil_regularized import sadil
+    from dl_attack_on_imagenet_b200.utils import QuickAttackDataset
+    model = O.tiny_classifier(seed=0).cuda()
+    xtr, ytr, _, _ = tiny_data()
+    D, v, loss = sadil(QuickAttackDataset(xtr, ytr), model, nepochs=3, dictionary=torch.from_numpy(golden[tag + "_D0"]),
+                       model_file="sadil_%s.bin" % tag, **kw)
+    assert (D.cpu() - torch.from_numpy(golden[tag + "_D"])).abs().max() <= 1e-5
+    assert (v.cpu() - torch.from_numpy(golden[tag + "_v"])).abs().max() <= 1e-5
+    assert np.allclose(loss, golden[tag + "_loss"], rtol=2e-6, atol=1e-5)
+    Df, lf = torch.load("sadil_%s.bin" % tag, weights_only=True)
+    assert torch.equal(Df, D) and lf == loss
+    norms = D.flatten(0, 2).norm(dim=0)
+    assert (norms <= 1 + 1e-5).all() if kw["dict_set"] == 'l2ball' else (norms - 1).abs().max() <= 1e-5

@@ -392,7 +392,8 @@ def test_host_index_arrays_need_the_tensor_core_path(ops):
         out = torch.empty(8, 37, device="cuda")
         rc = _lib.lib().adil_grad(None, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(gd.data_ptr()),
                                   ctypes.c_void_p(Dd.data_ptr()), ctypes.c_void_p(vd.data_ptr()),
-                                  ctypes.c_void_p(host_idx.data_ptr()), 8, 300, 37, 1, 300, None, 0, None, None, 0, None)
+                                  ctypes.c_void_p(host_idx.data_ptr()), 8, 300, 37, 1, 300, None, None, 0.0, 0, None, None, 0,
+                                  None)
         assert rc == -4 and b"host index" in _lib.lib().adil_last_error()
     finally:
         ops.set_impl(ops.IMPL_AUTO)
@@ -602,3 +603,68 @@ def test_fused_step_at_the_benchmarked_size(ops, K, steps):
     part_b = ops.grad_dict_step(D2b, mb, sb, g, v, idx, ops.adamw_params(steps[-1], 0.01), STD, ops.ATOMS_CLAMP1,
                                 keep_partials=True)
     assert torch.equal(D2b, D2) and torch.equal(mb, m) and torch.equal(part_b.reduce(), dvb)
+
+
+# ---- primitives of the regularised variants (adil_regularized.py) -----------------------------
+@pytest.mark.parametrize("B,hw,K", [(4, 64, 6), (100, 784, 50), (33, 400, 64), (16, 256, 200), (150, 100, 37)])
+def test_l2_penalised_contractions(ops, B, hw, K):
+    """adil_grad with (delta, l2_coef): contractions of g / std + l2_coef * delta (adil_regularized.py:112-114)."""
+    D2, v, x, idx, g = make_problem(B, hw, K, seed=21)
+    vb = v[idx]
+    delta = vb @ D2.t()
+    l2 = 0.7
+    C = 3
+    gx = g.double() / O.channel_vec(STD, C, hw, torch.float64) + l2 * delta.double()
+    ref_dD, ref_dv = gx.t() @ vb.double(), gx @ D2.double()
+    _, dl = ops.synth(dev(D2), dev(v), idx, delta_out=torch.empty(B, 3 * hw, device="cuda"), want_out=False)
+    assert (dl.cpu() - delta).abs().max() <= 1e-7
+    dD, dvb = ops.grad(dev(g), dev(D2), dev(v), idx, STD, delta=dl, l2_coef=l2)
+    assert (dD.cpu().double() - ref_dD).abs().max() <= 1e-5 * ref_dD.abs().max()
+    assert (dvb.cpu().double() - ref_dv).abs().max() <= 1e-5 * ref_dv.abs().max()
+    dD0, dv0 = ops.grad(dev(g), dev(D2), dev(v), idx, STD, delta=dl, l2_coef=0.0)       # coefficient 0: no penalty
+    dD1, dv1 = ops.grad(dev(g), dev(D2), dev(v), idx, STD)
+    assert (dD0 - dD1).abs().max() <= 1e-5 * dD1.abs().max() and (dv0 - dv1).abs().max() <= 1e-5 * dv1.abs().max()
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 8, 6), (3, 28, 28, 50), (3, 16, 16, 200), (1, 4, 4, 1)])
+def test_dict_step_with_per_atom_projection(ops, shape):
+    """adil_dict_step_atoms: plain gradient step or AdamW, then NONE / CLAMP1 / L2BALL / L2SPHERE
+    (adil_regularized.py:283-285: D = constraint_dict(D - stepsize * grad_D))."""
+    gen = torch.Generator().manual_seed(22)
+    D = torch.randn(*shape, generator=gen) * 0.3
+    dD = torch.randn(*shape, generator=gen) * 0.1
+    K = shape[-1]
+    for mode, omode in ((ops.ATOMS_L2BALL, O.ATOMS_L2BALL), (ops.ATOMS_L2SPHERE, O.ATOMS_L2SPHERE),
+                        (ops.ATOMS_CLAMP1, O.ATOMS_CLAMP1), (ops.ATOMS_NONE, O.ATOMS_NONE)):
+        ref = O.project_atoms(D - 0.5 * dD, omode)
+        got = ops.dict_step_atoms(dev(D).view(-1, K), dev(dD).view(-1, K), mode, step=0.5).cpu().view(shape)
+        assert (got - ref).abs().max() <= 2e-6, mode
+        # AdamW + per-atom projection
+        p, m, s = D.clone().view(-1, K), torch.zeros(D.numel() // K, K), torch.zeros(D.numel() // K, K)
+        O.adamw_step_(p, dD.view(-1, K), m, s, 1, 0.01)
+        ref2 = O.project_atoms(p.view(shape), omode)
+        Dd, md, sd = dev(D).view(-1, K), dev(torch.zeros_like(m)), dev(torch.zeros_like(s))
+        ops.dict_step_atoms(Dd, dev(dD).view(-1, K), mode, hp=ops.adamw_params(1, 0.01), m=md, s=sd)
+        assert (Dd.cpu().view(shape) - ref2).abs().max() <= 2e-6, mode
+        assert (md.cpu() - m).abs().max() <= 1e-6 * m.abs().max()
+    a = ops.dict_step_atoms(dev(D).view(-1, K), dev(dD).view(-1, K), ops.ATOMS_L2BALL, step=0.5)
+    b = ops.dict_step_atoms(dev(D).view(-1, K), dev(dD).view(-1, K), ops.ATOMS_L2BALL, step=0.5)
+    assert torch.equal(a, b)                                       # fixed summation order of the column norms
+
+
+@pytest.mark.parametrize("N,K,B", [(10, 6, 4), (64, 50, 16), (40, 200, 40), (300, 10, 100)])
+def test_code_prox_step(ops, N, K, B):
+    """adil_code_prox_step: v[idx] = softshrink(v[idx] - step * dvb, step * lambda) on the batch rows only
+    (adil_regularized.py:304); the other row projections as modes."""
+    gen = torch.Generator().manual_seed(23)
+    v = torch.randn(N, K, generator=gen) * 0.05
+    idx = torch.randperm(N, generator=gen)[:B]
+    dvb = torch.randn(B, K, generator=gen) * 0.1
+    for mode, radius in ((ops.ROWS_SOFTSHRINK, 0.02), (ops.ROWS_L1BALL, EPS), (ops.ROWS_L2BALL, 0.1), (ops.ROWS_NONE, 0.0)):
+        ref = v.clone()
+        ref[idx] = O.project_rows(v[idx] - 0.3 * dvb, mode, radius)
+        got = ops.code_prox_step(dev(v), dev(dvb), dev(idx), 0.3, mode, radius).cpu()
+        assert (got - ref).abs().max() <= 2e-7, mode
+        out = torch.ones(N, dtype=torch.bool)
+        out[idx] = False
+        assert torch.equal(got[out], v[out])
