@@ -483,7 +483,7 @@ class ADIL(Attack):
             raise RuntimeError("begin_fit(distributed=True) needs an initialised torch.distributed process group")
         st0 = self._init_state(n_img, nc, nx, ny, warm_start)
         dist.broadcast(st0.D, 0)
-        shard = dsh.ShardedDictStep(nc * nx * ny, self.n_atoms, self.device)
+        shard = dsh.make_dict_step(nc * nx * ny, self.n_atoms, self.device)
         self.state = AdilState(st0.D, st0.v, shard=shard)
         return self.state
 
@@ -596,7 +596,7 @@ class ADIL(Attack):
         v_full = st_full.v if rank == 0 else torch.empty(n_img, self.n_atoms, device=self.device)
         dist.broadcast(D, 0)
         dist.broadcast(v_full, 0)
-        st = AdilState(D, v_full[lo:hi].clone(), shard=dsh.ShardedDictStep(P, self.n_atoms, self.device))
+        st = AdilState(D, v_full[lo:hi].clone(), shard=dsh.make_dict_step(P, self.n_atoms, self.device))
         self.state = st
         del v_full, st_full, D
         with torch.no_grad():

@@ -58,6 +58,55 @@ __global__ void __launch_bounds__(256) adamw_elem_kernel(float* __restrict__ p, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused reduce-scatter + AdamW (+ clamp) + all-gather over peer-mapped memory: one pass, 128-bit accesses.  Per float4 of
+// this rank's slice: `world` peer loads of the gradient (all in flight together, added in rank order), the local D / m /
+// s, one AdamW update, `world` stores of the new dictionary values (the local copy included) and the local m / s.
+// NVLink traffic per rank and step: (world-1)/world * 4PK bytes in, the same out -- what reduce-scatter + all-gather
+// move -- with the optimizer pass riding on the same kernel.
+// ---------------------------------------------------------------------------------------------
+struct PeerPtrs {
+  const float* dD[ADIL_MAX_PEERS];
+  float* D[ADIL_MAX_PEERS];
+};
+
+template <int WORLD>
+__global__ void __launch_bounds__(256) dict_step_peer_kernel(const PeerPtrs pp, float* __restrict__ m, float* __restrict__ s,
+                                                             long long begin, long long n4, int rank, int world,
+                                                             AdamwDev hp, float bound) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int nw = WORLD > 0 ? WORLD : world;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const size_t off = (size_t)begin + 4 * (size_t)i;
+    float4 gq[WORLD > 0 ? WORLD : ADIL_MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < (WORLD > 0 ? WORLD : ADIL_MAX_PEERS); ++q)
+      if (q < nw) gq[q] = ld_global4(pp.dD[q] + off);        // (not .nc: written by other GPUs since the last launch)
+    float4 pv = ld_global4(pp.D[rank] + off);
+    float4 mv = reinterpret_cast<const float4*>(m)[i];
+    float4 sv = reinterpret_cast<const float4*>(s)[i];
+    float4 g = gq[0];
+#pragma unroll
+    for (int q = 1; q < (WORLD > 0 ? WORLD : ADIL_MAX_PEERS); ++q)
+      if (q < nw) { g.x += gq[q].x; g.y += gq[q].y; g.z += gq[q].z; g.w += gq[q].w; }
+    adamw_update_fast(pv.x, mv.x, sv.x, g.x, hp);
+    adamw_update_fast(pv.y, mv.y, sv.y, g.y, hp);
+    adamw_update_fast(pv.z, mv.z, sv.z, g.z, hp);
+    adamw_update_fast(pv.w, mv.w, sv.w, g.w, hp);
+    if (bound > 0.0f) {
+      pv.x = fminf(fmaxf(pv.x, -bound), bound);
+      pv.y = fminf(fmaxf(pv.y, -bound), bound);
+      pv.z = fminf(fmaxf(pv.z, -bound), bound);
+      pv.w = fminf(fmaxf(pv.w, -bound), bound);
+    }
+#pragma unroll
+    for (int q = 0; q < (WORLD > 0 ? WORLD : ADIL_MAX_PEERS); ++q)
+      if (q < nw) st_stream4(pp.D[q] + off, pv);
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(s)[i] = sv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // row projections: one warp per row, EPL elements per lane (k = lane + 32*i), K <= 32*EPL
 // ---------------------------------------------------------------------------------------------
 template <int EPL>
@@ -574,6 +623,41 @@ extern "C" int adil_code_prox_step(float* v, const float* dvb, const int64_t* v_
   else if (K <= 128) code_prox_kernel<4><<<grid, 256, 0, st>>>(v, dvb, v_index, B, N, K, step, rows_mode, radius);
   else code_prox_kernel<8><<<grid, 256, 0, st>>>(v, dvb, v_index, B, N, K, step, rows_mode, radius);
   return check_cuda(cudaGetLastError(), "code_prox_kernel launch");
+}
+
+extern "C" int adil_dict_step_peer(const void* const* D_peers, const void* const* dD_peers, float* m, float* s,
+                                   long long slice_begin, long long slice_elems, int rank, int world,
+                                   const adil_adamw_t* hp, int atoms_mode, void* stream) {
+  if (!D_peers || !dD_peers || !m || !s || !hp) return set_error(-1, "adil_dict_step_peer: null pointer");
+  if (world < 1 || world > ADIL_MAX_PEERS || rank < 0 || rank >= world)
+    return set_error(-1, "adil_dict_step_peer: bad rank %d / world %d (max %d)", rank, world, ADIL_MAX_PEERS);
+  if (atoms_mode != ADIL_ATOMS_NONE && atoms_mode != ADIL_ATOMS_CLAMP1)
+    return set_error(-1, "adil_dict_step_peer: atoms_mode %d cannot be fused", atoms_mode);
+  if (slice_begin < 0 || slice_elems < 0 || (slice_begin & 3) || (slice_elems & 3))
+    return set_error(-1, "adil_dict_step_peer: slice [%lld, +%lld) must be multiples of 4 elements", slice_begin, slice_elems);
+  if (slice_elems == 0) return 0;
+  PeerPtrs pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int q = 0; q < world; ++q) {
+    if (!D_peers[q] || !dD_peers[q]) return set_error(-1, "adil_dict_step_peer: null peer pointer for rank %d", q);
+    if ((((uintptr_t)D_peers[q] | (uintptr_t)dD_peers[q]) & 15) != 0)
+      return set_error(-1, "adil_dict_step_peer: peer buffers must be 16-byte aligned");
+    pp.D[q] = (float*)D_peers[q];
+    pp.dD[q] = (const float*)dD_peers[q];
+  }
+  if ((((uintptr_t)m | (uintptr_t)s) & 15) != 0) return set_error(-1, "adil_dict_step_peer: m/s must be 16-byte aligned");
+  const long long n4 = slice_elems >> 2;
+  const AdamwDev dev = make_adamw(hp);
+  const float bound = atoms_mode == ADIL_ATOMS_CLAMP1 ? 1.0f : 0.0f;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = elem_grid(n4);
+  switch (world) {
+    case 2: dict_step_peer_kernel<2><<<grid, 256, 0, st>>>(pp, m, s, slice_begin, n4, rank, world, dev, bound); break;
+    case 4: dict_step_peer_kernel<4><<<grid, 256, 0, st>>>(pp, m, s, slice_begin, n4, rank, world, dev, bound); break;
+    case 8: dict_step_peer_kernel<8><<<grid, 256, 0, st>>>(pp, m, s, slice_begin, n4, rank, world, dev, bound); break;
+    default: dict_step_peer_kernel<0><<<grid, 256, 0, st>>>(pp, m, s, slice_begin, n4, rank, world, dev, bound); break;
+  }
+  return check_cuda(cudaGetLastError(), "dict_step_peer_kernel launch");
 }
 
 extern "C" int adil_adamw_clamp(float* p, float* m, float* s, const float* grad, long long n, const adil_adamw_t* hp,

@@ -172,3 +172,79 @@ class ShardedDictStep(object):
         if self._done is not None:
             torch.cuda.current_stream(self.device).wait_event(self._done)
             self._done = None
+
+
+class PeerDictStep(ShardedDictStep):
+    """The same sharded dictionary step as ONE kernel over peer-mapped memory (adil_dict_step_peer): the dictionary and
+    the gradient buffers are allocated as torch symmetric memory (every rank's buffer mapped into every process over
+    NVLink / NVSwitch), and per step
+
+        cross-rank barrier           every rank's adil_grad has written its dD buffer
+        adil_dict_step_peer          peer loads of the R gradient slices, AdamW + clamp, peer stores of the new slice
+        cross-rank barrier           every rank's stores have landed before D is read again
+
+    replace reduce-scatter -> slice step -> all-gather (three launches through NCCL, two staging passes).  PyTorch only
+    provides the mapping and the barrier; the data movement is the kernel's own loads and stores."""
+
+    def __init__(self, P, K, device, group=None, side_stream=True):
+        super().__init__(P, K, device, group=group, step_fn=None, side_stream=side_stream)
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.pg = group if group is not None else self.dist.group.WORLD
+        self._handles = {}
+        self._bufs = []
+
+    def alloc(self):
+        t = self.symm_mem.empty(self.rows_total * self.K, dtype=torch.float32, device=self.device)
+        hdl = self.symm_mem.rendezvous(t, self.pg)
+        t.zero_()
+        self._handles[t.data_ptr()] = hdl
+        self._bufs.append(t)
+        return t.view(self.rows_total, self.K)
+
+    def step(self, D_full, dD_full, hp, atoms_mode):
+        from . import ops
+        hD, hG = self._handles[D_full.data_ptr()], self._handles[dD_full.data_ptr()]
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            ctx = torch.cuda.stream(self.stream)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            hG.barrier(channel=0, timeout_ms=20000)   # (bounded: a protocol bug traps instead of hanging the GPU)
+            self.t += 1
+            ops.dict_step_peer(list(hD.buffer_ptrs), list(hG.buffer_ptrs), self.m, self.s, self.lo * self.K,
+                               self.rows * self.K, self.rank, hp, atoms_mode, device=self.device)
+            hD.barrier(channel=1, timeout_ms=20000)
+            if self.stream is not None:
+                self._done = torch.cuda.Event()
+                self._done.record(self.stream)
+
+
+def make_dict_step(P, K, device, group=None, mode=None):
+    """The sharded dictionary step for this process group: the fused peer-memory kernel when symmetric memory can be
+    set up on every rank (NCCL group, CUDA device, world > 1; ADIL_DICT_STEP=nccl forces the NCCL path), else
+    reduce-scatter / slice step / all-gather through NCCL.  Collective: every rank must call it."""
+    import os
+    import torch.distributed as dist
+    mode = mode or os.environ.get("ADIL_DICT_STEP", "auto")
+    world = dist.get_world_size(group)
+    dev = torch.device(device)
+    if mode != "nccl" and world > 1 and dev.type == 'cuda' and dist.get_backend(group) == 'nccl':
+        step, ok = None, 1
+        try:
+            step = PeerDictStep(P, K, dev, group=group)
+            probe = step.alloc()                              # symmetric allocation + rendezvous work on this rank
+            step._handles.pop(probe.data_ptr(), None)
+            step._bufs.clear()
+            del probe
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # all ranks take the same path
+        if int(flag.item()) == 1:
+            return step
+        if mode == "peer":
+            raise RuntimeError("ADIL_DICT_STEP=peer: symmetric memory could not be set up on every rank")
+    return ShardedDictStep(P, K, dev, group=group)

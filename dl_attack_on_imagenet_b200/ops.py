@@ -393,6 +393,22 @@ def dict_step_atoms(D2, dD2, atoms_mode, hp=None, m=None, s=None, step=0.0):
     return D2
 
 
+def dict_step_peer(D_ptrs, dD_ptrs, m, s, slice_begin, slice_elems, rank, hp, atoms_mode=ATOMS_CLAMP1, device=None):
+    """Fused reduce-scatter + AdamW + clamp + all-gather over peer-mapped buffers (adil_dict_step_peer).  D_ptrs / dD_ptrs:
+    device pointers (ints) of every rank's padded dictionary / gradient buffer as mapped into this process."""
+    m, s = _f32(m, "m"), _f32(s, "s")
+    world = len(D_ptrs)
+    if len(dD_ptrs) != world:
+        raise ValueError("dict_step_peer: %d dictionary pointers, %d gradient pointers" % (world, len(dD_ptrs)))
+    arr_D = (ctypes.c_void_p * world)(*[int(p) for p in D_ptrs])
+    arr_g = (ctypes.c_void_p * world)(*[int(p) for p in dD_ptrs])
+    dev = m.device if device is None else device
+    with _Timed("adil_dict_step_peer", dev):
+        rc = _lib.lib().adil_dict_step_peer(arr_D, arr_g, _ptr(m), _ptr(s), int(slice_begin), int(slice_elems), int(rank),
+                                            world, ctypes.byref(hp), int(atoms_mode), _stream(dev))
+    _lib.check(rc, "adil_dict_step_peer")
+
+
 def code_prox_step(v, dvb, v_index, step, rows_mode=ROWS_SOFTSHRINK, radius=0.0):
     """v[v_index] = prox(v[v_index] - step * dvb) on the rows of one minibatch (adil_regularized.py:304,414-416)."""
     v, dvb = _f32(v, "v"), _f32(dvb, "dvb")

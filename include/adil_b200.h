@@ -152,6 +152,22 @@ int adil_dict_step_atoms(float* D2, float* m, float* s, const float* dD2, int P,
 int adil_code_prox_step(float* v, const float* dvb, const int64_t* v_index, int B, int N, int K, float step,
                         int rows_mode, float radius, void* stream);
 
+/* The dictionary side of one multi-GPU minibatch step as ONE kernel over peer-mapped memory (NVLink 5 / NVSwitch P2P;
+ * the intent of the reference's DDP variant, adil.py:379-383):
+ *     slice gradient = sum over ranks q of dD_peers[q][slice]           peer loads, summed in rank order
+ *     AdamW + projection on this rank's slice of the dictionary          moments m, s exist for the slice only
+ *     the new slice is stored into D_peers[q][slice] for every rank q    peer stores
+ * i.e. reduce-scatter + optimizer step + all-gather without a collective library call or a staging buffer.
+ * D_peers / dD_peers: HOST arrays of `world` device pointers to every rank's [rows_total, K] dictionary / gradient
+ * buffer, mapped into this process (e.g. torch symmetric memory); entry `rank` is the local buffer.  The slice is
+ * elements [slice_begin, slice_begin + slice_elems) of those buffers (multiples of 4).  The caller places the launch
+ * between two cross-rank barriers on `stream`: every rank's gradient complete before, every rank's stores landed
+ * before the dictionary is read again.  atoms_mode: ADIL_ATOMS_NONE or ADIL_ATOMS_CLAMP1.  world <= ADIL_MAX_PEERS. */
+#define ADIL_MAX_PEERS 16
+int adil_dict_step_peer(const void* const* D_peers, const void* const* dD_peers, float* m, float* s,
+                        long long slice_begin, long long slice_elems, int rank, int world, const adil_adamw_t* hp,
+                        int atoms_mode, void* stream);
+
 /* Code AdamW step over ALL N rows (dense gradient, zero outside the batch -- adil.py:154,186) fused with the
  * scatter of dvb by v_index (duplicates accumulate, like index_put_(accumulate=True)) and the row projection
  * (adil.py:187 update_v).  v, m, s: [N,K]; dvb: [B,K] (NULL: zero gradient).

@@ -48,7 +48,7 @@ def project_rows_l1(v, radius):
     j = torch.arange(1, k + 1, device=x.device)
     ok = (mu * j > (csum - radius))                                    # utils.py:37
     rho = (ok * j).max(dim=1).values                                   # largest j with ok (>=1 when the row is outside)
-    theta = (csum[torch.arange(n), rho - 1] - radius) / rho            # utils.py:38 (rho==0 -> index -1, value unused)
+    theta = (csum[torch.arange(n, device=x.device), rho - 1] - radius) / rho   # utils.py:38 (rho==0 -> index -1, value unused)
     proj = (a - theta.unsqueeze(1)).clamp(min=0) * torch.sign(x)       # utils.py:39-40
     m = inside.float().unsqueeze(1)
     out = m * x + (1 - m) * proj                                       # utils.py:40 (arithmetic blend, keeps NaN semantics)
@@ -201,7 +201,7 @@ def dict_step_(st, dD2, lr, atoms_mode=ATOMS_CLAMP1, wd=1e-2):
 def code_step_(st, dvb, v_index, lr, radius, rows_mode=ROWS_L1BALL, wd=1e-2):
     """AdamW on ALL rows of v (dense grad, zero outside the batch: adil.py:154,186) then row projection."""
     gV = torch.zeros_like(st.v)
-    gV.index_put_((torch.as_tensor(v_index, dtype=torch.long),), dvb, accumulate=True)
+    gV.index_put_((torch.as_tensor(v_index, dtype=torch.long).to(st.v.device),), dvb, accumulate=True)
     st.tv += 1
     adamw_step_(st.v, gV, st.mv, st.sv, st.tv, lr, wd=wd)
     st.v.copy_(project_rows(st.v, rows_mode, radius))

@@ -119,6 +119,7 @@ def main():
               worst["D_frac_gt_1e-6"] <= 1e-3 and worst["replicas_gap"] == 0.0)
         report["pass"] = bool(ok)
         report["optimizer_state_rows_per_rank"] = int(st.shard.rows)
+        report["dict_step_backend"] = type(st.shard).__name__
 
     # ---- timing: pieces of the sharded step and the collectives at the BASELINE payloads -----------------------------
     def timed(fn, iters=20, warm=5):
@@ -166,16 +167,48 @@ def main():
             ar()
             ops.dict_step(Df, mf, sf, full, hp, ops.ATOMS_CLAMP1)
 
-        times["K=%d (%.1f MB)" % (Kc, nbytes / 1e6)] = {
+        entry = {
             "reduce_scatter_us": timed(rs), "all_gather_us": timed(ag), "all_reduce_us": timed(ar),
             "sharded_step_us (rs + slice AdamW + ag)": timed(sharded),
             "replicated_step_us (all-reduce + full AdamW)": timed(replicated)}
+        if isinstance(st.shard, dsh.PeerDictStep):
+            peer = dsh.PeerDictStep(P, Kc, dev, side_stream=False)
+            Dp, Gp = peer.alloc(), peer.alloc()
+            Dp.uniform_(-1, 1)
+            Gp.normal_()
+
+            def fused():
+                peer.step(Dp, Gp, hp, ops.ATOMS_CLAMP1)
+            entry["peer_step_us (barrier + one fused kernel over NVLink + barrier)"] = timed(fused)
+            hD, hG = peer._handles[Dp.data_ptr()], peer._handles[Gp.data_ptr()]
+
+            def kernel_only():
+                ops.dict_step_peer(list(hD.buffer_ptrs), list(hG.buffer_ptrs), peer.m, peer.s, peer.lo * Kc, peer.rows * Kc,
+                                   rank, hp, ops.ATOMS_CLAMP1, device=dev)
+            entry["peer_kernel_only_us"] = timed(kernel_only)
+            # the fused kernel against the NCCL chain on the same inputs: same sum, same AdamW
+            Dn = Dp.clone()
+            mn, sn = torch.zeros(rows, Kc, device=dev), torch.zeros(rows, Kc, device=dev)
+            peer.m.zero_(); peer.s.zero_()
+            Gn = Gp.clone()
+            dist.barrier()
+            peer.step(Dp, Gp, hp, ops.ATOMS_CLAMP1)
+            dist.reduce_scatter_tensor(sl, Gn, op=dist.ReduceOp.SUM)
+            ops.dict_step(Dn[lo_r:lo_r + rows], mn, sn, sl, hp, ops.ATOMS_CLAMP1)
+            dist.all_gather_into_tensor(Dn, Dn[lo_r:lo_r + rows])
+            torch.cuda.synchronize()
+            entry["peer_vs_nccl_m_rel"] = ((peer.m - mn).abs().max() / mn.abs().max()).item()
+            entry["peer_vs_nccl_D_frac_gt_1e-6"] = ((Dp - Dn).abs() > 1e-6).float().mean().item()
+            del peer, Dp, Gp, Dn, Gn
+        times["K=%d (%.1f MB)" % (Kc, nbytes / 1e6)] = entry
         del full, sl, Df, ms_, ss_, mf, sf
     if rank == 0:
         report["collective_times_max_over_ranks"] = times
-        with open(os.path.join(ROOT, "gpurun_out", "dist_parity_r02_w%d.json" % world), "w") as f:
+        tag = os.environ.get("ADIL_DICT_STEP", "auto")
+        with open(os.path.join(ROOT, "gpurun_out", "dist_parity_r02_w%d_%s.json" % (world, tag)), "w") as f:
             json.dump(report, f, indent=1)
-        print(json.dumps({"pass": report["pass"], "worst": report["worst"], "times": times}, indent=1))
+        print(json.dumps({"backend": report["dict_step_backend"], "pass": report["pass"], "worst": report["worst"],
+                          "times": times}, indent=1))
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
