@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kThreads) grad_fma_kernel(const GradArgs a) {
 // in flight together), then the 32 partial sums are combined in warp order -- the summation tree depends only on
 // nslabs, so results are bit-reproducible.
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(float* __restrict__ dvb, const float* __restrict__ partial,
-                                                               int n, int nslabs) {
+                                                               int n, int nslabs, int K, int ld_out) {
   __shared__ float part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(float* __restrict
     float t = part[0][lane];
 #pragma unroll
     for (int w = 1; w < 32; ++w) t += part[w][lane];
-    dvb[e] = t;
+    dvb[ld_out == K ? (size_t)e : (size_t)(e / K) * ld_out + (e % K)] = t;  // (rows of a wider [B, ld_out] array)
   }
 }
 
@@ -493,7 +493,7 @@ int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
 
 }  // namespace
 
-int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, cudaStream_t st) {
+int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, int K, int ld_out, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((n + 31) / 32));
   cfg.blockDim = dim3(1024);
@@ -504,7 +504,8 @@ int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, dvb, partial, n, nslabs), "reduce_partials_kernel launch");
+  return check_cuda(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, dvb, partial, n, nslabs, K, ld_out),
+                    "reduce_partials_kernel launch");
 }
 
 int launch_synth_fma(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
@@ -592,7 +593,7 @@ int launch_grad_fma(float* dD2, float* D2_rw, float* m, float* s, float* dvb, co
       if (opt.nslabs_out) *opt.nslabs_out = grid;
       return 0;
     }
-    return launch_reduce_partials(dvb, scratch, B * K, grid, st);
+    return launch_reduce_partials(dvb, scratch, B * K, grid, K, K, st);
   }
   return 0;
 }

@@ -40,7 +40,7 @@
 
 namespace adil {
 
-int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, cudaStream_t st);
+int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, int K, int ld_out, cudaStream_t st);
 
 namespace {
 
@@ -786,6 +786,9 @@ struct GradArgs {
   unsigned gdiv;      // ceil(2^32 / ceil(K / 8)): 8-atom groups of the G_SCALED dictionary split
   uint32_t tmem_cols;
   int want_dD, want_dv, atoms_mode;
+  int ldk;            // row pitch (floats) of D2 / m / s / dD2 / v in global memory: K, or the full atom count when this
+                      // launch handles a window of K columns of a wider dictionary (STRIDED: more than 128 atoms)
+  unsigned k4div;     // ceil(2^32 / (K / 4)) (STRIDED: float4 index inside a dense tile -> row)
   int accumulate;     // plain dD output: dD2 += tile (TMA reduce-add store) instead of dD2 = tile
   int early;          // host indices: code loads at kernel entry, bulk loads right after the set-up barrier
   ChannelConsts cc;
@@ -794,7 +797,11 @@ struct GradArgs {
 
 // FUSED (AdamW + clamp in the epilogue warps) is a template parameter: the two variants get their own register
 // allocation -- at the 72-register cap of 896 threads the epilogue code of the one perturbed the other's spills.
-template <int TP, bool FUSED>
+// STRIDED: this launch handles a window of K columns of a dictionary whose rows are `ldk` floats apart (more than 128
+// atoms: two column windows, two launches).  Tiles are dense [TP][K] in shared memory as always; only the global
+// addresses change: the D rows of a tile arrive as one bulk copy PER ROW (issued by the 32 lanes of the loader warp),
+// the moments / outputs are addressed by (row, column) instead of a flat offset.
+template <int TP, bool FUSED, bool STRIDED>
 __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a) {
   constexpr int Q4 = TP / 4;                           // float4 per gradient row
   constexpr int GJ = (128 * Q4 + NT - 1) / NT;         // float4 per worker thread (B <= 128)
@@ -850,26 +857,42 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
   for (int b = tid; b < 128; b += NTHREADS_GRAD)  // element offset of the code row of image b (rows >= B: row of image B-1)
     vrow_s[b] = (a.hv_on ? (long long)a.hv[min(b, B - 1)] : a.vidx ? (long long)a.vidx[min(b, B - 1)] : (long long)min(b, B - 1)) *
-                (long long)K;
+                (long long)a.ldk;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // global element offset of float4 `e4` of the dense tile that starts at pixel p0
+  auto goff = [&](int p0, int e4) -> size_t {
+    if constexpr (STRIDED) {
+      const int r = div_magic_dev(e4, a.k4div);
+      return (size_t)(p0 + r) * (size_t)a.ldk + 4 * (size_t)(e4 - r * (K >> 2));
+    } else {
+      return (size_t)p0 * K + 4 * (size_t)e4;
+    }
+  };
   // tensor memory: [0, 2 TP) two dD^T accumulators | [2 TP, 2 TP + Kp) dv accumulator | then the codes, 3 x Bp/2 columns
   const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
   const uint32_t codes = acc_dv + (uint32_t)a.Kp;
 
   // D tile `it` -> raw stage it % NS: a contiguous run, one TMA bulk copy (the stages are never zero-filled: a ragged
   // last tile is handled by the consumers).
-  auto load_raw = [&](int it) {
+  auto load_raw = [&](int it, bool leader) {  // (called by the whole loader warp)
     const int p0 = (blockIdx.x + it * gridDim.x) * TP;
     const int rows = min(TP, P - p0);
     const int s = it % NS;
     const uint32_t bytes = (uint32_t)(rows * K * 4);
     float* dst = raw + s * a.raw_floats;
-    const size_t off = (size_t)p0 * K;
-    mbar_expect_tx(full_raw + s, bytes);
-    bulk_g2s(dst, a.D2 + off, bytes, full_raw + s);
+    if constexpr (STRIDED) {
+      if (leader) mbar_expect_tx(full_raw + s, bytes);
+      __syncwarp();
+      for (int r = lane; r < rows; r += 32)
+        bulk_g2s(dst + r * K, a.D2 + (size_t)(p0 + r) * (size_t)a.ldk, (uint32_t)(K * 4), full_raw + s);
+    } else if (leader) {
+      mbar_expect_tx(full_raw + s, bytes);
+      bulk_g2s(dst, a.D2 + (size_t)p0 * K, bytes, full_raw + s);
+    }
+    __syncwarp();
   };
   // workers: fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q.
   // The rows of tile 0 are requested before the batch codes (both are on the critical path of the first tile).
@@ -944,16 +967,28 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     // the stage is reused when the copy engine has read it. =====
     const bool leader = elect_one();
     const bool dD_out = a.want_dD && !fused;
-    if (a.nraw > 0 && leader)
-      for (int it = 0; it < NS && it < my_tiles; ++it) load_raw(it);
-    __syncwarp();
+    if (a.nraw > 0)
+      for (int it = 0; it < NS && it < my_tiles; ++it) load_raw(it, leader);
     for (int it = NS; it < my_tiles + NS; ++it) {
       const int jt = it - NS;  // the tile whose stage is recycled now
       {
         const int sj = jt % NS;
         if (dD_out) {
           mbar_wait(epi_done + sj, (jt / NS) & 1);
-          if (leader) {
+          if constexpr (STRIDED) {
+            const int p0 = (blockIdx.x + jt * gridDim.x) * TP;
+            const int rows = min(TP, P - p0);
+            for (int r = lane; r < rows; r += 32) {  // one bulk store per row of the column window
+              float* gd = a.dD2 + (size_t)(p0 + r) * (size_t)a.ldk;
+              const float* sr = raw + sj * a.raw_floats + r * K;
+              if (a.accumulate) bulk_red_add_s2g(gd, sr, (uint32_t)(K * 4));
+              else bulk_s2g(gd, sr, (uint32_t)(K * 4));
+            }
+            bulk_commit();
+            if (it < my_tiles) bulk_wait_read0();  // the stage is about to be refilled
+            __syncwarp();
+            if (leader && it < my_tiles && a.nraw == 0) mbar_arrive(full_raw + sj);
+          } else if (leader) {
             const int p0 = (blockIdx.x + jt * gridDim.x) * TP;
             if (a.accumulate) bulk_red_add_s2g(a.dD2 + (size_t)p0 * K, raw + sj * a.raw_floats, (uint32_t)(min(TP, P - p0) * K * 4));
             else bulk_s2g(a.dD2 + (size_t)p0 * K, raw + sj * a.raw_floats, (uint32_t)(min(TP, P - p0) * K * 4));
@@ -967,12 +1002,9 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         }
         if ((a.want_dv || fused) && it < my_tiles) mbar_wait(empty_raw + sj, (jt / NS) & 1);  // D rows consumed
       }
-      if (it < my_tiles && a.nraw > 0) {
-        if (leader) load_raw(it);
-        __syncwarp();
-      }
+      if (it < my_tiles && a.nraw > 0) load_raw(it, leader);
     }
-    if (leader && dD_out) bulk_wait0();  // every output tile has been written before the CTA retires
+    if ((STRIDED || leader) && dD_out) bulk_wait0();  // every output tile has been written before the CTA retires
     __syncwarp();
   } else if (warp == WARP_MMA_G) {
     // ===== issuer =====
@@ -1061,13 +1093,13 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       auto prefetch_ms = [&](int j) {
         const int p0 = (blockIdx.x + j * gridDim.x) * TP;
         const int n4 = (min(TP, P - p0) * K) >> 2;
-        const size_t base = (size_t)p0 * K;
 #pragma unroll
         for (int u = 0; u < NPF; ++u) {
           const int e4 = etid + u * (NE * 32);
           if (e4 < n4) {
-            Mp[u] = ld_global4(a.m + base + 4 * (size_t)e4);
-            Sp[u] = ld_global4(a.s + base + 4 * (size_t)e4);
+            const size_t go = goff(p0, e4);
+            Mp[u] = ld_global4(a.m + go);
+            Sp[u] = ld_global4(a.s + go);
           }
         }
       };
@@ -1135,7 +1167,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           bar_sync(3, NE * 32);  // gradient tile complete (and every warp is done with the tile two steps back)
           mbar_wait(full_raw + sj, (j / NS) & 1);  // D rows landed
           const int n4 = (rows * K) >> 2;
-          const size_t base = (size_t)p0 * K;
 #ifndef ADIL_EXP_NO_EPI
 #pragma unroll
           for (int u = 0; u < NPF; ++u) {
@@ -1150,15 +1181,17 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
               if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
                 Dv.x = clamp1(Dv.x); Dv.y = clamp1(Dv.y); Dv.z = clamp1(Dv.z); Dv.w = clamp1(Dv.w);
               }
-              *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv;
-              *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mp[u];
-              *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sp[u];
+              const size_t go = goff(p0, e4);
+              *reinterpret_cast<float4*>(a.D2w + go) = Dv;
+              *reinterpret_cast<float4*>(a.m + go) = Mp[u];
+              *reinterpret_cast<float4*>(a.s + go) = Sp[u];
             }
           }
           for (int e4 = etid + NPF * (NE * 32); e4 < n4; e4 += NE * 32) {  // (large K: beyond the prefetched part)
             float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
-            float4 Mv = ld_global4(a.m + base + 4 * (size_t)e4);
-            float4 Sv = ld_global4(a.s + base + 4 * (size_t)e4);
+            const size_t go = goff(p0, e4);
+            float4 Mv = ld_global4(a.m + go);
+            float4 Sv = ld_global4(a.s + go);
             const float4 gd = *reinterpret_cast<const float4*>(gtile + 4 * e4);
             adamw_update_fast(Dv.x, Mv.x, Sv.x, gd.x, a.hp);
             adamw_update_fast(Dv.y, Mv.y, Sv.y, gd.y, a.hp);
@@ -1167,9 +1200,9 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
             if (a.atoms_mode == ADIL_ATOMS_CLAMP1) {
               Dv.x = clamp1(Dv.x); Dv.y = clamp1(Dv.y); Dv.z = clamp1(Dv.z); Dv.w = clamp1(Dv.w);
             }
-            *reinterpret_cast<float4*>(a.D2w + base + 4 * (size_t)e4) = Dv;
-            *reinterpret_cast<float4*>(a.m + base + 4 * (size_t)e4) = Mv;
-            *reinterpret_cast<float4*>(a.s + base + 4 * (size_t)e4) = Sv;
+            *reinterpret_cast<float4*>(a.D2w + go) = Dv;
+            *reinterpret_cast<float4*>(a.m + go) = Mv;
+            *reinterpret_cast<float4*>(a.s + go) = Sv;
           }
 #endif
           __syncwarp();
@@ -1516,9 +1549,6 @@ int launch_synth_tp(const SynthArgs& a, size_t smem, int grid, cudaStream_t st) 
 }  // namespace
 
 bool tc_synth_ok(int B, int P, int K, int hw) { return plan_synth(B > 128 ? 128 : B, P, K, hw).ok; }
-bool tc_grad_ok(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool fused) {
-  return plan_grad(B, P, K, hw, want_dD, want_dv, fused).ok;
-}
 
 int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
@@ -1601,23 +1631,60 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
 }
 
 namespace {
-template <int TP, bool FUSED>
+template <int TP, bool FUSED, bool STRIDED>
 int launch_grad_tpf(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
-  int rc = set_smem(grad_kernel<TP, FUSED>, smem, "cudaFuncSetAttribute(grad_kernel)");
+  int rc = set_smem(grad_kernel<TP, FUSED, STRIDED>, smem, "cudaFuncSetAttribute(grad_kernel)");
   if (rc) return rc;
-  grad_kernel<TP, FUSED><<<grid, NTHREADS_GRAD, smem, st>>>(a);
+  grad_kernel<TP, FUSED, STRIDED><<<grid, NTHREADS_GRAD, smem, st>>>(a);
   return check_cuda(cudaGetLastError(), "grad_kernel launch");
 }
 template <int TP>
 int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
-  return a.D2w != nullptr ? launch_grad_tpf<TP, true>(a, smem, grid, st) : launch_grad_tpf<TP, false>(a, smem, grid, st);
+  if (a.ldk != a.K)
+    return a.D2w != nullptr ? launch_grad_tpf<TP, true, true>(a, smem, grid, st) : launch_grad_tpf<TP, false, true>(a, smem, grid, st);
+  return a.D2w != nullptr ? launch_grad_tpf<TP, true, false>(a, smem, grid, st) : launch_grad_tpf<TP, false, false>(a, smem, grid, st);
 }
+
+// One launch over a window of K columns (K <= 128) of arrays whose rows are ldk floats apart; dvb rows are dv_ld apart.
+int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
+                       const float* v, const int64_t* v_index, int B, int P, int K, int ldk, int dv_ld,
+                       const ChannelConsts& cc, const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes,
+                       const GradOpts& opt, cudaStream_t st);
 }  // namespace
+
+bool tc_grad_ok(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool fused) {
+  if (K <= 128) return plan_grad(B, P, K, hw, want_dD, want_dv, fused).ok;
+  // more than 128 atoms: two column windows of K/2 atoms (row pitch and window offsets must keep 16-byte alignment)
+  if (K > 256 || K % 8 != 0) return false;
+  return plan_grad(B, P, K / 2, hw, want_dD, want_dv, fused).ok;
+}
 
 int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, const GradOpts& opt,
                    cudaStream_t st) {
+  if (K <= 128)
+    return launch_grad_window(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, K, K, cc, hp, atoms_mode, scratch,
+                              scratch_bytes, opt, st);
+  if (opt.keep_partials)
+    return set_error(-5, "adil_grad: ADIL_GRAD_KEEP_PARTIALS is limited to K <= 128 on the tcgen05 path (K=%d runs as two "
+                     "column windows): pass dvb", K);
+  const int Kh = K / 2;
+  for (int h = 0; h < 2; ++h) {  // each window reads g once more: 4BP extra bytes against 4P(B+6K) of the step
+    const int k0 = h * Kh;
+    int rc = launch_grad_window(dD2 ? dD2 + k0 : nullptr, D2_rw ? D2_rw + k0 : nullptr, m ? m + k0 : nullptr,
+                                s ? s + k0 : nullptr, dvb ? dvb + k0 : nullptr, g, D2 + k0, v + k0, v_index, B, P, Kh, K,
+                                K, cc, hp, atoms_mode, scratch, scratch_bytes, opt, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+namespace {
+int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
+                       const float* v, const int64_t* v_index, int B, int P, int K, int ldk, int dv_ld,
+                       const ChannelConsts& cc, const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes,
+                       const GradOpts& opt, cudaStream_t st) {
   const bool want_dD = dD2 != nullptr || D2_rw != nullptr, want_dv = dvb != nullptr || opt.keep_partials != 0,
              fused = D2_rw != nullptr;
   if (!want_dD && !want_dv) return 0;
@@ -1635,6 +1702,7 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
   a.B = B; a.P = P; a.K = K; a.Bp = pl.Bp; a.Kp = pl.Kp; a.Sg = pl.Sg; a.Sd = pl.Sd;
   a.dimg = pl.dimg; a.gimg = pl.gimg; a.raw_floats = pl.raw_floats; a.nraw = pl.nraw;
   a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.gdiv = div_magic((K + 7) / 8); a.tmem_cols = pl.tmem_cols;
+  a.ldk = ldk; a.k4div = div_magic(K >> 2 > 0 ? K >> 2 : 1);
   a.want_dD = want_dD ? 1 : 0; a.want_dv = want_dv ? 1 : 0; a.atoms_mode = atoms_mode; a.cc = cc;
   a.accumulate = (opt.accumulate && !fused) ? 1 : 0;
   static const int early_knob = getenv("ADIL_GRAD_EARLY") ? atoi(getenv("ADIL_GRAD_EARLY")) : 1;  // tuning knob
@@ -1679,9 +1747,10 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
       if (opt.nslabs_out) *opt.nslabs_out = grid;
       return 0;
     }
-    return launch_reduce_partials(dvb, scratch, B * K, grid, st);
+    return launch_reduce_partials(dvb, scratch, B * K, grid, K, dv_ld, st);
   }
   return 0;
 }
+}  // namespace
 
 }  // namespace adil

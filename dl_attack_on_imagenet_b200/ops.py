@@ -270,6 +270,7 @@ def grad(g, D2, v, v_index=None, std=None, want_dD=True, want_dv=True, dD2=None,
     B = v_index.numel() if v_index is not None else v.shape[0]
     if g.numel() != B * P:
         raise ValueError("g has %d elements, expected B*P = %d" % (g.numel(), B * P))
+    keep_partials = keep_partials and K <= 128       # (more than 128 atoms run as two column windows: reduced dvb only)
     if accumulate and (dD2 is None or not want_dD):
         raise ValueError("grad: accumulate needs an existing dD2")
     if want_dD and dD2 is None:
@@ -333,6 +334,7 @@ def grad_dict_step(D2, m, s, g, v, v_index, hp, std=None, atoms_mode=ATOMS_CLAMP
     if g.numel() != B * P:
         raise ValueError("g has %d elements, expected B*P = %d" % (g.numel(), B * P))
     C = len(std) if std is not None else 1
+    keep_partials = keep_partials and K <= 128       # (more than 128 atoms run as two column windows: reduced dvb only)
     bmax = grad_max_batch(P, K, P // C, True)
     if bmax < 1:
         raise RuntimeError("grad_dict_step: shape P=%d K=%d is not supported by the selected kernel family" % (P, K))
