@@ -73,36 +73,51 @@ template <int WORLD>
 __global__ void __launch_bounds__(256) dict_step_peer_kernel(const PeerPtrs pp, float* __restrict__ m, float* __restrict__ s,
                                                              long long begin, long long n4, int rank, int world,
                                                              AdamwDev hp, float bound) {
+  constexpr int NQ = WORLD > 0 ? WORLD : ADIL_MAX_PEERS;
+  constexpr int U = WORLD > 0 && WORLD <= 4 ? 2 : 1;  // float4 items per thread in flight (NVLink round trips are long)
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int nw = WORLD > 0 ? WORLD : world;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const size_t off = (size_t)begin + 4 * (size_t)i;
-    float4 gq[WORLD > 0 ? WORLD : ADIL_MAX_PEERS];
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+    float4 gq[U][NQ], pv[U], mv[U], sv[U];
 #pragma unroll
-    for (int q = 0; q < (WORLD > 0 ? WORLD : ADIL_MAX_PEERS); ++q)
-      if (q < nw) gq[q] = ld_global4(pp.dD[q] + off);        // (not .nc: written by other GPUs since the last launch)
-    float4 pv = ld_global4(pp.D[rank] + off);
-    float4 mv = reinterpret_cast<const float4*>(m)[i];
-    float4 sv = reinterpret_cast<const float4*>(s)[i];
-    float4 g = gq[0];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        const size_t off = (size_t)begin + 4 * (size_t)i;
 #pragma unroll
-    for (int q = 1; q < (WORLD > 0 ? WORLD : ADIL_MAX_PEERS); ++q)
-      if (q < nw) { g.x += gq[q].x; g.y += gq[q].y; g.z += gq[q].z; g.w += gq[q].w; }
-    adamw_update_fast(pv.x, mv.x, sv.x, g.x, hp);
-    adamw_update_fast(pv.y, mv.y, sv.y, g.y, hp);
-    adamw_update_fast(pv.z, mv.z, sv.z, g.z, hp);
-    adamw_update_fast(pv.w, mv.w, sv.w, g.w, hp);
-    if (bound > 0.0f) {
-      pv.x = fminf(fmaxf(pv.x, -bound), bound);
-      pv.y = fminf(fmaxf(pv.y, -bound), bound);
-      pv.z = fminf(fmaxf(pv.z, -bound), bound);
-      pv.w = fminf(fmaxf(pv.w, -bound), bound);
+        for (int q = 0; q < NQ; ++q)
+          if (q < nw) gq[u][q] = ld_global4(pp.dD[q] + off);   // (not .nc: written by other GPUs since the last launch)
+        pv[u] = ld_global4(pp.D[rank] + off);
+        mv[u] = reinterpret_cast<const float4*>(m)[i];
+        sv[u] = reinterpret_cast<const float4*>(s)[i];
+      }
     }
 #pragma unroll
-    for (int q = 0; q < (WORLD > 0 ? WORLD : ADIL_MAX_PEERS); ++q)
-      if (q < nw) st_stream4(pp.D[q] + off, pv);
-    reinterpret_cast<float4*>(m)[i] = mv;
-    reinterpret_cast<float4*>(s)[i] = sv;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        const size_t off = (size_t)begin + 4 * (size_t)i;
+        float4 g = gq[u][0];
+#pragma unroll
+        for (int q = 1; q < NQ; ++q)
+          if (q < nw) { g.x += gq[u][q].x; g.y += gq[u][q].y; g.z += gq[u][q].z; g.w += gq[u][q].w; }
+        adamw_update_fast(pv[u].x, mv[u].x, sv[u].x, g.x, hp);
+        adamw_update_fast(pv[u].y, mv[u].y, sv[u].y, g.y, hp);
+        adamw_update_fast(pv[u].z, mv[u].z, sv[u].z, g.z, hp);
+        adamw_update_fast(pv[u].w, mv[u].w, sv[u].w, g.w, hp);
+        if (bound > 0.0f) {
+          pv[u].x = fminf(fmaxf(pv[u].x, -bound), bound);
+          pv[u].y = fminf(fmaxf(pv[u].y, -bound), bound);
+          pv[u].z = fminf(fmaxf(pv[u].z, -bound), bound);
+          pv[u].w = fminf(fmaxf(pv[u].w, -bound), bound);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+          if (q < nw) st_stream4(pp.D[q] + off, pv[u]);
+        reinterpret_cast<float4*>(m)[i] = mv[u];
+        reinterpret_cast<float4*>(s)[i] = sv[u];
+      }
+    }
   }
 }
 

@@ -80,11 +80,13 @@ def empty_transfer_performance(model_transfer):
     return {name: dict(fooling_rate=nan, rmse=nan, mse=nan) for name in model_transfer}
 
 
-def get_transfer_performance_aux(attack, model_transfer, data, device=None):
+def get_transfer_performance_aux(attack, model_transfer, data, device=None, errors_fn=None):
     """performance.py:205-232: craft the adversarial images once per batch, evaluate them on every model.  Sharded
     evaluation: when torch.distributed is initialised each rank passes its own shard of `data` and the counters are
-    summed (images are independent; no other exchange)."""
+    summed (images are independent; no other exchange).  `errors_fn(adv, clean) -> (err2, ref2, linf)` defaults to the
+    CUDA kernel; the multi-process host test injects a host implementation."""
     device = attack.device
+    _errors = errors_fn if errors_fn is not None else globals()['_errors']
     names = list(model_transfer.keys())
     acc = torch.zeros(len(names), 3, dtype=torch.float64, device=device)
     count = torch.zeros((), dtype=torch.float64, device=device)
@@ -112,8 +114,9 @@ def get_transfer_performance_aux(attack, model_transfer, data, device=None):
     return {name: {'fooling_rate': vals[i][0], 'rmse': vals[i][1], 'mse': vals[i][2]} for i, name in enumerate(names)}
 
 
-def get_transfer_performance(atks, models, data, device=None):
+def get_transfer_performance(atks, models, data, device=None, errors_fn=None):
     """Transfer performance of the first attack of every family on every model (performance.py:183-195)."""
-    return {family: (get_transfer_performance_aux(members[0], models, data=data, device=device) if len(members) > 0
+    return {family: (get_transfer_performance_aux(members[0], models, data=data, device=device, errors_fn=errors_fn)
+                     if len(members) > 0
                      else empty_transfer_performance(models))
             for family, members in atks.items()}

@@ -105,6 +105,10 @@ def main():
     ADIL._fit_step = fit_step
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     os.chdir(os.path.join(ROOT, "gpurun_out"))
+    stale = os.path.join("trained_dicts", "ImageNet_dist_parity_%d.bin" % rank)
+    if os.path.exists(stale):                    # (a saved dictionary would skip the fit, adil.py:94)
+        os.remove(stale)
+    dist.barrier()
     torch.manual_seed(1234)
     atk = ADIL(model, eps=EPS, steps=EPOCHS, n_atoms=K, batch_size=B, data_train=data, model_name="dist_parity_%d" % rank,
                is_distributed=True, loss='ce', method='gd')

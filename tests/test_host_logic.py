@@ -190,3 +190,65 @@ def test_sharded_dict_step_with_padded_slices(tmp_path):
         O.adamw_step_(D, gr.sum(0), m, s, t + 1, 0.01)
         D.clamp_(-1, 1)
     assert (got["D"][:P] - D).abs().max() < 2e-6 and (got["D"][P:] == 0).all()
+
+
+# ---- transfer sweep (performance.py:183-232), sharded over 2 gloo ranks: the counters are all-reduced ------------------
+class _ShiftAttack(object):
+    device = torch.device("cpu")
+
+    def __call__(self, x, y):
+        return (x + 0.2 * torch.sign(x - 0.5)).clamp(0, 1)
+
+
+def _host_errors(adv, clean):
+    d = (adv - clean).flatten(1)
+    return (d ** 2).sum(1), (clean.flatten(1) ** 2).sum(1), d.abs().amax(1)
+
+
+def _sweep_models():
+    torch.manual_seed(5)
+    return {"a": torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 7)),
+            "b": torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 7))}
+
+
+def _sweep_data():
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(22, 3, 8, 8, generator=g)
+    y = torch.randint(0, 7, (22,), generator=g)
+    return x, y
+
+
+def _sweep_worker(rank, world, port, out_dir):
+    from dl_attack_on_imagenet_b200 import performance as perf
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x, y = _sweep_data()
+    lo, hi = dsh.shard_bounds(len(x), world, rank)                       # unequal shards: 11 + 11, batches of 4
+    data = [(x[i:min(i + 4, hi)], y[i:min(i + 4, hi)]) for i in range(lo, hi, 4)]
+    res = perf.get_transfer_performance({"adil": [_ShiftAttack()], "none": []}, _sweep_models(), data,
+                                        errors_fn=_host_errors)
+    if rank == 1:
+        torch.save(res, os.path.join(out_dir, "sweep.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_transfer_sweep_counters_are_summed_over_ranks(tmp_path):
+    from dl_attack_on_imagenet_b200 import performance as perf
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_sweep_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "sweep.pt"))
+    x, y = _sweep_data()
+    ref = perf.get_transfer_performance({"adil": [_ShiftAttack()], "none": []}, _sweep_models(), [(x, y)],
+                                        errors_fn=_host_errors)            # one process, the whole set
+    for name in ("a", "b"):
+        for key in ("fooling_rate", "rmse", "mse"):
+            assert got["adil"][name][key] == pytest.approx(ref["adil"][name][key], rel=1e-6)
+        assert got["none"][name]["mse"] != got["none"][name]["mse"]       # NaN, performance.py:198-202
+    # against the reference's formulas (performance.py:238-266)
+    adv = _ShiftAttack()(x, y)
+    m = _sweep_models()["b"]
+    assert got["adil"]["b"]["fooling_rate"] == pytest.approx((m(x).argmax(1) != m(adv).argmax(1)).float().mean().item(), rel=1e-6)
+    assert got["adil"]["a"]["mse"] == pytest.approx(((adv - x) ** 2).sum(dim=[1, 2, 3]).mean().item(), rel=1e-6)
