@@ -40,7 +40,7 @@ SIGNATURES = {
                                  _P]),
     "adil_dict_step": (_I, [_P, _P, _P, _P, _LL, _HP, _I, _P]),
     "adil_dict_step_atoms": (_I, [_P, _P, _P, _P, _I, _I, _HP, _F, _I, _P, _P]),
-    "adil_dict_step_peer": (_I, [_PP, _PP, _P, _P, _LL, _LL, _I, _I, _HP, _I, _P]),
+    "adil_dict_step_peer": (_I, [_PP, _PP, _P, _P, _LL, _LL, _I, _I, _HP, _I, _P, _P, _P]),
     "adil_code_prox_step": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _F, _P]),
     "adil_code_step": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _HP, _I, _F, _P, _I, _P]),
     "adil_project_rows": (_I, [_P, _I, _I, _I, _F, _P]),

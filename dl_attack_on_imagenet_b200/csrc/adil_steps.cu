@@ -119,6 +119,67 @@ __global__ void __launch_bounds__(256) dict_step_peer_kernel(const PeerPtrs pp, 
       }
     }
   }
+  __threadfence_system();  // the peer stores are performed system-wide before this CTA retires (the barrier follows)
+}
+
+// The same step through the NVSwitch's multicast / in-switch reduction (NVLS): ONE multimem.ld_reduce returns the sum of
+// every rank's gradient value (added inside the switch: 4PK/R bytes arrive per rank instead of (R-1)/R * 4PK), ONE
+// multimem.st delivers the new dictionary value to every rank.
+__device__ __forceinline__ float4 multimem_ld_reduce_add4(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256) dict_step_multimem_kernel(const float* __restrict__ dD_mc, float* __restrict__ D_mc,
+                                                                 const float* __restrict__ D_local, float* __restrict__ m,
+                                                                 float* __restrict__ s, long long begin, long long n4,
+                                                                 AdamwDev hp, float bound) {
+  constexpr int U = 4;  // items per thread in flight: the reduced value makes a round trip through the switch
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+    float4 g[U], pv[U], mv[U], sv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        const size_t off = (size_t)begin + 4 * (size_t)i;
+        g[u] = multimem_ld_reduce_add4(dD_mc + off);
+        pv[u] = ld_global4(D_local + off);
+        mv[u] = reinterpret_cast<const float4*>(m)[i];
+        sv[u] = reinterpret_cast<const float4*>(s)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        const size_t off = (size_t)begin + 4 * (size_t)i;
+        adamw_update_fast(pv[u].x, mv[u].x, sv[u].x, g[u].x, hp);
+        adamw_update_fast(pv[u].y, mv[u].y, sv[u].y, g[u].y, hp);
+        adamw_update_fast(pv[u].z, mv[u].z, sv[u].z, g[u].z, hp);
+        adamw_update_fast(pv[u].w, mv[u].w, sv[u].w, g[u].w, hp);
+        if (bound > 0.0f) {
+          pv[u].x = fminf(fmaxf(pv[u].x, -bound), bound);
+          pv[u].y = fminf(fmaxf(pv[u].y, -bound), bound);
+          pv[u].z = fminf(fmaxf(pv[u].z, -bound), bound);
+          pv[u].w = fminf(fmaxf(pv[u].w, -bound), bound);
+        }
+        multimem_st4(D_mc + off, pv[u]);
+        reinterpret_cast<float4*>(m)[i] = mv[u];
+        reinterpret_cast<float4*>(s)[i] = sv[u];
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -642,7 +703,8 @@ extern "C" int adil_code_prox_step(float* v, const float* dvb, const int64_t* v_
 
 extern "C" int adil_dict_step_peer(const void* const* D_peers, const void* const* dD_peers, float* m, float* s,
                                    long long slice_begin, long long slice_elems, int rank, int world,
-                                   const adil_adamw_t* hp, int atoms_mode, void* stream) {
+                                   const adil_adamw_t* hp, int atoms_mode, const void* D_mc, const void* dD_mc,
+                                   void* stream) {
   if (!D_peers || !dD_peers || !m || !s || !hp) return set_error(-1, "adil_dict_step_peer: null pointer");
   if (world < 1 || world > ADIL_MAX_PEERS || rank < 0 || rank >= world)
     return set_error(-1, "adil_dict_step_peer: bad rank %d / world %d (max %d)", rank, world, ADIL_MAX_PEERS);
@@ -666,6 +728,15 @@ extern "C" int adil_dict_step_peer(const void* const* D_peers, const void* const
   const float bound = atoms_mode == ADIL_ATOMS_CLAMP1 ? 1.0f : 0.0f;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = elem_grid(n4);
+  if ((D_mc != nullptr) != (dD_mc != nullptr))
+    return set_error(-1, "adil_dict_step_peer: give both multicast addresses or neither");
+  if (D_mc != nullptr) {
+    if ((((uintptr_t)D_mc | (uintptr_t)dD_mc) & 15) != 0)
+      return set_error(-1, "adil_dict_step_peer: multicast addresses must be 16-byte aligned");
+    dict_step_multimem_kernel<<<grid, 256, 0, st>>>((const float*)dD_mc, (float*)D_mc, pp.D[rank], m, s, slice_begin, n4, dev,
+                                                    bound);
+    return check_cuda(cudaGetLastError(), "dict_step_multimem_kernel launch");
+  }
   switch (world) {
     case 2: dict_step_peer_kernel<2><<<grid, 256, 0, st>>>(pp, m, s, slice_begin, n4, rank, world, dev, bound); break;
     case 4: dict_step_peer_kernel<4><<<grid, 256, 0, st>>>(pp, m, s, slice_begin, n4, rank, world, dev, bound); break;

@@ -184,7 +184,9 @@ class PeerDictStep(ShardedDictStep):
         cross-rank barrier           every rank's stores have landed before D is read again
 
     replace reduce-scatter -> slice step -> all-gather (three launches through NCCL, two staging passes).  PyTorch only
-    provides the mapping and the barrier; the data movement is the kernel's own loads and stores."""
+    provides the mapping and the barrier; the data movement is the kernel's own loads and stores -- through the
+    NVSwitch's multicast address when the allocation has one (multimem.ld_reduce / multimem.st: the switch adds the R
+    gradient values in flight and replicates the result), else R peer loads and R peer stores per element."""
 
     def __init__(self, P, K, device, group=None, side_stream=True):
         super().__init__(P, K, device, group=group, step_fn=None, side_stream=side_stream)
@@ -193,6 +195,10 @@ class PeerDictStep(ShardedDictStep):
         self.pg = group if group is not None else self.dist.group.WORLD
         self._handles = {}
         self._bufs = []
+        import os
+        # NVLS (multicast + in-switch reduction) when the symmetric allocation carries a multicast address;
+        # ADIL_DICT_STEP_MULTICAST=0 keeps the plain peer loads / stores
+        self.use_multicast = os.environ.get("ADIL_DICT_STEP_MULTICAST", "1") != "0"
 
     def alloc(self):
         t = self.symm_mem.empty(self.rows_total * self.K, dtype=torch.float32, device=self.device)
@@ -214,8 +220,10 @@ class PeerDictStep(ShardedDictStep):
         with ctx:
             hG.barrier(channel=0, timeout_ms=20000)   # (bounded: a protocol bug traps instead of hanging the GPU)
             self.t += 1
+            mc_D, mc_G = (int(hD.multicast_ptr or 0), int(hG.multicast_ptr or 0)) if self.use_multicast else (0, 0)
             ops.dict_step_peer(list(hD.buffer_ptrs), list(hG.buffer_ptrs), self.m, self.s, self.lo * self.K,
-                               self.rows * self.K, self.rank, hp, atoms_mode, device=self.device)
+                               self.rows * self.K, self.rank, hp, atoms_mode, device=self.device,
+                               D_mc=mc_D if (mc_D and mc_G) else 0, dD_mc=mc_G if (mc_D and mc_G) else 0)
             hD.barrier(channel=1, timeout_ms=20000)
             if self.stream is not None:
                 self._done = torch.cuda.Event()

@@ -395,9 +395,12 @@ def dict_step_atoms(D2, dD2, atoms_mode, hp=None, m=None, s=None, step=0.0):
     return D2
 
 
-def dict_step_peer(D_ptrs, dD_ptrs, m, s, slice_begin, slice_elems, rank, hp, atoms_mode=ATOMS_CLAMP1, device=None):
+def dict_step_peer(D_ptrs, dD_ptrs, m, s, slice_begin, slice_elems, rank, hp, atoms_mode=ATOMS_CLAMP1, device=None,
+                   D_mc=0, dD_mc=0):
     """Fused reduce-scatter + AdamW + clamp + all-gather over peer-mapped buffers (adil_dict_step_peer).  D_ptrs / dD_ptrs:
-    device pointers (ints) of every rank's padded dictionary / gradient buffer as mapped into this process."""
+    device pointers (ints) of every rank's padded dictionary / gradient buffer as mapped into this process.  D_mc /
+    dD_mc: multicast addresses of the two buffers (0: none) -- then the reduction happens inside the NVSwitch
+    (multimem.ld_reduce) and the result is replicated by it (multimem.st)."""
     m, s = _f32(m, "m"), _f32(s, "s")
     world = len(D_ptrs)
     if len(dD_ptrs) != world:
@@ -407,7 +410,9 @@ def dict_step_peer(D_ptrs, dD_ptrs, m, s, slice_begin, slice_elems, rank, hp, at
     dev = m.device if device is None else device
     with _Timed("adil_dict_step_peer", dev):
         rc = _lib.lib().adil_dict_step_peer(arr_D, arr_g, _ptr(m), _ptr(s), int(slice_begin), int(slice_elems), int(rank),
-                                            world, ctypes.byref(hp), int(atoms_mode), _stream(dev))
+                                            world, ctypes.byref(hp), int(atoms_mode),
+                                            ctypes.c_void_p(int(D_mc)) if D_mc else None,
+                                            ctypes.c_void_p(int(dD_mc)) if dD_mc else None, _stream(dev))
     _lib.check(rc, "adil_dict_step_peer")
 
 

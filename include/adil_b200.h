@@ -164,9 +164,13 @@ int adil_code_prox_step(float* v, const float* dvb, const int64_t* v_index, int 
  * between two cross-rank barriers on `stream`: every rank's gradient complete before, every rank's stores landed
  * before the dictionary is read again.  atoms_mode: ADIL_ATOMS_NONE or ADIL_ATOMS_CLAMP1.  world <= ADIL_MAX_PEERS. */
 #define ADIL_MAX_PEERS 16
+/* D_mc / dD_mc (optional, both or neither): MULTICAST addresses of the same two buffers (NVLS: one address that names
+ * the buffer of every rank; torch symmetric memory's multicast_ptr).  When given, the gradient slice is read with
+ * multimem.ld_reduce -- the NVSwitch adds the ranks' values in flight, each rank receives 4PK/R bytes instead of
+ * (R-1)/R * 4PK -- and the new dictionary slice is written with multimem.st, which the switch replicates to every rank. */
 int adil_dict_step_peer(const void* const* D_peers, const void* const* dD_peers, float* m, float* s,
                         long long slice_begin, long long slice_elems, int rank, int world, const adil_adamw_t* hp,
-                        int atoms_mode, void* stream);
+                        int atoms_mode, const void* D_mc, const void* dD_mc, void* stream);
 
 /* Code AdamW step over ALL N rows (dense gradient, zero outside the batch -- adil.py:154,186) fused with the
  * scatter of dvb by v_index (duplicates accumulate, like index_put_(accumulate=True)) and the row projection

@@ -124,6 +124,9 @@ def main():
         report["pass"] = bool(ok)
         report["optimizer_state_rows_per_rank"] = int(st.shard.rows)
         report["dict_step_backend"] = type(st.shard).__name__
+        if isinstance(st.shard, dsh.PeerDictStep):
+            h0 = next(iter(st.shard._handles.values()))
+            report["dict_step_multicast"] = bool(st.shard.use_multicast and int(h0.multicast_ptr or 0))
 
     # ---- timing: pieces of the sharded step and the collectives at the BASELINE payloads -----------------------------
     def timed(fn, iters=20, warm=5):
@@ -183,13 +186,24 @@ def main():
 
             def fused():
                 peer.step(Dp, Gp, hp, ops.ATOMS_CLAMP1)
-            entry["peer_step_us (barrier + one fused kernel over NVLink + barrier)"] = timed(fused)
             hD, hG = peer._handles[Dp.data_ptr()], peer._handles[Gp.data_ptr()]
+            mc = (int(hD.multicast_ptr or 0), int(hG.multicast_ptr or 0))
+            entry["multicast_available"] = bool(mc[0] and mc[1])
+            peer.use_multicast = False
+            entry["peer_step_us (barrier + one fused kernel over NVLink + barrier)"] = timed(fused)
 
             def kernel_only():
                 ops.dict_step_peer(list(hD.buffer_ptrs), list(hG.buffer_ptrs), peer.m, peer.s, peer.lo * Kc, peer.rows * Kc,
                                    rank, hp, ops.ATOMS_CLAMP1, device=dev)
             entry["peer_kernel_only_us"] = timed(kernel_only)
+            if mc[0] and mc[1]:
+                peer.use_multicast = True
+                entry["multimem_step_us (barrier + one NVLS kernel: multimem.ld_reduce / multimem.st + barrier)"] = timed(fused)
+
+                def mc_kernel_only():
+                    ops.dict_step_peer(list(hD.buffer_ptrs), list(hG.buffer_ptrs), peer.m, peer.s, peer.lo * Kc,
+                                       peer.rows * Kc, rank, hp, ops.ATOMS_CLAMP1, device=dev, D_mc=mc[0], dD_mc=mc[1])
+                entry["multimem_kernel_only_us"] = timed(mc_kernel_only)
             # the fused kernel against the NCCL chain on the same inputs: same sum, same AdamW
             Dn = Dp.clone()
             mn, sn = torch.zeros(rows, Kc, device=dev), torch.zeros(rows, Kc, device=dev)
@@ -211,7 +225,8 @@ def main():
         tag = os.environ.get("ADIL_DICT_STEP", "auto")
         with open(os.path.join(ROOT, "gpurun_out", "dist_parity_r02_w%d_%s.json" % (world, tag)), "w") as f:
             json.dump(report, f, indent=1)
-        print(json.dumps({"backend": report["dict_step_backend"], "pass": report["pass"], "worst": report["worst"],
+        print(json.dumps({"backend": report["dict_step_backend"], "multicast": report.get("dict_step_multicast"),
+                          "pass": report["pass"], "worst": report["worst"],
                           "times": times}, indent=1))
     dist.barrier()
     dist.destroy_process_group()

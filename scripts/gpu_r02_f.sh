@@ -6,7 +6,7 @@ OUT=gpurun_out
 N=${1:-2}
 for mode in auto nccl; do
   ADIL_DICT_STEP=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621 scripts/dist_parity.py > $OUT/f_dist_parity_w${N}_$mode.log 2>&1; echo "dist_parity[$mode] rc=$?" | tee -a $OUT/f_summary.log
-  grep -E '"backend"|"pass"|m_rel|v_abs|D_abs|D_frac|replicas|peer|sharded_step|replicated|K=' $OUT/f_dist_parity_w${N}_$mode.log | tee -a $OUT/f_summary.log
+  grep -E "backend|multicast|multimem|\"pass\"|m_rel|v_abs|D_abs|D_frac|replicas|peer|sharded_step|replicated|K=" $OUT/f_dist_parity_w${N}_$mode.log | tee -a $OUT/f_summary.log
   tail -5 $OUT/f_dist_parity_w${N}_$mode.log | grep -v "^ \|^}" | tee -a $OUT/f_summary.log
 done
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29622 bench.py --gpus $N --steps 20 --warmup 5 > $OUT/f_bench_n$N.json 2> $OUT/f_bench_n$N.err; echo "bench rc=$?" | tee -a $OUT/f_summary.log
