@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256) dict_step_peer_kernel(const PeerPtrs pp, 
       }
     }
   }
-  __threadfence_system();  // the peer stores are performed system-wide before this CTA retires (the barrier follows)
+  // (no system fence here: the cross-rank barrier that follows is a later kernel on the same stream; its release at
+  //  system scope is cumulative over everything this kernel wrote -- a per-thread MEMBAR.SYS cost 15 us at 2 ranks)
 }
 
 // The same step through the NVSwitch's multicast / in-switch reduction (NVLS): ONE multimem.ld_reduce returns the sum of
@@ -179,7 +180,6 @@ __global__ void __launch_bounds__(256) dict_step_multimem_kernel(const float* __
       }
     }
   }
-  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -196,9 +196,10 @@ class PeerDictStep(ShardedDictStep):
         self._handles = {}
         self._bufs = []
         import os
-        # NVLS (multicast + in-switch reduction) when the symmetric allocation carries a multicast address;
-        # ADIL_DICT_STEP_MULTICAST=0 keeps the plain peer loads / stores
-        self.use_multicast = os.environ.get("ADIL_DICT_STEP_MULTICAST", "1") != "0"
+        # ADIL_DICT_STEP_MULTICAST=1: NVLS (multicast + in-switch reduction) when the symmetric allocation carries a
+        # multicast address.  Off by default: measured slower than the plain peer loads / stores at 2 ranks (115 vs 66
+        # us at K = 50), where the switch saves no traffic; scripts/dist_parity.py times both.
+        self.use_multicast = os.environ.get("ADIL_DICT_STEP_MULTICAST", "0") == "1"
 
     def alloc(self):
         t = self.symm_mem.empty(self.rows_total * self.K, dtype=torch.float32, device=self.device)
