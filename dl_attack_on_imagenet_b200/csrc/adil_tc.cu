@@ -791,6 +791,7 @@ struct GradArgs {
   unsigned k4div;     // ceil(2^32 / (K / 4)) (STRIDED: float4 index inside a dense tile -> row)
   int accumulate;     // plain dD output: dD2 += tile (TMA reduce-add store) instead of dD2 = tile
   int early;          // host indices: code loads at kernel entry, bulk loads right after the set-up barrier
+  int mma_order;      // 0: the dD MMAs of a tile, then its dv MMAs; 1: interleaved
   ChannelConsts cc;
   AdamwDev hp;
 };
@@ -1032,7 +1033,27 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       mbar_wait(staged + buf, (it >> 1) & 1);  // workers staged tile `it` (mbarrier: fast warps run one tile ahead)
       tc_fence_after();
       CHAIN(1, it);
-      if (leader) {
+      if (leader && a.want_dD && a.want_dv && a.mma_order == 1) {
+        // Interleaved issue: a dD MMA (A in tensor memory: 2 KB of operand reads, bound by the tensor pipe) next to a dv
+        // MMA (both operands in shared memory: 6 KB of operand reads, bound by the shared-memory port), so that the
+        // operand fetch of the one overlaps the arithmetic of the other.
+        const uint32_t acc = tmem_base + (uint32_t)(buf * TP);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, tv[6] = {0, 2, 1, 0, 1, 0};
+          uint32_t at = codes + (uint32_t)tv[t] * cterm;
+          uint64_t bD = dD_b0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
+          uint64_t ad = dv_a0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
+          uint64_t bv = dv_b0 + (uint64_t)buf * db16 + (uint64_t)tv[t] * ds16;
+          const int nks = ksteps_dD > TP / 16 ? ksteps_dD : TP / 16;
+#pragma unroll 1
+          for (int ks = 0; ks < nks; ++ks) {
+            if (ks < ksteps_dD) { mma_bf16_ts(acc, at, bD, idesc_dD, (t | ks) ? 1u : 0u); at += 8; bD += 16; }
+            if (ks < TP / 16) { mma_bf16(acc_dv, ad, bv, idesc_dv, (it | t | ks) ? 1u : 0u); ad += astep; bv += 16; }
+          }
+        }
+        mma_commit(mma_done + buf);
+      } else if (leader) {
 #ifdef ADIL_EXP_NO_DDMMA
         if (false) {
 #else
@@ -1707,6 +1728,8 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
   a.accumulate = (opt.accumulate && !fused) ? 1 : 0;
   static const int early_knob = getenv("ADIL_GRAD_EARLY") ? atoi(getenv("ADIL_GRAD_EARLY")) : 1;  // tuning knob
   a.early = early_knob;
+  static const int order_knob = getenv("ADIL_GRAD_MMA_ORDER") ? atoi(getenv("ADIL_GRAD_MMA_ORDER")) : 0;  // tuning knob
+  a.mma_order = order_knob;
   if (hp) a.hp = *hp;
   const int ntiles = (P + pl.TP - 1) / pl.TP;
   int grid = sm_count();

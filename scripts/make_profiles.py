@@ -34,7 +34,7 @@ def launches():
             pass
     tot = sum(t for _, t, _ in recs)
     out = [f"ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 2 --warmup 3 "
-           f"--no-cpu-baseline --no-e2e --no-cudnn-autotune",
+           f"--no-cpu-baseline --no-e2e --no-cudnn-autotune   (kernels inside the replayed CUDA graphs are listed one by one)",
            "(B200; cold-cache serialised per-launch times: compare SHARES, not absolutes)",
            f"{len(recs)} launches, {tot / 1e3:.1f} ms total device time", "",
            "every libadil_b200 launch (ID, us, kernel):"]
@@ -82,6 +82,8 @@ def kernel(name, regex, only):
 
 launches()
 traffic = {"adil_synth": kernel("synth", "synth_kernel", "synth"),
-           "adil_grad_dict_step": kernel("grad", "grad_kernel", "grad_dict_step")}
+           "adil_grad_dict_step": kernel("grad", "grad_kernel", "grad_dict_step_partials")}
+if os.path.exists(os.path.join(GO, f"prof_{tag}_gradplain.ncu-rep")):
+    traffic["adil_grad"] = kernel("gradplain", "grad_kernel", "grad_partials")
 json.dump(traffic, open(os.path.join(PR, "ncu_traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))

@@ -377,3 +377,36 @@ def test_sadil_on_the_kernels_matches_the_reference(golden, tag, kw):
     assert torch.equal(Df, D) and lf == loss
     norms = D.flatten(0, 2).norm(dim=0)
     assert (norms <= 1 + 1e-5).all() if kw["dict_set"] == 'l2ball' else (norms - 1).abs().max() <= 1e-5
+
+
+def test_fit_with_the_whole_set_as_one_minibatch(monkeypatch):
+    """batch_size=None is the reference's documented default (len(data_train), adil.py:124): 150 images in one minibatch
+    exceed the 128 images one kernel pass takes, so the synthesis runs in two passes and the backward as chunked plain
+    contractions that accumulate dD, followed by the stand-alone dictionary step.  Against the oracle's free-running fit
+    on the same seeds (smooth classifier: trajectories comparable tightly)."""
+    from dl_attack_on_imagenet_b200 import ADIL, AdilState, IndexedTensorDataset
+    n = 150
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand(n, C, H, W, generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    torch.manual_seed(32)
+    st0 = O.init_state(C, H, W, n, K, EPS)
+    import copy
+    st = copy.deepcopy(st0)
+    torch.manual_seed(33)
+    st, loss_all, fool_all, _ = O.learn_dictionary_a(O.tiny_classifier(seed=0), O.IndexedTensorDataset(x, y), EPS, steps=3,
+                                                    n_atoms=K, batch_size=None, state=st, fused_normalize=True)
+    monkeypatch.setattr(ADIL, "_init_state",
+                        lambda self, n_, nc, nx, ny, warm_start, v_zero=False: AdilState(st0.D().cuda(), st0.v.clone().cuda()))
+    monkeypatch.setattr(ADIL, "verbose", False)
+    monkeypatch.setattr(ADIL, "run_validation", False)
+    torch.manual_seed(33)
+    atk = ADIL(O.tiny_classifier(seed=0).cuda(), eps=EPS, steps=3, n_atoms=K, batch_size=None,
+               data_train=IndexedTensorDataset(x, y), model_name='t_fullbatch')
+    D, v, l_gpu, f_gpu, _ = torch.load(atk.model_file, weights_only=True)
+    assert len(l_gpu) == 3
+    assert np.allclose(l_gpu, loss_all, rtol=0, atol=2e-3)
+    assert np.abs(np.asarray(f_gpu) - np.asarray(fool_all)).max() <= 1.0 / n + 1e-9
+    assert (v.cpu() - st.v).abs().max() <= 1e-3
+    dD = (D.cpu() - st.D()).abs()
+    assert dD.median() <= 1e-5 and (dD > 1e-5).float().mean() <= 0.25
