@@ -32,7 +32,7 @@ SIGNATURES = {
     "adil_set_impl": (_I, [_I]),
     "adil_get_impl": (_I, []),
     "adil_tc_supported": (_I, [_I, _I, _I]),
-    "adil_synth": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float_p, c_float_p, _F, _I, _P]),
+    "adil_synth": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float_p, c_float_p, _F, _I, _P]),
     "adil_grad_scratch_bytes": (_SZ, [_I, _I]),
     "adil_grad": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float_p, _P, _F, _I, _IP, _P, _SZ, _P]),
     "adil_grad_max_batch": (_I, [_I, _I, _I, _I]),

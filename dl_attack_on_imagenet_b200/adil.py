@@ -266,6 +266,15 @@ class ADIL(Attack):
             self._graphs[key] = gr
         return gr
 
+    def _codes_buffer(self, nb, K):
+        """[nb, K] buffer for the gathered code rows of a batch (written by the synthesis kernel, read by the backward
+        kernel of the same step)."""
+        buf = getattr(self, '_vb', None)
+        if buf is None or buf.shape[0] < nb or buf.shape[1] != K or buf.device != torch.device(self.device):
+            buf = torch.empty((max(nb, 1), K), dtype=torch.float32, device=self.device)
+            self._vb = buf
+        return buf[:nb]
+
     def _xin_buffer(self, nb, shape, reduction):
         """Static classifier-input buffer [nb, P] of the captured graph for this batch shape -- the synthesis kernel
         writes into it directly -- or None when the classifier runs eagerly."""
@@ -404,27 +413,30 @@ class ADIL(Attack):
                 st.tv += 1
                 ops.code_step(st.v, st.mv, st.sv, None, None, ops.adamw_params(st.tv, lr_v), ops.ROWS_L1BALL, self.eps)
             return torch.zeros((), device=self.device), torch.zeros((), dtype=torch.long, device=self.device)
+        # the synthesis kernel leaves the gathered code rows of the batch behind as a contiguous block: the backward
+        # kernel reads THAT (same values: autograd saves the tensor the forward used, adil.py:25,185) with one bulk copy
+        vb = self._codes_buffer(nb, st.v.shape[1])
         xin, _ = ops.synth(st.D2, st.v, kv_index, x=x_src, x_index=kx_index, mean=self._mean, std=self._std, flags=flags,
-                           n_channels=shape[0], out=self._xin_buffer(nb, shape, 'sum'))
+                           n_channels=shape[0], out=self._xin_buffer(nb, shape, 'sum'), codes_out=vb)
         loss, g, out = self._classifier_grad(xin.view(-1, *shape), labels, 'sum')
         g = g.view(g.shape[0], -1)
         fooled = (out.argmax(dim=-1) != labels).sum()
         dvb = None   # (code gradient: left as per-CTA partial slabs that the code step adds up itself)
         if update in ('both', 'd') and shard is not None:
-            _, dvb = ops.grad(g, st.D2, st.v, kv_index, self._std, want_dv=(update == 'both'), dD2=st.dD2,
+            _, dvb = ops.grad(g, st.D2, vb, None, self._std, want_dv=(update == 'both'), dD2=st.dD2,
                               keep_partials=True)
             st.tD += 1
             shard.step(st.D_full, st.dD_full, ops.adamw_params(st.tD, lr_d), ops.ATOMS_CLAMP1)
         elif update == 'both':
             st.tD += 1
-            dvb = ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, kv_index, ops.adamw_params(st.tD, lr_d), self._std,
+            dvb = ops.grad_dict_step(st.D2, st.mD, st.sD, g, vb, None, ops.adamw_params(st.tD, lr_d), self._std,
                                      ops.ATOMS_CLAMP1, keep_partials=True)
         elif update == 'd':
             st.tD += 1
-            ops.grad_dict_step(st.D2, st.mD, st.sD, g, st.v, kv_index, ops.adamw_params(st.tD, lr_d), self._std,
+            ops.grad_dict_step(st.D2, st.mD, st.sD, g, vb, None, ops.adamw_params(st.tD, lr_d), self._std,
                                ops.ATOMS_CLAMP1, want_dv=False)
         else:
-            _, dvb = ops.grad(g, st.D2, st.v, kv_index, self._std, want_dD=False, keep_partials=True)
+            _, dvb = ops.grad(g, st.D2, vb, None, self._std, want_dD=False, keep_partials=True)
         if update in ('both', 'v'):
             st.tv += 1
             ops.code_step(st.v, st.mv, st.sv, dvb, v_index, ops.adamw_params(st.tv, lr_v), ops.ROWS_L1BALL, self.eps)

@@ -141,25 +141,25 @@ extern "C" int adil_tc_supported(int B, int P, int K) {
 }
 
 extern "C" int adil_synth(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
-                          const float* v, const int64_t* v_index, int B, int P, int K, int C, int hw,
+                          const float* v, const int64_t* v_index, float* codes_out, int B, int P, int K, int C, int hw,
                           const float* mean_host, const float* std_host, float eps, int flags, void* stream) {
   const bool norm = (flags & ADIL_SYNTH_NORMALIZE) != 0;
   int rc = check_shape("adil_synth", B, P, K, C, hw, norm);
   if (rc) return rc;
   if (!D2 || !v || (!out && !delta_out)) return set_error(-1, "adil_synth: null pointer");
   if (norm && (!mean_host || !std_host)) return set_error(-1, "adil_synth: NORMALIZE needs mean/std");
-  if (!aligned16(out) || !aligned16(delta_out) || !aligned16(x) || !aligned16(D2))
-    return set_error(-1, "adil_synth: out/delta/x/D2 must be 16-byte aligned");
+  if (!aligned16(out) || !aligned16(delta_out) || !aligned16(x) || !aligned16(D2) || !aligned16(codes_out))
+    return set_error(-1, "adil_synth: out/delta/x/D2/codes_out must be 16-byte aligned");
   if (B == 0) return 0;
   ChannelConsts cc = make_consts(C, hw, mean_host, std_host, norm);
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(tc_synth_ok(B, P, K, norm ? hw : P), B, P, K, &rc, "adil_synth"))
-    return launch_synth_tc(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
+    return launch_synth_tc(out, delta_out, x, x_index, D2, v, v_index, codes_out, B, P, K, cc, eps, flags, st);
   if (rc) return rc;
   if (is_host_pointer(x_index) || is_host_pointer(v_index))
     return set_error(-4, "adil_synth: host index arrays travel as kernel parameters of the tcgen05 path; shape B=%d P=%d K=%d "
                      "(or ADIL_IMPL_FMA) needs device index arrays", B, P, K);
-  return launch_synth_fma(out, delta_out, x, x_index, D2, v, v_index, B, P, K, cc, eps, flags, st);
+  return launch_synth_fma(out, delta_out, x, x_index, D2, v, v_index, codes_out, B, P, K, cc, eps, flags, st);
 }
 
 extern "C" size_t adil_grad_scratch_bytes(int B, int K) {

@@ -136,8 +136,8 @@ struct GradOpts {
 
 // FMA-path launchers (adil_fma.cu)
 int launch_synth_fma(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
-                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
-                     int flags, cudaStream_t st);
+                     const float* v, const int64_t* v_index, float* codes_out, int B, int P, int K,
+                     const ChannelConsts& cc, float eps, int flags, cudaStream_t st);
 int launch_grad_fma(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
                     const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, const GradOpts& opt,
@@ -148,8 +148,8 @@ int grad_fma_max_batch(int K, bool want_dD, bool want_dv);
 bool tc_synth_ok(int B, int P, int K, int hw);
 bool tc_grad_ok(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool fused);
 int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
-                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
-                    int flags, cudaStream_t st);
+                    const float* v, const int64_t* v_index, float* codes_out, int B, int P, int K,
+                    const ChannelConsts& cc, float eps, int flags, cudaStream_t st);
 int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc,
                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, const GradOpts& opt,

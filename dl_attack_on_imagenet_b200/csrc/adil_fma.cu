@@ -508,9 +508,23 @@ int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, 
                     "reduce_partials_kernel launch");
 }
 
+namespace {
+// codes_out[b, :] = v[v_index ? v_index[b] : b, :]  (the contiguous block adil_synth leaves for the backward kernel)
+__global__ void gather_codes_kernel(float* codes_out, const float* v, const int64_t* vidx, int K) {
+  const int b = blockIdx.x;
+  const long long row = vidx ? (long long)vidx[b] : (long long)b;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) codes_out[(size_t)b * K + k] = v[row * K + k];
+}
+}  // namespace
+
 int launch_synth_fma(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
-                     const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
-                     int flags, cudaStream_t st) {
+                     const float* v, const int64_t* v_index, float* codes_out, int B, int P, int K,
+                     const ChannelConsts& cc, float eps, int flags, cudaStream_t st) {
+  if (codes_out != nullptr) {
+    gather_codes_kernel<<<B, 64, 0, st>>>(codes_out, v, v_index, K);
+    int rcg = check_cuda(cudaGetLastError(), "gather_codes_kernel launch");
+    if (rcg) return rcg;
+  }
   SynthArgs a;
   a.out = out; a.delta = delta_out; a.x = x; a.xidx = x_index; a.D2 = D2; a.v = v; a.vidx = v_index;
   a.B = B; a.P = P; a.K = K; a.Kp = round_up(K, 4);

@@ -68,14 +68,21 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 __device__ long long g_chain[16];
 __device__ __forceinline__ long long gtime2() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define CHAIN(i, tile) do { if (blockIdx.x == 5 && (tile) == 6 && (threadIdx.x & 31) == 0) g_chain[i] = gtime2(); } while (0)
-__device__ long long g_stamp[8];
+__device__ long long g_stamp[16];
 #define STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_stamp[i] = gtime2(); } while (0)
 __device__ long long g_sstamp[16];
 #define SSTAMP(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_sstamp[i] = gtime2(); } while (0)
+__device__ long long g_wstamp[16];  // backward kernel, CTA 0: lane 0 of whichever warp passes the probe
+#define WSTAMP(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_wstamp[i] = gtime2(); } while (0)
+#else
+#ifdef ADIL_V_CBAR
+#define CHAIN(i, tile) asm volatile("" ::: "memory")
 #else
 #define CHAIN(i, tile)
+#endif
 #define STAMP(i)
 #define SSTAMP(i)
+#define WSTAMP(i)
 #endif
 
 constexpr int NW = 16;              // worker warps
@@ -83,6 +90,8 @@ constexpr int NT = NW * 32;         // worker threads
 constexpr int WARP_MMA = NW;        // issuer warp
 constexpr int WARP_LOAD = NW + 1;   // loader warp
 constexpr int NE = 8;               // backward: epilogue warps 16..23 (TMEM quadrant = warp & 3, pixel half = (warp - 16) / 4)
+constexpr int NEP_MAX = 10;         // backward, fused step: warps 16..25 share the AdamW pass when it has at most 3 items per
+                                    // thread (24, 25 only do that); with 4 items per thread: the eight epilogue warps
 constexpr int WARP_EPI = NW;
 // The active epilogue warps sit on schedulers 0 and 1 (quadrant = warp % 4 = scheduler) whenever K <= 64; the issuer
 // and the loader go to schedulers 2 and 3 so that they do not queue behind them for issue slots.
@@ -139,13 +148,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.
 // try_wait suspends the warp in hardware for a while before it returns false, so the loop is cheap.
+// (out of line, reading the special registers itself: inlined, the message kept threadIdx.x alive -- and spilled -- across
+// the whole kernel for the sake of a path that never runs)
+__device__ __noinline__ void mbar_timeout() {
+  printf("adil_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("adil_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 24)) mbar_timeout();
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -171,6 +183,39 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+// `n` floats (1, 2 or 4: 4 / 8 / 16 bytes, both addresses aligned to the size)
+__device__ __forceinline__ void cp_async_floats(void* smem_dst, const void* gsrc, int n) {
+  if (n == 4) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+  } else if (n == 2) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Gather of `nrows` (<= ROWS) rows of `cpr` copies of CW floats each by one warp: lane l holds the global address of
+// row (l % ROWS) in `myrow`; the rows are handed round by shuffle and land `dpitch` floats apart.  A rolled loop with a
+// minimal body on purpose: code that runs once costs its instruction fetch (cold: ~0.5 us per KB of straight-line
+// code, measured by unrolling this), and a fat body (parameter loads, width dispatch and address arithmetic per row)
+// ran at 0.19 us per row.
+template <int CW>
+__device__ __forceinline__ void gather_rows(float* dst, int dpitch, const float* myrow, int nrows, int cpr, int lane) {
+#pragma unroll 1
+  for (int i = 0; i < nrows; ++i) {
+    const float* src = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myrow), i));
+#pragma unroll 1
+    for (int c = lane; c < cpr; c += 32) cp_async_floats(dst + c * CW, src + c * CW, CW);
+    dst += dpitch;
+  }
+}
+template <int ROWS>
+__device__ __forceinline__ void gather_rows_cw(float* dst, int dpitch, const float* myrow, int nrows, int K, int cw, int lane) {
+  nrows = nrows < ROWS ? nrows : ROWS;
+  if (cw == 4) gather_rows<4>(dst, dpitch, myrow, nrows, K >> 2, lane);
+  else if (cw == 2) gather_rows<2>(dst, dpitch, myrow, nrows, K >> 1, lane);
+  else gather_rows<1>(dst, dpitch, myrow, nrows, K, lane);
+}
 // the mbarrier receives one arrival once all cp.async issued so far by this thread have landed
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -178,6 +223,9 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 // named barrier id 2 = worker-only barrier (hand-offs between roles use mbarriers)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -339,6 +387,38 @@ __device__ __forceinline__ void tile_chan_update(TileChan& t, const ChannelConst
   t.bnd = t.hi - p0;
 }
 
+// synthesis: staged code row (fp32, `crow`) -> hi / lo TF32 terms in tensor memory, 8-atom chunks c = c0, c0 + 4, ...
+// (the four warps of a TMEM quadrant share the chunks); atoms >= K and rows of images >= B are written as zeros.
+template <int CW>
+__device__ __forceinline__ void synth_codes_to_tmem(const float* crow, bool b_ok, int K, int Kp8, int c0, uint32_t lane_base) {
+  const int nchunks = Kp8 >> 3;
+#pragma unroll 1
+  for (int c = c0; c < nchunks; c += 4) {
+    float val[8];
+    const int k0 = 8 * c;
+    if (CW == 4) {
+      const float4 v0 = *reinterpret_cast<const float4*>(crow + k0);  // (k0 < K always: c < ceil(K / 8))
+      const float4 v1 = (k0 + 4 < K) ? *reinterpret_cast<const float4*>(crow + k0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      val[0] = v0.x; val[1] = v0.y; val[2] = v0.z; val[3] = v0.w;
+      val[4] = v1.x; val[5] = v1.y; val[6] = v1.z; val[7] = v1.w;
+    } else if (CW == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = (k0 + 2 * i < K) ? *reinterpret_cast<const float2*>(crow + k0 + 2 * i) : make_float2(0.f, 0.f);
+        val[2 * i] = t.x; val[2 * i + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) val[i] = (k0 + i < K) ? crow[k0 + i] : 0.0f;
+    }
+    float hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_tf32(b_ok ? val[i] : 0.0f, hi[i], lo[i]);
+    tmem_st8(lane_base + (uint32_t)(8 * c), hi);
+    tmem_st8(lane_base + (uint32_t)(Kp8 + 8 * c), lo);
+  }
+}
+
 // =========================================================================================================
 // synthesis:  acc[b, p] = sum_k v[b,k] D[p,k]      M = 128 image lanes, N = TP pixels, contraction over atoms
 //   A = batch codes (hi/lo) in TENSOR MEMORY: lane = image, column = atom (written once per CTA with tcgen05.st) --
@@ -353,13 +433,14 @@ __device__ __forceinline__ void tile_chan_update(TileChan& t, const ChannelConst
 struct SynthArgs {
   float* out;
   float* delta;
+  float* codes_out;      // [B, K] (may be NULL): the code rows of the batch, contiguous, for the backward kernel of the step
   const float* x;
   const int64_t* xidx;
   const float* D2;
   const float* v;
   const int64_t* vidx;
-  int hx_on, hv_on;      // the batch indices travel in the kernel parameters (host index arrays, B <= 128): no
-  int hx[128], hv[128];  // dependent cold miss on an index array at the top of the kernel
+  int hx_on, hv_on;      // the batch indices travel in the kernel parameters (host index arrays hx[], hv[] at the end,
+                         // B <= 128): no dependent cold miss on an index array at the top of the kernel
   int B, P, K;
   int Kp8;               // contraction length: round_up(K, 8)
   int Sd;                // byte stride between 4-atom groups of a dictionary image
@@ -370,8 +451,12 @@ struct SynthArgs {
   uint32_t tmem_cols;
   float eps;
   int flags;
-  int early_x;           // image-row stages requested before the zero fill (0..NSX)
+  int stage_codes;       // the code rows are gathered by cp.async into the second image buffer (they fit), pitch cpitch
+  int cpitch;            // floats between staged code rows: K, or K + 4 when K % 8 == 0 (conflict-free 128-bit reads)
+  int cw;                // floats per cp.async of the gather / per shared-memory read: 4, 2 or 1
+  int rpw;               // rows of the gather per warp: ceil(B / 25)
   ChannelConsts cc;
+  int hx[128], hv[128];
 };
 
 // TRAIN = the learning-loop configuration (x and out given, no delta output, no clamps): those branches vanish.
@@ -381,17 +466,21 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   constexpr int Q4 = TP / 4;       // float4 per image row
   constexpr int NCG = TP / 16;     // 16-column groups of the accumulator
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // (contiguous, in this order: the issuer warp initialises them one per lane)
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS]
   uint64_t* empty_raw = full_raw + NS;                         // [NS]
   uint64_t* full_x = empty_raw + NS;                           // [NSX] rows landed / stage free (I/O warps -> workers)
   uint64_t* out_ready = full_x + NSX;                          // [NSX] finished tile staged (workers -> I/O warps)
   uint64_t* mma_done = out_ready + NSX;                        // [2] MMAs of the tiles using buffer 0 / 1 retired
   uint64_t* staged = mma_done + 2;                             // [2] dictionary images of buffer 0 / 1 written
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
+  uint64_t* codes_ready = staged + 2;                          // [1] batch codes written to tensor memory (workers -> issuer)
+  uint64_t* codes_landed = codes_ready + 1;                    // [1] code rows of the batch gathered into shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(codes_landed + 1);
   long long* xoff_s = reinterpret_cast<long long*>(smem_raw + 256);  // [128]
   float* raw = reinterpret_cast<float*>(smem_raw + HDR_BYTES);       // [NS][raw_floats]
   float* Dimg = raw + NS * a.raw_floats;                             // [2 buffers][hi, lo][dimg]
   float* xs = Dimg + 4 * a.dimg;                                     // [NSX][B][XP]
+  float* cstage = Dimg + 2 * a.dimg;                                 // [B][cpitch] code rows, until they are in TMEM
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
@@ -401,57 +490,8 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   const int xstage = B * XP;
   const bool ragged = (P % TP) != 0;
   if (tid == 0) SSTAMP(0);
-  // The batch codes are the first thing on the critical path of tile 0: their loads go out at kernel entry, ahead of
-  // the set-up barrier and of any bulk prefetch (which would queue megabytes ahead of them), and fly during the zero
-  // fill.  With host indices (kernel parameters) or identity rows this is one cold miss, with a device index array two.
-  // worker thread <-> image b = 32*quad + lane (its TMEM lane); the warps of a quadrant share the 8-atom chunks.
-  float vv[4][8];
-  if (warp < NW) {
-    const int b = (warp & 3) * 32 + lane;
-    const int bi = min(b, B - 1);
-    const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
-    const float* vrow = a.v + row * K;
-#pragma unroll
-    for (int ci = 0; ci < 4; ++ci) {
-      const int k0 = 8 * ((warp >> 2) + 4 * ci);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
-    }
-  }
-
-  if (tid == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, NW); }
-    for (int i = 0; i < NSX; ++i) { mbar_init(full_x + i, NTIO); mbar_init(out_ready + i, NW); }
-    mbar_init(mma_done, 1);
-    mbar_init(mma_done + 1, 1);
-    mbar_init(staged, NW);
-    mbar_init(staged + 1, NW);
-    fence_mbar_init();
-    // The dictionary tiles depend on nothing: without a ragged last tile (whose stale stage rows must be zeroed first)
-    // the first NS of them are requested right here, ahead of the index -> code-row chain of the prologue.
-    if (!ragged) {
-      for (int it = 0; it < NS && it < my_tiles; ++it) {
-        const int p0 = (blockIdx.x + it * gridDim.x) * TP;
-        mbar_expect_tx(full_raw + it, (uint32_t)(TP * K * 4));
-        bulk_g2s(raw + it * a.raw_floats, a.D2 + (size_t)p0 * K, (uint32_t)(TP * K * 4), full_raw + it);
-      }
-    }
-  }
-  if (tid == 0) SSTAMP(13);
-  if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  if (tid == 0) SSTAMP(12);
-  for (int b = tid; b < B; b += NTHREADS_SYNTH) {
-    xoff_s[b] = (a.hx_on ? (long long)a.hx[b] : a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (tid == 0) SSTAMP(1);
-  const uint32_t tmem_base = *tmem_slot;
-  // I/O warps: the image rows of the first tiles are requested as soon as the row offsets are known (the row stages
-  // are never zero-filled), next to the code loads.
   const int iot = tid - WARP_LOAD * 32;
-  auto load_x = [&](int j) {
+  auto request_x = [&](int j) {
     if (need_x && j < my_tiles) {
       const int p0 = (blockIdx.x + j * gridDim.x) * TP;
       float* dst = xs + (j % NSX) * xstage;
@@ -460,20 +500,96 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
         if (p0 + col < P) cp_async16(dst + b * XP + col, a.x + xoff_s[b] + p0 + col);
       }
     }
+  };
+  auto load_x = [&](int j) {
+    request_x(j);
     cp_async_arrive_noinc(full_x + (j % NSX));  // rows landed (or, without x, simply: stage free)
   };
-  if (warp >= WARP_LOAD) {
-    for (int j = 0; j < a.early_x; ++j) load_x(j);
-  } else {
-    // zero the dictionary images (contraction padding k in [K, Kp8) must be zero) and, with a ragged last tile, the
-    // raw stages (stale rows must stay finite).  The proxy fence is a MEMBAR.ALL.CTA -- it waits for the loads in
-    // flight -- so the I/O warps stay out of this.
-    float4* z = reinterpret_cast<float4*>(ragged ? raw : Dimg);
-    const int nz = ((ragged ? NS * a.raw_floats : 0) + 4 * a.dimg) >> 2;
-    for (int e = tid; e < nz; e += WARP_LOAD * 32) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the async-proxy accesses
+  // raw dictionary tile `it` -> stage it % NS by one TMA bulk copy (issuer's elected lane)
+  auto load_D = [&](int it) {
+    const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+    const uint32_t bytes = (uint32_t)(min(TP, P - p0) * K * 4);
+    mbar_expect_tx(full_raw + it % NS, bytes);
+    bulk_g2s(raw + (it % NS) * a.raw_floats, a.D2 + (size_t)p0 * K, bytes, full_raw + it % NS);
+  };
+  // contraction padding k in [K, Kp8) of a dictionary image buffer must be zero (everything else is rewritten per tile)
+  auto zero_padding = [&](float* Dhi, int t0, int nt) {
+    const int npad = a.Kp8 - K;
+    float* Dlo = Dhi + a.dimg;
+    for (int e = t0; e < TP * npad; e += nt) {
+      const int p = e / npad, k = K + (e - p * npad);
+      const int o = (k >> 2) * (a.Sd >> 2) + (p >> 3) * 32 + (p & 7) * 4 + (k & 3);
+      Dhi[o] = 0.0f;
+      Dlo[o] = 0.0f;
+    }
+  };
+
+  // ---- Kernel entry.  Everything tile 0 needs is one cold miss away and depends on nothing but the kernel parameters:
+  // every role puts its requests out before any set-up work -- the I/O warps the image rows of tile 0, the issuer the
+  // first dictionary tile (TMA), the workers the code rows of the batch (cp.async gather into the second image buffer;
+  // when they do not fit there: straight into registers).  The requests of the later tiles follow after the set-up
+  // barrier so that they queue behind these. ----
+  float vv[4][8];
+  if (a.stage_codes) {
+    // code rows: warp w gathers rows [w rpw, (w + 1) rpw) -- a warp keeps only about four cp.async in flight (8 rows per
+    // warp took two latencies), so the rows are spread over all the warps; lane l holds the address of row
+    // w rpw + (l & 7) (one line of the parameters or of the index array per warp)
+    const int r0 = warp * a.rpw;
+    if (r0 < B) {
+      const int rb = min(r0 + (lane & 7), B - 1);
+      const long long row = a.hv_on ? (long long)a.hv[rb] : (a.vidx ? (long long)a.vidx[rb] : (long long)rb);
+      gather_rows_cw<8>(cstage + r0 * a.cpitch, a.cpitch, a.v + row * K, min(a.rpw, B - r0), K, a.cw, lane);
+    }
   }
+  if (warp < NW) {
+    if (!a.stage_codes) {
+      // worker thread <-> image b = 32*quad + lane (its TMEM lane); the warps of a quadrant share the 8-atom chunks
+      const int b = (warp & 3) * 32 + lane;
+      const int bi = min(b, B - 1);
+      const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
+      const float* vrow = a.v + row * K;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int k0 = 8 * ((warp >> 2) + 4 * ci);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+      }
+    }
+    if (tid == 0) SSTAMP(13);
+#pragma unroll 1
+    for (int buf = 0; buf < (a.stage_codes ? 1 : 2); ++buf) zero_padding(Dimg + buf * 2 * a.dimg, tid, NT);
+    if (ragged) {  // stale rows of the raw stages must stay finite; the tiles are requested after the set-up barrier
+      float4* z = reinterpret_cast<float4*>(raw);
+      for (int e = tid; e < (NS * a.raw_floats) >> 2; e += NT) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      fence_proxy_async();  // the zero fill (generic proxy) must be ordered before the TMA writes
+    }
+  } else if (warp == WARP_MMA) {
+    if (lane < 2 * NS + 2 * NSX + 6) {  // one mbarrier per lane
+      uint32_t cnt = NW;                                                     // empty_raw, out_ready, staged, codes_ready
+      if (lane == 2 * NS + 2 * NSX + 5) cnt = NTHREADS_SYNTH;                // codes_landed
+      else if (lane < NS) cnt = 1;                                           // full_raw
+      else if (lane >= 2 * NS && lane < 2 * NS + NSX) cnt = NTIO;            // full_x
+      else if (lane >= 2 * NS + 2 * NSX && lane < 2 * NS + 2 * NSX + 2) cnt = 1;  // mma_done
+      mbar_init(full_raw + lane, cnt);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    const bool leader = elect_one();
+    if (leader && !ragged && my_tiles > 0) load_D(0);
+    __syncwarp();
+    tmem_alloc(tmem_slot, a.tmem_cols);
+    if (lane == 0) SSTAMP(12);
+  } else {
+    for (int b = iot; b < B; b += NTIO)
+      xoff_s[b] = (a.hx_on ? (long long)a.hx[b] : a.xidx ? (long long)a.xidx[b] : (long long)b) * (long long)P;
+    bar_sync(4, NTIO);
+  }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  if (a.stage_codes) cp_async_arrive_noinc(codes_landed);  // this thread's share of the gather (and nothing else: the image rows follow)
+  if (tid == 0) SSTAMP(1);
+  const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) SSTAMP(2);
   // From here the roles run free: the issuer and the I/O warps start fetching at once, the workers write the codes to
   // tensor memory (the issuer cannot start before every worker has handed over tile 0).
@@ -484,20 +600,23 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     // streaming stores, and refill the stage with the rows of tile j+NSX by cp.async (each thread overwrites exactly
     // the elements it has just read). =====
     float* dstg = a.out != nullptr ? a.out : a.delta;
-    for (int j = a.early_x; j < NSX; ++j) load_x(j);
-    for (int j = 0; j < my_tiles; ++j) {
-      const int p0 = (blockIdx.x + j * gridDim.x) * TP;
-      const int sx = j % NSX;
-      const float* xt = xs + sx * xstage;
-      mbar_wait(out_ready + sx, (j / NSX) & 1);
-      if (warp == WARP_LOAD && j == 0) SSTAMP(7);
-      if (warp == WARP_LOAD && j == my_tiles - 1) SSTAMP(9);
+    // (one loop, one call site of the row request: rounds -NSX .. -1 only request the first NSX tiles)
+#pragma unroll 1
+    for (int j = -NSX; j < my_tiles; ++j) {
+      if (j >= 0) {
+        const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+        const int sx = j % NSX;
+        const float* xt = xs + sx * xstage;
+        mbar_wait(out_ready + sx, (j / NSX) & 1);
+        if (warp == WARP_LOAD && j == 0) SSTAMP(7);
+        if (warp == WARP_LOAD && j == my_tiles - 1) SSTAMP(9);
 #pragma unroll 4
-      for (int e = iot; e < B * Q4; e += NTIO) {
-        const int b = e / Q4, col = (e - b * Q4) * 4;
-        if (p0 + col < P) st_stream4(dstg + (size_t)b * P + p0 + col, *reinterpret_cast<const float4*>(xt + b * XP + col));
+        for (int e = iot; e < B * Q4; e += NTIO) {
+          const int b = e / Q4, col = (e - b * Q4) * 4;
+          if (p0 + col < P) st_stream4(dstg + (size_t)b * P + p0 + col, *reinterpret_cast<const float4*>(xt + b * XP + col));
+        }
+        if (warp == WARP_LOAD && j == 0) SSTAMP(8);
       }
-      if (warp == WARP_LOAD && j == 0) SSTAMP(8);
       load_x(j + NSX);
     }
     if (warp == WARP_LOAD) SSTAMP(10);
@@ -510,21 +629,16 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     const uint64_t bstep = (uint64_t)((2 * a.Sd) >> 4);
     const int ksteps = a.Kp8 / 8;
     const bool leader = elect_one();
-    // raw dictionary tile `it` -> stage it % NS by one TMA bulk copy.  The stage is known to be free: the copy for
-    // tile it is issued right after the hand-off of tile it-NS, i.e. after every worker has finished splitting it.
-    auto load_D = [&](int it) {
-      const int p0 = (blockIdx.x + it * gridDim.x) * TP;
-      const uint32_t bytes = (uint32_t)(min(TP, P - p0) * K * 4);
-      mbar_expect_tx(full_raw + it % NS, bytes);
-      bulk_g2s(raw + (it % NS) * a.raw_floats, a.D2 + (size_t)p0 * K, bytes, full_raw + it % NS);
-    };
-    if (leader && ragged)
-      for (int it = 0; it < NS && it < my_tiles; ++it) load_D(it);
+    // (A raw stage is known to be free when its next tile is requested: the copy for tile it is issued right after the
+    // hand-off of tile it-NS, i.e. after every worker has finished splitting it.)
+    if (leader)
+      for (int it = ragged ? 0 : 1; it < NS && it < my_tiles; ++it) load_D(it);
     for (int it = 0; it < my_tiles; ++it) {
       // Workers staged tile `it`.  An mbarrier per image buffer, not a named barrier: with double-buffered images a
       // fast warp reaches the hand-off of tile it+1 before a slow warp has arrived for tile it, and a second
       // bar.arrive of the same warp would complete the named barrier early.
       mbar_wait(staged + (it & 1), (it >> 1) & 1);
+      if (it == 0) mbar_wait(codes_ready, 0);  // the workers have written the batch codes to tensor memory
       tc_fence_after();
       if (it == 0) SSTAMP(4);
       if (leader) {
@@ -559,37 +673,31 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     TileChan tc;
     tile_chan_init(tc);
     TIM_DECL;
-    // batch codes (hi / lo) -> tensor memory, once per CTA
+    // batch codes (hi / lo) -> tensor memory, once per CTA: thread <-> image b = 32 quad + lane (its TMEM lane), the four
+    // warps of a quadrant share the 8-atom chunks
     {
       const int nchunks = a.Kp8 / 8;
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * TP);
-#pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c = cg + 4 * ci;
-        if (c < nchunks) {  // warp-uniform
-          float hi[8], lo[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) split_tf32(vv[ci][i], hi[i], lo[i]);
-          tmem_st8(lane_base + (uint32_t)(8 * c), hi);
-          tmem_st8(lane_base + (uint32_t)(a.Kp8 + 8 * c), lo);
+      if (a.stage_codes) {
+        mbar_wait(codes_landed, 0);  // every warp's share of the gather has landed
+        if (a.codes_out != nullptr && blockIdx.x == gridDim.x - 1) {
+          // the last CTA (never one with more tiles than the others) leaves the gathered rows behind as a contiguous
+          // [B, K] block: the backward kernel of the step fetches it with one bulk copy instead of a gather of its own
+          for (int r = warp; r < B; r += NW)
+            for (int k = lane; k < K; k += 32) a.codes_out[r * K + k] = cstage[r * a.cpitch + k];
         }
-      }
-      if (nchunks > 16) {
-        // more than 128 atoms (up to 224: the codes take 2 Kp8 of the 512 TMEM columns): the chunks beyond the 16 that
-        // were loaded at kernel entry follow in a second round -- one more cold miss, at large K only
         const int b = quad * 32 + lane;
-        const int bi = min(b, B - 1);
-        const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
-        const float* vrow = a.v + row * K;
+        const float* crow = cstage + min(b, B - 1) * a.cpitch;
+        if (a.cw == 4) synth_codes_to_tmem<4>(crow, b < B, K, a.Kp8, cg, lane_base);
+        else if (a.cw == 2) synth_codes_to_tmem<2>(crow, b < B, K, a.Kp8, cg, lane_base);
+        else synth_codes_to_tmem<1>(crow, b < B, K, a.Kp8, cg, lane_base);
+        tmem_st_wait();
+        bar_sync(2, NT);  // every worker has read its rows: the second image buffer is free
+        zero_padding(Dimg + 2 * a.dimg, tid, NT);
+      } else {
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-          const int k0 = 8 * (16 + cg + 4 * ci);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
-        }
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const int c = 16 + cg + 4 * ci;
+          const int c = cg + 4 * ci;
           if (c < nchunks) {  // warp-uniform
             float hi[8], lo[8];
 #pragma unroll
@@ -598,8 +706,36 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
             tmem_st8(lane_base + (uint32_t)(a.Kp8 + 8 * c), lo);
           }
         }
+        if (nchunks > 16) {
+          // more than 128 atoms (up to 224: the codes take 2 Kp8 of the 512 TMEM columns): the chunks beyond the 16 that
+          // were loaded at kernel entry follow in a second round -- one more cold miss, at large K only
+          const int b = quad * 32 + lane;
+          const int bi = min(b, B - 1);
+          const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
+          const float* vrow = a.v + row * K;
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            const int k0 = 8 * (16 + cg + 4 * ci);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+          }
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            const int c = 16 + cg + 4 * ci;
+            if (c < nchunks) {  // warp-uniform
+              float hi[8], lo[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) split_tf32(vv[ci][i], hi[i], lo[i]);
+              tmem_st8(lane_base + (uint32_t)(8 * c), hi);
+              tmem_st8(lane_base + (uint32_t)(a.Kp8 + 8 * c), lo);
+            }
+          }
+        }
+        tmem_st_wait();
       }
-      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(codes_ready);
     }
     if (warp == 0) SSTAMP(3);
 
@@ -743,7 +879,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, a.tmem_cols);
   if (tid == 0) SSTAMP(11);
 }
 
@@ -772,8 +908,7 @@ struct GradArgs {
   const float* D2;
   const float* v;
   const int64_t* vidx;
-  int hv_on;          // the batch indices travel in the kernel parameters (host index array)
-  int hv[128];
+  int hv_on;          // the batch indices travel in the kernel parameters (host index array hv[], at the end)
   int B, P, K;
   int Bp;             // contraction length of dD: round_up(B, 16)
   int Kp;             // N of the dv MMA: round_up(K, 16)
@@ -790,10 +925,14 @@ struct GradArgs {
                       // launch handles a window of K columns of a wider dictionary (STRIDED: more than 128 atoms)
   unsigned k4div;     // ceil(2^32 / (K / 4)) (STRIDED: float4 index inside a dense tile -> row)
   int accumulate;     // plain dD output: dD2 += tile (TMA reduce-add store) instead of dD2 = tile
-  int early;          // host indices: code loads at kernel entry, bulk loads right after the set-up barrier
-  int mma_order;      // 0: the dD MMAs of a tile, then its dv MMAs; 1: interleaved
+  int dreg;           // bytes of the dictionary-image region; at kernel entry it stages the code rows of the batch
+  int cw;             // floats per cp.async of the code-row gather: 4, 2 or 1 (alignment of v, ldk and K)
+  int rpw;            // rows of the code gather per warp: ceil(B / 25) (warps 0..24 take part)
+  int pfast;          // dictionary split: consecutive lanes take consecutive pixels (K % 8 != 0) instead of atom groups
+  int codes_contig;   // the code rows are rows 0..B-1 of v, K floats apart, 16-byte aligned as a block: one bulk copy
   ChannelConsts cc;
   AdamwDev hp;
+  int hv[128];
 };
 
 // FUSED (AdamW + clamp in the epilogue warps) is a template parameter: the two variants get their own register
@@ -802,27 +941,39 @@ struct GradArgs {
 // atoms: two column windows, two launches).  Tiles are dense [TP][K] in shared memory as always; only the global
 // addresses change: the D rows of a tile arrive as one bulk copy PER ROW (issued by the 32 lanes of the loader warp),
 // the moments / outputs are addressed by (row, column) instead of a flat offset.
-template <int TP, bool FUSED, bool STRIDED>
+template <int TP, bool FUSED, bool STRIDED, int NPF>
 __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a) {
   constexpr int Q4 = TP / 4;                           // float4 per gradient row
   constexpr int GJ = (128 * Q4 + NT - 1) / NT;         // float4 per worker thread (B <= 128)
   constexpr int HALF = TP / 2;                         // accumulator columns per epilogue warp
-  constexpr int NPF = 4;                               // float4 items per epilogue thread whose moments are prefetched
+  // NPF: float4 items per thread of the AdamW pass whose moments are prefetched into registers: 3 when the tile has at
+  // most 3 * 320 of them (K <= 60 at TP = 64) -- ten warps then share the pass; else 4 items on the eight epilogue warps.
+  // (Ten warps with 4 items, or any spill in this kernel, cost more than they save: a reload from local memory queues
+  // behind the stores of the pass.)
+  constexpr int NEP = (FUSED && NPF == 3) ? NEP_MAX : NE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // (contiguous, in this order: the loader initialises them one per lane)
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem_raw);  // [NS] D (, m, s) tile landed
   uint64_t* empty_raw = full_raw + NS;                         // [NS] stage consumed (workers: split, epilogue warps: AdamW)
   uint64_t* mma_done = empty_raw + NS;                         // [2] MMAs of the tiles using image buffer 0 / 1 retired
   uint64_t* staged = mma_done + 2;                             // [2] images of buffer 0 / 1 written (workers -> issuer)
   uint64_t* acc_empty = staged + 2;                            // [2] dD accumulator 0 / 1 read out (epilogue warps -> issuer)
   uint64_t* epi_done = acc_empty + 2;                          // [NS] output tile written into the stage (epilogue warps -> loader)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + NS);
-  long long* vrow_s = reinterpret_cast<long long*>(smem_raw + 256 + 1024);  // [128] row of v of each image
+  uint64_t* dD_done = epi_done + NS;                           // [2] dD MMAs of the tiles using accumulator 0 / 1 retired
+  uint64_t* codes_ready = dD_done + 2;                         // [1] batch codes written to tensor memory (epilogue warps)
+  uint64_t* codes_landed = codes_ready + 1;                    // [1] code rows of the batch gathered into shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(codes_landed + 1);
   typedef unsigned short bf16_t;
   const int dbuf = 3 * a.dimg, gbuf = 3 * a.gimg + 1024;          // bf16 elements per buffer (gradient: + 2 KB pad)
-  bf16_t* Di = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);   // [2 buffers][3 terms] dictionary images
-  bf16_t* Gi = Di + 2 * dbuf;                                     // [2 buffers][3 terms (+ over-read pad)] gradient images
+  bf16_t* Di = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES);   // [2 buffers][3 terms] dictionary images (a.dreg bytes)
+  bf16_t* Gi = reinterpret_cast<bf16_t*>(smem_raw + HDR_BYTES + a.dreg);  // [2 buffers][3 terms (+ over-read pad)] gradient images
   float* dDs = reinterpret_cast<float*>(Gi + 2 * gbuf);           // [2][TP*K] dD tiles, flat like the dictionary (fused step)
   float* raw = dDs + (a.D2w != nullptr ? 2 * TP * a.K : 0);       // [NS][raw_floats]
+  // [B][K] code rows of the batch, until they are in TMEM: in the dD tiles when they fit there (fused step, B <= 2 TP: first
+  // written after the MMAs of tile 0, which need the codes), else in the dictionary-image region (whose first use then
+  // waits for the codes)
+  const bool codes_in_dDs = FUSED && a.B <= 2 * TP;
+  float* cstage = codes_in_dDs ? dDs : reinterpret_cast<float*>(Di);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
@@ -843,26 +994,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   const int tile_elems = TP * K;
   const uint32_t ne_tmem = 2u * (uint32_t)((K + 31) / 32);  // epilogue warps whose TMEM quadrant holds atoms
   STAMP(0);
-  // `early`: with host indices (kernel parameters) or identity rows the code rows of the batch are ONE cold miss away,
-  // and the roles start their bulk traffic right after the set-up barrier, next to the code loads.  With a device index
-  // array the codes are a chain of two dependent misses, and the bulk traffic -- 148 CTAs x 3 stages of D tiles plus the
-  // gradient rows of the first tiles would queue ~15 MB ahead of the second hop: measured 4 us on the first MMA -- is
-  // held back until the codes are in.
-  const bool early = (a.hv_on != 0 || a.vidx == nullptr) && a.early != 0;
-  if (tid == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + i, 1); mbar_init(empty_raw + i, (a.want_dv ? NW : 0) + (fused ? NE : 0) + ((a.want_dv || fused) ? 0 : 1));
-                                   mbar_init(epi_done + i, ne_tmem); }
-    for (int i = 0; i < 2; ++i) { mbar_init(mma_done + i, 1); mbar_init(staged + i, NW); mbar_init(acc_empty + i, ne_tmem); }
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-  for (int b = tid; b < 128; b += NTHREADS_GRAD)  // element offset of the code row of image b (rows >= B: row of image B-1)
-    vrow_s[b] = (a.hv_on ? (long long)a.hv[min(b, B - 1)] : a.vidx ? (long long)a.vidx[min(b, B - 1)] : (long long)min(b, B - 1)) *
-                (long long)a.ldk;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
   // global element offset of float4 `e4` of the dense tile that starts at pixel p0
   auto goff = [&](int p0, int e4) -> size_t {
     if constexpr (STRIDED) {
@@ -872,10 +1003,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       return (size_t)p0 * K + 4 * (size_t)e4;
     }
   };
-  // tensor memory: [0, 2 TP) two dD^T accumulators | [2 TP, 2 TP + Kp) dv accumulator | then the codes, 3 x Bp/2 columns
-  const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
-  const uint32_t codes = acc_dv + (uint32_t)a.Kp;
-
   // D tile `it` -> raw stage it % NS: a contiguous run, one TMA bulk copy (the stages are never zero-filled: a ragged
   // last tile is handled by the consumers).
   auto load_raw = [&](int it, bool leader) {  // (called by the whole loader warp)
@@ -896,7 +1023,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     __syncwarp();
   };
   // workers: fixed per-thread share of the gradient tile: float4 e = tid + j*NT -> image b = e / Q4, 4-pixel column q.
-  // The rows of tile 0 are requested before the batch codes (both are on the critical path of the first tile).
   int gsrc[GJ], gdst[GJ];  // gsrc: 4q, the pixel column (-1: none); gdst: bf16 offset inside an image
   const float* grow[GJ];   // &g[b, 4q]
   float4 greg[GJ];
@@ -908,6 +1034,27 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       if (gsrc[j] >= 0 && p0 + gsrc[j] < P) greg[j] = ld_stream4(grow[j] + p0);
     }
   };
+
+  // ---- Kernel entry.  Everything the first tile needs is ONE cold miss away and depends on nothing but the kernel
+  // parameters, so every role puts its requests out before any set-up work: the workers the gradient rows of tile 0
+  // (registers), the epilogue warps the code rows of the batch (cp.async gather into shared memory: B rows of K floats
+  // in ceil(K / 32 cw) requests per row -- the former register gather was 512 requests of 128 bytes per CTA and took
+  // 3 us just to issue), the loader the first NS dictionary tiles (TMA).  Barrier init, the TMEM allocation and the zero
+  // fill of the operand images run underneath. ----
+  // Code rows of the batch -> shared memory.  Contiguous rows (no index, 16-byte-aligned block: the caller passes the
+  // [B, K] block that adil_synth left behind) arrive as ONE bulk copy issued by the loader; else every warp but the
+  // loader's gathers rows [w rpw, (w + 1) rpw) by cp.async: lane l holds the address of row w rpw + (l & 7) (one line
+  // of the parameters or of the index array per warp).  The load/store unit accepts such a sub-line cp.async only every
+  // ~20 ns, SM-wide (measured: B = 100 rows take 2 us however they are spread over the warps), so the gather is the
+  // slow path.
+  auto gather_share = [&]() {
+    const int r0 = warp * a.rpw;
+    if (a.want_dD && !a.codes_contig && r0 < B) {
+      const int rb = min(r0 + (lane & 7), B - 1);
+      const long long row = a.hv_on ? (long long)a.hv[rb] : (a.vidx ? (long long)a.vidx[rb] : (long long)rb);
+      gather_rows_cw<8>(cstage + r0 * K, K, a.v + row * (long long)a.ldk, min(a.rpw, B - r0), K, a.cw, lane);
+    }
+  };
   if (warp < NW) {
 #pragma unroll
     for (int j = 0; j < GJ; ++j) {
@@ -917,46 +1064,56 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       grow[j] = a.g + (size_t)min(b, B - 1) * P + 4 * q;
       gdst[j] = (q >> 1) * (a.Sg >> 1) + (b >> 3) * 64 + (b & 7) * 8 + (q & 1) * 4;
     }
+    if (my_tiles > 0) prefetch(0);
   }
-  // The batch codes are the first thing on the critical path of tile 0: their loads go out first (one straight-line
-  // block: a per-element choice of the index source turns into 32 branchy, serialised misses -- measured +8 us) and fly
-  // during the zero fill.  worker thread <-> atom m = 32*quad + lane; the warps of a quadrant share the 16-image chunks.
-  float vv[2][16];
-#pragma unroll
-  for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) vv[ci][i] = 0.0f;
-  if (warp < NW && a.want_dD && (warp & 3) * 32 < K) {  // (a quadrant whose 32 atoms are all padding keeps zeros)
-    const int m = (warp & 3) * 32 + lane;
-    const float* vcol = a.v + min(m, K - 1);
-    const float keep = m < K ? 1.0f : 0.0f;
-#pragma unroll
-    for (int ci = 0; ci < 2; ++ci) {
-      const int b0 = 16 * ((warp >> 2) + 4 * ci);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) vv[ci][i] = __ldg(vcol + vrow_s[b0 + i]) * ((b0 + i < B) ? keep : 0.0f);
+  if (warp != WARP_LOAD_G) gather_share();  // (one call site: the workers' share queues behind their gradient rows)
+  if (warp < NW) {
+    STAMP(8);
+    // zero the operand images once: contraction padding (images B..Bp, atoms K..Kp) must be zero, over-read regions
+    // finite.  (No proxy fence here: it is a MEMBAR.ALL.CTA and would wait for the loads in flight; every thread fences
+    // before its first hand-off to the tensor core, which covers these stores too.)  The dictionary-image region is
+    // left alone while it stages the code rows.
+    uint4* z = reinterpret_cast<uint4*>(codes_in_dDs || !a.want_dD ? reinterpret_cast<bf16_t*>(Di) : Gi);
+    const int nz = ((codes_in_dDs || !a.want_dD ? a.dreg : 0) >> 4) + ((2 * gbuf) >> 3);
+    for (int e = tid; e < nz; e += NT) z[e] = make_uint4(0u, 0u, 0u, 0u);
+    STAMP(12);
+  } else if (warp == WARP_EPI + NE) {
+    tmem_alloc(tmem_slot, a.tmem_cols);
+    WSTAMP(1);
+  } else if (warp == WARP_LOAD_G) {
+    // the loader initialises the mbarriers, one per lane (they are contiguous from full_raw on), and requests the first
+    // NS dictionary tiles
+    if (lane < 3 * NS + 10) {
+      const uint32_t c_empty = (uint32_t)((a.want_dv ? NW : 0) + (fused ? NEP : 0) + ((a.want_dv || fused) ? 0 : 1));
+      uint32_t cnt = 1;                                            // full_raw, mma_done, dD_done
+      if (lane >= NS && lane < 2 * NS) cnt = c_empty;              // empty_raw
+      else if (lane >= 2 * NS + 2 && lane < 2 * NS + 4) cnt = NW;  // staged
+      else if (lane >= 2 * NS + 4 && lane < 3 * NS + 6) cnt = ne_tmem;  // acc_empty, epi_done
+      else if (lane == 3 * NS + 8) cnt = NE;                       // codes_ready
+      else if (lane == 3 * NS + 9) cnt = a.codes_contig ? 1 : NTHREADS_GRAD - 32;  // codes_landed: the bulk copy / every gathering thread
+      mbar_init(full_raw + lane, cnt);
+      fence_mbar_init();
     }
-  }
-  if (early) {
-    // only the workers zero the operand images and meet at a named barrier: the loader, the epilogue warps and the
-    // issuer go straight to their roles (the issuer's first MMA follows the workers' first hand-off)
-    if (warp < NW) {
-      uint4* z = reinterpret_cast<uint4*>(Di);
-      const int nz = (2 * (dbuf + gbuf)) >> 3;
-      for (int e = tid; e < nz; e += NT) z[e] = make_uint4(0u, 0u, 0u, 0u);
-      fence_proxy_async();
-      bar_sync(2, NT);
+    __syncwarp();
+    const bool leader = elect_one();
+    if (leader && a.want_dD && a.codes_contig) {
+      mbar_expect_tx(codes_landed, (uint32_t)(B * K * 4));
+      bulk_g2s(cstage, a.v, (uint32_t)(B * K * 4), codes_landed);
     }
-  } else {
-    // zero the operand images once: contraction padding must be zero, over-read regions finite
-    uint4* z = reinterpret_cast<uint4*>(Di);
-    const int nz = (2 * (dbuf + gbuf)) >> 3;
-    for (int e = tid; e < nz; e += NTHREADS_GRAD) z[e] = make_uint4(0u, 0u, 0u, 0u);
-    // zero fill (generic proxy) ordered before the tensor core's (async proxy) reads.  The fence is a MEMBAR.ALL.CTA: it
-    // also waits for the code loads above, which is what the bulk traffic below is held back for.
-    fence_proxy_async();
-    __syncthreads();
+    // (only the first dictionary tile now: the others would queue megabytes ahead of what tile 0 is waiting for)
+    if (a.nraw > 0 && my_tiles > 0) load_raw(0, leader);
+    WSTAMP(2);
   }
+  // set-up barrier: the operand images are zeroed, the mbarriers initialised, tensor memory allocated
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (a.want_dD && !a.codes_contig && warp != WARP_LOAD_G) cp_async_arrive_noinc(codes_landed);  // this thread's share of the gather
+  STAMP(10);
+  const uint32_t tmem_base = *tmem_slot;
+  // tensor memory: [0, 2 TP) two dD^T accumulators | [2 TP, 2 TP + Kp) dv accumulator | then the codes, 3 x Bp/2 columns
+  const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
+  const uint32_t codes = acc_dv + (uint32_t)a.Kp;
   STAMP(1);
   // (the setmaxnreg instructions open the role branches below)
 
@@ -969,7 +1126,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     const bool leader = elect_one();
     const bool dD_out = a.want_dD && !fused;
     if (a.nraw > 0)
-      for (int it = 0; it < NS && it < my_tiles; ++it) load_raw(it, leader);
+      for (int it = 1; it < NS && it < my_tiles; ++it) load_raw(it, leader);  // (tile 0 was requested at kernel entry)
     for (int it = NS; it < my_tiles + NS; ++it) {
       const int jt = it - NS;  // the tile whose stage is recycled now
       {
@@ -1032,68 +1189,62 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       CHAIN(0, it);
       mbar_wait(staged + buf, (it >> 1) & 1);  // workers staged tile `it` (mbarrier: fast warps run one tile ahead)
       tc_fence_after();
+      if (it == 0) WSTAMP(6);
       CHAIN(1, it);
-      if (leader && a.want_dD && a.want_dv && a.mma_order == 1) {
-        // Interleaved issue: a dD MMA (A in tensor memory: 2 KB of operand reads, bound by the tensor pipe) next to a dv
-        // MMA (both operands in shared memory: 6 KB of operand reads, bound by the shared-memory port), so that the
-        // operand fetch of the one overlaps the arithmetic of the other.
+      auto issue_dD = [&]() {
         const uint32_t acc = tmem_base + (uint32_t)(buf * TP);
 #pragma unroll
         for (int t = 0; t < 6; ++t) {
           constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, tv[6] = {0, 2, 1, 0, 1, 0};
-          uint32_t at = codes + (uint32_t)tv[t] * cterm;
-          uint64_t bD = dD_b0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
+          const uint32_t at = codes + (uint32_t)tv[t] * cterm;
+          const uint64_t bd = dD_b0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
+          // unrolled over the (at most 8) 16-image steps: as a rolled loop every MMA cost ~11 dependent uniform-datapath
+          // instructions (descriptor arithmetic, loop control) on a warp that shares its scheduler with six busy ones,
+          // and the 42 dD MMAs of a tile were issue-bound (tensor pipe 36 % active)
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            if (ks < ksteps_dD) mma_bf16_ts(acc, at + 8u * ks, bd + 16u * ks, idesc_dD, (t | ks) ? 1u : 0u);
+        }
+      };
+      auto issue_dv = [&]() {
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, td[6] = {0, 2, 1, 0, 1, 0};
           uint64_t ad = dv_a0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
-          uint64_t bv = dv_b0 + (uint64_t)buf * db16 + (uint64_t)tv[t] * ds16;
-          const int nks = ksteps_dD > TP / 16 ? ksteps_dD : TP / 16;
-#pragma unroll 1
-          for (int ks = 0; ks < nks; ++ks) {
-            if (ks < ksteps_dD) { mma_bf16_ts(acc, at, bD, idesc_dD, (t | ks) ? 1u : 0u); at += 8; bD += 16; }
-            if (ks < TP / 16) { mma_bf16(acc_dv, ad, bv, idesc_dv, (it | t | ks) ? 1u : 0u); ad += astep; bv += 16; }
-          }
+          uint64_t bd = dv_b0 + (uint64_t)buf * db16 + (uint64_t)td[t] * ds16;
+#pragma unroll
+          for (int ks = 0; ks < TP / 16; ++ks, ad += astep, bd += 16)
+            mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
         }
-        mma_commit(mma_done + buf);
-      } else if (leader) {
-#ifdef ADIL_EXP_NO_DDMMA
-        if (false) {
-#else
+      };
+      // Tile 0: the dv MMAs need no codes, so they go first and the code conversion of the epilogue warps hides behind
+      // them; from tile 1 on the dD MMAs go first and are committed on their own, so that the epilogue warps start on
+      // the accumulator while the dv MMAs of the tile run.
+      if (it == 0) {
+        if (leader && a.want_dv) issue_dv();
+        __syncwarp();
         if (a.want_dD) {
-#endif
-          const uint32_t acc = tmem_base + (uint32_t)(buf * TP);
-#pragma unroll
-          for (int t = 0; t < 6; ++t) {
-            constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, tv[6] = {0, 2, 1, 0, 1, 0};
-            uint32_t at = codes + (uint32_t)tv[t] * cterm;
-            uint64_t bd = dD_b0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
-#pragma unroll 1
-            for (int ks = 0; ks < ksteps_dD; ++ks, at += 8, bd += 16) mma_bf16_ts(acc, at, bd, idesc_dD, (t | ks) ? 1u : 0u);
-          }
+          mbar_wait(codes_ready, 0);  // the epilogue warps have written the batch codes to TMEM
+          tc_fence_after();
+          if (leader) { issue_dD(); mma_commit(dD_done + buf); }
         }
-#ifdef ADIL_EXP_NO_DVMMA
-        if (false) {
-#else
-        if (a.want_dv) {
-#endif
-#pragma unroll
-          for (int t = 0; t < 6; ++t) {
-            constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, td[6] = {0, 2, 1, 0, 1, 0};
-            uint64_t ad = dv_a0 + (uint64_t)buf * gb16 + (uint64_t)tg[t] * gs16;
-            uint64_t bd = dv_b0 + (uint64_t)buf * db16 + (uint64_t)td[t] * ds16;
-#pragma unroll
-            for (int ks = 0; ks < TP / 16; ++ks, ad += astep, bd += 16)
-              mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
-          }
-        }
+        if (leader) mma_commit(mma_done + buf);
+        WSTAMP(7);
+      } else if (leader) {
+        if (a.want_dD) { issue_dD(); mma_commit(dD_done + buf); }
+        if (a.want_dv) issue_dv();
         mma_commit(mma_done + buf);
       }
       __syncwarp();
+      if (it == 0) WSTAMP(8);
       CHAIN(2, it);
     }
-  } else if (warp >= WARP_EPI + NE) {
-    // (warps 24, 25: idle filler so that the issuer and the loader land on schedulers 2 and 3)
+  } else if (warp >= WARP_EPI + NEP || (warp >= WARP_EPI + NE && !a.want_dD)) {
+    // (warps 24, 25 outside the fused step: idle filler so that the issuer and the loader land on schedulers 2 and 3)
     reg_dealloc<24>();
   } else if (warp >= WARP_EPI) {
     reg_alloc<96>();
+    const bool helper = warp >= WARP_EPI + NE;  // warps 24, 25: the AdamW pass only (no TMEM quadrant of their own)
     // ===== epilogue warps (8, two per scheduler).  Phase A: the warps whose TMEM quadrant holds atoms (quadrant q,
     // pixel half h: atoms [32q, 32q+32) of pixels [h TP/2, (h+1) TP/2)) read the dD^T accumulator (lane = atom,
     // column = pixel), release it to the tensor core, multiply by 1/std and write it flat -- [pixel][atom], like the
@@ -1102,7 +1253,44 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     // the TMA-landed D / m / s rows IN PLACE.  Plain dD output: straight into the stage.  Either way the finished
     // stage leaves through the loader warp as TMA bulk stores. =====
     const int quad = warp & 3, half = (warp - WARP_EPI) >> 2;
-    const bool has_atoms = quad * 32 < K;
+    const bool has_atoms = quad * 32 < K && !helper;
+    if (a.want_dD && !helper) {
+      // batch codes (three bf16 terms) -> tensor memory, once per CTA: lane = atom, a column holds the image pair
+      // (2c, 2c+1).  The rows were gathered into shared memory at kernel entry; thread <-> atom m = 32 quad + lane reads
+      // its column (consecutive lanes, consecutive words: conflict-free); the two warps of a quadrant share the
+      // 16-image chunks.  A quadrant whose 32 atoms are all padding writes zeros.
+      mbar_wait(codes_landed, 0);  // every warp's share of the gather has landed
+      if (warp == WARP_EPI) { WSTAMP(3); WSTAMP(4); }
+      const int m = quad * 32 + lane;
+      const bool m_ok = m < K;
+      const int nchunks = a.Bp / 16;  // 8-column chunks per term
+      const uint32_t lane_base = codes + ((uint32_t)(quad * 32) << 16);
+      const float* ccol = cstage + min(m, K - 1);
+#pragma unroll 1
+      for (int c = half; c < nchunks; c += 2) {  // (rolled: unrolled, the cold instruction fetch of 16 KB cost 5 us)
+        uint32_t t0[8], t1[8], t2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int b0 = 16 * c + 2 * i;
+          const float x0 = (m_ok && b0 < B) ? ccol[b0 * K] : 0.0f;
+          const float x1 = (m_ok && b0 + 1 < B) ? ccol[(b0 + 1) * K] : 0.0f;
+          uint32_t a0, a1, a2, b0w, b1w, b2w;
+          split_bf16x3(x0, a0, a1, a2);
+          split_bf16x3(x1, b0w, b1w, b2w);
+          t0[i] = pack_hi16(a0, b0w);
+          t1[i] = pack_hi16(a1, b1w);
+          t2[i] = pack_hi16(a2, b2w);
+        }
+        tmem_st8u(lane_base + (uint32_t)(8 * c), t0);
+        tmem_st8u(lane_base + (uint32_t)(a.Bp / 2 + 8 * c), t1);
+        tmem_st8u(lane_base + (uint32_t)(a.Bp + 8 * c), t2);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(codes_ready);
+      if (warp == WARP_EPI) WSTAMP(5);
+    }
     if (a.want_dD && (fused || has_atoms)) {  // (plain dD output: a quadrant without atoms has nothing to do)
       const int k = quad * 32 + lane;
       const bool k_ok = k < K;
@@ -1111,12 +1299,11 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       tile_chan_init(tc);
       // AdamW moments: straight from global memory into registers, one tile ahead (they never need shared memory)
       float4 Mp[NPF], Sp[NPF];
-      auto prefetch_ms = [&](int j) {
-        const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+      auto prefetch_ms = [&](int p0) {  // p0: first pixel of the tile
         const int n4 = (min(TP, P - p0) * K) >> 2;
 #pragma unroll
         for (int u = 0; u < NPF; ++u) {
-          const int e4 = etid + u * (NE * 32);
+          const int e4 = etid + u * (NEP * 32);
           if (e4 < n4) {
             const size_t go = goff(p0, e4);
             Mp[u] = ld_global4(a.m + go);
@@ -1124,18 +1311,23 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           }
         }
       };
-      if (fused && my_tiles > 0) prefetch_ms(0);
+      if (fused && my_tiles > 0) prefetch_ms((int)blockIdx.x * TP);
+      // (p0 advances by gridDim.x * TP with gridDim.x read as a constant-bank operand: written as j * gridDim.x ptxas hoisted
+      // the factor into a register, SPILLED it, and reloaded it from local memory at the top of every round -- a load
+      // that queues behind the twelve stores of the round before: 8 % of all stall samples, +6 us per launch.)
+      int p0 = (int)blockIdx.x * TP - (int)gridDim.x * TP;
       for (int j = 0; j < my_tiles; ++j) {
-        const int p0 = (blockIdx.x + j * gridDim.x) * TP;
+        p0 += (int)gridDim.x * TP;
         const int rows = min(TP, P - p0);
         const int sj = j % NS, buf = j & 1;
         float* stage = raw + sj * a.raw_floats;
         float* gtile = fused ? dDs + buf * tile_elems : stage;
         if (has_atoms) {
           if (a.cc.use) tile_chan_update(tc, a.cc, p0);
-          mbar_wait(mma_done + buf, (j >> 1) & 1);  // MMAs of tile j retired: its dD accumulator is complete
+          mbar_wait(dD_done + buf, (j >> 1) & 1);  // dD MMAs of tile j retired: its accumulator is complete
           tc_fence_after();
           if (warp == WARP_EPI) CHAIN(3, j);
+          if (warp == WARP_EPI && j == 0) WSTAMP(9);
           // (plain dD output with dv: the stage held the D rows of the dictionary split, which every worker finished
           // before the MMAs of this tile were issued; without dv it is a staging buffer handed back by the loader)
           if (!fused && a.nraw == 0 && j >= NS) mbar_wait(full_raw + sj, ((j / NS) - 1) & 1);
@@ -1185,13 +1377,15 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           if (warp == WARP_EPI) CHAIN(4, j);
         }
         if (fused) {
-          bar_sync(3, NE * 32);  // gradient tile complete (and every warp is done with the tile two steps back)
+          bar_sync(3, NEP * 32);  // gradient tile complete (and every warp is done with the tile two steps back)
+          if (warp == WARP_EPI) CHAIN(11, j);
           mbar_wait(full_raw + sj, (j / NS) & 1);  // D rows landed
+          if (warp == WARP_EPI) CHAIN(12, j);
           const int n4 = (rows * K) >> 2;
 #ifndef ADIL_EXP_NO_EPI
 #pragma unroll
           for (int u = 0; u < NPF; ++u) {
-            const int e4 = etid + u * (NE * 32);
+            const int e4 = etid + u * (NEP * 32);
             if (e4 < n4) {
               float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
               const float4 gd = *reinterpret_cast<const float4*>(gtile + 4 * e4);
@@ -1208,7 +1402,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
               *reinterpret_cast<float4*>(a.s + go) = Sp[u];
             }
           }
-          for (int e4 = etid + NPF * (NE * 32); e4 < n4; e4 += NE * 32) {  // (large K: beyond the prefetched part)
+          for (int e4 = etid + NPF * (NEP * 32); e4 < n4; e4 += NEP * 32) {  // (large K: beyond the prefetched part)
             float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
             const size_t go = goff(p0, e4);
             float4 Mv = ld_global4(a.m + go);
@@ -1228,13 +1422,15 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
 #endif
           __syncwarp();
           if (lane == 0) mbar_arrive(empty_raw + sj);  // this warp is done with the D rows of the stage
-          if (j + 1 < my_tiles) prefetch_ms(j + 1);    // the moments of the next tile fly while its MMAs run
+          if (j + 1 < my_tiles) prefetch_ms(p0 + (int)gridDim.x * TP);  // the moments of the next tile fly while its MMAs run
         } else {
           fence_proxy_async();  // the dD tile in the stage is read by the copy engine
           __syncwarp();
           if (lane == 0) mbar_arrive(epi_done + sj);
         }
         if (warp == WARP_EPI) CHAIN(5, j);
+        if (warp == WARP_EPI && j == 0) WSTAMP(10);
+        if (warp == WARP_EPI && j == my_tiles - 1) WSTAMP(11);
       }
     }
   } else {
@@ -1246,37 +1442,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     TileChan tc;
     tile_chan_init(tc);
     STAMP(3);
-    if (a.want_dD) {
-      // batch codes (three bf16 terms) -> tensor memory, once per CTA: a column holds the image pair (2c, 2c+1)
-      const int nchunks = a.Bp / 16;  // 8-column chunks per term
-      const uint32_t lane_base = codes + ((uint32_t)(quad * 32) << 16);
-#pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c = cg + 4 * ci;
-        if (c < nchunks) {  // warp-uniform
-          uint32_t t0[8], t1[8], t2[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint32_t a0, a1, a2, b0w, b1w, b2w;
-            split_bf16x3(vv[ci][2 * i], a0, a1, a2);
-            split_bf16x3(vv[ci][2 * i + 1], b0w, b1w, b2w);
-            t0[i] = pack_hi16(a0, b0w);
-            t1[i] = pack_hi16(a1, b1w);
-            t2[i] = pack_hi16(a2, b2w);
-          }
-          tmem_st8u(lane_base + (uint32_t)(8 * c), t0);
-          tmem_st8u(lane_base + (uint32_t)(a.Bp / 2 + 8 * c), t1);
-          tmem_st8u(lane_base + (uint32_t)(a.Bp + 8 * c), t2);
-        }
-      }
-      STAMP(7);
-      if (my_tiles > 0) prefetch(0);  // gradient rows of tile 0 (requested only now: next to the 32 code registers the
-                                      // compiler would spill the load targets, i.e. wait for the loads, first)
-      tmem_st_wait();
-    } else if (my_tiles > 0) {
-      prefetch(0);
-    }
-    STAMP(2);
     for (int it = 0; it < my_tiles; ++it) {
       const int p0 = (blockIdx.x + it * gridDim.x) * TP;
       const int s = it % NS;
@@ -1310,6 +1475,15 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         // dictionary tile (pre-update values): TMA-landed raw rows -> three bf16 images of D / std.  Rows past the end
         // of the array (ragged last tile) were never written: they are staged as zeros.
         if (warp == 0) { CHAIN(7, it - NS); CHAIN(10, it); }
+        if (it == 0 && a.want_dD && !codes_in_dDs) {
+          // the dictionary-image region staged the code rows until now: once they are in tensor memory it is zeroed
+          // (contraction padding must be zero, rows past a ragged end finite)
+          mbar_wait(codes_ready, 0);
+          uint4* zd = reinterpret_cast<uint4*>(Di);
+          for (int e = tid; e < (a.dreg >> 4); e += NT) zd[e] = make_uint4(0u, 0u, 0u, 0u);
+          bar_sync(2, NT);
+        }
+        if (it == 0) STAMP(7);
         mbar_wait(full_raw + s, (it / NS) & 1);
         if (warp == 0) CHAIN(8, it - NS);
         if constexpr (G_SCALED) {
@@ -1318,8 +1492,15 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           const float* rt = raw + s * a.raw_floats;
           const int rows = min(TP, P - p0);
           const int ngroups = (K + 7) / 8;
+          // item order: consecutive lanes take consecutive PIXELS of one atom group unless K is a multiple of 8 -- the
+          // row pitch K then maps the 8-float reads of 16 (8) lanes onto distinct banks and the 16-byte stores of 8 lanes
+          // onto one 128-byte line of an image; with consecutive groups of one pixel both were 2-way conflicts (ncu: 0.66 M
+          // of the kernel's 3.07 M shared-memory wavefronts).  K % 8 == 0: consecutive groups (contiguous reads).
           for (int e = tid; e < TP * ngroups; e += NT) {
-            const int p = div_magic_dev(e, a.gdiv), gq = e - p * ngroups, k0 = 8 * gq;
+            int p, gq;
+            if (a.pfast) { gq = e / TP; p = e - gq * TP; }
+            else { p = div_magic_dev(e, a.gdiv); gq = e - p * ngroups; }
+            const int k0 = 8 * gq;
             float val[8];
             const float* src = rt + p * K + k0;
             if (p < rows) {
@@ -1476,7 +1657,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (warp == WARP_EPI + NE) tmem_dealloc(tmem_base, a.tmem_cols);
   STAMP(6);
 }
 
@@ -1520,7 +1701,7 @@ SynthPlan plan_synth(int B, int P, int K, int hw) {
 }
 
 struct GradPlan {
-  int TP, Bp, Kp, Sg, Sd, dimg, gimg, raw_floats, nraw;
+  int TP, Bp, Kp, Sg, Sd, dimg, gimg, raw_floats, nraw, dreg;
   size_t smem;
   uint32_t tmem_cols;
   bool ok;
@@ -1545,9 +1726,12 @@ GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool
     pl.gimg = (TP / 8) * (pl.Sg / 2);
     pl.nraw = (fused || want_dv) ? 1 : 0;
     pl.raw_floats = (pl.nraw > 0 ? pl.nraw : 1) * TP * K;  // (dD only: the stage is the staging buffer of the output tile)
-    pl.smem = HDR_BYTES + 2 * 2 * (3 * ((size_t)pl.dimg + pl.gimg) + 1024) +  // two buffers of bf16 images
+    // dictionary-image region: two buffers of three bf16 images; at kernel entry it stages the B code rows (fp32), and at
+    // the end the [B][K] slab of the code gradient
+    pl.dreg = rup(2 * 2 * 3 * pl.dimg, 128);
+    if (pl.dreg < rup(4 * B * K, 128)) pl.dreg = rup(4 * B * K, 128);
+    pl.smem = HDR_BYTES + (size_t)pl.dreg + 2 * 2 * (3 * (size_t)pl.gimg + 1024) +  // + two buffers of gradient images
               sizeof(float) * ((fused ? 2 * (size_t)TP * K : 0) + (size_t)NS * pl.raw_floats);
-    if (want_dv && pl.smem < HDR_BYTES + sizeof(float) * (size_t)B * K) pl.smem = HDR_BYTES + sizeof(float) * (size_t)B * K;
     pl.tmem_cols = pow2_cols(2 * TP + pl.Kp + 3 * (pl.Bp / 2));  // accumulators + the codes
     if (pl.smem <= (size_t)SMEM_LIMIT && pl.tmem_cols <= 512) { pl.ok = true; return pl; }
   }
@@ -1557,6 +1741,18 @@ GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool
 template <typename KernelT>
 int set_smem(KernelT kern, size_t smem, const char* what) {
   return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), what);
+}
+
+// codes_out[b, :] = v[row(b), :] -- the export of the code rows when the synthesis kernel itself does not stage them in
+// shared memory (more atoms than its second image buffer holds): a launch of its own, off the benchmarked shapes
+struct GatherIdx {
+  int on;
+  int idx[128];
+};
+__global__ void gather_codes_kernel(float* codes_out, const float* v, const int64_t* vidx, const GatherIdx h, int K) {
+  const int b = blockIdx.x;
+  const long long row = h.on ? (long long)h.idx[b] : (vidx ? (long long)vidx[b] : (long long)b);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) codes_out[(size_t)b * K + k] = v[row * K + k];
 }
 
 template <int TP, bool TRAIN>
@@ -1572,8 +1768,8 @@ int launch_synth_tp(const SynthArgs& a, size_t smem, int grid, cudaStream_t st) 
 bool tc_synth_ok(int B, int P, int K, int hw) { return plan_synth(B > 128 ? 128 : B, P, K, hw).ok; }
 
 int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2,
-                    const float* v, const int64_t* v_index, int B, int P, int K, const ChannelConsts& cc, float eps,
-                    int flags, cudaStream_t st) {
+                    const float* v, const int64_t* v_index, float* codes_out, int B, int P, int K,
+                    const ChannelConsts& cc, float eps, int flags, cudaStream_t st) {
   const bool norm = (flags & ADIL_SYNTH_NORMALIZE) != 0;
   const int hw = norm ? cc.hw : P;
   const bool x_index_on_host = x_index && is_host_pointer(x_index), v_index_on_host = v_index && is_host_pointer(v_index);
@@ -1585,6 +1781,7 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     SynthArgs a;
     a.out = out ? out + (size_t)b0 * P : nullptr;
     a.delta = delta_out ? delta_out + (size_t)b0 * P : nullptr;
+    a.codes_out = codes_out ? codes_out + (size_t)b0 * K : nullptr;
     a.x = x ? (x_index ? x : x + (size_t)b0 * P) : nullptr;
     a.xidx = x_index ? x_index + b0 : nullptr;
     a.hx_on = 0; a.hv_on = 0;
@@ -1605,9 +1802,23 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     a.raw_floats = pl.raw_floats; a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.tmem_cols = pl.tmem_cols;
     a.eps = eps; a.flags = flags; a.cc = cc;
     a.cc.use = norm ? 1 : 0;
-    static const int early_x_knob = getenv("ADIL_SYNTH_EARLY_X") ? atoi(getenv("ADIL_SYNTH_EARLY_X")) : 0;    // tuning knobs
-    a.early_x = early_x_knob < 0 ? 0 : (early_x_knob > NSX ? NSX : early_x_knob);
-    if (x_index && !a.hx_on) a.early_x = 0;  // device x indices: the row offsets are a dependent load
+    {  // code-row gather: widest cp.async / shared-memory read the alignment of v and K allows; rows staged K (+4) apart
+      const uintptr_t va = reinterpret_cast<uintptr_t>(a.v);
+      a.cw = (va % 16 == 0 && K % 4 == 0) ? 4 : ((va % 8 == 0 && K % 2 == 0) ? 2 : 1);
+      a.cpitch = K + ((K % 8 == 0) ? 4 : 0);
+      static const int stage_knob = getenv("ADIL_SYNTH_STAGE_CODES") ? atoi(getenv("ADIL_SYNTH_STAGE_CODES")) : 1;  // A/B knob
+      a.stage_codes = (stage_knob != 0 && (size_t)nb * a.cpitch <= 2 * (size_t)pl.dimg) ? 1 : 0;
+      a.rpw = (nb + NTHREADS_SYNTH / 32 - 1) / (NTHREADS_SYNTH / 32);
+    }
+    if (a.codes_out != nullptr && !a.stage_codes) {
+      GatherIdx h;
+      h.on = a.hv_on;
+      if (a.hv_on) for (int i = 0; i < nb; ++i) h.idx[i] = a.hv[i];
+      gather_codes_kernel<<<nb, 64, 0, st>>>(a.codes_out, a.v, a.vidx, h, K);
+      int rcg = check_cuda(cudaGetLastError(), "gather_codes_kernel launch");
+      if (rcg) return rcg;
+      a.codes_out = nullptr;
+    }
     const int ntiles = (P + pl.TP - 1) / pl.TP;
     int grid = sm_count();
     if (grid > ntiles) grid = ntiles;
@@ -1623,7 +1834,7 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
     if (rc) return rc;
     rc = check_cuda(cudaGetLastError(), "synth_kernel launch");
     if (rc) return rc;
-#ifdef ADIL_CHAIN
+#if defined(ADIL_CHAIN) && !defined(ADIL_CHAIN_QUIET)
     {
       cudaDeviceSynchronize();
       long long h[16];
@@ -1652,12 +1863,17 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
 }
 
 namespace {
+template <int TP, bool FUSED, bool STRIDED, int NPF>
+int launch_grad_tpfn(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
+  int rc = set_smem(grad_kernel<TP, FUSED, STRIDED, NPF>, smem, "cudaFuncSetAttribute(grad_kernel)");
+  if (rc) return rc;
+  grad_kernel<TP, FUSED, STRIDED, NPF><<<grid, NTHREADS_GRAD, smem, st>>>(a);
+  return check_cuda(cudaGetLastError(), "grad_kernel launch");
+}
 template <int TP, bool FUSED, bool STRIDED>
 int launch_grad_tpf(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
-  int rc = set_smem(grad_kernel<TP, FUSED, STRIDED>, smem, "cudaFuncSetAttribute(grad_kernel)");
-  if (rc) return rc;
-  grad_kernel<TP, FUSED, STRIDED><<<grid, NTHREADS_GRAD, smem, st>>>(a);
-  return check_cuda(cudaGetLastError(), "grad_kernel launch");
+  if (FUSED && (TP * a.K) / 4 <= 3 * NEP_MAX * 32) return launch_grad_tpfn<TP, FUSED, STRIDED, FUSED ? 3 : 4>(a, smem, grid, st);
+  return launch_grad_tpfn<TP, FUSED, STRIDED, 4>(a, smem, grid, st);
 }
 template <int TP>
 int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
@@ -1726,10 +1942,14 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
   a.ldk = ldk; a.k4div = div_magic(K >> 2 > 0 ? K >> 2 : 1);
   a.want_dD = want_dD ? 1 : 0; a.want_dv = want_dv ? 1 : 0; a.atoms_mode = atoms_mode; a.cc = cc;
   a.accumulate = (opt.accumulate && !fused) ? 1 : 0;
-  static const int early_knob = getenv("ADIL_GRAD_EARLY") ? atoi(getenv("ADIL_GRAD_EARLY")) : 1;  // tuning knob
-  a.early = early_knob;
-  static const int order_knob = getenv("ADIL_GRAD_MMA_ORDER") ? atoi(getenv("ADIL_GRAD_MMA_ORDER")) : 0;  // tuning knob
-  a.mma_order = order_knob;
+  a.dreg = pl.dreg;
+  {  // widest cp.async the code-row gather may use: source rows start at v + row * ldk, destination rows at b * K floats
+    const uintptr_t va = reinterpret_cast<uintptr_t>(v);
+    a.cw = (va % 16 == 0 && ldk % 4 == 0 && K % 4 == 0) ? 4 : ((va % 8 == 0 && ldk % 2 == 0 && K % 2 == 0) ? 2 : 1);
+    a.rpw = (B + 24) / 25;
+    a.pfast = (K % 8 != 0) ? 1 : 0;
+    a.codes_contig = (v_index == nullptr && ldk == K && va % 16 == 0 && (B * K) % 4 == 0) ? 1 : 0;
+  }
   if (hp) a.hp = *hp;
   const int ntiles = (P + pl.TP - 1) / pl.TP;
   int grid = sm_count();
@@ -1748,21 +1968,27 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
     default: rc = launch_grad_tp<16>(a, pl.smem, grid, st); break;
   }
   if (rc) return rc;
-#ifdef ADIL_CHAIN
+#if defined(ADIL_CHAIN) && !defined(ADIL_CHAIN_QUIET)
   {
     cudaDeviceSynchronize();
     long long ch[16];
     cudaMemcpyFromSymbol(ch, g_chain, sizeof(ch));
-    fprintf(stderr, "grad CTA5 tile 6 chain (ns after worker D-split start of tile 6): issuer_waits=%lld staged=%lld mma_issued=%lld E_sees_done=%lld E_ld_done=%lld E_adamw_done=%lld loader_sees_empty=%lld | worker_staged6=%lld worker_at_raw9=%lld raw9_landed=%lld\n",
-            ch[0] - ch[10], ch[1] - ch[10], ch[2] - ch[10], ch[3] - ch[10], ch[4] - ch[10], ch[5] - ch[10], ch[6] - ch[10], ch[9] - ch[10], ch[7] - ch[10], ch[8] - ch[10]);
+    fprintf(stderr, "grad CTA5 tile 6 chain (ns after worker D-split start of tile 6): issuer_waits=%lld staged=%lld mma_issued=%lld E_sees_done=%lld E_ld_done=%lld E_bar=%lld E_raw_landed=%lld E_adamw_done=%lld | worker_staged6=%lld worker_at_raw9=%lld raw9_landed=%lld\n",
+            ch[0] - ch[10], ch[1] - ch[10], ch[2] - ch[10], ch[3] - ch[10], ch[4] - ch[10], ch[11] - ch[10], ch[12] - ch[10], ch[5] - ch[10], ch[9] - ch[10], ch[7] - ch[10], ch[8] - ch[10]);
   }
 #endif
-#ifdef ADIL_CHAIN
+#if defined(ADIL_CHAIN) && !defined(ADIL_CHAIN_QUIET)
   {
-    long long st8[8];
+    long long st8[16];
     cudaMemcpyFromSymbol(st8, g_stamp, sizeof(st8));
-    fprintf(stderr, "grad CTA0 stamps (ns from entry): sync=%lld prefetched=%lld codes_stored=%lld codes_built=%lld loop_end=%lld last_epi=%lld exit=%lld\n",
-            st8[1] - st8[0], st8[3] - st8[0], st8[7] - st8[0], st8[2] - st8[0], st8[4] - st8[0], st8[5] - st8[0], st8[6] - st8[0]);
+    long long w[16];
+    cudaMemcpyFromSymbol(w, g_wstamp, sizeof(w));
+    fprintf(stderr, "grad CTA0 stamps (ns from entry): W: g0_requested+mbar_init=%lld g_zeroed=%lld sync1=%lld D_region_zeroed=%lld loop_end=%lld last_mma_seen=%lld exit=%lld | "
+            "E: codes_requested=%lld codes_landed=%lld bar=%lld codes_in_tmem=%lld dD0_seen=%lld epi0_done=%lld epi_last_done=%lld | alloc=%lld | L: tma_issued=%lld | "
+            "I: staged0=%lld codes_ready=%lld mma0_issued=%lld | E gather: start=%lld row0=%lld row3=%lld\n",
+            st8[8] - st8[0], st8[12] - st8[0], st8[10] - st8[0], st8[7] - st8[0], st8[4] - st8[0], st8[5] - st8[0], st8[6] - st8[0],
+            w[0] - st8[0], w[3] - st8[0], w[4] - st8[0], w[5] - st8[0], w[9] - st8[0], w[10] - st8[0], w[11] - st8[0], w[1] - st8[0], w[2] - st8[0],
+            w[6] - st8[0], w[7] - st8[0], w[8] - st8[0], w[12] - st8[0], w[13] - st8[0], w[14] - st8[0]);
   }
 #endif
   if (want_dv) {

@@ -184,10 +184,12 @@ def device_info():
 
 
 def synth(D2, v, v_index=None, x=None, x_index=None, mean=None, std=None, eps=0.0, flags=0, out=None,
-          delta_out=None, want_out=True, n_channels=None):
+          delta_out=None, want_out=True, n_channels=None, codes_out=None):
     """out[b] = f(x[x_index[b]] + D2 @ v[v_index[b]])  -- adil.py:25-26 fused with Normalize / clamps.
 
-    D2: [P,K]; v: [N,K]; x: [B,P] (or [Nx,P] with x_index).  Returns (out, delta_out) ([B,P] or None each)."""
+    D2: [P,K]; v: [N,K]; x: [B,P] (or [Nx,P] with x_index).  Returns (out, delta_out) ([B,P] or None each).
+    codes_out: optional [B,K] buffer that receives v[v_index] -- pass it as `v` (with v_index=None) to the backward
+    call of the same step, which then fetches the rows with one bulk copy instead of gathering them again."""
     D2 = _f32(D2, "D2")
     v = _f32(v, "v")
     dev = D2.device
@@ -206,12 +208,17 @@ def synth(D2, v, v_index=None, x=None, x_index=None, mean=None, std=None, eps=0.
         _f32(out, "out")
     if delta_out is not None:
         _f32(delta_out, "delta_out")
+    if codes_out is not None:
+        _f32(codes_out, "codes_out")
+        if tuple(codes_out.shape) != (B, K):
+            raise ValueError("codes_out must be [B=%d, K=%d], got %s" % (B, K, tuple(codes_out.shape)))
     C = n_channels if n_channels is not None else (len(mean) if mean is not None else 1)
     hw = P // C
     mean_h, std_h = _host3(mean, C), _host3(std, C)
     with _Timed("adil_synth", dev, (B + 127) // 128):
         rc = _lib.lib().adil_synth(_ptr(out), _ptr(delta_out), _ptr(x), _ptr(x_index), _ptr(D2), _ptr(v),
-                                   _ptr(v_index), B, P, K, C, hw, mean_h, std_h, float(eps), int(flags), _stream(dev))
+                                   _ptr(v_index), _ptr(codes_out), B, P, K, C, hw, mean_h, std_h, float(eps),
+                                   int(flags), _stream(dev))
     _lib.check(rc, "adil_synth")
     return out, delta_out
 

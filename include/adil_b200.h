@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ADIL_VERSION 200
+#define ADIL_VERSION 210
 
 #define ADIL_MAX_CHANNELS 8
 #define ADIL_MAX_ATOMS 256
@@ -97,9 +97,13 @@ int adil_tc_supported(int B, int P, int K);
  *     delta[b,:] = sum_k v[v_index ? v_index[b] : b, k] * D2[:, k]
  *     out[b,:]   = f( x[x_index ? x_index[b] : b, :] + delta[b,:] )   (x == NULL: out = f(delta))
  * out, delta_out: [B,P] (either may be NULL, not both).  mean/std: HOST arrays of C floats (may be NULL when
- * NORMALIZE is not set). */
+ * NORMALIZE is not set).
+ * codes_out (may be NULL): [B,K], receives the gathered code rows v[v_index[b], :] of the batch.  Handing this block
+ * to adil_grad / adil_grad_dict_step of the same step as `v` with v_index == NULL (the rows do not change in between:
+ * autograd saves the same tensor, adil.py:25,185) spares the backward kernel a gather of its own: a contiguous,
+ * 16-byte-aligned block arrives in its shared memory as one bulk copy. */
 int adil_synth(float* out, float* delta_out, const float* x, const int64_t* x_index, const float* D2, const float* v,
-               const int64_t* v_index, int B, int P, int K, int C, int hw, const float* mean_host,
+               const int64_t* v_index, float* codes_out, int B, int P, int K, int C, int hw, const float* mean_host,
                const float* std_host, float eps, int flags, void* stream);
 
 /* Scratch (bytes) the grad entry points need for the deterministic cross-CTA reduction of the code gradients. */

@@ -42,7 +42,7 @@ def test_binding_covers_header_exactly():
 def test_host_only_entry_points(library):
     from dl_attack_on_imagenet_b200 import _lib
     lib = _lib.lib()
-    assert lib.adil_version() >= 200
+    assert lib.adil_version() >= 210
     assert lib.adil_grad_max_batch(150528, 50, 50176, 1) == 128 and lib.adil_grad_max_batch(150528, 300, 50176, 0) == 0
     assert lib.adil_grad_scratch_bytes(100, 50) >= 148 * 100 * 50 * 4
     assert lib.adil_grad_scratch_bytes(0, 50) == 0
@@ -57,9 +57,9 @@ def test_argument_errors_are_reported_without_a_gpu():
     from dl_attack_on_imagenet_b200 import _lib
     lib = _lib.lib()
     one = ctypes.c_void_p(16)
-    rc = lib.adil_synth(one, None, None, None, one, one, None, 4, 10, 3, 1, 10, None, None, 0.0, 0, None)
+    rc = lib.adil_synth(one, None, None, None, one, one, None, None, 4, 10, 3, 1, 10, None, None, 0.0, 0, None)
     assert rc < 0 and b"multiple of 4" in lib.adil_last_error()
-    rc = lib.adil_synth(one, None, None, None, one, one, None, 4, 12, 300, 1, 12, None, None, 0.0, 0, None)
+    rc = lib.adil_synth(one, None, None, None, one, one, None, None, 4, 12, 300, 1, 12, None, None, 0.0, 0, None)
     assert rc < 0 and b"ADIL_MAX_ATOMS" in lib.adil_last_error()
     rc = lib.adil_grad(None, None, one, one, one, None, 4, 12, 3, 1, 12, None, None, 0.0, 0, None, None, 0, None)
     assert rc < 0 and b"nothing to compute" in lib.adil_last_error()

@@ -379,6 +379,39 @@ def test_host_index_arrays_give_identical_results(ops, B, hw, K):
     assert torch.equal(Da, Db) and torch.equal(ma, mb) and torch.equal(sa, sb) and torch.equal(dva, dvb)
 
 
+# ---- the code rows that synthesis leaves behind for the backward kernel ----------------------------------------------
+@pytest.mark.parametrize("B,hw,K", [(100, 784, 50), (33, 400, 64), (1, 64, 1), (37, 5300, 33), (128, 196, 100), (16, 256, 200),
+                                    (130, 100, 37), (100, 50176, 50)])
+@pytest.mark.parametrize("impl", ["fma", "auto"])
+@pytest.mark.parametrize("host_index", [False, True])
+def test_codes_block_left_by_synth_gives_identical_backward(ops, B, hw, K, impl, host_index):
+    """adil_synth(codes_out) exports v[v_index] bit-exactly, and the backward entry points fed with that contiguous block
+    (v_index = None: one bulk copy instead of a gather) return the same bits as with (v, v_index)."""
+    D2, v, x, idx, g = make_problem(B, hw, K, seed=9)
+    Dd, vd, xd, gd = dev(D2), dev(v), dev(x), dev(g)
+    ix = idx if host_index else dev(idx)
+    ops.set_impl({"fma": ops.IMPL_FMA, "auto": ops.IMPL_AUTO}[impl])
+    try:
+        vb = torch.full((B, K), float("nan"), device="cuda")
+        out_a, _ = ops.synth(Dd, vd, ix, x=xd, x_index=ix, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE, codes_out=vb)
+        out_b, _ = ops.synth(Dd, vd, ix, x=xd, x_index=ix, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE)
+        assert torch.equal(vb, vd[dev(idx)])
+        assert torch.equal(out_a, out_b)
+        out_c, _ = ops.synth(Dd, vb, None, x=xd, x_index=ix, mean=MEAN, std=STD, flags=ops.SYNTH_NORMALIZE)
+        assert torch.equal(out_a, out_c)
+        dD_a, dv_a = ops.grad(gd, Dd, vd, ix, STD)
+        dD_b, dv_b = ops.grad(gd, Dd, vb, None, STD)
+        assert torch.equal(dD_a, dD_b) and torch.equal(dv_a, dv_b)
+        hp = ops.adamw_params(2, 0.01)
+        Da, ma, sa = Dd.clone(), torch.zeros_like(Dd), torch.zeros_like(Dd)
+        Db, mb, sb = Dd.clone(), torch.zeros_like(Dd), torch.zeros_like(Dd)
+        dva = ops.grad_dict_step(Da, ma, sa, gd, vd, ix, hp, STD)
+        dvb = ops.grad_dict_step(Db, mb, sb, gd, vb, None, hp, STD)
+        assert torch.equal(Da, Db) and torch.equal(ma, mb) and torch.equal(sa, sb) and torch.equal(dva, dvb)
+    finally:
+        ops.set_impl(ops.IMPL_AUTO)
+
+
 def test_host_index_arrays_need_the_tensor_core_path(ops):
     """Outside the tcgen05 limits (B > 128 for the backward kernels) the binding moves CPU indices to the device itself;
     the C ABI refuses host arrays on the FMA path instead of dereferencing them on the GPU."""
