@@ -148,16 +148,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.
 // try_wait suspends the warp in hardware for a while before it returns false, so the loop is cheap.
-// (out of line, reading the special registers itself: inlined, the message kept threadIdx.x alive -- and spilled -- across
-// the whole kernel for the sake of a path that never runs)
-__device__ __noinline__ void mbar_timeout() {
-  printf("adil_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-  __trap();
-}
+// (No message: a printf here kept threadIdx.x alive -- and spilled -- across the whole kernel, and as an out-of-line call it
+// cost the fused step 9-18 us at K = 64 / 100 through the register allocation around the call sites.  A reload from
+// local memory queues behind the stores of the AdamW pass: this kernel must stay free of spills.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) mbar_timeout();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -1872,7 +1869,8 @@ int launch_grad_tpfn(const GradArgs& a, size_t smem, int grid, cudaStream_t st) 
 }
 template <int TP, bool FUSED, bool STRIDED>
 int launch_grad_tpf(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
-  if (FUSED && (TP * a.K) / 4 <= 3 * NEP_MAX * 32) return launch_grad_tpfn<TP, FUSED, STRIDED, FUSED ? 3 : 4>(a, smem, grid, st);
+  static const int npf_knob = getenv("ADIL_GRAD_NPF") ? atoi(getenv("ADIL_GRAD_NPF")) : 0;  // tuning knob: 4 forces the 8-warp pass
+  if (FUSED && npf_knob != 4 && (TP * a.K) / 4 <= 3 * NEP_MAX * 32) return launch_grad_tpfn<TP, FUSED, STRIDED, FUSED ? 3 : 4>(a, smem, grid, st);
   return launch_grad_tpfn<TP, FUSED, STRIDED, 4>(a, smem, grid, st);
 }
 template <int TP>
