@@ -75,11 +75,7 @@ __device__ long long g_sstamp[16];
 __device__ long long g_wstamp[16];  // backward kernel, CTA 0: lane 0 of whichever warp passes the probe
 #define WSTAMP(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_wstamp[i] = gtime2(); } while (0)
 #else
-#ifdef ADIL_V_CBAR
-#define CHAIN(i, tile) asm volatile("" ::: "memory")
-#else
 #define CHAIN(i, tile)
-#endif
 #define STAMP(i)
 #define SSTAMP(i)
 #define WSTAMP(i)

@@ -10,8 +10,8 @@ run_ncu () {  # name, kernel regex, --only value, skip count
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $4 -c 1 -f -o $OUT/prof_${TAG}_$1 $KB --only $3 > $OUT/prof_${TAG}_$1.ncu.log 2>&1
   echo "ncu $1 rc=$?" | tee -a $OUT/prof_${TAG}_summary.log
 }
-run_ncu grad grad_kernel grad_dict_step_partials 3
-run_ncu gradplain grad_kernel grad_partials 3
+run_ncu grad grad_kernel grad_dict_step_contig 3
+run_ncu gradplain grad_kernel grad_contig 3
 run_ncu synth synth_kernel synth 3
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-cudnn-autotune"
 $BENCH > $OUT/prof_${TAG}_bench.plain.log 2>&1 &&

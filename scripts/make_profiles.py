@@ -82,8 +82,8 @@ def kernel(name, regex, only):
 
 launches()
 traffic = {"adil_synth": kernel("synth", "synth_kernel", "synth"),
-           "adil_grad_dict_step": kernel("grad", "grad_kernel", "grad_dict_step_partials")}
+           "adil_grad_dict_step": kernel("grad", "grad_kernel", "grad_dict_step_contig")}
 if os.path.exists(os.path.join(GO, f"prof_{tag}_gradplain.ncu-rep")):
-    traffic["adil_grad"] = kernel("gradplain", "grad_kernel", "grad_partials")
+    traffic["adil_grad"] = kernel("gradplain", "grad_kernel", "grad_contig")
 json.dump(traffic, open(os.path.join(PR, "ncu_traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
