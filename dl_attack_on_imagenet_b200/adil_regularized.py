@@ -1,7 +1,8 @@
-"""Regularised ADiL variant on the B200 kernels: SADiL, the stochastic forward-backward scheme of the reference's
-attacks/attacks_classes/adil_regularized.py:200-312 (the penalised objective  coeff * CE(x + D v) + 0.5 * l2_fool *
-||D v||^2 + lambdaCoding * ||v||_1  with D constrained per atom).  Same function name and arguments as the reference;
-the arithmetic runs in the CUDA kernels behind the C ABI (include/adil_b200.h) -- there is no CPU path:
+"""Regularised ADiL variants on the B200 kernels: `sadil`, the stochastic forward-backward scheme of the reference's
+attacks/attacks_classes/adil_regularized.py:200-312, and `adil`, its full-batch scheme with backtracking line search
+(:31-197), for the penalised objective  coeff * CE(x + D v) + 0.5 * l2_fool * ||D v||^2 + lambdaCoding * ||v||_1  with
+D constrained per atom.  Same function names and arguments as the reference; the arithmetic of the path runs in the
+CUDA kernels behind the C ABI (include/adil_b200.h) -- there is no CPU path:
 
     synthesis + perturbation output   adil_synth (delta_out)              adil_regularized.py:272,290
     penalised backward contractions   adil_grad (delta, l2_coef)          loss_smooth.backward(), :277,295
@@ -38,6 +39,21 @@ def penalised_loss(model, batches, D2, v, coeff, l2_fool, lambdaCoding, targeted
             ce = torch.nn.functional.cross_entropy(model(adv.view_as(x)), target, reduction='sum')
             total += (coeff * ce + 0.5 * l2_fool * delta.square().sum()).double()
     return total.item() + (lambdaCoding * v.abs().sum()).item()
+
+
+def _smooth_loss(model, batches, D2, v, coeff, l2_fool, targeted):
+    """sum over the batches of coeff * CE_sum + 0.5 * l2_fool * ||D v||^2 as an fp32 device scalar, accumulated in the
+    reference's order (adil_regularized.py:112-117,166-174): the loss-only pass of the line search"""
+    total = torch.zeros((), device=D2.device)
+    with torch.no_grad():
+        for x, y, rows in batches:
+            n = x.shape[0]
+            pert = torch.empty(n, D2.shape[0], device=D2.device)
+            adv, _ = ops.synth(D2, v, rows, x=x.view(n, -1), delta_out=pert)
+            target = get_target(x, y, targeted, model)
+            total = total + coeff * torch.nn.functional.cross_entropy(model(adv.view_as(x)), target, reduction='sum') \
+                + .5 * l2_fool * pert.square().sum()
+    return total
 
 
 def sadil(dataset, model, targeted=True, nepochs=1e3, batchsize=1, lambdaCoding=1., l2_fool=1., stepsize=1., n_atom=5,
@@ -111,3 +127,114 @@ def sadil(dataset, model, targeted=True, nepochs=1e3, batchsize=1, lambdaCoding=
     if model_file is not None:
         torch.save([D, loss], model_file)                        # adil_regularized.py:310
     return D, v, loss
+
+
+def adil(dataset, model, targeted=True, niter=1e3, lambdaCoding=1., l2_fool=1., batchsize=None, step_size=.1, n_atom=10,
+         dict_set='l2ball', device=None, dictionary=None, trace=None):
+    """ADiL, full batch, with the backtracking of Bonettini et al. (adil_regularized.py:31-197).  Returns
+    (D [C,H,W,K], v [N,K], loss_all [niter], NaN where an iteration never ran).
+
+    Per iteration: penalised loss + gradients over the whole set (adil_synth with the perturbation output, the classifier's
+    input gradient, the l2-penalised backward contractions accumulating dD over the batches), the Lipschitz estimate from
+    the third iteration on (:126-130), v <- soft threshold, D <- constraint_dict(D - step grad) (adil_code_prox_step,
+    adil_dict_step_atoms), and the line search over the segment old -> new with loss-only passes (`penalised_loss`).
+    `dictionary` given: D is fixed and only the codes are learned, like the reference.  `trace` (a list) receives the
+    accepted line-search index of every iteration (51: no decrease found, the iteration stops -- :189-192)."""
+    import numpy as np
+    dev = _device_of(model)
+    model = model.eval()
+    net, mean, std = split_normalize(model)
+    flags = ops.SYNTH_NORMALIZE if mean is not None else 0
+    nimg = len(dataset)
+    x0, _ = next(iter(dataset))
+    nc, nx, ny = x0.shape
+    P = nc * nx * ny
+    learn_D = dictionary is None
+    if batchsize is None:
+        batchsize = nimg
+    delta_ls, gamma, beta = .5, 1., .5
+    lipschitz = .9 / step_size
+    coeff = 1. if targeted else -1.
+    atoms_mode = _ATOMS.get(dict_set, ops.ATOMS_L1BALL)
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False)
+    batches, start = [], 0
+    for x, y in loader:                                         # the set stays resident in HBM (shuffle=False: fixed slices)
+        n = x.shape[0]
+        batches.append((x.to(dev).float().contiguous(), y.to(dev), torch.arange(start, start + n, device=dev)))
+        start += n
+    if learn_D:
+        K = n_atom
+        D = ops.project_atoms(torch.randn(3, nx, ny, K, device=dev), atoms_mode)   # adil_regularized.py:83-84
+    else:
+        D = dictionary.to(dev).float().contiguous().clone()
+        K = D.shape[-1]
+    D2 = D.view(P, K)
+    v = torch.zeros(nimg, K, device=dev)
+    all_rows = torch.arange(nimg, device=dev)
+
+    def loss_and_grads():
+        """loss_smooth (:109-117) with its gradients w.r.t. v (all rows) and D (summed over the batches)"""
+        gD = torch.zeros(P, K, device=dev)
+        gv = torch.zeros(nimg, K, device=dev)
+        total = torch.zeros((), device=dev)
+        for i, (x, y, rows) in enumerate(batches):
+            n = x.shape[0]
+            target = get_target(x, y, targeted, model)
+            pert = torch.empty(n, P, device=dev)
+            xin, _ = ops.synth(D2, v, rows, x=x.view(n, -1), mean=mean, std=std, flags=flags, delta_out=pert, n_channels=nc)
+            xin = xin.view_as(x).requires_grad_(True)
+            ce = coeff * torch.nn.functional.cross_entropy(net(xin), target, reduction='sum')
+            (g,) = torch.autograd.grad(ce, xin)
+            _, dvb = ops.grad(g.contiguous().view(n, P), D2, v, rows, std, want_dD=learn_D, dD2=gD if learn_D else None,
+                              accumulate=learn_D and i > 0, delta=pert, l2_coef=l2_fool)
+            gv[rows] = dvb
+            total = total + ce.detach() + .5 * l2_fool * pert.square().sum()
+        return total, gD, gv
+
+    D_old, v_old = torch.zeros_like(D2), torch.zeros_like(v)
+    gD_old, gv_old = torch.zeros_like(D2), torch.zeros_like(v)
+    loss_all = np.nan * np.ones(int(niter))
+    loss_ns_old = torch.zeros((), device=dev)
+    stop = False
+    for it in range(int(niter)):
+        if stop:
+            continue
+        loss_ns = lambdaCoding * v.abs().sum()
+        loss_s, gD, gv = loss_and_grads()
+        loss_full = loss_s + loss_ns
+        if it > 1:                                                                          # :126-130
+            num = torch.sqrt(torch.norm(gv - gv_old) ** 2 + torch.norm(gD - gD_old) ** 2)
+            lipschitz = num / torch.sqrt(torch.norm(v - v_old) ** 2 + torch.norm(D2 - D_old) ** 2)
+        D_old.copy_(D2); v_old.copy_(v); gv_old.copy_(gv); gD_old.copy_(gD)
+        loss_old = loss_full
+        step = float(.9 / lipschitz)                                                        # :140
+        ops.code_prox_step(v, gv, all_rows, step, ops.ROWS_SOFTSHRINK, step * lambdaCoding)  # :143
+        if learn_D:                                                                         # :144-147
+            if atoms_mode == ops.ATOMS_L1BALL:
+                ops.dict_step_atoms(D2, gD, ops.ATOMS_NONE, step=step)
+                ops.project_atoms(D, ops.ATOMS_L1BALL)
+            else:
+                ops.dict_step_atoms(D2, gD, atoms_mode, step=step)
+        d_v, d_d = v - v_old, D2 - D_old
+        h = (d_d * gD).sum() + (d_v * gv).sum() + .5 * (gamma / step) * (torch.norm(d_d) ** 2 + torch.norm(d_v) ** 2) \
+            + loss_ns - loss_ns_old                                                          # :154-156
+        i = 0
+        new_v, new_D2 = torch.empty_like(v), torch.empty_like(D2)
+        while True:                                                                          # :158-192
+            torch.add(v_old, d_v, alpha=delta_ls ** i, out=new_v)
+            torch.add(D_old, d_d, alpha=delta_ls ** i, out=new_D2)
+            loss_ns = lambdaCoding * new_v.abs().sum()
+            loss_full = _smooth_loss(model, batches, new_D2, new_v, coeff, l2_fool, targeted) + loss_ns
+            if bool(loss_full <= loss_old + beta * (delta_ls ** i) * h):
+                v.copy_(new_v)
+                D2.copy_(new_D2)
+                loss_ns_old = loss_ns
+                break
+            i += 1
+            if i > 50:
+                stop = True
+                break
+        if trace is not None:
+            trace.append(i)
+        loss_all[it] = float(loss_full)
+    return D, v, loss_all

@@ -601,3 +601,109 @@ def sadil(model, dataset, targeted=True, nepochs=10, batchsize=1, lambda_coding=
         if abs(loss[-1] - loss[-2]) < 1e-6:
             break
     return D2.reshape(nc, nx, ny, n_atom), v, loss
+
+
+# ------------------------------------------------------------------------------------------------
+# regularised variant, full batch: ADiL with backtracking line search (adil_regularized.py:31-197)
+# ------------------------------------------------------------------------------------------------
+def adil_fb(model, dataset, targeted=True, niter=10, lambda_coding=1., l2_fool=1., batchsize=None, step_size=.1, n_atom=10,
+            dict_set='l2ball', D0=None, learn_dictionary=True, trace=None):
+    """Full-batch forward-backward scheme with the backtracking of Bonettini et al. (adil_regularized.py:31-197).
+
+    Per iteration: the penalised loss and its gradients over the WHOLE set (:109-120); from the third iteration on a
+    Barzilai-Borwein-like Lipschitz estimate ||delta grad|| / ||delta (v, D)|| (:126-130) and step 0.9 / L (:140);
+    v <- soft threshold(v - step grad_v, step * lambda), D <- constraint_dict(D - step grad_D) (:143-147); then the
+    line search over the segment (v_old, D_old) -> (v, D): the first i in 0..50 with
+    loss(v_old + 0.5^i dv, D_old + 0.5^i dD) <= loss_old + 0.5 * 0.5^i * h is accepted (:158-188); none: stop (:189-192).
+    `learn_dictionary=False` is the reference's `dictionary is not None` mode (D fixed, :103-105,119,145).
+    `trace` (a list) receives the accepted line-search index of every iteration (51: stopped).
+    Returns (D [C,H,W,K], v [N,K], loss_all [niter] with NaN for iterations that never ran)."""
+    import numpy as np
+    nimg = len(dataset)
+    x0, _ = next(iter(dataset))
+    nc, nx, ny = x0.shape
+    P = nc * nx * ny
+    if batchsize is None:
+        batchsize = nimg
+    delta, gamma, beta = .5, 1., .5
+    lipschitz = .9 / step_size
+    coeff = 1. if targeted else -1.
+    slices = [list(range(i, min(i + batchsize, nimg))) for i in range(0, nimg, batchsize)]   # utils.py:153-156
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False)
+    mode = {'l2ball': ATOMS_L2BALL, 'l2sphere': ATOMS_L2SPHERE}.get(dict_set, ATOMS_L1BALL)
+    D = project_atoms(torch.randn(3, nx, ny, n_atom), mode) if D0 is None else D0.clone()
+    D2 = D.reshape(P, n_atom).clone()
+    v = torch.zeros(nimg, n_atom)
+
+    def smooth_loss(D2_, v_, want_grad):
+        """sum over the batches of coeff * CE_sum + 0.5 * l2_fool * ||D v||^2 (:112-117); optionally its gradients"""
+        total = torch.zeros(())
+        gD = torch.zeros_like(D2_) if want_grad else None
+        gv = torch.zeros_like(v_) if want_grad else None
+        for i, (x, y) in enumerate(loader):
+            ind = slices[i]
+            target = get_target(model, x, y, targeted)
+            if want_grad:
+                # (same accumulation order as the reference's fp32 tensors: (loss + coeff * CE) + 0.5 * l2 * ||dv||^2)
+                n = x.shape[0]
+                vb = v_[ind]
+                dv = vb @ D2_.t()
+                xin = (x.reshape(n, P) + dv).reshape(x.shape).detach().requires_grad_(True)
+                ce = coeff * torch.nn.functional.cross_entropy(model(xin), target, reduction='sum')
+                (g,) = torch.autograd.grad(ce, xin)
+                gx = g.reshape(n, P) + l2_fool * dv
+                gD += gx.t() @ vb
+                gv[ind] = gx @ D2_
+                total = total + ce.detach() + .5 * l2_fool * torch.sum(dv ** 2)
+            else:
+                with torch.no_grad():
+                    n = x.shape[0]
+                    dv = v_[ind] @ D2_.t()
+                    out = model((x.reshape(n, -1) + dv).reshape(x.shape))
+                    total = total + coeff * torch.nn.functional.cross_entropy(out, target, reduction='sum') \
+                        + .5 * l2_fool * torch.sum(dv ** 2)
+        return total, gD, gv
+
+    D_old, v_old = torch.zeros_like(D2), torch.zeros_like(v)
+    gD_old, gv_old = torch.zeros_like(D2), torch.zeros_like(v)
+    loss_all = np.nan * np.ones(int(niter))
+    loss_ns_old = torch.zeros(())
+    stop = False
+    for it in range(int(niter)):
+        if stop:
+            continue
+        loss_ns = lambda_coding * torch.sum(torch.abs(v))
+        loss_s, gD, gv = smooth_loss(D2, v, True)
+        if not learn_dictionary:
+            gD = torch.zeros_like(D2)
+        loss_full = loss_s + loss_ns
+        if it > 1:
+            num = torch.sqrt(torch.norm(gv - gv_old) ** 2 + torch.norm(gD - gD_old) ** 2)
+            lipschitz = num / torch.sqrt(torch.norm(v - v_old) ** 2 + torch.norm(D2 - D_old) ** 2)
+        D_old, v_old, gv_old, gD_old = D2.clone(), v.clone(), gv.clone(), gD.clone()
+        loss_old = loss_full
+        step = .9 / lipschitz
+        v = softshrink(v - step * gv, step * lambda_coding)
+        if learn_dictionary:
+            D2 = project_atoms((D2 - step * gD).reshape(nc, nx, ny, n_atom), mode).reshape(P, n_atom)
+        d_v, d_d = v - v_old, D2 - D_old
+        h = torch.sum(d_d * gD) + torch.sum(d_v * gv) + .5 * (gamma / step) * (torch.norm(d_d) ** 2 + torch.norm(d_v) ** 2) \
+            + loss_ns - loss_ns_old
+        i = 0
+        while True:
+            new_v, new_D = v_old + (delta ** i) * d_v, D_old + (delta ** i) * d_d
+            loss_ns = lambda_coding * torch.sum(torch.abs(new_v))
+            loss_s, _, _ = smooth_loss(new_D, new_v, False)
+            loss_full = loss_s + loss_ns
+            if loss_full <= loss_old + beta * (delta ** i) * h:
+                v, D2 = new_v, new_D
+                loss_ns_old = loss_ns
+                break
+            i += 1
+            if i > 50:
+                stop = True
+                break
+        if trace is not None:
+            trace.append(i)
+        loss_all[it] = float(loss_full)
+    return D2.reshape(nc, nx, ny, n_atom), v, loss_all

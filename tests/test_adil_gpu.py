@@ -379,6 +379,43 @@ def test_sadil_on_the_kernels_matches_the_reference(golden, tag, kw):
     assert (norms <= 1 + 1e-5).all() if kw["dict_set"] == 'l2ball' else (norms - 1).abs().max() <= 1e-5
 
 
+@pytest.mark.parametrize("tag,kw,accepted", [
+    ("fb_untargeted", dict(targeted=False, niter=8, lambdaCoding=0.01, l2_fool=0.5, batchsize=4, step_size=0.05, n_atom=6,
+                           dict_set='l2ball'), [0] * 8),
+    ("fb_targeted", dict(targeted=True, niter=8, lambdaCoding=0.02, l2_fool=2.0, batchsize=None, step_size=0.02, n_atom=5,
+                         dict_set='l2sphere'), [0] * 8),
+    ("fb_backtrack", dict(targeted=False, niter=8, lambdaCoding=0.05, l2_fool=0.5, batchsize=4, step_size=10.0, n_atom=6,
+                          dict_set='l2ball'), [4, 5, 0, 0, 0, 0, 0, 0])])
+def test_full_batch_line_search_variant_on_the_kernels_matches_the_reference(tag, kw, accepted):
+    """dl_attack_on_imagenet_b200.adil_regularized.adil -- full-batch penalised gradients (dD accumulated over the
+    batches), Lipschitz estimate, proximal / projected step and the backtracking line search on loss-only passes --
+    against the output of the reference's own adil() (adil_regularized.py:31-197; tests/golden/adil_fb_reference_golden.npz)
+    from the same initial dictionary: same accepted line-search indices, loss per iteration, final D and v."""
+    import os
+    from dl_attack_on_imagenet_b200.adil_regularized import adil
+    from dl_attack_on_imagenet_b200.utils import QuickAttackDataset
+    gfb = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adil_fb_reference_golden.npz"))
+    model = O.tiny_classifier(seed=0).cuda()
+    xtr, ytr, _, _ = tiny_data()
+    D0 = torch.from_numpy(gfb[tag + "_D0"])
+    # the reference learns D from its own draw; handing D0 in as `dictionary` would freeze it, so the draw is patched
+    import dl_attack_on_imagenet_b200.adil_regularized as reg
+    orig = reg.ops.project_atoms
+    try:
+        reg.ops.project_atoms = lambda D, mode: D.copy_(D0.to(D.device))
+        trace = []
+        D, v, loss = adil(QuickAttackDataset(xtr, ytr), model, trace=trace, **kw)
+    finally:
+        reg.ops.project_atoms = orig
+    assert trace == accepted
+    assert np.allclose(loss, gfb[tag + "_loss"], rtol=2e-6, atol=5e-5)
+    assert (D.cpu() - torch.from_numpy(gfb[tag + "_D"])).abs().max() <= 1e-5
+    assert (v.cpu() - torch.from_numpy(gfb[tag + "_v"])).abs().max() <= 1e-5
+    # codes only, on a fixed dictionary (the reference's `dictionary is not None` mode): D comes back untouched
+    Df, vf, lossf = adil(QuickAttackDataset(xtr, ytr), model, dictionary=D.clone(), **dict(kw, niter=3))
+    assert torch.equal(Df, D) and np.isfinite(lossf).all() and lossf[-1] <= lossf[0]
+
+
 def test_fit_with_the_whole_set_as_one_minibatch(monkeypatch):
     """batch_size=None is the reference's documented default (len(data_train), adil.py:124): 150 images in one minibatch
     exceed the 128 images one kernel pass takes, so the synthesis runs in two passes and the backward as chunked plain
