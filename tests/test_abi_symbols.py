@@ -104,3 +104,34 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_hot_tensor_core_kernels_have_no_register_spills():
+    """The benchmarked instantiations of the tcgen05 kernels must not touch local memory: a spill reload queues behind the
+    global stores of the AdamW pass and cost the fused step 5-10 us whenever an unrelated edit made ptxas spill one
+    loop-carried value.  Checked on the built library with cuobjdump (no GPU needed)."""
+    import re
+    import shutil
+    import subprocess
+    from dl_attack_on_imagenet_b200.build import build_library
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = build_library()
+    res = subprocess.run([cuobjdump, "-res-usage", lib], capture_output=True, text=True).stdout
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True).stdout
+    hot = re.compile(r"(grad_kernelILi64ELb[01]ELb0ELi[34]E|grad_kernelILi32ELb1ELb0ELi3E|synth_kernelILi(64|48)ELb1E)")
+    seen = 0
+    for m in re.finditer(r"Function (\S+?):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", res):
+        if hot.search(m.group(1)):
+            seen += 1
+            assert int(m.group(3)) == 0 and int(m.group(5)) == 0, "%s uses a stack frame / local memory: %s" % (m.group(1), m.group(0))
+    assert seen >= 6
+    cur, local_ops = None, {}
+    for line in sass.splitlines():
+        f = re.search(r"Function : (\S+)", line)
+        if f:
+            cur = f.group(1)
+        elif cur and hot.search(cur) and re.search(r"\b(LDL|STL)\b", line):
+            local_ops[cur] = local_ops.get(cur, 0) + 1
+    assert not local_ops, "local-memory instructions in hot kernels: %s" % local_ops
