@@ -1,6 +1,6 @@
 """Regularised ADiL variants on the B200 kernels: `sadil`, the stochastic forward-backward scheme of the reference's
-attacks/attacks_classes/adil_regularized.py:200-312, and `adil`, its full-batch scheme with backtracking line search
-(:31-197), for the penalised objective  coeff * CE(x + D v) + 0.5 * l2_fool * ||D v||^2 + lambdaCoding * ||v||_1  with
+attacks/attacks_classes/adil_regularized.py:200-312, `adil`, its full-batch scheme with backtracking line search
+(:31-197), and `learn_coding_vectors`, the coder on a fixed dictionary (:508-628), for the penalised objective  coeff * CE(x + D v) + 0.5 * l2_fool * ||D v||^2 + lambdaCoding * ||v||_1  with
 D constrained per atom.  Same function names and arguments as the reference; the arithmetic of the path runs in the
 CUDA kernels behind the C ABI (include/adil_b200.h) -- there is no CPU path:
 
@@ -238,3 +238,108 @@ def adil(dataset, model, targeted=True, niter=1e3, lambdaCoding=1., l2_fool=1., 
             trace.append(i)
         loss_all[it] = float(loss_full)
     return D, v, loss_all
+
+
+def learn_coding_vectors(dataset, model, targeted=True, niter=1e2, lambda_l1=1., lambda_l2=1., batch_size=None,
+                         step_size=.1, n_atom=10, dict_set='l2ball', device=None, dictionary=None, verbose=False, trace=None):
+    """The coder of the regularised variant (adil_regularized.py:508-628): codes of `dataset` on the FIXED `dictionary`
+    [C,H,W,K] for  coeff * CE(x + D v) + 0.5 * lambda_l2 * ||D v||^2 + lambda_l1 * ||v||_1 , full-batch proximal gradient
+    from v = 0 with the reference's line search over the segment v_old -> prox step (factor 0.9, at most 10 shortenings;
+    a shortened point is kept -- and the step size shrunk with it -- only when its loss is below the full step's).
+    Returns v [N,K] like the reference; `trace` (a list) receives (index the search ended at, shortened point kept,
+    recorded loss) per iteration.
+
+    On the kernels: adil_synth with the perturbation output, the classifier's input gradient, the l2-penalised code-gradient
+    contraction (adil_grad, dv only), adil_code_prox_step (soft threshold) and loss-only passes for the search."""
+    import numpy as np
+    dev = _device_of(model)
+    model = model.eval()
+    net, mean, std = split_normalize(model)
+    flags = ops.SYNTH_NORMALIZE if mean is not None else 0
+    nimg = len(dataset)
+    D = dictionary.to(dev).float().contiguous()
+    nc, nx, ny, K = D.shape
+    P = nc * nx * ny
+    D2 = D.view(P, K)
+    delta_ls, gamma, beta = .9, 1, .5
+    batch_size = nimg if batch_size is None else batch_size
+    coeff = 1. if targeted else -1.
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False)
+    batches, start = [], 0
+    for x, y in loader:                                         # the set stays resident in HBM (shuffle=False: fixed slices)
+        n = x.shape[0]
+        batches.append((x.to(dev).float().contiguous(), y.to(dev), torch.arange(start, start + n, device=dev)))
+        start += n
+    targets = [get_target(x, y, targeted, model) for x, y, _ in batches]   # (clean images, fixed classifier: loop invariant)
+    # the step size lives as an fp32 scalar and is updated with the reference's expressions (its default is a tensor, :509)
+    step_t = torch.as_tensor(step_size, dtype=torch.float32).cpu()
+    v = torch.zeros(nimg, K, device=dev)
+    v_old = torch.zeros_like(v)
+    all_rows = torch.arange(nimg, device=dev)
+
+    def loss_and_grad():
+        """loss_smooth (:553-559) and its gradient w.r.t. every code row (:565)"""
+        gv = torch.zeros(nimg, K, device=dev)
+        total = torch.zeros((), device=dev)
+        for (x, _, rows), target in zip(batches, targets):
+            n = x.shape[0]
+            pert = torch.empty(n, P, device=dev)
+            xin, _ = ops.synth(D2, v, rows, x=x.view(n, -1), mean=mean, std=std, flags=flags, delta_out=pert, n_channels=nc)
+            xin = xin.view_as(x).requires_grad_(True)
+            ce = coeff * torch.nn.functional.cross_entropy(net(xin), target, reduction='sum')
+            (g,) = torch.autograd.grad(ce, xin)
+            _, dvb = ops.grad(g.contiguous().view(n, P), D2, v, rows, std, want_dD=False, delta=pert, l2_coef=lambda_l2)
+            gv[rows] = dvb
+            total = total + ce.detach() + .5 * lambda_l2 * pert.square().sum()
+        return total, gv
+
+    def loss_only(v_):
+        total = torch.zeros((), device=dev)
+        with torch.no_grad():
+            for (x, _, rows), target in zip(batches, targets):
+                n = x.shape[0]
+                pert = torch.empty(n, P, device=dev)
+                adv, _ = ops.synth(D2, v_, rows, x=x.view(n, -1), delta_out=pert)
+                total = total + coeff * torch.nn.functional.cross_entropy(model(adv.view_as(x)), target, reduction='sum') \
+                    + .5 * lambda_l2 * pert.square().sum()
+        return total
+
+    loss_all = [np.nan]
+    for _ in range(int(niter)):
+        loss_s, gv = loss_and_grad()
+        loss_old = (loss_s + lambda_l1 * v.abs().sum()).item()
+        v_old.copy_(v)
+        step = float(step_t)
+        ops.code_prox_step(v, gv, all_rows, step, ops.ROWS_SOFTSHRINK, float(step_t * lambda_l1))          # :574-577
+        d_v = v - v_old
+        h = (d_v * gv).sum() + .5 * float(gamma / step_t) * (torch.norm(d_v) ** 2) \
+            + lambda_l1 * v.abs().sum() - lambda_l1 * v_old.abs().sum()                                    # :583-584
+        index_i, kept = 0, False
+        new_v = torch.empty_like(v)
+        while True:                                                                                        # :589-622
+            torch.add(v_old, d_v, alpha=delta_ls ** index_i, out=new_v)
+            loss_full = (loss_only(new_v) + lambda_l1 * new_v.abs().sum()).item()
+            if index_i == 0:
+                loss_cur = loss_full
+            if bool(loss_full <= loss_old + beta * (delta_ls ** index_i) * h):
+                if loss_cur > loss_full:
+                    v.copy_(new_v)
+                    step_t = step_t * delta_ls ** index_i
+                    loss_all.append(loss_full)
+                    kept = True
+                else:
+                    loss_all.append(loss_cur)
+                break
+            index_i += 1
+            if index_i > 10:                                    # no sufficient decrease found: the last point tried is taken
+                v.copy_(new_v)
+                loss_all.append(loss_full)
+                kept = True
+                break
+        if trace is not None:
+            trace.append((index_i, kept, loss_all[-1]))
+        if verbose:
+            print("learn_coding_vectors: loss %.6f step %.4g (search ended at %d)" % (loss_all[-1], float(step_t), index_i))
+        if loss_all[-2] - loss_all[-1] < 1e-6:
+            break
+    return v

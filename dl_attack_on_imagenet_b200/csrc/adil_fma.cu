@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kThreads) grad_fma_kernel(const GradArgs a) {
 // in flight together), then the 32 partial sums are combined in warp order -- the summation tree depends only on
 // nslabs, so results are bit-reproducible.
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(float* __restrict__ dvb, const float* __restrict__ partial,
-                                                               int n, int nslabs, int K, int ld_out) {
+                                                               int n, int nslabs, int K, int ld_out, int slab_step) {
   __shared__ float part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(float* __restrict
   float acc = 0.0f;
   if (e < n) {
 #pragma unroll 4
-    for (int c = warp; c < nslabs; c += 32) acc += partial[(size_t)c * n + e];
+    for (int c = warp; c < nslabs; c += 32) acc += partial[(size_t)c * slab_step * n + e];
   }
   part[warp][lane] = acc;
   __syncthreads();
@@ -493,7 +493,9 @@ int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
 
 }  // namespace
 
-int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, int K, int ld_out, cudaStream_t st) {
+// (slab_step: the slabs to add are slab_step slabs apart -- two column windows contracted by one launch)
+int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, int K, int ld_out, cudaStream_t st,
+                           int slab_step = 1) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((n + 31) / 32));
   cfg.blockDim = dim3(1024);
@@ -504,7 +506,7 @@ int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, dvb, partial, n, nslabs, K, ld_out),
+  return check_cuda(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, dvb, partial, n, nslabs, K, ld_out, slab_step),
                     "reduce_partials_kernel launch");
 }
 

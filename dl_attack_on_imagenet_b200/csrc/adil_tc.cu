@@ -35,12 +35,14 @@
 // c = M/N index: LBO = 128, SBO = S).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "adil_common.cuh"
 
 namespace adil {
 
-int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, int K, int ld_out, cudaStream_t st);
+int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, int K, int ld_out, cudaStream_t st,
+                           int slab_step = 1);
 
 namespace {
 
@@ -917,6 +919,16 @@ struct GradArgs {
   int ldk;            // row pitch (floats) of D2 / m / s / dD2 / v in global memory: K, or the full atom count when this
                       // launch handles a window of K columns of a wider dictionary (STRIDED: more than 128 atoms)
   unsigned k4div;     // ceil(2^32 / (K / 4)) (STRIDED: float4 index inside a dense tile -> row)
+  int wsh;            // nwin >> 1
+  int dv2;            // two dv accumulators, tiles alternate (a CTA of a window pair runs twice as many tiles: the fp32
+                      // accumulation chains in tensor memory keep the length of the single-window kernels)
+  int fullrow;        // STRIDED: the raw stage holds the FULL dictionary rows of a tile (ldk floats apart: one bulk copy per
+                      // tile instead of one per row; this CTA's window starts `wof` floats into each row)
+  int rpitch;         // floats between the rows of a tile in the raw stage: ldk (fullrow) or K
+  unsigned rmask;     // all ones (fullrow) or 0: masks `wof` in stage offsets
+  int rsv_[2];        // (keeps `hp` 16-byte aligned in the constant bank: the AdamW pass fetches it with one LDCU.128)
+  int nwin;           // STRIDED: 1, or 2 = BOTH column windows in this launch: CTA c takes window c & 1 (columns
+                      // [K (c & 1), K (c & 1) + K) of every array) and the pixel tiles (c >> 1) + j (gridDim.x >> 1)
   int accumulate;     // plain dD output: dD2 += tile (TMA reduce-add store) instead of dD2 = tile
   int dreg;           // bytes of the dictionary-image region; at kernel entry it stages the code rows of the batch
   int cw;             // floats per cp.async of the code-row gather: 4, 2 or 1 (alignment of v, ldk and K)
@@ -971,7 +983,33 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, P = a.P, B = a.B;
   const int ntiles = (P + TP - 1) / TP;
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Two column windows in one launch (STRIDED, a.nwin == 2): neighbouring CTAs 2i, 2i+1 work on the SAME pixel tiles at
+  // the same time, one window each -- the gradient rows are fetched from HBM once (the second CTA hits L2), both halves
+  // of every dictionary / moment row are touched together (full DRAM pages, the shared sectors at the window boundary
+  // merge in L2), and the step costs one launch instead of two.
+  // (cta_x, cta_n, wof are recomputed from the special registers / the constant bank where they are used: held in
+  // registers across the kernel they made the 4-item AdamW pass spill)
+#define cta_x ((int)blockIdx.x >> a.wsh)
+#define cta_n ((int)gridDim.x >> a.wsh)
+#define wof ((unsigned)(((int)blockIdx.x & a.wsh) * a.K))
+  // float offset of float4 `e4` of the dense [rows][K] tile inside a raw stage
+  auto soff = [&](int e4) -> int {
+    if constexpr (STRIDED) {
+      const int r = div_magic_dev(e4, a.k4div);  // (shared with goff)
+      return r * a.rpitch + (int)(wof & a.rmask) + 4 * (e4 - r * (K >> 2));
+    } else {
+      return 4 * e4;
+    }
+  };
+  auto W = [&](auto* ptr) { if constexpr (STRIDED) return ptr + wof; else return ptr; };
+  auto tile_p0 = [&](int it) -> int {
+    if constexpr (STRIDED) return (cta_x + it * cta_n) * TP;
+    else return (blockIdx.x + it * gridDim.x) * TP;
+  };
+  const int my_tiles = [&]() -> int {
+    if constexpr (STRIDED) return (ntiles - cta_x + cta_n - 1) / cta_n;
+    else return (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  }();
   constexpr bool fused = FUSED;
   // G_SCALED: 1/std is folded into the gradient images (gx = g * (1/std): one multiply per gradient element; both
   // contractions want gx) and the dictionary tile is split as it is, eight atoms per item with 16-byte stores; otherwise
@@ -991,7 +1029,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   auto goff = [&](int p0, int e4) -> size_t {
     if constexpr (STRIDED) {
       const int r = div_magic_dev(e4, a.k4div);
-      return (size_t)(p0 + r) * (size_t)a.ldk + 4 * (size_t)(e4 - r * (K >> 2));
+      return (size_t)(p0 + r) * (size_t)a.ldk + (size_t)(wof + 4u * (unsigned)(e4 - r * (K >> 2)));  // (+ this CTA's window)
     } else {
       return (size_t)p0 * K + 4 * (size_t)e4;
     }
@@ -999,16 +1037,23 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   // D tile `it` -> raw stage it % NS: a contiguous run, one TMA bulk copy (the stages are never zero-filled: a ragged
   // last tile is handled by the consumers).
   auto load_raw = [&](int it, bool leader) {  // (called by the whole loader warp)
-    const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+    const int p0 = tile_p0(it);
     const int rows = min(TP, P - p0);
     const int s = it % NS;
     const uint32_t bytes = (uint32_t)(rows * K * 4);
     float* dst = raw + s * a.raw_floats;
     if constexpr (STRIDED) {
-      if (leader) mbar_expect_tx(full_raw + s, bytes);
-      __syncwarp();
-      for (int r = lane; r < rows; r += 32)
-        bulk_g2s(dst + r * K, a.D2 + (size_t)(p0 + r) * (size_t)a.ldk, (uint32_t)(K * 4), full_raw + s);
+      if (a.fullrow) {  // whole rows, both windows: a contiguous run
+        if (leader) {
+          mbar_expect_tx(full_raw + s, (uint32_t)(rows * a.ldk * 4));
+          bulk_g2s(dst, a.D2 + (size_t)p0 * (size_t)a.ldk, (uint32_t)(rows * a.ldk * 4), full_raw + s);
+        }
+      } else {
+        if (leader) mbar_expect_tx(full_raw + s, bytes);
+        __syncwarp();
+        for (int r = lane; r < rows; r += 32)
+          bulk_g2s(dst + r * K, W(a.D2) + (size_t)(p0 + r) * (size_t)a.ldk, (uint32_t)(K * 4), full_raw + s);
+      }
     } else if (leader) {
       mbar_expect_tx(full_raw + s, bytes);
       bulk_g2s(dst, a.D2 + (size_t)p0 * K, bytes, full_raw + s);
@@ -1020,7 +1065,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   const float* grow[GJ];   // &g[b, 4q]
   float4 greg[GJ];
   auto prefetch = [&](int it) {
-    const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+    const int p0 = tile_p0(it);
 #pragma unroll
     for (int j = 0; j < GJ; ++j) {
       greg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1045,7 +1090,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     if (a.want_dD && !a.codes_contig && r0 < B) {
       const int rb = min(r0 + (lane & 7), B - 1);
       const long long row = a.hv_on ? (long long)a.hv[rb] : (a.vidx ? (long long)a.vidx[rb] : (long long)rb);
-      gather_rows_cw<8>(cstage + r0 * K, K, a.v + row * (long long)a.ldk, min(a.rpw, B - r0), K, a.cw, lane);
+      gather_rows_cw<8>(cstage + r0 * K, K, W(a.v) + row * (long long)a.ldk, min(a.rpw, B - r0), K, a.cw, lane);
     }
   };
   if (warp < NW) {
@@ -1106,7 +1151,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   const uint32_t tmem_base = *tmem_slot;
   // tensor memory: [0, 2 TP) two dD^T accumulators | [2 TP, 2 TP + Kp) dv accumulator | then the codes, 3 x Bp/2 columns
   const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
-  const uint32_t codes = acc_dv + (uint32_t)a.Kp;
+  const uint32_t codes = acc_dv + (uint32_t)(a.dv2 ? 2 * a.Kp : a.Kp);
   STAMP(1);
   // (the setmaxnreg instructions open the role branches below)
 
@@ -1127,10 +1172,10 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         if (dD_out) {
           mbar_wait(epi_done + sj, (jt / NS) & 1);
           if constexpr (STRIDED) {
-            const int p0 = (blockIdx.x + jt * gridDim.x) * TP;
+            const int p0 = tile_p0(jt);
             const int rows = min(TP, P - p0);
             for (int r = lane; r < rows; r += 32) {  // one bulk store per row of the column window
-              float* gd = a.dD2 + (size_t)(p0 + r) * (size_t)a.ldk;
+              float* gd = W(a.dD2) + (size_t)(p0 + r) * (size_t)a.ldk;
               const float* sr = raw + sj * a.raw_floats + r * K;
               if (a.accumulate) bulk_red_add_s2g(gd, sr, (uint32_t)(K * 4));
               else bulk_s2g(gd, sr, (uint32_t)(K * 4));
@@ -1200,6 +1245,9 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         }
       };
       auto issue_dv = [&]() {
+        // (two dv accumulators, tiles alternate: see GradArgs::dv2)
+        const uint32_t acc_t = acc_dv + (uint32_t)((a.dv2 && (it & 1)) ? a.Kp : 0);
+        const int it_t = a.dv2 ? (it >> 1) : it;
 #pragma unroll
         for (int t = 0; t < 6; ++t) {
           constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, td[6] = {0, 2, 1, 0, 1, 0};
@@ -1207,7 +1255,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           uint64_t bd = dv_b0 + (uint64_t)buf * db16 + (uint64_t)td[t] * ds16;
 #pragma unroll
           for (int ks = 0; ks < TP / 16; ++ks, ad += astep, bd += 16)
-            mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
+            mma_bf16(acc_t, ad, bd, idesc_dv, (it_t | t | ks) ? 1u : 0u);
         }
       };
       // Tile 0: the dv MMAs need no codes, so they go first and the code conversion of the epilogue warps hides behind
@@ -1304,13 +1352,20 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           }
         }
       };
-      if (fused && my_tiles > 0) prefetch_ms((int)blockIdx.x * TP);
+      if constexpr (STRIDED) {
+        if (fused && my_tiles > 0) prefetch_ms(cta_x * TP);
+      } else {
+        if (fused && my_tiles > 0) prefetch_ms((int)blockIdx.x * TP);
+      }
       // (p0 advances by gridDim.x * TP with gridDim.x read as a constant-bank operand: written as j * gridDim.x ptxas hoisted
       // the factor into a register, SPILLED it, and reloaded it from local memory at the top of every round -- a load
       // that queues behind the twelve stores of the round before: 8 % of all stall samples, +6 us per launch.)
-      int p0 = (int)blockIdx.x * TP - (int)gridDim.x * TP;
+      int p0;
+      if constexpr (STRIDED) p0 = (cta_x - cta_n) * TP;
+      else p0 = (int)blockIdx.x * TP - (int)gridDim.x * TP;
       for (int j = 0; j < my_tiles; ++j) {
-        p0 += (int)gridDim.x * TP;
+        if constexpr (STRIDED) p0 += cta_n * TP;
+        else p0 += (int)gridDim.x * TP;
         const int rows = min(TP, P - p0);
         const int sj = j % NS, buf = j & 1;
         float* stage = raw + sj * a.raw_floats;
@@ -1380,7 +1435,9 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           for (int u = 0; u < NPF; ++u) {
             const int e4 = etid + u * (NEP * 32);
             if (e4 < n4) {
-              float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
+              float4 Dv;
+              if constexpr (STRIDED) Dv = *reinterpret_cast<const float4*>(stage + soff(e4));
+              else Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
               const float4 gd = *reinterpret_cast<const float4*>(gtile + 4 * e4);
               adamw_update_fast(Dv.x, Mp[u].x, Sp[u].x, gd.x, a.hp);
               adamw_update_fast(Dv.y, Mp[u].y, Sp[u].y, gd.y, a.hp);
@@ -1396,7 +1453,9 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
             }
           }
           for (int e4 = etid + NPF * (NEP * 32); e4 < n4; e4 += NEP * 32) {  // (large K: beyond the prefetched part)
-            float4 Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
+            float4 Dv;
+            if constexpr (STRIDED) Dv = *reinterpret_cast<const float4*>(stage + soff(e4));
+            else Dv = *reinterpret_cast<const float4*>(stage + 4 * e4);
             const size_t go = goff(p0, e4);
             float4 Mv = ld_global4(a.m + go);
             float4 Sv = ld_global4(a.s + go);
@@ -1415,7 +1474,11 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
 #endif
           __syncwarp();
           if (lane == 0) mbar_arrive(empty_raw + sj);  // this warp is done with the D rows of the stage
-          if (j + 1 < my_tiles) prefetch_ms(p0 + (int)gridDim.x * TP);  // the moments of the next tile fly while its MMAs run
+          if constexpr (STRIDED) {
+            if (j + 1 < my_tiles) prefetch_ms(p0 + cta_n * TP);
+          } else {
+            if (j + 1 < my_tiles) prefetch_ms(p0 + (int)gridDim.x * TP);
+          }  // the moments of the next tile fly while its MMAs run
         } else {
           fence_proxy_async();  // the dD tile in the stage is read by the copy engine
           __syncwarp();
@@ -1436,7 +1499,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
     tile_chan_init(tc);
     STAMP(3);
     for (int it = 0; it < my_tiles; ++it) {
-      const int p0 = (blockIdx.x + it * gridDim.x) * TP;
+      const int p0 = tile_p0(it);
       const int s = it % NS;
       const int buf = it & 1;
       bf16_t* Gb = Gi + buf * gbuf;
@@ -1496,6 +1559,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
             const int k0 = 8 * gq;
             float val[8];
             const float* src = rt + p * K + k0;
+            if constexpr (STRIDED) src = rt + p * a.rpitch + (int)(wof & a.rmask) + k0;
             if (p < rows) {
               if (a.vk == 4) {
                 const float4 lo4 = *reinterpret_cast<const float4*>(src);
@@ -1629,6 +1693,12 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         for (int c0 = cg * 16; c0 < a.Kp; c0 += 64) {  // warp-uniform
           float r[16];
           tmem_ld16(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+          if (a.dv2 && my_tiles > 1) {  // (odd tiles accumulated in the second accumulator)
+            float r2[16];
+            tmem_ld16(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a.Kp + c0), r2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] += r2[i];
+          }
           if (b < B) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
@@ -1652,6 +1722,9 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   __syncthreads();
   if (warp == WARP_EPI + NE) tmem_dealloc(tmem_base, a.tmem_cols);
   STAMP(6);
+#undef cta_x
+#undef cta_n
+#undef wof
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1866,7 +1939,8 @@ int launch_grad_tpfn(const GradArgs& a, size_t smem, int grid, cudaStream_t st) 
 template <int TP, bool FUSED, bool STRIDED>
 int launch_grad_tpf(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
   static const int npf_knob = getenv("ADIL_GRAD_NPF") ? atoi(getenv("ADIL_GRAD_NPF")) : 0;  // tuning knob: 4 forces the 8-warp pass
-  if (FUSED && npf_knob != 4 && (TP * a.K) / 4 <= 3 * NEP_MAX * 32) return launch_grad_tpfn<TP, FUSED, STRIDED, FUSED ? 3 : 4>(a, smem, grid, st);
+  // (knob 3: the ten-warp pass also for tiles of up to 4 * 320 items -- the items beyond 3 * 320 run unprefetched)
+  if (FUSED && npf_knob != 4 && ((TP * a.K) / 4 <= 3 * NEP_MAX * 32 || (npf_knob == 3 && (TP * a.K) / 4 <= 4 * NEP_MAX * 32))) return launch_grad_tpfn<TP, FUSED, STRIDED, FUSED ? 3 : 4>(a, smem, grid, st);
   return launch_grad_tpfn<TP, FUSED, STRIDED, 4>(a, smem, grid, st);
 }
 template <int TP>
@@ -1878,7 +1952,7 @@ int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
 
 // One launch over a window of K columns (K <= 128) of arrays whose rows are ldk floats apart; dvb rows are dv_ld apart.
 int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
-                       const float* v, const int64_t* v_index, int B, int P, int K, int ldk, int dv_ld,
+                       const float* v, const int64_t* v_index, int B, int P, int K, int ldk, int dv_ld, int nwin,
                        const ChannelConsts& cc, const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes,
                        const GradOpts& opt, cudaStream_t st);
 }  // namespace
@@ -1895,17 +1969,23 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
                    const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes, const GradOpts& opt,
                    cudaStream_t st) {
   if (K <= 128)
-    return launch_grad_window(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, K, K, cc, hp, atoms_mode, scratch,
+    return launch_grad_window(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, K, K, K, 1, cc, hp, atoms_mode, scratch,
                               scratch_bytes, opt, st);
   if (opt.keep_partials)
     return set_error(-5, "adil_grad: ADIL_GRAD_KEEP_PARTIALS is limited to K <= 128 on the tcgen05 path (K=%d runs as two "
                      "column windows): pass dvb", K);
   const int Kh = K / 2;
-  for (int h = 0; h < 2; ++h) {  // each window reads g once more: 4BP extra bytes against 4P(B+6K) of the step
+  // Both windows in ONE launch (CTA parity = window; see grad_kernel) unless ADIL_GRAD_WINDOWS=serial asks for the former
+  // two launches (A/B runs; each window then reads g from HBM once more).
+  static const bool serial = getenv("ADIL_GRAD_WINDOWS") && !strcmp(getenv("ADIL_GRAD_WINDOWS"), "serial");
+  if (!serial && sm_count() >= 2)
+    return launch_grad_window(dD2, D2_rw, m, s, dvb, g, D2, v, v_index, B, P, Kh, K, K, 2, cc, hp, atoms_mode, scratch,
+                              scratch_bytes, opt, st);
+  for (int h = 0; h < 2; ++h) {
     const int k0 = h * Kh;
     int rc = launch_grad_window(dD2 ? dD2 + k0 : nullptr, D2_rw ? D2_rw + k0 : nullptr, m ? m + k0 : nullptr,
                                 s ? s + k0 : nullptr, dvb ? dvb + k0 : nullptr, g, D2 + k0, v + k0, v_index, B, P, Kh, K,
-                                K, cc, hp, atoms_mode, scratch, scratch_bytes, opt, st);
+                                K, 1, cc, hp, atoms_mode, scratch, scratch_bytes, opt, st);
     if (rc) return rc;
   }
   return 0;
@@ -1913,7 +1993,7 @@ int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, con
 
 namespace {
 int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
-                       const float* v, const int64_t* v_index, int B, int P, int K, int ldk, int dv_ld,
+                       const float* v, const int64_t* v_index, int B, int P, int K, int ldk, int dv_ld, int nwin,
                        const ChannelConsts& cc, const AdamwDev* hp, int atoms_mode, float* scratch, size_t scratch_bytes,
                        const GradOpts& opt, cudaStream_t st) {
   const bool want_dD = dD2 != nullptr || D2_rw != nullptr, want_dv = dvb != nullptr || opt.keep_partials != 0,
@@ -1932,8 +2012,24 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
   }
   a.B = B; a.P = P; a.K = K; a.Bp = pl.Bp; a.Kp = pl.Kp; a.Sg = pl.Sg; a.Sd = pl.Sd;
   a.dimg = pl.dimg; a.gimg = pl.gimg; a.raw_floats = pl.raw_floats; a.nraw = pl.nraw;
+  size_t smem_bytes = pl.smem;
+  a.fullrow = 0; a.rpitch = K; a.rmask = 0u;
+  {  // column windows: full dictionary rows in the raw stages when the wider stages fit (A/B knob: ADIL_GRAD_FULLROW=0)
+    static const bool fullrow_knob = !(getenv("ADIL_GRAD_FULLROW") && atoi(getenv("ADIL_GRAD_FULLROW")) == 0);
+    const size_t wider = pl.smem + sizeof(float) * (size_t)NS * pl.TP * (size_t)(ldk - K);
+    if (ldk != K && pl.nraw > 0 && fullrow_knob && ADIL_G_SCALED_FUSED && ADIL_G_SCALED_PLAIN && wider <= (size_t)SMEM_LIMIT) {
+      a.fullrow = 1; a.rpitch = ldk; a.rmask = 0xffffffffu;
+      a.raw_floats = pl.TP * ldk;
+      smem_bytes = wider;
+    }
+  }
   a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.gdiv = div_magic((K + 7) / 8); a.tmem_cols = pl.tmem_cols;
-  a.ldk = ldk; a.k4div = div_magic(K >> 2 > 0 ? K >> 2 : 1);
+  a.ldk = ldk; a.k4div = div_magic(K >> 2 > 0 ? K >> 2 : 1); a.nwin = nwin; a.wsh = nwin >> 1;
+  {  // two dv accumulators when tensor memory has the columns (A/B knob: ADIL_GRAD_DV2=0 / 1 = column windows only / 2 = always)
+    static const int dv2_knob = getenv("ADIL_GRAD_DV2") ? atoi(getenv("ADIL_GRAD_DV2")) : 1;
+    a.dv2 = ((dv2_knob == 2 || (dv2_knob == 1 && nwin == 2)) && want_dv && 2 * pl.TP + 2 * pl.Kp + 3 * (pl.Bp / 2) <= 512) ? 1 : 0;
+  }
+  if (a.dv2) a.tmem_cols = pow2_cols(2 * pl.TP + 2 * pl.Kp + 3 * (pl.Bp / 2));
   a.want_dD = want_dD ? 1 : 0; a.want_dv = want_dv ? 1 : 0; a.atoms_mode = atoms_mode; a.cc = cc;
   a.accumulate = (opt.accumulate && !fused) ? 1 : 0;
   a.dreg = pl.dreg;
@@ -1947,8 +2043,13 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
   if (hp) a.hp = *hp;
   const int ntiles = (P + pl.TP - 1) / pl.TP;
   int grid = sm_count();
-  if (grid > ntiles) grid = ntiles;
   if (grid > kMaxGradCtas) grid = kMaxGradCtas;
+  if (nwin == 2) {  // CTA pairs: (window 0, window 1) of the same pixel tiles
+    grid &= ~1;
+    if (grid > 2 * ntiles) grid = 2 * ntiles;
+  } else if (grid > ntiles) {
+    grid = ntiles;
+  }
   if (want_dv) {
     const size_t need = (size_t)grid * B * K * sizeof(float);
     if (scratch == nullptr || scratch_bytes < need)
@@ -1956,10 +2057,10 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
   }
   int rc;
   switch (pl.TP) {
-    case 64: rc = launch_grad_tp<64>(a, pl.smem, grid, st); break;
-    case 48: rc = launch_grad_tp<48>(a, pl.smem, grid, st); break;
-    case 32: rc = launch_grad_tp<32>(a, pl.smem, grid, st); break;
-    default: rc = launch_grad_tp<16>(a, pl.smem, grid, st); break;
+    case 64: rc = launch_grad_tp<64>(a, smem_bytes, grid, st); break;
+    case 48: rc = launch_grad_tp<48>(a, smem_bytes, grid, st); break;
+    case 32: rc = launch_grad_tp<32>(a, smem_bytes, grid, st); break;
+    default: rc = launch_grad_tp<16>(a, smem_bytes, grid, st); break;
   }
   if (rc) return rc;
 #if defined(ADIL_CHAIN) && !defined(ADIL_CHAIN_QUIET)
@@ -1989,6 +2090,11 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
     if (opt.keep_partials) {
       if (opt.nslabs_out) *opt.nslabs_out = grid;
       return 0;
+    }
+    if (nwin == 2) {  // slabs of window h: CTAs h, h + 2, ... -> columns [h K, h K + K) of dvb
+      int rc2 = launch_reduce_partials(dvb, scratch, B * K, grid / 2, K, dv_ld, st, 2);
+      if (rc2) return rc2;
+      return launch_reduce_partials(dvb + K, scratch + (size_t)B * K, B * K, grid / 2, K, dv_ld, st, 2);
     }
     return launch_reduce_partials(dvb, scratch, B * K, grid, K, dv_ld, st);
   }

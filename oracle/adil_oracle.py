@@ -707,3 +707,93 @@ def adil_fb(model, dataset, targeted=True, niter=10, lambda_coding=1., l2_fool=1
             trace.append(i)
         loss_all[it] = float(loss_full)
     return D2.reshape(nc, nx, ny, n_atom), v, loss_all
+
+
+# ------------------------------------------------------------------------------------------------
+# regularised variant: the coder on a fixed dictionary (learn_coding_vectors, adil_regularized.py:508-628)
+# ------------------------------------------------------------------------------------------------
+def learn_coding_vectors(model, dataset, D, targeted=True, niter=10, lambda_l1=1., lambda_l2=1., batch_size=None,
+                         step_size=.1, trace=None):
+    """Codes of `dataset` on the FIXED dictionary D [C,H,W,K] for the penalised objective
+    coeff * CE_sum(x + D v) + 0.5 * lambda_l2 * ||D v||^2 + lambda_l1 * ||v||_1  (adil_regularized.py:508-628): full-batch
+    proximal gradient from v = 0 (:538) with a backtracking line search over the segment v_old -> prox step (:573-622).
+
+    Per iteration: loss and gradient over the whole set (:553-565); v <- soft threshold(v - step grad, step * lambda_l1)
+    (:574-577); h = <dv, grad> + 0.5 / step * ||dv||^2 + lambda_l1 (|v|_1 - |v_old|_1) (:583-584); then the first i in
+    0..10 with loss(v_old + 0.9^i dv) <= loss_old + 0.5 * 0.9^i * h ends the search (:589-613) -- the shortened point is
+    KEPT only if its loss is below the full step's (`loss_cur > loss_full`, :607-610: then the step size shrinks by
+    0.9^i too), otherwise the full prox step stays and its loss is recorded; no i <= 10 qualifies: the last point tried
+    is taken (:615-620).  Stops when the recorded loss decreased by less than 1e-6 (:626).
+    `trace` (a list) receives (index at which the search ended, kept the shortened point) per iteration.
+    Returns (v [N,K], loss_all list starting with NaN like the reference's, final step size)."""
+    import numpy as np
+    nimg = len(dataset)
+    nc, nx, ny, n_atom = D.shape
+    P = nc * nx * ny
+    D2 = D.reshape(P, n_atom)
+    delta, gamma, beta = .9, 1, .5
+    batch_size = nimg if batch_size is None else batch_size
+    coeff = 1. if targeted else -1.
+    slices = [list(range(i, min(i + batch_size, nimg))) for i in range(0, nimg, batch_size)]   # utils.py:153-156
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False)
+    step_size = torch.as_tensor(step_size, dtype=torch.float32)   # (the reference's default is a tensor, :509)
+    v = torch.zeros(nimg, n_atom)
+
+    def smooth_loss(v_, want_grad):
+        """(:553-559 / :597-603) sum over the batches, accumulated as the reference's fp32 tensor expression"""
+        total = 0
+        gv = torch.zeros_like(v_) if want_grad else None
+        for i, (x, y) in enumerate(loader):
+            ind = slices[i]
+            n = x.shape[0]
+            target = get_target(model, x, y, targeted)
+            dv = v_[ind] @ D2.t()
+            if want_grad:
+                xin = (x.reshape(n, P) + dv).reshape(x.shape).detach().requires_grad_(True)
+                ce = coeff * torch.nn.functional.cross_entropy(model(xin), target, reduction='sum')
+                (g,) = torch.autograd.grad(ce, xin)
+                gv[ind] = (g.reshape(n, P) + lambda_l2 * dv) @ D2
+                total = total + ce.detach() + .5 * lambda_l2 * torch.sum(dv ** 2)
+            else:
+                with torch.no_grad():
+                    out = model((x.reshape(n, P) + dv).reshape(x.shape))
+                    total = total + coeff * torch.nn.functional.cross_entropy(out, target, reduction='sum') \
+                        + .5 * lambda_l2 * torch.sum(dv ** 2)
+        return total, gv
+
+    loss_all = [np.nan]
+    for _ in range(int(niter)):
+        loss_s, grad_v = smooth_loss(v, True)
+        loss_old = (loss_s + lambda_l1 * torch.sum(torch.abs(v))).item()
+        v_old = v.clone()
+        v = softshrink(v - step_size * grad_v, float(step_size * lambda_l1))
+        d_v = v - v_old
+        h = torch.sum((v - v_old) * grad_v) + .5 * (gamma / step_size) * (torch.norm(v - v_old, 'fro') ** 2) \
+            + lambda_l1 * torch.sum(torch.abs(v)) - lambda_l1 * torch.sum(torch.abs(v_old))
+        index_i, kept = 0, False
+        while True:
+            new_v = v_old + (delta ** index_i) * d_v
+            loss_s, _ = smooth_loss(new_v, False)
+            loss_full = (loss_s + lambda_l1 * torch.sum(torch.abs(new_v))).item()
+            if index_i == 0:
+                loss_cur = loss_full
+            if loss_full <= loss_old + beta * (delta ** index_i) * h:
+                if loss_cur > loss_full:
+                    v = new_v
+                    step_size = step_size * delta ** index_i
+                    loss_all.append(loss_full)
+                    kept = True
+                else:
+                    loss_all.append(loss_cur)
+                break
+            index_i += 1
+            if index_i > 10:
+                v = new_v
+                loss_all.append(loss_full)
+                kept = True
+                break
+        if trace is not None:
+            trace.append((index_i, kept))
+        if loss_all[-2] - loss_all[-1] < 1e-6:
+            break
+    return v, loss_all, float(step_size)

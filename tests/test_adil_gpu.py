@@ -416,6 +416,30 @@ def test_full_batch_line_search_variant_on_the_kernels_matches_the_reference(tag
     assert torch.equal(Df, D) and np.isfinite(lossf).all() and lossf[-1] <= lossf[0]
 
 
+@pytest.mark.parametrize("tag,kw,ended", [
+    ("lcv_untargeted", dict(targeted=False, niter=8, lambda_l1=0.01, lambda_l2=0.5, batch_size=4, step_size=0.05), [0] * 8),
+    ("lcv_targeted", dict(targeted=True, niter=8, lambda_l1=0.02, lambda_l2=2.0, batch_size=None, step_size=0.02), [0] * 8),
+    ("lcv_backtrack", dict(targeted=False, niter=8, lambda_l1=0.05, lambda_l2=0.5, batch_size=4, step_size=10.0), [11, 11]),
+    ("lcv_linesearch", dict(targeted=False, niter=8, lambda_l1=0.05, lambda_l2=0.5, batch_size=4, step_size=1.0),
+     [5, 0, 3, 2, 5, 0, 2, 0])])
+def test_coder_on_a_fixed_dictionary_on_the_kernels_matches_the_reference(tag, kw, ended):
+    """dl_attack_on_imagenet_b200.adil_regularized.learn_coding_vectors -- l2-penalised code-gradient contraction,
+    soft-threshold proximal step, line search on loss-only passes -- against the output of the reference's own
+    learn_coding_vectors() (adil_regularized.py:508-628; tests/golden/lcv_reference_golden.npz) on the same dictionary:
+    the search ends at the same indices, same recorded losses and codes."""
+    import os
+    from dl_attack_on_imagenet_b200.adil_regularized import learn_coding_vectors
+    from dl_attack_on_imagenet_b200.utils import QuickAttackDataset
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lcv_reference_golden.npz"))
+    model = O.tiny_classifier(seed=0).cuda()
+    xtr, ytr, _, _ = tiny_data()
+    trace = []
+    v = learn_coding_vectors(QuickAttackDataset(xtr, ytr), model, dictionary=torch.from_numpy(g[tag + "_D"]), trace=trace, **kw)
+    assert [t[0] for t in trace] == ended
+    assert np.allclose([t[2] for t in trace], g[tag + "_loss"][1:], rtol=2e-6, atol=5e-5)
+    assert (v.cpu() - torch.from_numpy(g[tag + "_v"])).abs().max() <= 1e-5
+
+
 def test_fit_with_the_whole_set_as_one_minibatch(monkeypatch):
     """batch_size=None is the reference's documented default (len(data_train), adil.py:124): 150 images in one minibatch
     exceed the 128 images one kernel pass takes, so the synthesis runs in two passes and the backward as chunked plain
