@@ -1151,7 +1151,10 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
   const uint32_t tmem_base = *tmem_slot;
   // tensor memory: [0, 2 TP) two dD^T accumulators | [2 TP, 2 TP + Kp) dv accumulator | then the codes, 3 x Bp/2 columns
   const uint32_t acc_dv = tmem_base + (uint32_t)(2 * TP);
-  const uint32_t codes = acc_dv + (uint32_t)(a.dv2 ? 2 * a.Kp : a.Kp);
+  const uint32_t codes = [&]() -> uint32_t {
+    if constexpr (STRIDED) return acc_dv + (uint32_t)(a.dv2 ? 2 * a.Kp : a.Kp);
+    else return acc_dv + (uint32_t)a.Kp;
+  }();
   STAMP(1);
   // (the setmaxnreg instructions open the role branches below)
 
@@ -1245,9 +1248,6 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         }
       };
       auto issue_dv = [&]() {
-        // (two dv accumulators, tiles alternate: see GradArgs::dv2)
-        const uint32_t acc_t = acc_dv + (uint32_t)((a.dv2 && (it & 1)) ? a.Kp : 0);
-        const int it_t = a.dv2 ? (it >> 1) : it;
 #pragma unroll
         for (int t = 0; t < 6; ++t) {
           constexpr int tg[6] = {2, 0, 1, 1, 0, 0}, td[6] = {0, 2, 1, 0, 1, 0};
@@ -1255,7 +1255,12 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
           uint64_t bd = dv_b0 + (uint64_t)buf * db16 + (uint64_t)td[t] * ds16;
 #pragma unroll
           for (int ks = 0; ks < TP / 16; ++ks, ad += astep, bd += 16)
-            mma_bf16(acc_t, ad, bd, idesc_dv, (it_t | t | ks) ? 1u : 0u);
+            if constexpr (STRIDED) {
+              const bool two = a.dv2 != 0;
+              mma_bf16(acc_dv + (uint32_t)((two && (it & 1)) ? a.Kp : 0), ad, bd, idesc_dv, ((two ? (it >> 1) : it) | t | ks) ? 1u : 0u);
+            } else {
+              mma_bf16(acc_dv, ad, bd, idesc_dv, (it | t | ks) ? 1u : 0u);
+            }
         }
       };
       // Tile 0: the dv MMAs need no codes, so they go first and the code conversion of the epilogue warps hides behind
@@ -1693,11 +1698,13 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         for (int c0 = cg * 16; c0 < a.Kp; c0 += 64) {  // warp-uniform
           float r[16];
           tmem_ld16(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-          if (a.dv2 && my_tiles > 1) {  // (odd tiles accumulated in the second accumulator)
-            float r2[16];
-            tmem_ld16(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a.Kp + c0), r2);
+          if constexpr (STRIDED) {
+            if (a.dv2 && my_tiles > 1) {  // (odd tiles accumulated in the second accumulator)
+              float r2[16];
+              tmem_ld16(acc_dv + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a.Kp + c0), r2);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] += r2[i];
+              for (int i = 0; i < 16; ++i) r[i] += r2[i];
+            }
           }
           if (b < B) {
 #pragma unroll
@@ -2025,9 +2032,10 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
   }
   a.vk = vec_width(K); a.kdiv = div_magic(K / a.vk); a.gdiv = div_magic((K + 7) / 8); a.tmem_cols = pl.tmem_cols;
   a.ldk = ldk; a.k4div = div_magic(K >> 2 > 0 ? K >> 2 : 1); a.nwin = nwin; a.wsh = nwin >> 1;
-  {  // two dv accumulators when tensor memory has the columns (A/B knob: ADIL_GRAD_DV2=0 / 1 = column windows only / 2 = always)
-    static const int dv2_knob = getenv("ADIL_GRAD_DV2") ? atoi(getenv("ADIL_GRAD_DV2")) : 1;
-    a.dv2 = ((dv2_knob == 2 || (dv2_knob == 1 && nwin == 2)) && want_dv && 2 * pl.TP + 2 * pl.Kp + 3 * (pl.Bp / 2) <= 512) ? 1 : 0;
+  {  // column windows in one launch: two dv accumulators when tensor memory has the columns (A/B knob: ADIL_GRAD_DV2=0).
+     // (Measured on the single-window kernels too, K = 50 ... 128: no change -- they keep one accumulator.)
+    static const bool dv2_knob = !(getenv("ADIL_GRAD_DV2") && atoi(getenv("ADIL_GRAD_DV2")) == 0);
+    a.dv2 = (dv2_knob && nwin == 2 && want_dv && 2 * pl.TP + 2 * pl.Kp + 3 * (pl.Bp / 2) <= 512) ? 1 : 0;
   }
   if (a.dv2) a.tmem_cols = pow2_cols(2 * pl.TP + 2 * pl.Kp + 3 * (pl.Bp / 2));
   a.want_dD = want_dD ? 1 : 0; a.want_dv = want_dv ? 1 : 0; a.atoms_mode = atoms_mode; a.cc = cc;

@@ -242,13 +242,20 @@ def _host_index_retry(call, v_index, dev):
     return rc
 
 
+def _n_launches_with_reduction(B, P, K):
+    """launches of a backward call that returns the reduced code gradient: the contraction kernel + the slab reduction --
+    on the tcgen05 path beyond 128 atoms ONE contraction launch covers both column windows, each window's slabs are
+    reduced by a launch of their own"""
+    return 3 if (K > 128 and get_impl() != IMPL_FMA and tc_supported(B, P, K)) else 2
+
+
 def _grad_call(dD2, dvb, g, D2, v, v_index, B, P, K, std, flags, dev, delta=None, l2_coef=0.0):
     """One adil_grad call (B within the per-call limit).  Returns nslabs (KEEP_PARTIALS) or 0."""
     C = len(std) if std is not None else 1
     scratch, nbytes = _grad_scratch(dev, B, K)
     nslabs = ctypes.c_int(0)
     v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
-    with _Timed("adil_grad", dev, 1 if (flags & GRAD_KEEP_PARTIALS or dvb is None) else 2):
+    with _Timed("adil_grad", dev, 1 if (flags & GRAD_KEEP_PARTIALS or dvb is None) else _n_launches_with_reduction(B, P, K)):
         rc = _host_index_retry(
             lambda ix: _lib.lib().adil_grad(_ptr(dD2), _ptr(dvb), _ptr(g), _ptr(D2), _ptr(v), _ptr(ix), B, P, K, C,
                                             P // C, _host3(std, C), _ptr(delta), float(l2_coef), int(flags),
@@ -356,7 +363,7 @@ def grad_dict_step(D2, m, s, g, v, v_index, hp, std=None, atoms_mode=ATOMS_CLAMP
     scratch, nbytes = _grad_scratch(dev, B, K)
     nslabs = ctypes.c_int(0)
     v_index = _idx_any(v_index, "v_index", dev, P, K, 2)
-    with _Timed("adil_grad_dict_step", dev, 2 if (want_dv and not keep_partials) else 1):
+    with _Timed("adil_grad_dict_step", dev, _n_launches_with_reduction(B, P, K) if (want_dv and not keep_partials) else 1):
         rc = _host_index_retry(
             lambda ix: _lib.lib().adil_grad_dict_step(_ptr(D2), _ptr(m), _ptr(s),
                                                       _ptr(dvb) if (want_dv and not keep_partials) else None, _ptr(g),

@@ -437,7 +437,8 @@ def test_coder_on_a_fixed_dictionary_on_the_kernels_matches_the_reference(tag, k
     v = learn_coding_vectors(QuickAttackDataset(xtr, ytr), model, dictionary=torch.from_numpy(g[tag + "_D"]), trace=trace, **kw)
     assert [t[0] for t in trace] == ended
     assert np.allclose([t[2] for t in trace], g[tag + "_loss"][1:], rtol=2e-6, atol=5e-5)
-    assert (v.cpu() - torch.from_numpy(g[tag + "_v"])).abs().max() <= 1e-5
+    vref = torch.from_numpy(g[tag + "_v"])     # (the case with the far too long step has codes of magnitude 7)
+    assert (v.cpu() - vref).abs().max() <= 1e-5 * max(1.0, vref.abs().max().item())
 
 
 def test_fit_with_the_whole_set_as_one_minibatch(monkeypatch):
