@@ -1175,17 +1175,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
         if (dD_out) {
           mbar_wait(epi_done + sj, (jt / NS) & 1);
           if constexpr (STRIDED) {
-            const int p0 = tile_p0(jt);
-            const int rows = min(TP, P - p0);
-            for (int r = lane; r < rows; r += 32) {  // one bulk store per row of the column window
-              float* gd = W(a.dD2) + (size_t)(p0 + r) * (size_t)a.ldk;
-              const float* sr = raw + sj * a.raw_floats + r * K;
-              if (a.accumulate) bulk_red_add_s2g(gd, sr, (uint32_t)(K * 4));
-              else bulk_s2g(gd, sr, (uint32_t)(K * 4));
-            }
-            bulk_commit();
-            if (it < my_tiles) bulk_wait_read0();  // the stage is about to be refilled
-            __syncwarp();
+            // (column window: the epilogue warps stored the tile themselves; the stage is free)
             if (leader && it < my_tiles && a.nraw == 0) mbar_arrive(full_raw + sj);
           } else if (leader) {
             const int p0 = (blockIdx.x + jt * gridDim.x) * TP;
@@ -1203,7 +1193,7 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
       }
       if (it < my_tiles && a.nraw > 0) load_raw(it, leader);
     }
-    if ((STRIDED || leader) && dD_out) bulk_wait0();  // every output tile has been written before the CTA retires
+    if (!STRIDED && leader && dD_out) bulk_wait0();  // every output tile has been written before the CTA retires
     __syncwarp();
   } else if (warp == WARP_MMA_G) {
     // ===== issuer =====
@@ -1485,9 +1475,30 @@ __global__ void __launch_bounds__(NTHREADS_GRAD, 1) grad_kernel(const GradArgs a
             if (j + 1 < my_tiles) prefetch_ms(p0 + (int)gridDim.x * TP);
           }  // the moments of the next tile fly while its MMAs run
         } else {
-          fence_proxy_async();  // the dD tile in the stage is read by the copy engine
-          __syncwarp();
-          if (lane == 0) mbar_arrive(epi_done + sj);
+          if constexpr (STRIDED) {
+            // Column window, plain dD output: the rows of the tile are K floats at a pitch of ldk in global memory.  As
+            // one TMA bulk store per row (issued and waited for by the loader, which then requested the next dictionary
+            // tile late) they were the slowest stage of the kernel -- K = 200: 192 us against 178 us for the FUSED step,
+            // which moves four times the bytes.  The warps that hold atoms store the tile themselves, 128 bits per lane.
+            const int nq = (K + 31) >> 5;  // TMEM quadrants that hold atoms: 2 nq warps take part
+            bar_sync(3, 2 * nq * 32);      // the tile is complete in the stage
+            const int n4 = (rows * K) >> 2;
+            for (int e4 = (half * nq + quad) * 32 + lane; e4 < n4; e4 += 2 * nq * 32) {
+              float4 t = *reinterpret_cast<const float4*>(stage + 4 * e4);
+              float* gp = a.dD2 + goff(p0, e4);
+              if (a.accumulate) {  // (chunks of a large batch run in stream order: plain read-modify-write)
+                const float4 o = ld_global4(gp);
+                t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+              }
+              *reinterpret_cast<float4*>(gp) = t;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(epi_done + sj);  // this warp is done with the stage
+          } else {
+            fence_proxy_async();  // the dD tile in the stage is read by the copy engine
+            __syncwarp();
+            if (lane == 0) mbar_arrive(epi_done + sj);
+          }
         }
         if (warp == WARP_EPI) CHAIN(5, j);
         if (warp == WARP_EPI && j == 0) WSTAMP(10);

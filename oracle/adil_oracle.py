@@ -797,3 +797,129 @@ def learn_coding_vectors(model, dataset, D, targeted=True, niter=10, lambda_l1=1
         if loss_all[-2] - loss_all[-1] < 1e-6:
             break
     return v, loss_all, float(step_size)
+
+
+# ------------------------------------------------------------------------------------------------
+# regularised variant: SADiL "updated" (sadil_updated, adil_regularized.py:315-501)
+# ------------------------------------------------------------------------------------------------
+def sadil_updated(model, dataset, targeted=True, nepochs=10, batchsize=1, lambda_coding=1., l2_fool=1., stepsize=1.,
+                  n_atom=5, dict_set='l2ball', D0=None, trace=None):
+    """Per epoch: a proximal step on the code rows of every minibatch, then ONE projected gradient step on D with the
+    gradient accumulated over the epoch, each followed by a backtracking test (factor 0.5, at most 5 halvings) that only
+    adapts the step sizes -- the full steps are always kept (adil_regularized.py:444-448,486-492).
+
+    What the reference's autograd bookkeeping amounts to (restated explicitly here):
+      * `v` is one tensor updated in place whose `.grad` is never zeroed (:392,398): every backward -- the V-step's (:398)
+        and the D-step's (:446, v takes part in D v) -- accumulates into it, and the V-step uses the accumulated rows;
+      * `D` requires grad from the first D-step backward of its lifetime on (:439), so from the SECOND minibatch on the
+        V-step backward (old codes) adds to `D.grad` as well as the D-step backward (new codes); a new D tensor (after
+        an accepted step, :460) starts without gradient, a skipped step (:451-452) keeps accumulating;
+      * the backtracking loop of the V-step measures the l1 term WITHOUT lambda (:433) and its first-order term has
+        |v_cur|_1 - |v[ind]|_1 = 0 (:420-421).
+    `trace` (a list) receives per epoch (i_max of the V-steps, halvings of the D-step or -1 when it was skipped).
+    Returns (D [C,H,W,K], v [N,K], loss list, (stepsize_v, stepsize_D))."""
+    nimg = len(dataset)
+    x0, _ = next(iter(dataset))
+    nc, nx, ny = x0.shape
+    P = nc * nx * ny
+    delta, beta = 0.5, 0.5
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False)
+    coeff = 1. if targeted else -1.
+    slices = [list(range(i, min(i + batchsize, nimg))) for i in range(0, nimg, batchsize)]   # utils.py:153-156
+    mode = {'l2ball': ATOMS_L2BALL, 'l2sphere': ATOMS_L2SPHERE}.get(dict_set, ATOMS_L1BALL)
+    D = project_atoms(torch.randn(3, nx, ny, n_atom), mode) if D0 is None else D0.clone()
+    D2 = D.reshape(P, n_atom).clone()
+    v = torch.zeros(nimg, n_atom)
+    stepsize_D = stepsize_v = stepsize
+
+    def smooth(x, target, vb, D2_, want_grad):
+        """coeff * CE_sum + 0.5 * l2_fool * ||D vb||^2 as the reference's fp32 tensor (:395-396) [, d/dD2, d/dvb]"""
+        n = x.shape[0]
+        dv = vb @ D2_.t()
+        if not want_grad:
+            with torch.no_grad():
+                out = model((x.reshape(n, P) + dv).reshape(x.shape))
+                return coeff * torch.nn.functional.cross_entropy(out, target, reduction='sum') + .5 * l2_fool * torch.sum(dv ** 2)
+        xin = (x.reshape(n, P) + dv).reshape(x.shape).detach().requires_grad_(True)
+        ce = coeff * torch.nn.functional.cross_entropy(model(xin), target, reduction='sum')
+        (g,) = torch.autograd.grad(ce, xin)
+        gx = g.reshape(n, P) + l2_fool * dv
+        return ce.detach() + .5 * l2_fool * torch.sum(dv ** 2), gx.t() @ vb, gx @ D2_
+
+    def loss_all(v_, D2_):
+        """:362-373"""
+        total = 0
+        for i, (x, y) in enumerate(loader):
+            total += smooth(x, get_target(model, x, y, targeted), v_[slices[i]], D2_, False).item()
+        return total + (lambda_coding * torch.sum(torch.abs(v_))).item()
+
+    loss = [loss_all(v, D2)]
+    gv_acc = torch.zeros(nimg, n_atom)            # v.grad
+    gD_acc = torch.zeros(P, n_atom)               # D.grad of the current D tensor
+    D_has_grad = False
+    for _ in range(int(nepochs)):
+        i_max = 0
+        for bi, (x, y) in enumerate(loader):
+            ind = slices[bi]
+            target = get_target(model, x, y, targeted)
+            # ---------- V-step (:391-448) ----------
+            loss_s, dD2, dvb = smooth(x, target, v[ind], D2, True)
+            gv_acc[ind] += dvb
+            if D_has_grad:
+                gD_acc += dD2
+            g_rows = gv_acc[ind]
+            v_old = v[ind].clone()
+            loss_batch_old = (loss_s + lambda_coding * torch.sum(torch.abs(v[ind]))).item()
+            v[ind] = softshrink(v[ind] - stepsize_v * g_rows, stepsize_v * lambda_coding)
+            loss_s = smooth(x, target, v[ind], D2, False)
+            v_cur = v[ind].clone()
+            loss_batch_cur = (loss_s + lambda_coding * torch.sum(torch.abs(v[ind]))).item()
+            loss_batch_cur_0 = loss_batch_cur
+            delta_h = (torch.sum(torch.mul(g_rows, (v_cur - v_old))) + 1 / 2 / stepsize_v * torch.norm(v_cur - v_old) ** 2
+                       + (torch.sum(torch.abs(v_cur)) - torch.sum(torch.abs(v[ind])))).item()
+            i = 0
+            while loss_batch_cur > loss_batch_old + delta_h * beta and i < 5:
+                i += 1
+                v[ind] = (delta ** i) * v_cur + (1 - delta ** i) * v_old
+                loss_s = smooth(x, target, v[ind], D2, False)
+                loss_batch_cur = (loss_s + torch.sum(torch.abs(v[ind]))).item()
+                delta_h = delta_h * delta
+            v[ind] = v_cur                         # (both branches of :444-448 keep the full step)
+            if not loss_batch_cur_0 <= loss_batch_cur:
+                i_max = max(i, i_max)
+            # ---------- gradient of the D-step, new codes (:450-461) ----------
+            _, dD2, dvb = smooth(x, target, v[ind], D2, True)
+            D_has_grad = True
+            gD_acc += dD2
+            gv_acc[ind] += dvb
+        stepsize_v = max(stepsize_v * (delta ** i_max), 1e-5)
+        grad_D = gD_acc
+        if torch.max(torch.abs(grad_D)).item() < 1e-4:
+            if trace is not None:
+                trace.append((i_max, -1))
+            continue
+        D_old = D2.clone()
+        loss_i_old = loss_all(v, D_old)
+        D2 = project_atoms((D2 - stepsize_D * grad_D).reshape(nc, nx, ny, n_atom), mode).reshape(P, n_atom)
+        D_cur = D2.clone()
+        loss_i_cur = loss_all(v, D_cur)
+        loss_i_cur_0 = loss_i_cur
+        delta_h_D = torch.sum(torch.mul(grad_D, (D_cur - D_old))) + 1 / 2 / stepsize_D * torch.norm(D_cur - D_old) ** 2
+        i = 0
+        while loss_i_cur > loss_i_old + delta_h_D * beta and i < 5:
+            i += 1
+            loss_i_cur = loss_all(v, (delta ** i) * D_cur + (1 - delta ** i) * D_old)
+            delta_h_D = delta_h_D * delta
+        D2 = D_cur                                 # (:486-492: the full step is kept either way)
+        if loss_i_cur_0 <= loss_i_cur:
+            loss.append(loss_i_cur_0)
+        else:
+            stepsize_D = max(stepsize_D * delta ** i, 1e-6)
+            loss.append(loss_i_cur)
+        gD_acc = torch.zeros(P, n_atom)            # a new D tensor: no gradient yet
+        D_has_grad = False
+        if trace is not None:
+            trace.append((i_max, i))
+        if abs(loss[-1] - loss[-2]) < 1e-6:
+            break
+    return D2.reshape(nc, nx, ny, n_atom), v, loss, (stepsize_v, stepsize_D)

@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 OUT=gpurun_out
 rm -f $OUT/paritw_r02.json $OUT/w_summary.log
-python -c "import __graft_entrw__ as g; g.smoke()" > $OUT/w_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/w_summary.log; tail -1 $OUT/w_smoke.log | tee -a $OUT/w_summary.log
+python -c "import __graft_entry__ as g; g.smoke()" > $OUT/w_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/w_summary.log; tail -1 $OUT/w_smoke.log | tee -a $OUT/w_summary.log
 python -m pytest tests -m gpu -q > $OUT/w_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/w_summary.log
 tail -6 $OUT/w_pytest.log | tee -a $OUT/w_summary.log
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/w_bench_ref.json 2> $OUT/w_bench_ref.err; echo "ref rc=$?" | tee -a $OUT/w_summary.log
