@@ -1,6 +1,7 @@
 """Regularised ADiL variants on the B200 kernels: `sadil`, the stochastic forward-backward scheme of the reference's
 attacks/attacks_classes/adil_regularized.py:200-312, `adil`, its full-batch scheme with backtracking line search
-(:31-197), and `learn_coding_vectors`, the coder on a fixed dictionary (:508-628), for the penalised objective  coeff * CE(x + D v) + 0.5 * l2_fool * ||D v||^2 + lambdaCoding * ||v||_1  with
+(:31-197), `sadil_updated` (:315-501) and `learn_coding_vectors`, the coder on a fixed dictionary (:508-628), for the
+penalised objective  coeff * CE(x + D v) + 0.5 * l2_fool * ||D v||^2 + lambdaCoding * ||v||_1  with
 D constrained per atom.  Same function names and arguments as the reference; the arithmetic of the path runs in the
 CUDA kernels behind the C ABI (include/adil_b200.h) -- there is no CPU path:
 
@@ -343,3 +344,148 @@ def learn_coding_vectors(dataset, model, targeted=True, niter=1e2, lambda_l1=1.,
         if loss_all[-2] - loss_all[-1] < 1e-6:
             break
     return v
+
+
+def sadil_updated(dataset, model, targeted=True, nepochs=1e3, batchsize=1, lambdaCoding=1., l2_fool=1., stepsize=1.,
+                  n_atom=5, dict_set='l2ball', device=None, model_file=None, dictionary=None, trace=None):
+    """SADiL, "updated" (adil_regularized.py:315-501): per epoch a proximal step on the code rows of every minibatch and ONE
+    projected gradient step on D with the gradient accumulated over the epoch; both steps are followed by a backtracking
+    test (factor 0.5, at most 5 halvings) that adapts the step sizes while the full steps are kept (:444-448,486-492).
+    Returns (D [C,H,W,K], v [N,K]) like the reference and saves [D, label, pred, v, loss] to `model_file` (:499);
+    `dictionary` optionally gives the initial D (the reference draws randn and projects it); `trace` (a list) receives
+    per epoch (largest number of halvings of the V-steps, halvings of the D-step or -1 when it was skipped, loss).
+
+    The reference's autograd bookkeeping is kept (restated explicitly in the test suite's CPU checker, which reproduces the
+    reference bit for bit): the
+    gradient of v accumulates over every backward of the run, the gradient of D over every backward since the first
+    D-step backward of the current D.  On the kernels: adil_synth (perturbation output), the classifier's input
+    gradient, the l2-penalised contractions with dD ACCUMULATED in place (adil_grad, ADIL_GRAD_ACCUMULATE_DD),
+    adil_code_prox_step, adil_dict_step_atoms and loss-only passes."""
+    dev = _device_of(model)
+    model = model.eval()
+    net, mean, std = split_normalize(model)
+    flags = ops.SYNTH_NORMALIZE if mean is not None else 0
+    nimg = len(dataset)
+    x0, _ = next(iter(dataset))
+    nc, nx, ny = x0.shape
+    P = nc * nx * ny
+    K = n_atom
+    delta_ls, beta = .5, .5
+    atoms_mode = _ATOMS.get(dict_set, ops.ATOMS_L1BALL)
+    coeff = 1. if targeted else -1.
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False)
+    batches, start = [], 0
+    for x, y in loader:                                         # the set stays resident in HBM (shuffle=False: fixed slices)
+        n = x.shape[0]
+        batches.append((x.to(dev).float().contiguous(), y.to(dev), torch.arange(start, start + n, device=dev)))
+        start += n
+    targets = [get_target(x, y, targeted, model) for x, y, _ in batches]   # (clean images, fixed classifier: loop invariant)
+    if dictionary is None:
+        D = ops.project_atoms(torch.randn(3, nx, ny, K, device=dev), atoms_mode)   # :357-358
+    else:
+        D = dictionary.to(dev).float().contiguous().clone()
+        K = D.shape[-1]
+    D2 = D.view(P, K)
+    v = torch.zeros(nimg, K, device=dev)
+    stepsize_D = stepsize_v = stepsize
+
+    def smooth_and_grads(x, target, rows, want_dD):
+        """loss_smooth (:395-396) as an fp32 device scalar; its code gradient; dD accumulated into gD_acc"""
+        n = x.shape[0]
+        pert = torch.empty(n, P, device=dev)
+        xin, _ = ops.synth(D2, v, rows, x=x.view(n, -1), mean=mean, std=std, flags=flags, delta_out=pert, n_channels=nc)
+        xin = xin.view_as(x).requires_grad_(True)
+        ce = coeff * torch.nn.functional.cross_entropy(net(xin), target, reduction='sum')
+        (g,) = torch.autograd.grad(ce, xin)
+        _, dvb = ops.grad(g.contiguous().view(n, P), D2, v, rows, std, want_dD=want_dD, dD2=gD_acc if want_dD else None,
+                          accumulate=want_dD, delta=pert, l2_coef=l2_fool)
+        return ce.detach() + .5 * l2_fool * pert.square().sum(), dvb
+
+    def smooth_only(x, target, rows, D2_):
+        n = x.shape[0]
+        with torch.no_grad():
+            pert = torch.empty(n, P, device=dev)
+            adv, _ = ops.synth(D2_, v, rows, x=x.view(n, -1), delta_out=pert)
+            return coeff * torch.nn.functional.cross_entropy(model(adv.view_as(x)), target, reduction='sum') \
+                + .5 * l2_fool * pert.square().sum()
+
+    def loss_all(D2_):                                                                       # :362-373
+        total = 0
+        for (x, _, rows), target in zip(batches, targets):
+            total += smooth_only(x, target, rows, D2_).item()
+        return total + (lambdaCoding * v.abs().sum()).item()
+
+    loss = [loss_all(D2)]
+    label, pred = [], []
+    gv_acc = torch.zeros(nimg, K, device=dev)       # v.grad of the reference: never zeroed
+    gD_acc = torch.zeros(P, K, device=dev)          # D.grad of the current D tensor
+    D_has_grad = False
+    D_old, D_try = torch.empty_like(D2), torch.empty_like(D2)
+    for epoch in range(int(nepochs)):
+        i_max = 0
+        for (x, y, rows), target in zip(batches, targets):
+            if epoch == 0:                                                                   # :387-389
+                label += y.tolist()
+                with torch.no_grad():
+                    pred += model(x).sort().indices[:, -1].tolist()
+            # ---------- V-step (:391-448) ----------
+            loss_s, dvb = smooth_and_grads(x, target, rows, D_has_grad)
+            gv_acc[rows] += dvb
+            g_rows = gv_acc[rows].contiguous()
+            v_old = v[rows].clone()
+            loss_batch_old = (loss_s + lambdaCoding * v_old.abs().sum()).item()
+            ops.code_prox_step(v, g_rows, rows, stepsize_v, ops.ROWS_SOFTSHRINK, stepsize_v * lambdaCoding)   # :412-416
+            v_cur = v[rows].clone()
+            loss_batch_cur = (smooth_only(x, target, rows, D2) + lambdaCoding * v_cur.abs().sum()).item()
+            loss_batch_cur_0 = loss_batch_cur
+            d = v_cur - v_old
+            delta_h = ((g_rows * d).sum() + 1 / 2 / stepsize_v * torch.norm(d) ** 2).item()   # (:420-421: the l1 terms cancel)
+            i = 0
+            while loss_batch_cur > loss_batch_old + delta_h * beta and i < 5:
+                i += 1
+                v[rows] = (delta_ls ** i) * v_cur + (1 - delta_ls ** i) * v_old
+                loss_batch_cur = (smooth_only(x, target, rows, D2) + v[rows].abs().sum()).item()   # (:433: no lambda)
+                delta_h = delta_h * delta_ls
+            v[rows] = v_cur                                                                  # :444-448 keep the full step
+            if not loss_batch_cur_0 <= loss_batch_cur:
+                i_max = max(i, i_max)
+            # ---------- gradient of the D-step at the new codes (:450-461) ----------
+            _, dvb = smooth_and_grads(x, target, rows, True)
+            D_has_grad = True
+            gv_acc[rows] += dvb
+        stepsize_v = max(stepsize_v * (delta_ls ** i_max), 1e-5)                              # :463
+        if gD_acc.abs().max().item() < 1e-4:                                                 # :466-467
+            if trace is not None:
+                trace.append((i_max, -1, loss[-1]))
+            continue
+        D_old.copy_(D2)
+        loss_i_old = loss_all(D_old)
+        if atoms_mode == ops.ATOMS_L1BALL:                                                   # :472-474
+            ops.dict_step_atoms(D2, gD_acc, ops.ATOMS_NONE, step=stepsize_D)
+            ops.project_atoms(D, ops.ATOMS_L1BALL)
+        else:
+            ops.dict_step_atoms(D2, gD_acc, atoms_mode, step=stepsize_D)
+        loss_i_cur = loss_all(D2)
+        loss_i_cur_0 = loss_i_cur
+        dd = D2 - D_old
+        delta_h_D = ((gD_acc * dd).sum() + 1 / 2 / stepsize_D * torch.norm(dd) ** 2).item()
+        i = 0
+        while loss_i_cur > loss_i_old + delta_h_D * beta and i < 5:                          # :481-485
+            i += 1
+            torch.add(D_old, dd, alpha=delta_ls ** i, out=D_try)
+            loss_i_cur = loss_all(D_try)
+            delta_h_D = delta_h_D * delta_ls
+        if loss_i_cur_0 <= loss_i_cur:                                                       # :486-492: D stays the full step
+            loss.append(loss_i_cur_0)
+        else:
+            stepsize_D = max(stepsize_D * delta_ls ** i, 1e-6)
+            loss.append(loss_i_cur)
+        gD_acc.zero_()                                 # the reference's new D tensor has no gradient yet
+        D_has_grad = False
+        if trace is not None:
+            trace.append((i_max, i, loss[-1]))
+        if abs(loss[-1] - loss[-2]) < 1e-6:
+            break
+    if model_file is not None:
+        torch.save([D, label, pred, v, loss], model_file)                                    # :499
+    return D, v
