@@ -1769,9 +1769,10 @@ SynthPlan plan_synth(int B, int P, int K, int hw) {
   pl.ok = false;
   if (B < 1 || B > 128 || K < 1 || K > 224 || P % 4 != 0 || hw % 4 != 0) return pl;  // (codes: 2 Kp8 <= 448 TMEM columns)
   const int tps[4] = {64, 48, 32, 16};
+  static const int max_tp = getenv("ADIL_SYNTH_MAX_TP") ? atoi(getenv("ADIL_SYNTH_MAX_TP")) : 64;  // tuning knob
   for (int i = 0; i < 4; ++i) {
     const int TP = tps[i];
-    if (hw < TP) continue;  // a tile may span at most two channels
+    if (hw < TP || TP > max_tp) continue;  // a tile may span at most two channels
     pl.TP = TP;
     pl.Kp8 = rup(K, 8);
     pl.Sd = img_stride(TP);

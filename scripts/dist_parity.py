@@ -34,7 +34,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     EPS = 8.0 / 255.0
-    N, K, B, EPOCHS = 32 * world, 50, 16, 2
+    N, K, B, EPOCHS = 32 * world, int(os.environ.get("ADIL_PARITY_K", "50")), 16, 2   # (K = 200: the column-window kernels)
     arch = os.environ.get("ADIL_PARITY_MODEL", "resnet18")
     model = build_classifier(arch, seed=0, device=dev)
     x, y = synthetic_images(N, seed=1)
@@ -223,7 +223,7 @@ def main():
     if rank == 0:
         report["collective_times_max_over_ranks"] = times
         tag = os.environ.get("ADIL_DICT_STEP", "auto")
-        with open(os.path.join(ROOT, "gpurun_out", "dist_parity_r02_w%d_%s.json" % (world, tag)), "w") as f:
+        with open(os.path.join(ROOT, "gpurun_out", "dist_parity_r02_w%d_%s%s.json" % (world, tag, "" if K == 50 else "_k%d" % K)), "w") as f:
             json.dump(report, f, indent=1)
         print(json.dumps({"backend": report["dict_step_backend"], "multicast": report.get("dict_step_multicast"),
                           "pass": report["pass"], "worst": report["worst"],
