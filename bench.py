@@ -84,13 +84,17 @@ def make_config(args, world):
     }
 
 
-def measured_traffic(kernel):
+def measured_traffic(kernel, B, K):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json):
-    dram__bytes_read.sum + dram__bytes_write.sum.  None when no capture is recorded for it."""
+    dram__bytes_read.sum + dram__bytes_write.sum.  None when no capture is recorded for this kernel AT THIS SHAPE (entries
+    are keyed `kernel` for the B=100, K=50 captures and `kernel@K=<K>` for the others; the shape is in their `config`)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
-            d = json.load(f)[kernel]
+            table = json.load(f)
+        d = table.get("%s@K=%d" % (kernel, K)) or table[kernel]
+        if ("B=%d, K=%d," % (B, K)) not in d.get("config", ""):
+            return None
         return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
     except Exception:
         return None
@@ -419,7 +423,7 @@ def run_ours(args):
     if dom in kernels:
         k = kernels[dom]
         roofline = {"bound": "hbm", "kernel": kname, "achieved": k["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": k["frac"], "traffic": measured_traffic(tname), "alg_bytes": k["alg_bytes"],
+                    "frac": k["frac"], "traffic": measured_traffic(tname, B, K), "alg_bytes": k["alg_bytes"],
                     "kernel_ms": k["ms"], "peak_source": peak_src}
     dkey = "dict_step_peer" if "dict_step_peer" in kernels else "dict_step_slice"
     if world > 1 and all(n in kernels for n in ("synth", "grad", dkey)):

@@ -1795,7 +1795,13 @@ struct GradPlan {
 // Tile cap of a column window of the fused step (two windows in one launch): measured at K = 136 / 176 / 200 / 256
 // (windows of 68 / 88 / 100 / 128 atoms): TP = 32 beats 64 and 48 (160 vs 180 us, 168 vs 252, -, -), and a window whose
 // 32-pixel tile has more than 3 x 320 float4 items (the ten-warp AdamW pass) is faster at TP = 16 (K = 256: 249 vs 294 us).
-int window_tp_cap(int Kwin) { return (32 * Kwin) / 4 <= 3 * NEP_MAX * 32 ? 32 : 16; }
+// The plain contractions of a window do not care (K = 200: 122 / 124 / 124 us at TP = 64 / 48 / 32; TP = 16 is slower): up to
+// 120 atoms per window they take the fused step's tile, so that the code gradient of the multi-GPU path (plain
+// contractions + sharded dictionary step) accumulates in the same order as the single-GPU fused step -- bit-identical dv.
+int window_tp_cap(int Kwin, bool fused) {
+  if ((32 * Kwin) / 4 <= 3 * NEP_MAX * 32) return 32;
+  return fused ? 16 : 64;
+}
 
 GradPlan plan_grad(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool fused, int tp_cap = 64) {
   GradPlan pl{};
@@ -1985,7 +1991,7 @@ bool tc_grad_ok(int B, int P, int K, int hw, bool want_dD, bool want_dv, bool fu
   if (K <= 128) return plan_grad(B, P, K, hw, want_dD, want_dv, fused).ok;
   // more than 128 atoms: two column windows of K/2 atoms (row pitch and window offsets must keep 16-byte alignment)
   if (K > 256 || K % 8 != 0) return false;
-  return plan_grad(B, P, K / 2, hw, want_dD, want_dv, fused, fused ? window_tp_cap(K / 2) : 64).ok;
+  return plan_grad(B, P, K / 2, hw, want_dD, want_dv, fused, window_tp_cap(K / 2, fused)).ok;
 }
 
 int launch_grad_tc(float* dD2, float* D2_rw, float* m, float* s, float* dvb, const float* g, const float* D2,
@@ -2024,7 +2030,7 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
              fused = D2_rw != nullptr;
   if (!want_dD && !want_dv) return 0;
   const int hw = cc.use ? cc.hw : P;
-  const GradPlan pl = plan_grad(B, P, K, hw, want_dD, want_dv, fused, (fused && nwin == 2) ? window_tp_cap(K) : 64);
+  const GradPlan pl = plan_grad(B, P, K, hw, want_dD, want_dv, fused, nwin == 2 ? window_tp_cap(K, fused) : 64);
   if (!pl.ok) return set_error(-4, "adil_grad: shape B=%d P=%d K=%d does not qualify for the tcgen05 path", B, P, K);
   GradArgs a;
   a.dD2 = dD2; a.D2w = D2_rw; a.m = m; a.s = s; a.partial = scratch; a.g = g; a.D2 = D2; a.v = v; a.vidx = v_index;

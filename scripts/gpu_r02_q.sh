@@ -19,3 +19,5 @@ try:
 except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/q_bench_cfg5_n%s.err" % sys.argv[1]).read()[-2500:])
 PY
+rm -rf gpurun_out/trained_dicts trained_dicts   # (the K = 200 dictionary files are 120 MB each: beyond what gpurun copies back)
+ls -la gpurun_out | head -30
