@@ -384,6 +384,35 @@ __device__ __forceinline__ void tile_chan_update(TileChan& t, const ChannelConst
 
 // synthesis: staged code row (fp32, `crow`) -> hi / lo TF32 terms in tensor memory, 8-atom chunks c = c0, c0 + 4, ...
 // (the four warps of a TMEM quadrant share the chunks); atoms >= K and rows of images >= B are written as zeros.
+// Eight consecutive code values of one row, straight from global memory (the register path of the synthesis kernel: code
+// rows that do not fit the staging buffer, i.e. more than ~100 atoms).  With 16-byte-aligned rows two 128-bit loads
+// instead of eight scalar ones: a worker thread issues 8 requests per round instead of 32 (K = 200: the scalar gather
+// was a fifth of all stall samples of the kernel, profiles/r02c5_synth_kernel_ncu_summary.txt).
+__device__ __forceinline__ void load_codes8(const float* vrow, int k0, int K, bool ok, bool vec4, float (&out)[8]) {
+  if (vec4) {
+    float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
+    if (ok && k0 < K) lo4 = __ldg(reinterpret_cast<const float4*>(vrow + k0));
+    if (ok && k0 + 4 < K) hi4 = __ldg(reinterpret_cast<const float4*>(vrow + k0 + 4));
+    out[0] = lo4.x; out[1] = lo4.y; out[2] = lo4.z; out[3] = lo4.w;
+    out[4] = hi4.x; out[5] = hi4.y; out[6] = hi4.z; out[7] = hi4.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = (ok && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+  }
+}
+
+// (the export of the same values as rows of the contiguous [B, K] block the backward kernel of the step fetches)
+__device__ __forceinline__ void store_codes8(float* orow, int k0, int K, bool vec4, const float (&val)[8]) {
+  if (vec4) {
+    if (k0 < K) *reinterpret_cast<float4*>(orow + k0) = make_float4(val[0], val[1], val[2], val[3]);
+    if (k0 + 4 < K) *reinterpret_cast<float4*>(orow + k0 + 4) = make_float4(val[4], val[5], val[6], val[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (k0 + i < K) orow[k0 + i] = val[i];
+  }
+}
+
 template <int CW>
 __device__ __forceinline__ void synth_codes_to_tmem(const float* crow, bool b_ok, int K, int Kp8, int c0, uint32_t lane_base) {
   const int nchunks = Kp8 >> 3;
@@ -544,10 +573,12 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
       const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
       const float* vrow = a.v + row * K;
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int k0 = 8 * ((warp >> 2) + 4 * ci);
+      for (int ci = 0; ci < 4; ++ci) load_codes8(vrow, 8 * ((warp >> 2) + 4 * ci), K, b < B, a.cw == 4, vv[ci]);
+      // the last CTA (never one with more tiles than the others) leaves the rows behind as the contiguous [B, K] block the
+      // backward kernel of the step fetches with one bulk copy (a launch of its own before: 5-7 us per step at K = 200)
+      if (a.codes_out != nullptr && blockIdx.x == gridDim.x - 1 && b < B) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+        for (int ci = 0; ci < 4; ++ci) store_codes8(a.codes_out + (size_t)b * K, 8 * ((warp >> 2) + 4 * ci), K, a.cw == 4, vv[ci]);
       }
     }
     if (tid == 0) SSTAMP(13);
@@ -709,10 +740,10 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
           const long long row = a.hv_on ? (long long)a.hv[bi] : (a.vidx ? (long long)a.vidx[bi] : (long long)bi);
           const float* vrow = a.v + row * K;
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
-            const int k0 = 8 * (16 + cg + 4 * ci);
+          for (int ci = 0; ci < 4; ++ci) load_codes8(vrow, 8 * (16 + cg + 4 * ci), K, b < B, a.cw == 4, vv[ci]);
+          if (a.codes_out != nullptr && blockIdx.x == gridDim.x - 1 && b < B) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vv[ci][i] = (b < B && k0 + i < K) ? __ldg(vrow + k0 + i) : 0.0f;
+            for (int ci = 0; ci < 4; ++ci) store_codes8(a.codes_out + (size_t)b * K, 8 * (16 + cg + 4 * ci), K, a.cw == 4, vv[ci]);
           }
 #pragma unroll
           for (int ci = 0; ci < 4; ++ci) {
@@ -1839,18 +1870,6 @@ int set_smem(KernelT kern, size_t smem, const char* what) {
   return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), what);
 }
 
-// codes_out[b, :] = v[row(b), :] -- the export of the code rows when the synthesis kernel itself does not stage them in
-// shared memory (more atoms than its second image buffer holds): a launch of its own, off the benchmarked shapes
-struct GatherIdx {
-  int on;
-  int idx[128];
-};
-__global__ void gather_codes_kernel(float* codes_out, const float* v, const int64_t* vidx, const GatherIdx h, int K) {
-  const int b = blockIdx.x;
-  const long long row = h.on ? (long long)h.idx[b] : (vidx ? (long long)vidx[b] : (long long)b);
-  for (int k = threadIdx.x; k < K; k += blockDim.x) codes_out[(size_t)b * K + k] = v[row * K + k];
-}
-
 template <int TP, bool TRAIN>
 int launch_synth_tp(const SynthArgs& a, size_t smem, int grid, cudaStream_t st) {
   int rc = set_smem(synth_kernel<TP, TRAIN>, smem, "cudaFuncSetAttribute(synth_kernel)");
@@ -1905,15 +1924,6 @@ int launch_synth_tc(float* out, float* delta_out, const float* x, const int64_t*
       static const int stage_knob = getenv("ADIL_SYNTH_STAGE_CODES") ? atoi(getenv("ADIL_SYNTH_STAGE_CODES")) : 1;  // A/B knob
       a.stage_codes = (stage_knob != 0 && (size_t)nb * a.cpitch <= 2 * (size_t)pl.dimg) ? 1 : 0;
       a.rpw = (nb + NTHREADS_SYNTH / 32 - 1) / (NTHREADS_SYNTH / 32);
-    }
-    if (a.codes_out != nullptr && !a.stage_codes) {
-      GatherIdx h;
-      h.on = a.hv_on;
-      if (a.hv_on) for (int i = 0; i < nb; ++i) h.idx[i] = a.hv[i];
-      gather_codes_kernel<<<nb, 64, 0, st>>>(a.codes_out, a.v, a.vidx, h, K);
-      int rcg = check_cuda(cudaGetLastError(), "gather_codes_kernel launch");
-      if (rcg) return rcg;
-      a.codes_out = nullptr;
     }
     const int ntiles = (P + pl.TP - 1) / pl.TP;
     int grid = sm_count();

@@ -381,7 +381,7 @@ def test_host_index_arrays_give_identical_results(ops, B, hw, K):
 
 # ---- the code rows that synthesis leaves behind for the backward kernel ----------------------------------------------
 @pytest.mark.parametrize("B,hw,K", [(100, 784, 50), (33, 400, 64), (1, 64, 1), (37, 5300, 33), (128, 196, 100), (16, 256, 200),
-                                    (130, 100, 37), (100, 50176, 50)])
+                                    (130, 100, 37), (100, 50176, 50), (100, 196, 128), (50, 400, 150), (100, 400, 224)])
 @pytest.mark.parametrize("impl", ["fma", "auto"])
 @pytest.mark.parametrize("host_index", [False, True])
 def test_codes_block_left_by_synth_gives_identical_backward(ops, B, hw, K, impl, host_index):
