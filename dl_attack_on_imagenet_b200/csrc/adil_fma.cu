@@ -457,6 +457,10 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(float* __restrict
   __shared__ float part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
+  // (slab_step > 1: the slabs of slab_step column windows are interleaved -- CTA c of the contraction kernel wrote window
+  // c % slab_step; blockIdx.y is the window: its slabs start at slab blockIdx.y, its outputs at column blockIdx.y * K)
+  partial += (size_t)blockIdx.y * n;
+  dvb += (size_t)blockIdx.y * K;
   // launched with programmatic stream serialisation: the grid may be resident before the contraction kernel has
   // finished; this waits for its completion and for the visibility of its slabs
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -493,11 +497,12 @@ int launch_grad_tp(const GradArgs& a, size_t smem, int grid, cudaStream_t st) {
 
 }  // namespace
 
-// (slab_step: the slabs to add are slab_step slabs apart -- two column windows contracted by one launch)
+// (slab_step: the slabs to add are slab_step slabs apart -- slab_step column windows contracted by one launch, all of
+// them reduced by this one launch: nslabs slabs each)
 int launch_reduce_partials(float* dvb, const float* partial, int n, int nslabs, int K, int ld_out, cudaStream_t st,
                            int slab_step = 1) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)((n + 31) / 32));
+  cfg.gridDim = dim3((unsigned)((n + 31) / 32), (unsigned)slab_step);
   cfg.blockDim = dim3(1024);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;

@@ -2132,11 +2132,8 @@ int launch_grad_window(float* dD2, float* D2_rw, float* m, float* s, float* dvb,
       if (opt.nslabs_out) *opt.nslabs_out = grid;
       return 0;
     }
-    if (nwin == 2) {  // slabs of window h: CTAs h, h + 2, ... -> columns [h K, h K + K) of dvb
-      int rc2 = launch_reduce_partials(dvb, scratch, B * K, grid / 2, K, dv_ld, st, 2);
-      if (rc2) return rc2;
-      return launch_reduce_partials(dvb + K, scratch + (size_t)B * K, B * K, grid / 2, K, dv_ld, st, 2);
-    }
+    // slabs of window h: CTAs h, h + 2, ... -> columns [h K, h K + K) of dvb (one launch, blockIdx.y = window)
+    if (nwin == 2) return launch_reduce_partials(dvb, scratch, B * K, grid / 2, K, dv_ld, st, 2);
     return launch_reduce_partials(dvb, scratch, B * K, grid, K, dv_ld, st);
   }
   return 0;

@@ -243,10 +243,9 @@ def _host_index_retry(call, v_index, dev):
 
 
 def _n_launches_with_reduction(B, P, K):
-    """launches of a backward call that returns the reduced code gradient: the contraction kernel + the slab reduction --
-    on the tcgen05 path beyond 128 atoms ONE contraction launch covers both column windows, each window's slabs are
-    reduced by a launch of their own"""
-    return 3 if (K > 128 and get_impl() != IMPL_FMA and tc_supported(B, P, K)) else 2
+    """launches of a backward call that returns the reduced code gradient: the contraction kernel (beyond 128 atoms ONE
+    launch covers both column windows) + the slab reduction (one launch, both windows)"""
+    return 2
 
 
 def _grad_call(dD2, dvb, g, D2, v, v_index, B, P, K, std, flags, dev, delta=None, l2_coef=0.0):
