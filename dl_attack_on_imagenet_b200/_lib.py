@@ -29,6 +29,7 @@ SIGNATURES = {
     "adil_version": (_I, []),
     "adil_last_error": (ctypes.c_char_p, []),
     "adil_device_info": (_I, [ctypes.POINTER(_I)] * 3),
+    "adil_l2_persist": (_I, [_P, _SZ, _P]),
     "adil_set_impl": (_I, [_I]),
     "adil_get_impl": (_I, []),
     "adil_tc_supported": (_I, [_I, _I, _I]),

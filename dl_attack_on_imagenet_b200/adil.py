@@ -45,6 +45,9 @@ class _IndexOnly(torch.utils.data.Dataset):
         return item
 
 
+_L2_PERSIST_D = os.environ.get("ADIL_L2_PERSIST_D", "0") == "1"
+
+
 class AdilState(object):
     """Learnables and AdamW state, all resident in HBM.  D: [C,H,W,K] (atoms innermost), v: [N,K].
 
@@ -402,6 +405,9 @@ class ADIL(Attack):
         shard = st.shard
         if shard is not None:
             shard.wait()                                   # the dictionary of the previous step is complete
+        if _L2_PERSIST_D and shard is None and not getattr(st, "_l2_persist_set", False):
+            ops.l2_persist(st.D2)                          # (opt-in experiment: ADIL_L2_PERSIST_D=1)
+            st._l2_persist_set = True
         nb = kv_index.numel() if kv_index is not None else x_src.shape[0]
         if nb == 0:
             if shard is None or update == 'v':

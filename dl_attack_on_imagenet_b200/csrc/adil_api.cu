@@ -127,6 +127,38 @@ extern "C" int adil_device_info(int* sm, int* cc_major, int* cc_minor) {
   return 0;
 }
 
+extern "C" int adil_l2_persist(const void* base, size_t bytes, void* stream) {
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  cudaStreamAttrValue val;
+  memset(&val, 0, sizeof(val));
+  if (base == nullptr || bytes == 0) {
+    val.accessPolicyWindow.num_bytes = 0;
+    rc = check_cuda(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &val),
+                    "cudaStreamSetAttribute(access policy window, off)");
+    if (rc) return rc;
+    return check_cuda(cudaCtxResetPersistingL2Cache(), "cudaCtxResetPersistingL2Cache");
+  }
+  int max_persist = 0, max_window = 0;
+  rc = check_cuda(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev), "cudaDeviceGetAttribute");
+  if (rc) return rc;
+  rc = check_cuda(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev), "cudaDeviceGetAttribute");
+  if (rc) return rc;
+  if (max_persist <= 0 || max_window <= 0) return set_error(-3, "adil_l2_persist: the device has no persisting L2 set-aside");
+  const size_t limit = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+  const size_t window = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+  rc = check_cuda(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, limit), "cudaDeviceSetLimit(persisting L2)");
+  if (rc) return rc;
+  val.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+  val.accessPolicyWindow.num_bytes = window;
+  val.accessPolicyWindow.hitRatio = limit >= window ? 1.0f : (float)((double)limit / (double)window);
+  val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  return check_cuda(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &val),
+                    "cudaStreamSetAttribute(access policy window)");
+}
+
 extern "C" int adil_set_impl(int impl) {
   if (impl < ADIL_IMPL_AUTO || impl > ADIL_IMPL_TC) return set_error(-1, "adil_set_impl: bad impl %d", impl);
   g_impl = impl;

@@ -484,7 +484,12 @@ struct SynthArgs {
 };
 
 // TRAIN = the learning-loop configuration (x and out given, no delta output, no clamps): those branches vanish.
-template <int TP, bool TRAIN>
+// STAGE = the code rows are staged in shared memory by cp.async (they fit the second image buffer: up to ~100 atoms);
+// otherwise every worker thread fetches its share straight into registers.  A template parameter, not a run-time branch:
+// the path that is not taken still costs its instruction fetch when the kernel starts with cold instruction caches, as it
+// does inside a step (measured at config 2: the 128-bit register path compiled into the same kernel took the synthesis
+// from 35.3 to 36.8 us in-step -- and nothing in an isolated loop, scripts/gpu_r02_v.sh).
+template <int TP, bool TRAIN, bool STAGE>
 __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArgs a) {
   constexpr int XP = TP + 4;       // floats per staged image row (pitch 16 bytes off a multiple of 128)
   constexpr int Q4 = TP / 4;       // float4 per image row
@@ -554,7 +559,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   // when they do not fit there: straight into registers).  The requests of the later tiles follow after the set-up
   // barrier so that they queue behind these. ----
   float vv[4][8];
-  if (a.stage_codes) {
+  if constexpr (STAGE) {
     // code rows: warp w gathers rows [w rpw, (w + 1) rpw) -- a warp keeps only about four cp.async in flight (8 rows per
     // warp took two latencies), so the rows are spread over all the warps; lane l holds the address of row
     // w rpw + (l & 7) (one line of the parameters or of the index array per warp)
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     }
   }
   if (warp < NW) {
-    if (!a.stage_codes) {
+    if constexpr (!STAGE) {
       // worker thread <-> image b = 32*quad + lane (its TMEM lane); the warps of a quadrant share the 8-atom chunks
       const int b = (warp & 3) * 32 + lane;
       const int bi = min(b, B - 1);
@@ -583,7 +588,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     }
     if (tid == 0) SSTAMP(13);
 #pragma unroll 1
-    for (int buf = 0; buf < (a.stage_codes ? 1 : 2); ++buf) zero_padding(Dimg + buf * 2 * a.dimg, tid, NT);
+    for (int buf = 0; buf < (STAGE ? 1 : 2); ++buf) zero_padding(Dimg + buf * 2 * a.dimg, tid, NT);
     if (ragged) {  // stale rows of the raw stages must stay finite; the tiles are requested after the set-up barrier
       float4* z = reinterpret_cast<float4*>(raw);
       for (int e = tid; e < (NS * a.raw_floats) >> 2; e += NT) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -613,7 +618,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (a.stage_codes) cp_async_arrive_noinc(codes_landed);  // this thread's share of the gather (and nothing else: the image rows follow)
+  if constexpr (STAGE) cp_async_arrive_noinc(codes_landed);  // this thread's share of the gather (and nothing else: the image rows follow)
   if (tid == 0) SSTAMP(1);
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) SSTAMP(2);
@@ -704,7 +709,7 @@ __global__ void __launch_bounds__(NTHREADS_SYNTH, 1) synth_kernel(const SynthArg
     {
       const int nchunks = a.Kp8 / 8;
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * TP);
-      if (a.stage_codes) {
+      if constexpr (STAGE) {
         mbar_wait(codes_landed, 0);  // every warp's share of the gather has landed
         if (a.codes_out != nullptr && blockIdx.x == gridDim.x - 1) {
           // the last CTA (never one with more tiles than the others) leaves the gathered rows behind as a contiguous
@@ -1872,9 +1877,15 @@ int set_smem(KernelT kern, size_t smem, const char* what) {
 
 template <int TP, bool TRAIN>
 int launch_synth_tp(const SynthArgs& a, size_t smem, int grid, cudaStream_t st) {
-  int rc = set_smem(synth_kernel<TP, TRAIN>, smem, "cudaFuncSetAttribute(synth_kernel)");
+  if (a.stage_codes) {
+    int rc = set_smem(synth_kernel<TP, TRAIN, true>, smem, "cudaFuncSetAttribute(synth_kernel)");
+    if (rc) return rc;
+    synth_kernel<TP, TRAIN, true><<<grid, NTHREADS_SYNTH, smem, st>>>(a);
+    return 0;
+  }
+  int rc = set_smem(synth_kernel<TP, TRAIN, false>, smem, "cudaFuncSetAttribute(synth_kernel)");
   if (rc) return rc;
-  synth_kernel<TP, TRAIN><<<grid, NTHREADS_SYNTH, smem, st>>>(a);
+  synth_kernel<TP, TRAIN, false><<<grid, NTHREADS_SYNTH, smem, st>>>(a);
   return 0;
 }
 

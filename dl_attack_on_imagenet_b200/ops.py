@@ -177,6 +177,17 @@ def tc_supported(B, P, K):
     return bool(_lib.lib().adil_tc_supported(int(B), int(P), int(K)))
 
 
+def l2_persist(t):
+    """Opt-in (adil_l2_persist): keep tensor `t` (the dictionary) in the persisting set-aside of the L2 cache for the
+    kernels of the current stream; `None` removes the window."""
+    if t is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        _lib.check(_lib.lib().adil_l2_persist(None, 0, _stream(dev)), "adil_l2_persist")
+        return
+    _f32(t, "t")
+    _lib.check(_lib.lib().adil_l2_persist(_ptr(t), t.numel() * 4, _stream(t.device)), "adil_l2_persist")
+
+
 def device_info():
     sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     _lib.check(_lib.lib().adil_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)), "adil_device_info")

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ADIL_VERSION 210
+#define ADIL_VERSION 211
 
 #define ADIL_MAX_CHANNELS 8
 #define ADIL_MAX_ATOMS 256
@@ -85,6 +85,14 @@ const char* adil_last_error(void);
 
 /* Number of SMs / compute capability of the current device (needs a GPU). */
 int adil_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Opt-in: keep [base, base + bytes) -- the dictionary D2, which adil_synth and adil_grad_dict_step both read every step
+ * with 28 ms of classifier traffic in between -- in the persisting set-aside of the L2 cache: sets the device's
+ * persisting-L2 limit to min(bytes, device maximum) and an access-policy window (hit ratio = limit / window) on `stream`,
+ * so that the accesses of every kernel launched in that stream afterwards mark the lines persisting.  base == NULL or
+ * bytes == 0 removes the window and resets the persisting lines.  The reference has no counterpart (cuBLAS / foreach
+ * kernels re-read D from HBM); off by default -- measured effect in DESIGN.md section 7.4. */
+int adil_l2_persist(const void* base, size_t bytes, void* stream);
 
 /* Select the kernel family used by adil_synth / adil_grad / adil_grad_dict_step (process-wide). */
 int adil_set_impl(int impl);
