@@ -42,7 +42,11 @@ def test_binding_covers_header_exactly():
 def test_host_only_entry_points(library):
     from dl_attack_on_imagenet_b200 import _lib
     lib = _lib.lib()
-    assert lib.adil_version() >= 210
+    assert lib.adil_version() >= 211
+    # tcgen05 coverage by atom count (bit 0: synthesis, bit 1: backward): one window up to 128 atoms, two column windows
+    # in one launch up to 256 (K % 8 == 0), the synthesis codes fit tensor memory up to 224 atoms
+    for K, want in ((50, 3), (128, 3), (136, 3), (200, 3), (224, 3), (232, 2), (256, 2), (260, 0), (204, 1)):
+        assert lib.adil_tc_supported(100, 150528, K) == want, K
     assert lib.adil_grad_max_batch(150528, 50, 50176, 1) == 128 and lib.adil_grad_max_batch(150528, 300, 50176, 0) == 0
     assert lib.adil_grad_scratch_bytes(100, 50) >= 148 * 100 * 50 * 4
     assert lib.adil_grad_scratch_bytes(0, 50) == 0
