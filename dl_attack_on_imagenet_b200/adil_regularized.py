@@ -27,6 +27,17 @@ def _device_of(model):
     return dev
 
 
+def _resident_batches(dataset, batchsize, dev):
+    """[(x [n,C,H,W], y [n], rows of v)] of the reference's DataLoader(dataset, batch_size, shuffle=False) with its
+    get_slices index lists (utils.py:153-156), moved to the device once: the set stays resident in HBM."""
+    batches, start = [], 0
+    for x, y in torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False):
+        n = x.shape[0]
+        batches.append((x.to(dev).float().contiguous(), y.to(dev), torch.arange(start, start + n, device=dev)))
+        start += n
+    return batches
+
+
 def penalised_loss(model, batches, D2, v, coeff, l2_fool, lambdaCoding, targeted):
     """loss_all of adil_regularized.py:245-254: one loss-only pass (synthesis + classifier forward, no backward) over
     `batches` = [(x [n,C,H,W] on the device, y, rows of v)] -- also the evaluation every line search repeats."""
@@ -72,13 +83,7 @@ def sadil(dataset, model, targeted=True, nepochs=1e3, batchsize=1, lambdaCoding=
     K = n_atom
     atoms_mode = _ATOMS.get(dict_set, ops.ATOMS_L1BALL)
     coeff = 1. if targeted else -1.
-    loader = torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False)
-    batches = []
-    start = 0
-    for x, y in loader:                                         # the set stays resident in HBM (shuffle=False: fixed slices)
-        n = x.shape[0]
-        batches.append((x.to(dev).float().contiguous(), y.to(dev), torch.arange(start, start + n, device=dev)))
-        start += n
+    batches = _resident_batches(dataset, batchsize, dev)
     if dictionary is None:
         D = ops.project_atoms(torch.randn(3, nx, ny, K, device=dev), atoms_mode)   # adil_regularized.py:241-242
     else:
@@ -157,12 +162,7 @@ def adil(dataset, model, targeted=True, niter=1e3, lambdaCoding=1., l2_fool=1., 
     lipschitz = .9 / step_size
     coeff = 1. if targeted else -1.
     atoms_mode = _ATOMS.get(dict_set, ops.ATOMS_L1BALL)
-    loader = torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False)
-    batches, start = [], 0
-    for x, y in loader:                                         # the set stays resident in HBM (shuffle=False: fixed slices)
-        n = x.shape[0]
-        batches.append((x.to(dev).float().contiguous(), y.to(dev), torch.arange(start, start + n, device=dev)))
-        start += n
+    batches = _resident_batches(dataset, batchsize, dev)
     if learn_D:
         K = n_atom
         D = ops.project_atoms(torch.randn(3, nx, ny, K, device=dev), atoms_mode)   # adil_regularized.py:83-84
@@ -265,12 +265,7 @@ def learn_coding_vectors(dataset, model, targeted=True, niter=1e2, lambda_l1=1.,
     delta_ls, gamma, beta = .9, 1, .5
     batch_size = nimg if batch_size is None else batch_size
     coeff = 1. if targeted else -1.
-    loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False)
-    batches, start = [], 0
-    for x, y in loader:                                         # the set stays resident in HBM (shuffle=False: fixed slices)
-        n = x.shape[0]
-        batches.append((x.to(dev).float().contiguous(), y.to(dev), torch.arange(start, start + n, device=dev)))
-        start += n
+    batches = _resident_batches(dataset, batch_size, dev)
     targets = [get_target(x, y, targeted, model) for x, y, _ in batches]   # (clean images, fixed classifier: loop invariant)
     # the step size lives as an fp32 scalar and is updated with the reference's expressions (its default is a tensor, :509)
     step_t = torch.as_tensor(step_size, dtype=torch.float32).cpu()
@@ -373,12 +368,7 @@ def sadil_updated(dataset, model, targeted=True, nepochs=1e3, batchsize=1, lambd
     delta_ls, beta = .5, .5
     atoms_mode = _ATOMS.get(dict_set, ops.ATOMS_L1BALL)
     coeff = 1. if targeted else -1.
-    loader = torch.utils.data.DataLoader(dataset, batch_size=batchsize, shuffle=False)
-    batches, start = [], 0
-    for x, y in loader:                                         # the set stays resident in HBM (shuffle=False: fixed slices)
-        n = x.shape[0]
-        batches.append((x.to(dev).float().contiguous(), y.to(dev), torch.arange(start, start + n, device=dev)))
-        start += n
+    batches = _resident_batches(dataset, batchsize, dev)
     targets = [get_target(x, y, targeted, model) for x, y, _ in batches]   # (clean images, fixed classifier: loop invariant)
     if dictionary is None:
         D = ops.project_atoms(torch.randn(3, nx, ny, K, device=dev), atoms_mode)   # :357-358
