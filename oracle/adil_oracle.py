@@ -1,11 +1,14 @@
 """TEST INFRASTRUCTURE -- CPU oracle for the ADiL attack-learning hot path.
 
 This file is a *restatement* (flattened, explicit formulas, torch-CPU fp32 / optional fp64) of the
-algorithm in the reference `attacks/attacks_classes/adil.py` + `attacks/utils.py`.  It is the
+algorithm in the reference `attacks/attacks_classes/adil.py` + `attacks/utils.py`, and of the four
+function-level drivers of `attacks/attacks_classes/adil_regularized.py` (`sadil` :200-312, `adil` :31-197,
+`sadil_updated` :315-501, `learn_coding_vectors` :508-628).  It is the
 checker for the CUDA kernels; it is NOT a product path.  Only `tests/`, `__graft_entry__.smoke()`
 and `bench.py`'s cpu_baseline / `--impl reference` legs may import it.
 
-Parity pin: PINNED.  `oracle/make_golden.py` ran the UNMODIFIED reference (through
+Parity pin: PINNED.  `oracle/make_golden.py` (and `make_golden_imagenet.py`, `make_golden_adil_fb.py`,
+`make_golden_sadil_updated.py`, `make_golden_lcv.py`) ran the UNMODIFIED reference (through
 `oracle/ref_shim.py`) in the build container and committed its outputs under `tests/golden/`;
 `tests/test_oracle_golden.py` checks every function here against those fixtures (bit-exact on
 CPU for the projections / AdamW / whole-fit trajectories) and against the known-answer vectors
